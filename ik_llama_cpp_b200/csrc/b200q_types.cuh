@@ -1,0 +1,547 @@
+// b200q_types.cuh — wire formats -> B200 device layout ("planes") -> canonical decode.
+//
+// The wire format of every type is the reference's GGUF payload, consumed verbatim
+// (reference: ggml/src/ggml-common.h:166-775 block_* structs; value tables :2212-2250).
+// Those AoS blocks (18 B, 210 B, 4-byte row headers, ...) are only 2-byte aligned, which
+// rules out 16-byte vector loads and TMA boxes.  On upload (set_tensor) each tensor is
+// therefore re-laid-out ONCE into structure-of-planes form with identical total size:
+//
+//     plane p of a tensor [M rows x K cols]:  base + plane_off[p] + (row*nb + blk)*BYTES[p]
+//
+// where nb = K/QK is the number of wire blocks per row and plane_off[] are 256-byte aligned.
+// Inside a plane the bit order is chosen so that the decode kernels need no cross-lane
+// shuffles: every 32 weights ("item") own 16 contiguous bytes of low bits whose nibble order
+// makes `(w & 0x0F0F0F0F)` / PRMT-lookups produce int8 lanes in NATURAL k order, matching
+// a q8_1-quantised activation vector stored in natural order.
+// The mapping is a bijection (b200q_unrepack restores the wire bytes bit-for-bit), so
+// get_tensor / state save stay exact — same contract as the reference's run-time repack (-rtr).
+//
+// Canonical decode of one item (32 consecutive weights of one row), shared by the decode
+// mat-vec (b200q_mmvq.cu), the bf16 dequantiser and the tcgen05 prefill kernel (b200q_gemm.cu):
+//
+//     w[e] = dl[e/16] * q[e] - ml[e/16],    q[e] = int8(va byte e) (+ int8(vb byte e) if HAS_B)
+//
+// Everything here is __host__ __device__ so that tests/test_host_emulation.py can run the
+// exact same bit manipulation on the CPU (compiled with g++) against the oracle.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define B200Q_HD __host__ __device__ __forceinline__
+#else
+#define B200Q_HD inline
+#endif
+
+// ggml_type ids (reference ggml/include/ggml.h:391-492)
+enum b200q_type : int {
+    B200Q_TYPE_Q4_0 = 2, B200Q_TYPE_Q8_0 = 8, B200Q_TYPE_Q4_K = 12, B200Q_TYPE_Q5_K = 13, B200Q_TYPE_Q6_K = 14,
+    B200Q_TYPE_IQ4_NL = 20, B200Q_TYPE_IQ4_XS = 23, B200Q_TYPE_IQ2_BN = 135, B200Q_TYPE_IQ4_K = 139,
+    B200Q_TYPE_IQ5_K = 140, B200Q_TYPE_IQ4_KS = 144,
+};
+
+// ---------------------------------------------------------------------------------------------
+// small portable intrinsics
+// ---------------------------------------------------------------------------------------------
+B200Q_HD int b200q_dp4a(int a, int b, int c) {
+#if defined(__CUDA_ARCH__)
+    return __dp4a(a, b, c);
+#else
+    for (int i = 0; i < 4; ++i) c += (int)(int8_t)(a >> (8 * i)) * (int)(int8_t)(b >> (8 * i));
+    return c;
+#endif
+}
+// PTX prmt.b32 (default mode): selector nibble = {bit3: replicate sign of the selected byte, bits0-2: byte index in {a,b}}
+B200Q_HD uint32_t b200q_prmt(uint32_t a, uint32_t b, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, s);
+#else
+    uint64_t ab = ((uint64_t)b << 32) | a; uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint32_t sel = (s >> (4 * i)) & 0xF; uint32_t byte = (uint32_t)(ab >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+#endif
+}
+B200Q_HD float b200q_h2f(uint16_t h) {
+#if defined(__CUDA_ARCH__)
+    return __half2float(__ushort_as_half(h));
+#else
+    uint32_t s = (uint32_t)(h & 0x8000) << 16, e = (h >> 10) & 0x1f, m = h & 0x3ff, u;
+    if (e == 0) { if (m == 0) u = s; else { int sh = 0; while (!(m & 0x400)) { m <<= 1; ++sh; } m &= 0x3ff; u = s | ((uint32_t)(113 - sh) << 23) | (m << 13); } }
+    else if (e == 31) u = s | 0x7f800000u | (m << 13);
+    else u = s | ((e + 112) << 23) | (m << 13);
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout descriptor
+// ---------------------------------------------------------------------------------------------
+#define B200Q_MAX_PLANES 5
+struct b200q_layout {
+    int      type;
+    int      qk;                            // weights per wire block
+    int      wire_block;                    // wire bytes per block
+    int      row_meta;                      // wire bytes of per-row header (row scale), 0 if none
+    int      n_planes;
+    int      plane_bytes[B200Q_MAX_PLANES]; // bytes per wire block in plane p (per ROW for the row-meta plane)
+    int      plane_per_row[B200Q_MAX_PLANES]; // 1 if the plane is indexed per row instead of per block
+    int64_t  M, K, nb;                      // rows, cols, blocks per row
+    int64_t  plane_off[B200Q_MAX_PLANES];
+    int64_t  total_bytes;
+};
+
+B200Q_HD int64_t b200q_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// Fills geometry for `type`; returns 0 on success, -1 if the type is unknown, -2 if K is not a multiple of the block.
+inline int b200q_make_layout(int type, int64_t M, int64_t K, b200q_layout * L) {
+    memset(L, 0, sizeof(*L));
+    L->type = type; L->M = M; L->K = K;
+    auto set = [&](int qk, int wire, int meta, int np, int b0, int b1, int b2, int b3, int rowplane) {
+        L->qk = qk; L->wire_block = wire; L->row_meta = meta; L->n_planes = np;
+        int b[4] = {b0, b1, b2, b3};
+        for (int i = 0; i < np; ++i) { L->plane_bytes[i] = b[i]; L->plane_per_row[i] = (i == rowplane); }
+    };
+    switch (type) {
+        //                         qk  wire meta np  planes...                         row-plane idx
+        case B200Q_TYPE_IQ4_NL: set(32,  18, 0, 2, 16, 2, 0, 0, -1); break;   // qs | d
+        case B200Q_TYPE_Q4_0:   set(32,  18, 0, 2, 16, 2, 0, 0, -1); break;   // qs | d
+        case B200Q_TYPE_Q8_0:   set(32,  34, 0, 2, 32, 2, 0, 0, -1); break;   // qs | d
+        case B200Q_TYPE_Q4_K:   set(256, 144, 0, 2, 128, 16, 0, 0, -1); break; // qs | {d,dmin,scales[12]}
+        case B200Q_TYPE_Q5_K:   set(256, 176, 0, 3, 128, 32, 16, 0, -1); break; // qs | qh | {d,dmin,scales[12]}
+        case B200Q_TYPE_Q6_K:   set(256, 210, 0, 4, 128, 64, 16, 2, -1); break; // ql | qh | scales[16] | d
+        case B200Q_TYPE_IQ4_XS: set(256, 136, 0, 2, 128, 8, 0, 0, -1); break;  // qs | {d,scales_h,scales_l[4]}
+        case B200Q_TYPE_IQ4_K:  set(256, 144, 0, 2, 128, 16, 0, 0, -1); break; // qs | {d,extra,scales_h[4],scales_l[8]}
+        case B200Q_TYPE_IQ5_K:  set(256, 176, 0, 3, 128, 32, 16, 0, -1); break; // qs | qh | {d,extra,scales_h[4],scales_l[8]}
+        case B200Q_TYPE_IQ4_KS: set(256, 136, 4, 3, 128, 8, 4, 0, 2); break;   // qs | scales[8] | row scale
+        case B200Q_TYPE_IQ2_BN: set(64,  16, 4, 2, 16, 4, 0, 0, 1); break;     // qs | row scale
+        default: return -1;
+    }
+    if (K <= 0 || K % L->qk) return -2;
+    L->nb = K / L->qk;
+    int64_t off = 0;
+    for (int p = 0; p < L->n_planes; ++p) {
+        L->plane_off[p] = off;
+        const int64_t n = L->plane_per_row[p] ? M : M * L->nb;
+        off = b200q_align_up(off + n * L->plane_bytes[p], 256);
+    }
+    L->total_bytes = off;
+    return 0;
+}
+inline int64_t b200q_wire_row_size(const b200q_layout & L) { return (int64_t)L.row_meta + L.nb * L.wire_block; }
+
+// ---------------------------------------------------------------------------------------------
+// nibble / bit re-ordering helpers used by repack (wire -> planes) and unrepack
+// ---------------------------------------------------------------------------------------------
+// "A-order" (arithmetic types): item of 32 values e=0..31, 16 bytes; byte (4w+b): low nibble = e 8w+b, high = e 8w+4+b
+B200Q_HD void b200q_pack_nib_A(const uint8_t idx[32], uint8_t out[16]) {
+    for (int w = 0; w < 4; ++w) for (int b = 0; b < 4; ++b) out[4 * w + b] = (uint8_t)((idx[8 * w + b] & 0xF) | ((idx[8 * w + 4 + b] & 0xF) << 4));
+}
+B200Q_HD void b200q_unpack_nib_A(const uint8_t in[16], uint8_t idx[32]) {
+    for (int w = 0; w < 4; ++w) for (int b = 0; b < 4; ++b) { idx[8 * w + b] = in[4 * w + b] & 0xF; idx[8 * w + 4 + b] = in[4 * w + b] >> 4; }
+}
+// "L-order" (PRMT-lookup types): nibble j of 32-bit word w = e 8w+j, i.e. byte (4w+b): low = e 8w+2b, high = e 8w+2b+1
+B200Q_HD void b200q_pack_nib_L(const uint8_t idx[32], uint8_t out[16]) {
+    for (int i = 0; i < 16; ++i) out[i] = (uint8_t)((idx[2 * i] & 0xF) | ((idx[2 * i + 1] & 0xF) << 4));
+}
+B200Q_HD void b200q_unpack_nib_L(const uint8_t in[16], uint8_t idx[32]) {
+    for (int i = 0; i < 16; ++i) { idx[2 * i] = in[i] & 0xF; idx[2 * i + 1] = in[i] >> 4; }
+}
+// high-bit plane for 5-bit types: 32 bits per item; bit (8b + w) = hb(e 8w+b), bit (8b+4+w) = hb(e 8w+4+b)
+B200Q_HD uint32_t b200q_pack_hb(const uint8_t hb[32]) {
+    uint32_t q = 0;
+    for (int w = 0; w < 4; ++w) for (int b = 0; b < 4; ++b) { q |= (uint32_t)(hb[8 * w + b] & 1) << (8 * b + w); q |= (uint32_t)(hb[8 * w + 4 + b] & 1) << (8 * b + 4 + w); }
+    return q;
+}
+B200Q_HD void b200q_unpack_hb(uint32_t q, uint8_t hb[32]) {
+    for (int w = 0; w < 4; ++w) for (int b = 0; b < 4; ++b) { hb[8 * w + b] = (q >> (8 * b + w)) & 1; hb[8 * w + 4 + b] = (q >> (8 * b + 4 + w)) & 1; }
+}
+// 2-bit high plane for 6-bit types: 64 bits per item (two u32 U[0], U[1]); U[u] byte b, field f=2w'+g (bits 2f..2f+1)
+// = high 2 bits of e 8(2u+w') + 4g + b.
+B200Q_HD void b200q_pack_h2(const uint8_t h2[32], uint32_t U[2]) {
+    U[0] = U[1] = 0;
+    for (int u = 0; u < 2; ++u) for (int wp = 0; wp < 2; ++wp) for (int g = 0; g < 2; ++g) for (int b = 0; b < 4; ++b)
+        U[u] |= (uint32_t)(h2[8 * (2 * u + wp) + 4 * g + b] & 3) << (8 * b + 2 * (2 * wp + g));
+}
+B200Q_HD void b200q_unpack_h2(const uint32_t U[2], uint8_t h2[32]) {
+    for (int u = 0; u < 2; ++u) for (int wp = 0; wp < 2; ++wp) for (int g = 0; g < 2; ++g) for (int b = 0; b < 4; ++b)
+        h2[8 * (2 * u + wp) + 4 * g + b] = (U[u] >> (8 * b + 2 * (2 * wp + g))) & 3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// repack / unrepack of ONE wire block (generic over the layout; runs as one GPU thread per block,
+// or on the host in tests).  `wire` points at the block, `row`/`blk` locate it; `dst` is the plane base.
+// ---------------------------------------------------------------------------------------------
+B200Q_HD uint8_t * b200q_plane_ptr(uint8_t * base, const b200q_layout & L, int p, int64_t row, int64_t blk) {
+    return base + L.plane_off[p] + (L.plane_per_row[p] ? row : row * L.nb + blk) * L.plane_bytes[p];
+}
+B200Q_HD const uint8_t * b200q_plane_cptr(const uint8_t * base, const b200q_layout & L, int p, int64_t row, int64_t blk) {
+    return base + L.plane_off[p] + (L.plane_per_row[p] ? row : row * L.nb + blk) * L.plane_bytes[p];
+}
+
+// wire nibble positions: for 32-blocks {qs[j] low = e j, high = e j+16}; for 256-superblocks with the K-quant
+// convention {chunk c of 64: qs[32c+l] low = e 64c+l, high = e 64c+32+l}; IQ4_XS/IQ4_K/IQ4_KS/IQ5_K use
+// per-32 sub-blocks {qs[16s+j] low = e 32s+j, high = e 32s+16+j} (IQ5_K: per 64: see below).
+B200Q_HD void b200q_repack_block(const b200q_layout & L, const uint8_t * wire, uint8_t * dst, int64_t row, int64_t blk, bool inverse) {
+    // `inverse` == false: wire -> planes ; true: planes -> wire (wire is then written through a const_cast by the caller)
+    uint8_t * w = const_cast<uint8_t *>(wire);
+    uint8_t idx[32], hb[32], tmp[16];
+    switch (L.type) {
+    case B200Q_TYPE_IQ4_NL: case B200Q_TYPE_Q4_0: {   // {half d; u8 qs[16]}
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * pd = b200q_plane_ptr(dst, L, 1, row, blk);
+        const bool lut = L.type == B200Q_TYPE_IQ4_NL;
+        if (!inverse) {
+            for (int j = 0; j < 16; ++j) { idx[j] = w[2 + j] & 0xF; idx[j + 16] = w[2 + j] >> 4; }
+            if (lut) b200q_pack_nib_L(idx, pq); else b200q_pack_nib_A(idx, pq);
+            pd[0] = w[0]; pd[1] = w[1];
+        } else {
+            if (lut) b200q_unpack_nib_L(pq, idx); else b200q_unpack_nib_A(pq, idx);
+            for (int j = 0; j < 16; ++j) w[2 + j] = (uint8_t)(idx[j] | (idx[j + 16] << 4));
+            w[0] = pd[0]; w[1] = pd[1];
+        }
+    } break;
+    case B200Q_TYPE_Q8_0: {                            // {half d; i8 qs[32]}
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * pd = b200q_plane_ptr(dst, L, 1, row, blk);
+        if (!inverse) { for (int j = 0; j < 32; ++j) pq[j] = w[2 + j]; pd[0] = w[0]; pd[1] = w[1]; }
+        else          { for (int j = 0; j < 32; ++j) w[2 + j] = pq[j]; w[0] = pd[0]; w[1] = pd[1]; }
+    } break;
+    case B200Q_TYPE_Q4_K: case B200Q_TYPE_Q5_K: {      // {half d,dmin; u8 scales[12]; [u8 qh[32];] u8 qs[128]}
+        const bool q5 = L.type == B200Q_TYPE_Q5_K;
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk);
+        uint8_t * ph = q5 ? b200q_plane_ptr(dst, L, 1, row, blk) : nullptr;
+        uint8_t * pm = b200q_plane_ptr(dst, L, q5 ? 2 : 1, row, blk);
+        uint8_t * wqh = w + 16; uint8_t * wqs = w + (q5 ? 48 : 16);
+        if (!inverse) { for (int j = 0; j < 16; ++j) pm[j] = w[j]; } else { for (int j = 0; j < 16; ++j) w[j] = pm[j]; }
+        if (inverse && q5) for (int j = 0; j < 32; ++j) wqh[j] = 0;
+        for (int s = 0; s < 8; ++s) {                  // sub-block s: chunk c = s/2, nibble half = s%2
+            const int c = s / 2, hi = s % 2;
+            if (!inverse) {
+                for (int l = 0; l < 32; ++l) { idx[l] = hi ? (wqs[32 * c + l] >> 4) : (wqs[32 * c + l] & 0xF); if (q5) hb[l] = (wqh[l] >> (2 * c + hi)) & 1; }
+                b200q_pack_nib_A(idx, pq + 16 * s);
+                if (q5) { uint32_t q = b200q_pack_hb(hb); memcpy(ph + 4 * s, &q, 4); }
+            } else {
+                b200q_unpack_nib_A(pq + 16 * s, idx);
+                if (q5) { uint32_t q; memcpy(&q, ph + 4 * s, 4); b200q_unpack_hb(q, hb); }
+                for (int l = 0; l < 32; ++l) {
+                    if (hi) wqs[32 * c + l] = (uint8_t)((wqs[32 * c + l] & 0x0F) | (idx[l] << 4)); else wqs[32 * c + l] = (uint8_t)((wqs[32 * c + l] & 0xF0) | idx[l]);
+                    if (q5) wqh[l] |= (uint8_t)(hb[l] << (2 * c + hi));
+                }
+            }
+        }
+    } break;
+    case B200Q_TYPE_Q6_K: {                            // {u8 ql[128]; u8 qh[64]; i8 scales[16]; half d}
+        uint8_t * pl = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * ph = b200q_plane_ptr(dst, L, 1, row, blk);
+        uint8_t * ps = b200q_plane_ptr(dst, L, 2, row, blk); uint8_t * pd = b200q_plane_ptr(dst, L, 3, row, blk);
+        if (!inverse) { for (int j = 0; j < 16; ++j) ps[j] = w[192 + j]; pd[0] = w[208]; pd[1] = w[209]; }
+        else { for (int j = 0; j < 16; ++j) w[192 + j] = ps[j]; w[208] = pd[0]; w[209] = pd[1]; for (int j = 0; j < 64; ++j) w[128 + j] = 0; }
+        for (int s = 0; s < 8; ++s) {                  // item s = weights 32s..32s+31 ; half h = s/4, quarter t = s%4
+            const int h = s / 4, t = s % 4;            // t: 0 -> ql[64h+l] low, 1 -> ql[64h+32+l] low, 2 -> ql[64h+l] high, 3 -> ql[64h+32+l] high
+            const int qoff = 64 * h + 32 * (t & 1); const bool hi = t >= 2;
+            if (!inverse) {
+                for (int l = 0; l < 32; ++l) { idx[l] = hi ? (w[qoff + l] >> 4) : (w[qoff + l] & 0xF); hb[l] = (w[128 + 32 * h + l] >> (2 * t)) & 3; }
+                b200q_pack_nib_A(idx, pl + 16 * s);
+                uint32_t U[2]; b200q_pack_h2(hb, U); memcpy(ph + 8 * s, U, 8);
+            } else {
+                b200q_unpack_nib_A(pl + 16 * s, idx);
+                uint32_t U[2]; memcpy(U, ph + 8 * s, 8); b200q_unpack_h2(U, hb);
+                for (int l = 0; l < 32; ++l) {
+                    if (hi) w[qoff + l] = (uint8_t)((w[qoff + l] & 0x0F) | (idx[l] << 4)); else w[qoff + l] = (uint8_t)((w[qoff + l] & 0xF0) | idx[l]);
+                    w[128 + 32 * h + l] |= (uint8_t)(hb[l] << (2 * t));
+                }
+            }
+        }
+    } break;
+    case B200Q_TYPE_IQ4_XS: case B200Q_TYPE_IQ4_K: case B200Q_TYPE_IQ4_KS: {
+        // IQ4_XS {half d; u16 scales_h; u8 scales_l[4]; u8 qs[128]}  meta 8
+        // IQ4_K  {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]; u8 qs[128]} meta 16
+        // IQ4_KS {u8 scales[8]; u8 qs[128]} meta 8 (+ f32 row scale, handled by the row pass)
+        const int meta = L.type == B200Q_TYPE_IQ4_K ? 16 : 8;
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * pm = b200q_plane_ptr(dst, L, 1, row, blk);
+        if (!inverse) { for (int j = 0; j < meta; ++j) pm[j] = w[j]; } else { for (int j = 0; j < meta; ++j) w[j] = pm[j]; }
+        uint8_t * wqs = w + meta;
+        for (int s = 0; s < 8; ++s) {
+            if (!inverse) { for (int j = 0; j < 16; ++j) { idx[j] = wqs[16 * s + j] & 0xF; idx[j + 16] = wqs[16 * s + j] >> 4; } b200q_pack_nib_L(idx, pq + 16 * s); }
+            else { b200q_unpack_nib_L(pq + 16 * s, idx); for (int j = 0; j < 16; ++j) wqs[16 * s + j] = (uint8_t)(idx[j] | (idx[j + 16] << 4)); }
+        }
+    } break;
+    case B200Q_TYPE_IQ5_K: {   // {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]; u8 qs[128]; u8 qh[32]}
+        // per 64 weights c: e 64c+j <- qs[32c+j] low (j<16), 64c+16+j <- qs[32c+16+j] low, 64c+32+j <- qs[32c+j] high, 64c+48+j <- qs[32c+16+j] high
+        // high bit: qh[(c/4)*32 + jj] >> (2*(c%4) + {0: first 32, 1: second 32}), jj = position within the 32 bytes (see iqk_quantize.cpp:3136-3141)
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * ph = b200q_plane_ptr(dst, L, 1, row, blk); uint8_t * pm = b200q_plane_ptr(dst, L, 2, row, blk);
+        if (!inverse) { for (int j = 0; j < 16; ++j) pm[j] = w[j]; } else { for (int j = 0; j < 16; ++j) w[j] = pm[j]; for (int j = 0; j < 32; ++j) w[144 + j] = 0; }
+        uint8_t * wqs = w + 16; uint8_t * wqh = w + 144;
+        for (int s = 0; s < 8; ++s) {                  // item s: c = s/2, second = s%2 (0: low nibbles, 1: high nibbles)
+            const int c = s / 2, second = s % 2;
+            if (!inverse) {
+                for (int l = 0; l < 32; ++l) { const uint8_t q = wqs[32 * c + l]; idx[l] = second ? (q >> 4) : (q & 0xF); hb[l] = (wqh[l] >> (2 * c + second)) & 1; }
+                b200q_pack_nib_L(idx, pq + 16 * s);    // LUT type -> L order (hb is re-ordered to match in decode)
+                uint32_t q = 0; for (int e = 0; e < 32; ++e) q |= (uint32_t)hb[e] << e;   // natural bit order for the LUT path
+                memcpy(ph + 4 * s, &q, 4);
+            } else {
+                b200q_unpack_nib_L(pq + 16 * s, idx);
+                uint32_t q; memcpy(&q, ph + 4 * s, 4);
+                for (int l = 0; l < 32; ++l) {
+                    if (second) wqs[32 * c + l] = (uint8_t)((wqs[32 * c + l] & 0x0F) | (idx[l] << 4)); else wqs[32 * c + l] = (uint8_t)((wqs[32 * c + l] & 0xF0) | idx[l]);
+                    wqh[l] |= (uint8_t)(((q >> l) & 1) << (2 * c + second));
+                }
+            }
+        }
+        (void)tmp;
+    } break;
+    case B200Q_TYPE_IQ2_BN: {                          // {u8 qs[16]} per 64 weights: already dp4a-friendly -> copy
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk);
+        if (!inverse) { for (int j = 0; j < 16; ++j) pq[j] = w[j]; } else { for (int j = 0; j < 16; ++j) w[j] = pq[j]; }
+    } break;
+    default: break;
+    }
+}
+// per-row header (row scale) pass
+B200Q_HD void b200q_repack_row_meta(const b200q_layout & L, const uint8_t * wire_row, uint8_t * dst, int64_t row, bool inverse) {
+    if (!L.row_meta) return;
+    int p = -1; for (int i = 0; i < L.n_planes; ++i) if (L.plane_per_row[i]) p = i;
+    if (p < 0) return;
+    uint8_t * pr = b200q_plane_ptr(dst, L, p, row, 0); uint8_t * w = const_cast<uint8_t *>(wire_row);
+    for (int j = 0; j < L.row_meta; ++j) { if (!inverse) pr[j] = w[j]; else w[j] = pr[j]; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical decode
+// ---------------------------------------------------------------------------------------------
+struct b200q_canon {        // 32 weights
+    int   va[8];            // int8 x4 per word, natural k order
+    int   vb[8];            // second addend (only for HAS_B types)
+    float dl[2];            // scale of weights 0..15 / 16..31
+    float ml[2];            // subtracted offset of weights 0..15 / 16..31
+};
+
+// value tables.  kvalues_iq4nl (ggml-common.h, used by IQ4_NL / IQ4_XS) and iq4k_values (:2227) as PRMT operands.
+// A = entries 0..7 (all negative  -> PRMT sign-fill of an unselected lane = 0xFF = -1)
+// B = entries 8..15 stored +1     (all positive -> sign-fill = 0x00), so that  byteA + byteB == value  exactly.
+#define B200Q_KV4_A0 0xBFAD9881u   /* -127,-104, -83, -65 */
+#define B200Q_KV4_A1 0xF6EADDCFu   /*  -49, -35, -22, -10 */
+#define B200Q_KV4_B0 0x271A0E02u   /*  1+1, 13+1, 25+1, 38+1 */
+#define B200Q_KV4_B1 0x725A4636u   /* 53+1, 69+1, 89+1,113+1 */
+
+B200Q_HD void b200q_lut4(uint32_t q, int & a_lo, int & b_lo, int & a_hi, int & b_hi) {
+    // q: 8 nibbles (L-order: nibble j = weight j).  lo = weights 0..3, hi = weights 4..7.
+    const uint32_t qx = q ^ 0x88888888u;
+    a_lo = (int)b200q_prmt(B200Q_KV4_A0, B200Q_KV4_A1, q);
+    b_lo = (int)b200q_prmt(B200Q_KV4_B0, B200Q_KV4_B1, qx);
+    a_hi = (int)b200q_prmt(B200Q_KV4_A0, B200Q_KV4_A1, q >> 16);
+    b_hi = (int)b200q_prmt(B200Q_KV4_B0, B200Q_KV4_B1, qx >> 16);
+}
+
+// byte i (0..15) of a 4-word register group, without dynamic register indexing
+B200Q_HD uint32_t b200q_byte(const uint32_t m[4], int i) {
+    const uint32_t w = (i & 8) ? ((i & 4) ? m[3] : m[2]) : ((i & 4) ? m[1] : m[0]);
+    return (w >> (8 * (i & 3))) & 0xFF;
+}
+// get_scale_min_k4 (reference ggml-quants.c:2036-2044); the 12 scale bytes are bytes 4..15 of the meta words m[0..3]
+B200Q_HD void b200q_scale_min_k4(int j, const uint32_t m4[4], int & sc, int & m) {
+    const int sh = 8 * (j & 3);
+    const uint32_t b0 = (m4[1] >> sh) & 0xFF, b1 = (m4[2] >> sh) & 0xFF, b2 = (m4[3] >> sh) & 0xFF;
+    if (j < 4) { sc = (int)(b0 & 63); m = (int)(b1 & 63); }
+    else { sc = (int)((b2 & 0xF) | ((b0 >> 6) << 4)); m = (int)((b2 >> 4) | ((b1 >> 6) << 4)); }
+}
+
+// iq5nl_values (ggml-common.h:2232), all +2 so that entries 16..31 are positive; 4 PRMT tables of 8.
+//   T0 = v[0..7]+2 (+1 fold), T1 = v[8..15]+2 (+1), T2 = v[16..23]+2, T3 = v[24..31]+2 — see b200q_lut5.
+// raw v: -126,-114,-103,-92,-83,-74,-65,-57 | -50,-43,-36,-30,-24,-18,-12,-6 | -1,5,11,17,23,29,36,43 | 51,59,68,77,87,97,109,121
+// Pair (T0,T1): both negative -> sign-fills are -1 each -> store +1:  T0' = v+2+1, T1' = v+2+1
+// Pair (T2,T3): both positive -> sign-fills are 0                ->  T2' = v+2,   T3' = v+2
+#define B200Q_KV5_T0_0 0xA79C9185u  /* -123,-111,-100, -89 */
+#define B200Q_KV5_T0_1 0xCAC2B9B0u  /*  -80, -71, -62, -54 */
+#define B200Q_KV5_T1_0 0xE5DFD8D1u  /*  -47, -40, -33, -27 */
+#define B200Q_KV5_T1_1 0xFDF7F1EBu  /*  -21, -15,  -9,  -3 */
+#define B200Q_KV5_T2_0 0x130D0701u  /*    1,   7,  13,  19 */
+#define B200Q_KV5_T2_1 0x2D261F19u  /*   25,  31,  38,  45 */
+#define B200Q_KV5_T3_0 0x4F463D35u  /*   53,  61,  70,  79 */
+#define B200Q_KV5_T3_1 0x7B6F6359u  /*   89,  99, 111, 123 */
+
+// Decode item `it` (32 weights) of row `row`.  `base` = plane base of the tensor.
+template <int TYPE> struct b200q_traits;
+
+#define B200Q_DEF_TRAITS(T, HASB, IK) template <> struct b200q_traits<T> { static constexpr bool HAS_B = HASB; static constexpr int ITEM_K = IK; };
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_NL, true, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q4_0,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q8_0,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q4_K,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q5_K,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q6_K,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_XS, true, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_K,  true, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_KS, true, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ5_K,  true, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ2_BN, false, 32)
+
+// Raw registers of one item, as loaded from the planes.
+struct b200q_item {
+    uint32_t q[8];     // low-bit plane words: 4 for 4-bit types, 8 for Q8_0
+    uint32_t h[2];     // high-bit plane words (Q5_K/IQ5_K: h[0]; Q6_K: h[0..1])
+    uint32_t m[4];     // block metadata words (scales etc.)
+    float    rs;       // row scale (types with a row header)
+};
+
+#if defined(__CUDACC__)
+#define B200Q_LDG128(dst, ptr) { const uint4 _t = __ldg(reinterpret_cast<const uint4 *>(ptr)); (dst)[0] = _t.x; (dst)[1] = _t.y; (dst)[2] = _t.z; (dst)[3] = _t.w; }
+#endif
+B200Q_HD void b200q_ld16(uint32_t * dst, const uint8_t * p) {
+#if defined(__CUDA_ARCH__)
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p)); dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+#else
+    memcpy(dst, p, 16);
+#endif
+}
+B200Q_HD void b200q_ld8(uint32_t * dst, const uint8_t * p) {
+#if defined(__CUDA_ARCH__)
+    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p)); dst[0] = t.x; dst[1] = t.y;
+#else
+    memcpy(dst, p, 8);
+#endif
+}
+B200Q_HD uint32_t b200q_ld4(const uint8_t * p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const uint32_t *>(p));
+#else
+    uint32_t v; memcpy(&v, p, 4); return v;
+#endif
+}
+B200Q_HD uint32_t b200q_ld2(const uint8_t * p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(reinterpret_cast<const uint16_t *>(p));
+#else
+    uint16_t v; memcpy(&v, p, 2); return v;
+#endif
+}
+
+// item index `it` counts 32-weight items along the row: it in [0, K/32)
+template <int TYPE>
+B200Q_HD void b200q_load_item(b200q_item & I, const uint8_t * base, const b200q_layout & L, int64_t row, int64_t it) {
+    const int64_t n32 = L.K / 32;
+    if (TYPE == B200Q_TYPE_IQ4_NL || TYPE == B200Q_TYPE_Q4_0) {
+        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
+        I.m[0] = b200q_ld2(base + L.plane_off[1] + (row * n32 + it) * 2);
+    } else if (TYPE == B200Q_TYPE_Q8_0) {
+        const uint8_t * p = base + L.plane_off[0] + (row * n32 + it) * 32;
+        b200q_ld16(I.q, p); b200q_ld16(I.q + 4, p + 16);
+        I.m[0] = b200q_ld2(base + L.plane_off[1] + (row * n32 + it) * 2);
+    } else if (TYPE == B200Q_TYPE_Q4_K || TYPE == B200Q_TYPE_IQ4_K) {
+        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
+        b200q_ld16(I.m, base + L.plane_off[1] + (row * L.nb + it / 8) * 16);
+    } else if (TYPE == B200Q_TYPE_Q5_K || TYPE == B200Q_TYPE_IQ5_K) {
+        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
+        I.h[0] = b200q_ld4(base + L.plane_off[1] + (row * n32 + it) * 4);
+        b200q_ld16(I.m, base + L.plane_off[2] + (row * L.nb + it / 8) * 16);
+    } else if (TYPE == B200Q_TYPE_Q6_K) {
+        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
+        b200q_ld8(I.h, base + L.plane_off[1] + (row * n32 + it) * 8);
+        I.m[0] = b200q_ld2(base + L.plane_off[2] + (row * n32 + it) * 2);     // two int8 scales of this item
+        I.m[1] = b200q_ld2(base + L.plane_off[3] + (row * L.nb + it / 8) * 2); // d
+    } else if (TYPE == B200Q_TYPE_IQ4_XS) {
+        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
+        b200q_ld8(I.m, base + L.plane_off[1] + (row * L.nb + it / 8) * 8);
+    } else if (TYPE == B200Q_TYPE_IQ4_KS) {
+        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
+        I.m[0] = (uint32_t)(base + L.plane_off[1] + (row * L.nb + it / 8) * 8)[it % 8];
+        uint32_t r = b200q_ld4(base + L.plane_off[2] + row * 4); memcpy(&I.rs, &r, 4);
+    } else if (TYPE == B200Q_TYPE_IQ2_BN) {           // 64 weights per wire block: item = half a block (8 bytes of the 16: see decode)
+        b200q_ld16(I.q, base + L.plane_off[0] + (row * L.nb + it / 2) * 16);
+        uint32_t r = b200q_ld4(base + L.plane_off[1] + row * 4); memcpy(&I.rs, &r, 4);
+    }
+}
+
+template <int TYPE>
+B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & C) {
+    if (TYPE == B200Q_TYPE_IQ4_NL) {
+        const float d = b200q_h2f((uint16_t)I.m[0]);
+        for (int w = 0; w < 4; ++w) b200q_lut4(I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
+        C.dl[0] = C.dl[1] = d; C.ml[0] = C.ml[1] = 0.0f;
+    } else if (TYPE == B200Q_TYPE_Q4_0) {
+        const float d = b200q_h2f((uint16_t)I.m[0]);
+        for (int w = 0; w < 4; ++w) { C.va[2 * w] = (int)(I.q[w] & 0x0F0F0F0Fu); C.va[2 * w + 1] = (int)((I.q[w] >> 4) & 0x0F0F0F0Fu); }
+        C.dl[0] = C.dl[1] = d; C.ml[0] = C.ml[1] = 8.0f * d;
+    } else if (TYPE == B200Q_TYPE_Q8_0) {
+        const float d = b200q_h2f((uint16_t)I.m[0]);
+        for (int w = 0; w < 8; ++w) C.va[w] = (int)I.q[w];
+        C.dl[0] = C.dl[1] = d; C.ml[0] = C.ml[1] = 0.0f;
+    } else if (TYPE == B200Q_TYPE_Q4_K || TYPE == B200Q_TYPE_Q5_K) {
+        const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)), dmin = b200q_h2f((uint16_t)(I.m[0] >> 16));
+        int sc, m; b200q_scale_min_k4((int)(it % 8), I.m, sc, m);
+        for (int w = 0; w < 4; ++w) {
+            uint32_t lo = I.q[w] & 0x0F0F0F0Fu, hi = (I.q[w] >> 4) & 0x0F0F0F0Fu;
+            if (TYPE == B200Q_TYPE_Q5_K) { lo |= (I.h[0] << (4 - w)) & 0x10101010u; hi |= (I.h[0] >> w) & 0x10101010u; }
+            C.va[2 * w] = (int)lo; C.va[2 * w + 1] = (int)hi;
+        }
+        C.dl[0] = C.dl[1] = d * sc; C.ml[0] = C.ml[1] = dmin * m;
+    } else if (TYPE == B200Q_TYPE_Q6_K) {
+        const float d = b200q_h2f((uint16_t)I.m[1]);
+        const int s0 = (int)(int8_t)(I.m[0] & 0xFF), s1 = (int)(int8_t)((I.m[0] >> 8) & 0xFF);
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t U = I.h[w / 2]; const int f0 = 2 * (w % 2), f1 = f0 + 1;
+            uint32_t lo = I.q[w] & 0x0F0F0F0Fu, hi = (I.q[w] >> 4) & 0x0F0F0F0Fu;
+            lo |= ((U >> (2 * f0)) & 0x03030303u) << 4; hi |= ((U >> (2 * f1)) & 0x03030303u) << 4;
+            C.va[2 * w] = (int)lo; C.va[2 * w + 1] = (int)hi;
+        }
+        C.dl[0] = d * s0; C.dl[1] = d * s1; C.ml[0] = 32.0f * C.dl[0]; C.ml[1] = 32.0f * C.dl[1];
+    } else if (TYPE == B200Q_TYPE_IQ4_XS) {           // meta {half d; u16 scales_h; u8 scales_l[4]}
+        const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const uint32_t sh = I.m[0] >> 16; const int ib = (int)(it % 8);
+        const uint32_t sl = (I.m[1] >> (8 * (ib / 2) + 4 * (ib % 2))) & 0xF;   // scales_l[ib/2] nibble ib%2
+        const int ls = (int)(sl | (((sh >> (2 * ib)) & 3) << 4)) - 32;
+        for (int w = 0; w < 4; ++w) b200q_lut4(I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
+        C.dl[0] = C.dl[1] = d * ls; C.ml[0] = C.ml[1] = 0.0f;
+    } else if (TYPE == B200Q_TYPE_IQ4_K) {            // meta {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]}
+        const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const int ib = (int)(it % 8);
+        const uint32_t extra = (I.m[0] >> 16) >> (2 * ib);
+        const uint32_t h = b200q_byte(I.m, 4 + ib / 2) >> (4 * (ib % 2)); const uint32_t sl = b200q_byte(I.m, 8 + ib);
+        const int ls1 = (int)((sl & 0xF) | ((h << 4) & 0x30)) - 32, ls2 = (int)((sl >> 4) | ((h << 2) & 0x30)) - 32;
+        for (int w = 0; w < 4; ++w) b200q_lut4(I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
+        C.dl[0] = d * ls1; C.dl[1] = d * ls2;
+        C.ml[0] = (extra & 1) ? -4.0f * C.dl[0] : 0.0f; C.ml[1] = (extra & 2) ? -4.0f * C.dl[1] : 0.0f;   // iq4k_values[16+i] = kvalues[i] + 4
+    } else if (TYPE == B200Q_TYPE_IQ4_KS) {           // m[0] = scale byte of this 32-block
+        const uint32_t s = I.m[0];
+        const float dl = I.rs * (float)((int)(s & 254) - 127);
+        for (int w = 0; w < 4; ++w) b200q_lut4(I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
+        C.dl[0] = C.dl[1] = dl; C.ml[0] = C.ml[1] = (s & 1) ? -4.0f * dl : 0.0f;
+    } else if (TYPE == B200Q_TYPE_IQ5_K) {            // meta {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]}
+        // item s: c = s/2 (64-chunk), second = s%2.  Weights 0..15 of the item use scale dl(2*second) and extra bit (2*second),
+        // weights 16..31 use dl(2*second+1) / extra bit (2*second+1)  (iqk_quantize.cpp:3128-3141).
+        const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const int s = (int)(it % 8), c = s / 2, second = s % 2;
+        const uint32_t extra = ((I.m[0] >> 16) >> (4 * c)) >> (2 * second);
+        const uint32_t sh = b200q_byte(I.m, 4 + c), sl = b200q_byte(I.m, 8 + 2 * c + second);
+        const int ls1 = (int)((sl & 0xF) | ((sh << (4 - 4 * second)) & 0x30)) - 32;     // second=0: sh<<4 ; second=1: sh>>0
+        const int ls2 = (int)((sl >> 4)  | (second ? ((sh >> 2) & 0x30) : ((sh << 2) & 0x30))) - 32;
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t q = I.q[w], qx = q ^ 0x88888888u; const uint32_t hb = (I.h[0] >> (8 * w)) & 0xFF;
+            // byte masks from the 5th bits: lane j of half -> 0xFF if set
+            const uint32_t m_lo = (((hb & 0xF) * 0x00204081u) & 0x01010101u) * 0xFFu;
+            const uint32_t m_hi = (((hb >> 4) * 0x00204081u) & 0x01010101u) * 0xFFu;
+            const uint32_t a_lo0 = b200q_prmt(B200Q_KV5_T0_0, B200Q_KV5_T0_1, q), b_lo0 = b200q_prmt(B200Q_KV5_T1_0, B200Q_KV5_T1_1, qx);
+            const uint32_t a_lo1 = b200q_prmt(B200Q_KV5_T2_0, B200Q_KV5_T2_1, q), b_lo1 = b200q_prmt(B200Q_KV5_T3_0, B200Q_KV5_T3_1, qx);
+            const uint32_t a_hi0 = b200q_prmt(B200Q_KV5_T0_0, B200Q_KV5_T0_1, q >> 16), b_hi0 = b200q_prmt(B200Q_KV5_T1_0, B200Q_KV5_T1_1, qx >> 16);
+            const uint32_t a_hi1 = b200q_prmt(B200Q_KV5_T2_0, B200Q_KV5_T2_1, q >> 16), b_hi1 = b200q_prmt(B200Q_KV5_T3_0, B200Q_KV5_T3_1, qx >> 16);
+            C.va[2 * w]     = (int)((a_lo1 & m_lo) | (a_lo0 & ~m_lo)); C.vb[2 * w]     = (int)((b_lo1 & m_lo) | (b_lo0 & ~m_lo));
+            C.va[2 * w + 1] = (int)((a_hi1 & m_hi) | (a_hi0 & ~m_hi)); C.vb[2 * w + 1] = (int)((b_hi1 & m_hi) | (b_hi0 & ~m_hi));
+        }
+        C.dl[0] = d * ls1; C.dl[1] = d * ls2;
+        // tables hold v+2: subtract 2 unless the extra bit selects the "+2" variant of the table
+        C.ml[0] = (extra & 1) ? 0.0f : 2.0f * C.dl[0]; C.ml[1] = (extra & 2) ? 0.0f : 2.0f * C.dl[1];
+    } else if (TYPE == B200Q_TYPE_IQ2_BN) {
+        // wire block: 64 weights, byte j%16 field j/16.  Item it covers weights 32*(it%2) .. +31 of the block = fields 2*(it%2), 2*(it%2)+1
+        const int f0 = 2 * (int)(it % 2);
+        for (int w = 0; w < 4; ++w) { C.va[w] = (int)((I.q[w] >> (2 * f0)) & 0x03030303u); C.va[4 + w] = (int)((I.q[w] >> (2 * f0 + 2)) & 0x03030303u); }
+        C.dl[0] = C.dl[1] = I.rs; C.ml[0] = C.ml[1] = I.rs;      // w = rs*(q-1)
+    }
+}
+
+// Dequantise canonical item to 32 floats (used by the bf16 dequantiser and by host tests)
+template <bool HAS_B>
+B200Q_HD void b200q_canon_to_float(const b200q_canon & C, float out[32]) {
+    for (int e = 0; e < 32; ++e) {
+        int q = (int)(int8_t)(C.va[e / 4] >> (8 * (e % 4)));
+        if (HAS_B) q += (int)(int8_t)(C.vb[e / 4] >> (8 * (e % 4)));
+        out[e] = C.dl[e / 16] * (float)q - C.ml[e / 16];
+    }
+}

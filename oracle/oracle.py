@@ -1,0 +1,225 @@
+"""oracle/oracle.py — TEST INFRASTRUCTURE: ctypes front-end for the CPU oracle and the reference library.
+
+* ``Oracle``   -> oracle/_build/liboracle.so, compiled from oracle/oracle_quants.c (our CPU restatement).
+* ``RefLib``   -> oracle/_ref/libggml_ref_<variant>.so, the UNMODIFIED reference CPU ggml built by
+                  oracle/Makefile.ref (+ oracle/ref_shim.c).  Exists wherever it was built in a container
+                  that has /root/reference; it travels to the GPU box as a prebuilt file.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint16, c_void_p, POINTER
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+BUILD = os.path.join(HERE, "_build")
+REFDIR = os.path.join(HERE, "_ref")
+REFERENCE_ROOT = "/root/reference"
+
+# ggml_type ids (reference ggml/include/ggml.h:391-492)
+GGML_TYPE = {
+    "F32": 0, "F16": 1, "Q4_0": 2, "Q4_1": 3, "Q5_0": 6, "Q5_1": 7, "Q8_0": 8, "Q2_K": 10, "Q3_K": 11,
+    "Q4_K": 12, "Q5_K": 13, "Q6_K": 14, "IQ2_XXS": 16, "IQ2_XS": 17, "IQ3_XXS": 18, "IQ1_S": 19,
+    "IQ4_NL": 20, "IQ3_S": 21, "IQ2_S": 22, "IQ4_XS": 23, "IQ1_M": 29, "BF16": 30, "MXFP4": 39,
+    "Q6_0": 133, "IQ1_BN": 134, "IQ2_BN": 135, "IQ2_K": 137, "IQ3_K": 138, "IQ4_K": 139, "IQ5_K": 140,
+    "IQ6_K": 141, "IQ4_KS": 144, "IQ2_KS": 145, "IQ4_KSS": 146, "IQ5_KS": 152, "IQ2_KT": 153,
+    "IQ3_KT": 154, "IQ4_KT": 155, "IQ3_KS": 156, "IQ2_KL": 157, "IQ1_KT": 158,
+}
+TYPE_NAME = {v: k for k, v in GGML_TYPE.items()}
+
+
+def build_oracle(force: bool = False) -> str:
+    """Compile oracle_quants.c -> _build/liboracle.so (plain gcc, no reference needed)."""
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "liboracle.so")
+    src = os.path.join(HERE, "oracle_quants.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-fvisibility=hidden",
+                               "-ffp-contract=off", "-o", so, src, "-lm"])
+    return so
+
+
+def build_ref(variant: str = "avx2", jobs: int = 8) -> str | None:
+    """Build oracle/_ref from the reference sources if they are present (this container only)."""
+    so = os.path.join(REFDIR, f"libggml_ref_{variant}.so")
+    if not os.path.isdir(REFERENCE_ROOT):
+        return so if os.path.exists(so) else None
+    args = ["make", "-f", os.path.join(HERE, "Makefile.ref"), f"-j{jobs}", f"VARIANT={variant}"]
+    if variant == "native":
+        args.append("ARCHFLAGS=-march=native")
+    subprocess.check_call(args, stdout=subprocess.DEVNULL)
+    return so
+
+
+def _p(a: np.ndarray, ty=c_void_p):
+    return a.ctypes.data_as(ty)
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = ctypes.CDLL(build_oracle())
+        L = self.lib
+        L.oracle_row_size.restype = c_int64
+        L.oracle_row_size.argtypes = [c_int, c_int64]
+        L.oracle_type_supported.argtypes = [c_int]
+        L.oracle_dequantize_row.argtypes = [c_int, c_void_p, c_void_p, c_int64]
+        L.oracle_quantize_q8_1.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
+        L.oracle_mul_mat_exact.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64]
+        L.oracle_mul_mat_q8_1.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64]
+        L.oracle_h2f.restype = c_float
+        L.oracle_h2f.argtypes = [c_uint16]
+        L.oracle_f2h.restype = c_uint16
+        L.oracle_f2h.argtypes = [c_float]
+
+    def supported(self, t: int) -> bool:
+        return bool(self.lib.oracle_type_supported(t))
+
+    def row_size(self, t: int, k: int) -> int:
+        r = self.lib.oracle_row_size(t, k)
+        if r < 0:
+            raise ValueError(f"oracle: type {t} / k {k} unsupported")
+        return r
+
+    def dequantize(self, t: int, wire: np.ndarray, m: int, k: int) -> np.ndarray:
+        rs = self.row_size(t, k)
+        wire = np.ascontiguousarray(wire, dtype=np.uint8).reshape(m, rs)
+        out = np.empty((m, k), np.float32)
+        for i in range(m):
+            rc = self.lib.oracle_dequantize_row(t, _p(wire[i]), _p(out[i]), k)
+            assert rc == 0
+        return out
+
+    def quantize_q8_1(self, x: np.ndarray):
+        x = np.ascontiguousarray(x, np.float32)
+        n, k = x.shape
+        q = np.empty((n, k), np.int8)
+        d = np.empty((n, k // 32), np.uint16)
+        s = np.empty((n, k // 32), np.uint16)
+        assert self.lib.oracle_quantize_q8_1(_p(x), n, k, _p(q), _p(d), _p(s)) == 0
+        return q, d.view(np.float16), s.view(np.float16)
+
+    def mul_mat_exact(self, t: int, wire: np.ndarray, x: np.ndarray, m: int) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32)
+        n, k = x.shape
+        wire = np.ascontiguousarray(wire, np.uint8)
+        assert wire.size == m * self.row_size(t, k)
+        out = np.empty((n, m), np.float32)
+        assert self.lib.oracle_mul_mat_exact(t, _p(wire), _p(x), _p(out), m, k, n) == 0
+        return out
+
+    def mul_mat_q8_1(self, t: int, wire: np.ndarray, x: np.ndarray, m: int) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float32)
+        n, k = x.shape
+        wire = np.ascontiguousarray(wire, np.uint8)
+        assert wire.size == m * self.row_size(t, k)
+        out = np.empty((n, m), np.float32)
+        assert self.lib.oracle_mul_mat_q8_1(t, _p(wire), _p(x), _p(out), m, k, n) == 0
+        return out
+
+
+def _cpu_flags() -> set[str]:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+class RefLib:
+    """The reference's own CPU ggml (IQK path), through oracle/ref_shim.c."""
+
+    @staticmethod
+    def find(prefer_native: bool = True) -> str | None:
+        cands = []
+        if prefer_native and {"avx512f", "avx512vnni", "avx512bw", "avx512vl"} <= _cpu_flags():
+            cands.append(os.path.join(REFDIR, "libggml_ref_native.so"))
+        cands.append(os.path.join(REFDIR, "libggml_ref_avx2.so"))
+        for c in cands:
+            if os.path.exists(c):
+                return c
+        return None
+
+    def __init__(self, path: str | None = None):
+        path = path or self.find(prefer_native=False)
+        if path is None:
+            raise FileNotFoundError("oracle/_ref not built (needs /root/reference: `make -f oracle/Makefile.ref`)")
+        self.path = path
+        self.lib = L = ctypes.CDLL(path)
+        L.refshim_blck_size.restype = c_int64
+        L.refshim_blck_size.argtypes = [c_int]
+        L.refshim_type_size.restype = c_size_t
+        L.refshim_type_size.argtypes = [c_int]
+        L.refshim_row_size.restype = c_size_t
+        L.refshim_row_size.argtypes = [c_int, c_int64]
+        L.refshim_type_name.restype = c_char_p
+        L.refshim_type_name.argtypes = [c_int]
+        L.refshim_row_meta_size.restype = c_int64
+        L.refshim_row_meta_size.argtypes = [c_int]
+        L.refshim_quantize.restype = c_size_t
+        L.refshim_quantize.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
+        L.refshim_to_float.argtypes = [c_int, c_void_p, c_void_p, c_int64]
+        L.refshim_mul_mat.restype = c_double
+        L.refshim_mul_mat.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int]
+        L.refshim_chain_new.restype = c_void_p
+        L.refshim_chain_new.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int]
+        L.refshim_chain_set.argtypes = [c_void_p, c_int, c_void_p, c_void_p]
+        L.refshim_chain_get.argtypes = [c_void_p, c_int, c_void_p]
+        L.refshim_chain_run.restype = c_double
+        L.refshim_chain_run.argtypes = [c_void_p]
+        L.refshim_chain_free.argtypes = [c_void_p]
+
+    def row_size(self, t: int, k: int) -> int:
+        return int(self.lib.refshim_row_size(t, k))
+
+    def row_meta_size(self, t: int) -> int:
+        return int(self.lib.refshim_row_meta_size(t))
+
+    def blck_size(self, t: int) -> int:
+        return int(self.lib.refshim_blck_size(t))
+
+    def type_name(self, t: int) -> str:
+        return self.lib.refshim_type_name(t).decode()
+
+    def quantize(self, t: int, w: np.ndarray) -> np.ndarray:
+        w = np.ascontiguousarray(w, np.float32)
+        m, k = w.shape
+        out = np.zeros(m * self.row_size(t, k), np.uint8)
+        n = self.lib.refshim_quantize(t, _p(w), _p(out), m, k, None)
+        assert n == out.size, (n, out.size)
+        return out
+
+    def to_float(self, t: int, wire: np.ndarray, m: int, k: int) -> np.ndarray:
+        """Reference to_float per row; for row-meta types the pointer passed is past the header
+        (to_float takes a block pointer) — the row scale is NOT applied (SURVEY.md §8c pitfall 1)."""
+        rs = self.row_size(t, k)
+        meta = self.row_meta_size(t)
+        wire = np.ascontiguousarray(wire, np.uint8).reshape(m, rs)
+        out = np.empty((m, k), np.float32)
+        for i in range(m):
+            row = np.ascontiguousarray(wire[i, meta:])
+            assert self.lib.refshim_to_float(t, _p(row), _p(out[i]), k) == 0
+        return out
+
+    def mul_mat(self, t: int, wire: np.ndarray, x: np.ndarray, m: int, n_threads: int = 4, reps: int = 1):
+        x = np.ascontiguousarray(x, np.float32)
+        n, k = x.shape
+        wire = np.ascontiguousarray(wire, np.uint8)
+        out = np.empty((n, m), np.float32)
+        sec = self.lib.refshim_mul_mat(t, _p(wire), _p(x), _p(out), m, k, n, n_threads, reps)
+        assert sec >= 0, sec
+        return out, sec
+
+
+def nmse(a: np.ndarray, b: np.ndarray) -> float:
+    """Normalised mean squared error, as tests/test-backend-ops.cpp:39-50 of the reference."""
+    a = a.astype(np.float64).ravel()
+    b = b.astype(np.float64).ravel()
+    return float(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-300))

@@ -1,0 +1,306 @@
+// oracle/oracle_quants.c — TEST INFRASTRUCTURE.  CPU restatement of the reference's arithmetic for
+// GGML_OP_MUL_MAT on block-quantized weights.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline leg may load this; the product (libb200q.so) never does and has no CPU fallback.
+//
+// What is restated, and from where (paths relative to /root/reference):
+//   * wire formats            ggml/src/ggml-common.h:166-775 (block_* structs), tables :2212-2250
+//   * dequantize_row_<type>   ggml/src/ggml-quants.c (legacy / K / IQ types), ggml/src/iqk/iqk_quantize.cpp (IQK types)
+//   * quantize_q8_1 (CUDA)    ggml/src/ggml-cuda/quantize.cu:13-47
+//   * MMVQ result             ggml/src/ggml-cuda/mmvq-templates.cuh:68-150 + vecdotq.cuh: for every type the
+//                             kernel evaluates  sum_k dequant(W)[m][k] * (d8_b * q8[k])  with integer
+//                             partial sums, i.e. the exact dot of the dequantized weights with the
+//                             q8_1-dequantized activations (d8 rounded to half) — oracle_mul_mat_q8_1 below.
+//   * exact result            dst[n][m] = sum_k dequant(W)[m][k] * x[n][k] in f64 — the ground truth the
+//                             reference's own test uses modulo NMSE (tests/test-backend-ops.cpp:979-981).
+// Pinning: tests/test_oracle.py checks every dequantizer here bit-for-bit against the reference's own
+// to_float (oracle/_ref, when built) and against committed golden vectors in tests/golden/.
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <math.h>
+#include <stdlib.h>
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+// ggml_type ids (ggml/include/ggml.h:391-492)
+enum {
+    T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
+    T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
+    T_IQ2_XXS = 16, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135,
+    T_IQ4_K = 139, T_IQ5_K = 140, T_IQ4_KS = 144,
+};
+
+static float h2f(uint16_t h) {                    // IEEE binary16 -> binary32 (GGML_FP16_TO_FP32)
+    uint32_t s = (uint32_t)(h & 0x8000) << 16, e = (h >> 10) & 0x1f, m = h & 0x3ff, u;
+    if (e == 0) {
+        if (m == 0) u = s;
+        else { int sh = 0; while (!(m & 0x400)) { m <<= 1; ++sh; } m &= 0x3ff; u = s | ((uint32_t)(113 - sh) << 23) | (m << 13); }
+    } else if (e == 31) u = s | 0x7f800000u | (m << 13);
+    else u = s | ((e + 112) << 23) | (m << 13);
+    float f; memcpy(&f, &u, 4); return f;
+}
+static uint16_t f2h(float f) {                    // binary32 -> binary16, round-to-nearest-even (__float2half_rn)
+    uint32_t x; memcpy(&x, &f, 4);
+    uint32_t s = (x >> 16) & 0x8000; int32_t e = (int32_t)((x >> 23) & 0xff) - 127 + 15; uint32_t m = x & 0x7fffff;
+    if (((x >> 23) & 0xff) == 0xff) return (uint16_t)(s | 0x7c00 | (m ? 0x200 : 0));
+    if (e >= 31) return (uint16_t)(s | 0x7c00);
+    if (e <= 0) {
+        if (e < -10) return (uint16_t)s;
+        m |= 0x800000; int sh = 14 - e; uint32_t r = m >> sh, rem = m & ((1u << sh) - 1), half = 1u << (sh - 1);
+        if (rem > half || (rem == half && (r & 1))) ++r;
+        return (uint16_t)(s | r);
+    }
+    uint32_t r = (uint32_t)(e << 10) | (m >> 13), rem = m & 0x1fff;
+    if (rem > 0x1000 || (rem == 0x1000 && (r & 1))) ++r;
+    return (uint16_t)(s | r);
+}
+ORACLE_API float    oracle_h2f(uint16_t h) { return h2f(h); }
+ORACLE_API uint16_t oracle_f2h(float f)    { return f2h(f); }
+
+static uint16_t rd16(const uint8_t * p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+// non-linear value tables (ggml-common.h: kvalues_iq4nl, iq4k_values :2227, iq5nl_values :2232)
+static const int8_t k_iq4nl[16] = {-127, -104, -83, -65, -49, -35, -22, -10, 1, 13, 25, 38, 53, 69, 89, 113};
+static int8_t k_iq4k[32];
+static int8_t k_iq5nl[64];
+static int tables_ready = 0;
+static void init_tables(void) {
+    if (tables_ready) return;
+    // iq4k_values = kvalues_iq4nl, then the same +4 (second row of the table at ggml-common.h:2227-2230)
+    for (int i = 0; i < 16; ++i) { k_iq4k[i] = k_iq4nl[i]; k_iq4k[16 + i] = (int8_t)(k_iq4nl[i] + 4); }
+    // iq5nl_values (ggml-common.h:2232-2235): 32 values, then the same +2
+    static const int8_t v5[32] = {-126, -114, -103, -92, -83, -74, -65, -57, -50, -43, -36, -30, -24, -18, -12, -6,
+                                  -1, 5, 11, 17, 23, 29, 36, 43, 51, 59, 68, 77, 87, 97, 109, 121};
+    for (int i = 0; i < 32; ++i) { k_iq5nl[i] = v5[i]; k_iq5nl[32 + i] = (int8_t)(v5[i] + 2); }
+    tables_ready = 1;
+}
+
+// ---- wire geometry: {block elements, block bytes, row meta bytes} (ggml.c type_traits :640-1460) ----
+static int geom(int type, int * qk, int * bs, int * meta) {
+    *meta = 0;
+    switch (type) {
+        case T_Q4_0:   *qk = 32;  *bs = 18;  return 0;
+        case T_Q4_1:   *qk = 32;  *bs = 20;  return 0;
+        case T_Q5_0:   *qk = 32;  *bs = 22;  return 0;
+        case T_Q5_1:   *qk = 32;  *bs = 24;  return 0;
+        case T_Q6_0:   *qk = 32;  *bs = 26;  return 0;
+        case T_Q8_0:   *qk = 32;  *bs = 34;  return 0;
+        case T_Q2_K:   *qk = 256; *bs = 84;  return 0;
+        case T_Q3_K:   *qk = 256; *bs = 110; return 0;
+        case T_Q4_K:   *qk = 256; *bs = 144; return 0;
+        case T_Q5_K:   *qk = 256; *bs = 176; return 0;
+        case T_Q6_K:   *qk = 256; *bs = 210; return 0;
+        case T_IQ4_NL: *qk = 32;  *bs = 18;  return 0;
+        case T_IQ4_XS: *qk = 256; *bs = 136; return 0;
+        case T_IQ4_K:  *qk = 256; *bs = 144; return 0;
+        case T_IQ5_K:  *qk = 256; *bs = 176; return 0;
+        case T_IQ4_KS: *qk = 256; *bs = 136; *meta = 4; return 0;
+        case T_IQ2_BN: *qk = 64;  *bs = 16;  *meta = 4; return 0;
+        default: return -1;
+    }
+}
+ORACLE_API int64_t oracle_row_size(int type, int64_t k) {
+    int qk, bs, meta; if (geom(type, &qk, &bs, &meta) || k % qk) return -1;
+    return (int64_t)meta + (k / qk) * bs;
+}
+ORACLE_API int oracle_type_supported(int type) { int a, b, c; return geom(type, &a, &b, &c) == 0; }
+
+// get_scale_min_k4 (ggml-quants.c:2036-2044)
+static void scale_min_k4(int j, const uint8_t * q, int * sc, int * m) {
+    if (j < 4) { *sc = q[j] & 63; *m = q[j + 4] & 63; }
+    else { *sc = (q[j + 4] & 0xF) | ((q[j - 4] >> 6) << 4); *m = (q[j + 4] >> 4) | ((q[j] >> 6) << 4); }
+}
+
+// Dequantize one wire row (pointer at row start, i.e. including any row-meta header) into y[k].
+ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, int64_t k) {
+    int qk, bs, meta; if (geom(type, &qk, &bs, &meta) || k % qk) return -1;
+    init_tables();
+    const int64_t nb = k / qk;
+    const uint8_t * x = row + meta;
+    float row_scale = 1.0f;
+    if (meta == 4) memcpy(&row_scale, row, 4);
+    for (int64_t i = 0; i < nb; ++i, x += bs, y += qk) {
+        switch (type) {
+        case T_Q4_0: {  // ggml-quants.c:1581-1599  {half d; u8 qs[16]}
+            const float d = h2f(rd16(x)); const uint8_t * qs = x + 2;
+            for (int j = 0; j < 16; ++j) { y[j] = ((qs[j] & 0xF) - 8) * d; y[j + 16] = ((qs[j] >> 4) - 8) * d; }
+        } break;
+        case T_Q4_1: {  // ggml-quants.c:1601-1620  {half d, m; u8 qs[16]}
+            const float d = h2f(rd16(x)), m = h2f(rd16(x + 2)); const uint8_t * qs = x + 4;
+            for (int j = 0; j < 16; ++j) { y[j] = (qs[j] & 0xF) * d + m; y[j + 16] = (qs[j] >> 4) * d + m; }
+        } break;
+        case T_Q5_0: {  // ggml-quants.c:1622-1646  {half d; u8 qh[4]; u8 qs[16]}
+            const float d = h2f(rd16(x)); uint32_t qh; memcpy(&qh, x + 2, 4); const uint8_t * qs = x + 6;
+            for (int j = 0; j < 16; ++j) {
+                const uint8_t xh0 = ((qh >> (j + 0)) << 4) & 0x10, xh1 = ((qh >> (j + 12))) & 0x10;
+                y[j] = (((qs[j] & 0xF) | xh0) - 16) * d; y[j + 16] = (((qs[j] >> 4) | xh1) - 16) * d;
+            }
+        } break;
+        case T_Q5_1: {  // ggml-quants.c:1648-1673
+            const float d = h2f(rd16(x)), m = h2f(rd16(x + 2)); uint32_t qh; memcpy(&qh, x + 4, 4); const uint8_t * qs = x + 8;
+            for (int j = 0; j < 16; ++j) {
+                const uint8_t xh0 = ((qh >> (j + 0)) << 4) & 0x10, xh1 = ((qh >> (j + 12))) & 0x10;
+                y[j] = ((qs[j] & 0xF) | xh0) * d + m; y[j + 16] = ((qs[j] >> 4) | xh1) * d + m;
+            }
+        } break;
+        case T_Q6_0: {  // ggml-quants.c:1675-1695  {half d; u8 qh[8]; u8 qs[16]}
+            const float d = h2f(rd16(x)); const uint8_t * qh = x + 2; const uint8_t * qs = x + 10;
+            for (int j = 0; j < 16; ++j) {
+                const uint8_t h = qh[j % 8] >> 4 * (j / 8);
+                y[j] = (((qs[j] & 0xF) | ((h << 4) & 0x30)) - 32) * d;
+                y[j + 16] = (((qs[j] >> 4) | ((h << 2) & 0x30)) - 32) * d;
+            }
+        } break;
+        case T_Q8_0: {  // ggml-quants.c:1697-1711  {half d; i8 qs[32]}
+            const float d = h2f(rd16(x)); const int8_t * qs = (const int8_t *)(x + 2);
+            for (int j = 0; j < 32; ++j) y[j] = qs[j] * d;
+        } break;
+        case T_Q4_K: {  // ggml-quants.c:2797-2822  {half d, dmin; u8 scales[12]; u8 qs[128]}
+            const float d = h2f(rd16(x)), mn = h2f(rd16(x + 2)); const uint8_t * sc = x + 4; const uint8_t * q = x + 16;
+            float * yy = y; int is = 0;
+            for (int j = 0; j < 256; j += 64) {
+                int s1, m1, s2, m2; scale_min_k4(is, sc, &s1, &m1); scale_min_k4(is + 1, sc, &s2, &m2);
+                const float d1 = d * s1, mm1 = mn * m1, d2 = d * s2, mm2 = mn * m2;
+                for (int l = 0; l < 32; ++l) *yy++ = d1 * (q[l] & 0xF) - mm1;
+                for (int l = 0; l < 32; ++l) *yy++ = d2 * (q[l] >> 4) - mm2;
+                q += 32; is += 2;
+            }
+        } break;
+        case T_Q5_K: {  // ggml-quants.c:3015-3041  {half d, dmin; u8 scales[12]; u8 qh[32]; u8 qs[128]}
+            const float d = h2f(rd16(x)), mn = h2f(rd16(x + 2)); const uint8_t * sc = x + 4; const uint8_t * qh = x + 16; const uint8_t * ql = x + 48;
+            float * yy = y; int is = 0; uint8_t u1 = 1, u2 = 2;
+            for (int j = 0; j < 256; j += 64) {
+                int s1, m1, s2, m2; scale_min_k4(is, sc, &s1, &m1); scale_min_k4(is + 1, sc, &s2, &m2);
+                const float d1 = d * s1, mm1 = mn * m1, d2 = d * s2, mm2 = mn * m2;
+                for (int l = 0; l < 32; ++l) *yy++ = d1 * ((ql[l] & 0xF) + (qh[l] & u1 ? 16 : 0)) - mm1;
+                for (int l = 0; l < 32; ++l) *yy++ = d2 * ((ql[l] >> 4) + (qh[l] & u2 ? 16 : 0)) - mm2;
+                ql += 32; is += 2; u1 <<= 2; u2 <<= 2;
+            }
+        } break;
+        case T_Q6_K: {  // ggml-quants.c:3231-3260  {u8 ql[128]; u8 qh[64]; i8 scales[16]; half d}
+            const uint8_t * ql = x; const uint8_t * qh = x + 128; const int8_t * sc = (const int8_t *)(x + 192); const float d = h2f(rd16(x + 208));
+            float * yy = y;
+            for (int n = 0; n < 256; n += 128) {
+                for (int l = 0; l < 32; ++l) {
+                    const int is = l / 16;
+                    const int8_t q1 = (int8_t)((ql[l] & 0xF) | (((qh[l] >> 0) & 3) << 4)) - 32;
+                    const int8_t q2 = (int8_t)((ql[l + 32] & 0xF) | (((qh[l] >> 2) & 3) << 4)) - 32;
+                    const int8_t q3 = (int8_t)((ql[l] >> 4) | (((qh[l] >> 4) & 3) << 4)) - 32;
+                    const int8_t q4 = (int8_t)((ql[l + 32] >> 4) | (((qh[l] >> 6) & 3) << 4)) - 32;
+                    yy[l] = d * sc[is] * q1; yy[l + 32] = d * sc[is + 2] * q2; yy[l + 64] = d * sc[is + 4] * q3; yy[l + 96] = d * sc[is + 6] * q4;
+                }
+                yy += 128; ql += 64; qh += 32; sc += 8;
+            }
+        } break;
+        case T_IQ4_NL: {  // ggml-quants.c:3913-3929  {half d; u8 qs[16]}
+            const float d = h2f(rd16(x)); const uint8_t * qs = x + 2;
+            for (int j = 0; j < 16; ++j) { y[j] = d * k_iq4nl[qs[j] & 0xf]; y[j + 16] = d * k_iq4nl[qs[j] >> 4]; }
+        } break;
+        case T_IQ4_XS: {  // ggml-quants.c:3931-3954  {half d; u16 scales_h; u8 scales_l[4]; u8 qs[128]}
+            const float d = h2f(rd16(x)); const uint16_t sh = rd16(x + 2); const uint8_t * sl = x + 4; const uint8_t * qs = x + 8;
+            float * yy = y;
+            for (int ib = 0; ib < 8; ++ib) {
+                const int ls = ((sl[ib / 2] >> 4 * (ib % 2)) & 0xf) | (((sh >> 2 * ib) & 3) << 4);
+                const float dl = d * (ls - 32);
+                for (int j = 0; j < 16; ++j) { yy[j] = dl * k_iq4nl[qs[j] & 0xf]; yy[j + 16] = dl * k_iq4nl[qs[j] >> 4]; }
+                yy += 32; qs += 16;
+            }
+        } break;
+        case T_IQ4_K: {  // iqk/iqk_quantize.cpp:2822-2850  {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]; u8 qs[128]}
+            const float d = h2f(rd16(x)); uint16_t extra = rd16(x + 2); const uint8_t * sh = x + 4; const uint8_t * sl = x + 8; const uint8_t * qs = x + 16;
+            float * yy = y;
+            for (int ib = 0; ib < 8; ++ib) {
+                const uint8_t h = sh[ib / 2] >> 4 * (ib % 2);
+                const int ls1 = ((sl[ib] & 0xf) | ((h << 4) & 0x30)) - 32;
+                const int ls2 = ((sl[ib] >> 4) | ((h << 2) & 0x30)) - 32;
+                const float dl1 = d * ls1, dl2 = d * ls2;
+                const int8_t * v1 = k_iq4k + ((extra & 1) << 4); const int8_t * v2 = k_iq4k + ((extra & 2) << 3); extra >>= 2;
+                for (int j = 0; j < 16; ++j) { yy[j] = dl1 * v1[qs[j] & 0xf]; yy[j + 16] = dl2 * v2[qs[j] >> 4]; }
+                yy += 32; qs += 16;
+            }
+        } break;
+        case T_IQ5_K: {  // iqk/iqk_quantize.cpp:3112-3150  {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]; u8 qs[128]; u8 qh[32]}
+            const float d = h2f(rd16(x)); uint16_t extra = rd16(x + 2); const uint8_t * sh = x + 4; const uint8_t * sl = x + 8;
+            const uint8_t * qs = x + 16; const uint8_t * qh = x + 144;
+            float * yy = y; int shift = 0;
+            for (int ib64 = 0; ib64 < 4; ++ib64) {
+                const float dl1 = d * (((sl[2 * ib64] & 0xf) | ((sh[ib64] << 4) & 0x30)) - 32);
+                const float dl2 = d * (((sl[2 * ib64] >> 4) | ((sh[ib64] << 2) & 0x30)) - 32);
+                const float dl3 = d * (((sl[2 * ib64 + 1] & 0xf) | ((sh[ib64] >> 0) & 0x30)) - 32);
+                const float dl4 = d * (((sl[2 * ib64 + 1] >> 4) | ((sh[ib64] >> 2) & 0x30)) - 32);
+                const int8_t * v1 = k_iq5nl + ((extra & 1) << 5); const int8_t * v2 = k_iq5nl + ((extra & 2) << 4);
+                const int8_t * v3 = k_iq5nl + ((extra & 4) << 3); const int8_t * v4 = k_iq5nl + ((extra & 8) << 2);
+                for (int j = 0; j < 16; ++j) {
+                    yy[j]      = dl1 * v1[(qs[j] & 0xf) | (((qh[j] >> shift) & 1) << 4)];
+                    yy[j + 16] = dl2 * v2[(qs[j + 16] & 0xf) | (((qh[j + 16] >> shift) & 1) << 4)];
+                    yy[j + 32] = dl3 * v3[(qs[j] >> 4) | (((qh[j] >> shift) & 2) << 3)];
+                    yy[j + 48] = dl4 * v4[(qs[j + 16] >> 4) | (((qh[j + 16] >> shift) & 2) << 3)];
+                }
+                yy += 64; qs += 32; extra >>= 4; shift += 2;
+                if (shift == 8) { qh += 32; shift = 0; }
+            }
+        } break;
+        case T_IQ4_KS: {  // iqk/iqk_quantize.cpp:4555-4580  row = {float d; blocks {u8 scales[8]; u8 qs[128]}}
+            const uint8_t * sc = x; const uint8_t * qs = x + 8; float * yy = y;
+            for (int ib = 0; ib < 8; ++ib) {
+                const float dl = row_scale * ((int)(sc[ib] & 254) - 127);
+                const int8_t * v = k_iq4k + ((sc[ib] & 1) << 4);
+                for (int j = 0; j < 16; ++j) { yy[j] = dl * v[qs[j] & 0xf]; yy[j + 16] = dl * v[qs[j] >> 4]; }
+                yy += 32; qs += 16;
+            }
+        } break;
+        case T_IQ2_BN: {  // iqk/iqk_quantize.cpp:418-436 + row scale written at :227-229 (SURVEY §8c pitfall 1):
+                          // w = row_scale * (q - 1), q = 2-bit field (j div 16) of byte (j mod 16)
+            for (int j = 0; j < 64; ++j) y[j] = row_scale * (float)(((x[j % 16] >> (2 * (j / 16))) & 3) - 1);
+        } break;
+        default: return -1;
+        }
+    }
+    return 0;
+}
+
+// quantize_q8_1 of the reference's CUDA path (ggml-cuda/quantize.cu:13-47): per 32 values
+//   d = amax/127 ; q = amax == 0 ? 0 : roundf(x/d) ; stored d -> half, s = sum(x) -> half.
+// q: int8 [n][k]; d_bits, s_bits: half bit patterns [n][k/32].  k must be a multiple of 32
+// (the reference pads K to a multiple of 512 with zeros, which quantize to q = 0 and do not change the result).
+ORACLE_API int oracle_quantize_q8_1(const float * x, int64_t n, int64_t k, int8_t * q, uint16_t * d_bits, uint16_t * s_bits) {
+    if (k % 32) return -1;
+    for (int64_t r = 0; r < n; ++r) for (int64_t b = 0; b < k / 32; ++b) {
+        const float * xb = x + r * k + b * 32; float amax = 0.0f, sum = 0.0f;
+        for (int j = 0; j < 32; ++j) { const float a = fabsf(xb[j]); if (a > amax) amax = a; }
+        // warp_reduce_sum butterfly order (xor 16,8,4,2,1) to reproduce the f32 sum bit-for-bit
+        float t[32]; for (int j = 0; j < 32; ++j) t[j] = xb[j];
+        for (int w = 16; w > 0; w >>= 1) { float u[32]; for (int j = 0; j < 32; ++j) u[j] = t[j] + t[j ^ w]; memcpy(t, u, sizeof t); }
+        sum = t[0];
+        const float d = amax / 127;
+        for (int j = 0; j < 32; ++j) q[r * k + b * 32 + j] = amax == 0.0f ? 0 : (int8_t)roundf(xb[j] / d);
+        d_bits[r * (k / 32) + b] = f2h(d); s_bits[r * (k / 32) + b] = f2h(sum);
+    }
+    return 0;
+}
+
+// dst[n][m] (f32) = exact f64 dot of dequant(W) rows with x columns.  W: m wire rows, x: f32 [n][k].
+ORACLE_API int oracle_mul_mat_exact(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n) {
+    const int64_t rs = oracle_row_size(type, k); if (rs < 0) return -1;
+    float * w = (float *)malloc(sizeof(float) * k);
+    for (int64_t i = 0; i < m; ++i) {
+        if (oracle_dequantize_row(type, W + i * rs, w, k)) { free(w); return -1; }
+        for (int64_t j = 0; j < n; ++j) { double acc = 0; const float * xr = x + j * k; for (int64_t l = 0; l < k; ++l) acc += (double)w[l] * xr[l]; dst[j * m + i] = (float)acc; }
+    }
+    free(w); return 0;
+}
+
+// dst[n][m] = the value the reference's MMVQ kernels compute up to f32 summation order (see header).
+ORACLE_API int oracle_mul_mat_q8_1(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n) {
+    const int64_t rs = oracle_row_size(type, k); if (rs < 0 || k % 32) return -1;
+    int8_t * q = (int8_t *)malloc((size_t)n * k); uint16_t * db = (uint16_t *)malloc(sizeof(uint16_t) * n * (k / 32)); uint16_t * sb = (uint16_t *)malloc(sizeof(uint16_t) * n * (k / 32));
+    float * xq = (float *)malloc(sizeof(float) * n * k); float * w = (float *)malloc(sizeof(float) * k);
+    oracle_quantize_q8_1(x, n, k, q, db, sb);
+    for (int64_t j = 0; j < n; ++j) for (int64_t l = 0; l < k; ++l) xq[j * k + l] = h2f(db[j * (k / 32) + l / 32]) * q[j * k + l];
+    int rc = 0;
+    for (int64_t i = 0; i < m && !rc; ++i) {
+        rc = oracle_dequantize_row(type, W + i * rs, w, k);
+        for (int64_t j = 0; j < n; ++j) { double acc = 0; const float * xr = xq + j * k; for (int64_t l = 0; l < k; ++l) acc += (double)w[l] * xr[l]; dst[j * m + i] = (float)acc; }
+    }
+    free(q); free(db); free(sb); free(xq); free(w); return rc;
+}
