@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py — llama-bench-shaped measurement of the quantized mat-mul hot path on B200.
+
+Workload (BASELINE.json configs[1]): Llama-3-8B, pure IQ4_NL (`llama-quantize --pure`), synthetic random-init weights.
+One "step" = one pass of the hot path over one batch:
+  * tg128: ONE token (n_batch = 1) through every MUL_MAT of the model, in graph order with real data dependencies:
+           32 x [ QKV (one multi-tensor mat-vec launch) -> wo -> fused up/gate/SiLU -> ffn_down ] -> output head.
+           129 launches of our k_mmvq kernel and nothing else (attention/norm/rope are NOT the hot path and are not run;
+           the q projection is fed straight to wo so the chain keeps the dependency structure).
+  * pp512: the same matrices with n_batch = 512 through the tcgen05 GEMM path (head on the last token only,
+           as llama-bench does); the SiLU*mul glue between up/gate and down is a torch elementwise op.
+Weights live in HBM in the plane layout (uploaded through the C-ABI repack); 4.2 GB of weights per pass >> 126 MB L2,
+so every timed iteration streams from HBM ("inputs larger than L2").
+
+value  = tok/s with inputs already resident in HBM (CUDA-graph replay of the step, CUDA-event timed, max over ranks)
+e2e    = tok/s through host buffers: pinned-host activations H2D + the same launches + logits D2H, every step
+N > 1  = the fork's "split mode graph" tensor parallelism: QKV/up/gate row-sharded, wo/down K-sharded + all-reduce (NCCL).
+
+--impl reference times the reference's own CPU IQK path (oracle/_ref, the unmodified ggml CPU backend) on a bounded
+sample of the same workload (one transformer layer's mat-muls), scaled to the whole token.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Llama-3-8B: per-layer matmul shapes (M x K)
+N_EMBD, N_FF, N_LAYER, N_VOCAB, N_KV_DIM = 4096, 14336, 32, 128256, 1024
+IQ4_NL = 20
+
+
+def model_bytes_per_token(n_layer=N_LAYER, tp=1):
+    per_layer_w = N_EMBD * N_EMBD * 2 + 2 * N_KV_DIM * N_EMBD + 3 * N_FF * N_EMBD
+    return (per_layer_w * n_layer + N_VOCAB * N_EMBD) * 18 // 32
+
+
+def model_flops_pp(n_tokens, n_layer=N_LAYER):
+    per_layer_w = N_EMBD * N_EMBD * 2 + 2 * N_KV_DIM * N_EMBD + 3 * N_FF * N_EMBD
+    return 2.0 * per_layer_w * n_layer * n_tokens + 2.0 * N_VOCAB * N_EMBD
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if len(s) >= 7 and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) >= 7 and s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def random_planes_iq4nl(be, torch, m, k, gen, scale):
+    """Random valid IQ4_NL wire blocks made on the GPU, then re-laid-out by the product's repack kernel."""
+    nb = m * (k // 32)
+    blocks = torch.randint(0, 256, (nb, 18), dtype=torch.uint8, device="cuda", generator=gen)
+    d = (torch.rand(nb, device="cuda", generator=gen) * 0.6 + 0.7) * scale
+    blocks[:, 0:2] = d.to(torch.float16).view(torch.uint8).view(nb, 2)
+    return be.set_tensor(IQ4_NL, blocks.view(-1), m, k)
+
+
+class Model:
+    """Llama-3-8B matmul skeleton, optionally one tensor-parallel shard (rank r of tp)."""
+
+    def __init__(self, be, torch, n_layer, tp=1, rank=0, seed=1234):
+        self.be, self.torch, self.tp, self.n_layer = be, torch, tp, n_layer
+        gen = torch.Generator(device="cuda")
+        gen.manual_seed(seed + rank)
+        s_e, s_f = 1.0 / (70.0 * N_EMBD ** 0.5), 1.0 / (70.0 * N_FF ** 0.5)
+        mk = lambda m, k, s: random_planes_iq4nl(be, torch, m, k, gen, s)
+        self.layers = []
+        for _ in range(n_layer):
+            self.layers.append(dict(
+                wq=mk(N_EMBD // tp, N_EMBD, s_e), wk=mk(N_KV_DIM // tp, N_EMBD, s_e), wv=mk(N_KV_DIM // tp, N_EMBD, s_e),
+                wo=mk(N_EMBD, N_EMBD // tp, s_e * 2), up=mk(N_FF // tp, N_EMBD, s_e * 2), gate=mk(N_FF // tp, N_EMBD, s_e * 2),
+                down=mk(N_EMBD, N_FF // tp, s_f * 4)))
+        self.head = mk(N_VOCAB // tp, N_EMBD, s_e)
+        self.launches_tg = n_layer * 4 + 1
+        self.weight_bytes = sum(t.nbytes_wire for L in self.layers for t in L.values()) + self.head.nbytes_wire
+
+    def alloc(self, n):
+        t, tp = self.torch, self.tp
+        f = lambda *s: t.empty(s, dtype=t.float32, device="cuda")
+        self.x = f(n, N_EMBD); self.q = f(n, N_EMBD // tp); self.kk = f(n, N_KV_DIM // tp); self.v = f(n, N_KV_DIM // tp)
+        self.h = f(n, N_EMBD); self.a = f(n, N_FF // tp); self.x2 = f(n, N_EMBD); self.logits = f(1, N_VOCAB // tp)
+        self.u = f(n, N_FF // tp) if n > 8 else None
+        self.g = f(n, N_FF // tp) if n > 8 else None
+
+    def allreduce(self, t):
+        if self.tp > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t)
+
+    def step_tg(self):
+        be = self.be
+        x = self.x
+        for L in self.layers:
+            be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v])
+            be.mul_mat(L["wo"], self.q, out=self.h); self.allreduce(self.h)
+            be.fused_up_gate(L["up"], L["gate"], self.h, "silu", out=self.a)
+            be.mul_mat(L["down"], self.a, out=self.x2); self.allreduce(self.x2)
+            x = self.x2
+        be.mul_mat(self.head, x, out=self.logits)
+
+    def step_pp(self):
+        be, t = self.be, self.torch
+        x = self.x
+        for L in self.layers:
+            be.mul_mat(L["wq"], x, out=self.q); be.mul_mat(L["wk"], x, out=self.kk); be.mul_mat(L["wv"], x, out=self.v)
+            be.mul_mat(L["wo"], self.q, out=self.h); self.allreduce(self.h)
+            be.mul_mat(L["up"], self.h, out=self.u); be.mul_mat(L["gate"], self.h, out=self.g)
+            t.mul(t.nn.functional.silu(self.g), self.u, out=self.a)         # glue, not the hot path
+            be.mul_mat(L["down"], self.a, out=self.x2); self.allreduce(self.x2)
+            x = self.x2
+        be.mul_mat(self.head, x[-1:], out=self.logits)
+
+
+def time_graph(torch, fn, steps, warmup, dist=None, pre=None, post=None):
+    """Capture fn into a CUDA graph, W warm-up replays, then K replays bracketed by barrier+sync, CUDA-event timed."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            fn()                                   # eager warm-up (sets func attributes, allocates workspaces)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+
+    def one():
+        if pre: pre()
+        g.replay()
+        if post: post()
+
+    for _ in range(max(warmup, 3)):
+        one()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def cpu_baseline(n_threads=None, budget_s=12.0, n=1):
+    """Reference CPU IQK path (oracle/_ref) on ONE transformer layer's mat-muls, scaled to the whole model."""
+    from oracle.oracle import RefLib
+    path = RefLib.find(prefer_native=True)
+    if path is None:
+        return None
+    R = RefLib(path)
+    n_threads = n_threads or max(1, (os.cpu_count() or 2) // 2)
+    shapes = [(N_EMBD, N_EMBD), (N_KV_DIM, N_EMBD), (N_KV_DIM, N_EMBD), (N_EMBD, N_EMBD), (N_FF, N_EMBD), (N_FF, N_EMBD), (N_EMBD, N_FF)]
+    import ctypes
+    nm = len(shapes)
+    types = (ctypes.c_int * nm)(*[IQ4_NL] * nm)
+    ms_ = (ctypes.c_int64 * nm)(*[s[0] for s in shapes]); ks_ = (ctypes.c_int64 * nm)(*[s[1] for s in shapes])
+    ch = R.lib.refshim_chain_new(nm, types, ms_, ks_, n, n_threads)
+    rng = np.random.default_rng(0)
+    for i, (m, k) in enumerate(shapes):
+        nb = m * (k // 32)
+        blocks = rng.integers(0, 256, (nb, 18), dtype=np.uint8)
+        blocks[:, 0:2] = (rng.uniform(0.7, 1.3, nb) / (70.0 * k ** 0.5)).astype(np.float16).view(np.uint8).reshape(nb, 2)
+        x = rng.standard_normal((n, k)).astype(np.float32)
+        R.lib.refshim_chain_set(ch, i, blocks.ctypes.data, x.ctypes.data)
+    R.lib.refshim_chain_run(ch)                    # warm-up
+    t0, times = time.time(), []
+    while time.time() - t0 < budget_s and len(times) < 200:
+        times.append(R.lib.refshim_chain_run(ch))
+    R.lib.refshim_chain_free(ch)
+    layer_s = float(np.median(times))
+    layer_w = sum(m * k for m, k in shapes)
+    total_w = layer_w * N_LAYER + N_VOCAB * N_EMBD * (1 if n == 1 else 1.0 / n)
+    step_s = layer_s * total_w / layer_w
+    return {"value": n / step_s, "unit": "tok/s", "cores": n_threads, "kind": "reference",
+            "sample": f"{len(times)} runs of one layer's 7 MUL_MATs (218 M weights, IQ4_NL, n={n}) through the unmodified reference CPU backend "
+                      f"({os.path.basename(path)}), median {layer_s*1e3:.2f} ms/layer, scaled x{total_w/layer_w:.2f} to the full model"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=N_LAYER, help="debug only: a run with fewer layers is not a bench value")
+    ap.add_argument("--no-pp", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    config = {"workload": "Llama-3-8B pure IQ4_NL, llama-bench tg128 (n_batch=1) / pp512 (n_ubatch=512): all MUL_MAT nodes in graph order",
+              "n_layer": args.layers, "l2_policy": "inputs larger than L2 (4.2 GB of weights streamed per step)",
+              "parallelism": f"tp{world}" if world > 1 else "none"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        cb = cpu_baseline(n_threads=os.cpu_count(), budget_s=20.0)
+        if cb is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference CPU build) not present"}))
+            return 0
+        line = {"metric": "llama-bench tg128 tok/s (MUL_MAT hot path)", "value": cb["value"], "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "int8 (IQ4_NL weights x Q8 activations, f32 accumulate)", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    from ik_llama_cpp_b200 import backend as be
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device — the hot path has no CPU fallback", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.manual_seed(0)
+
+    model = Model(be, torch, args.layers, tp=world, rank=rank)
+    # ---------------- tg128 ----------------
+    model.alloc(1)
+    x_host = torch.randn(1, N_EMBD).pin_memory()
+    logits_host = torch.empty(1, N_VOCAB // world).pin_memory()
+    model.x.copy_(x_host)
+    with ClockSampler(local_rank) as cs:
+        ms_tg = time_graph(torch, model.step_tg, args.steps, args.warmup, dist)
+    clocks = cs.summary()
+    ms_tg_e2e = time_graph(torch, model.step_tg, args.steps, args.warmup, dist,
+                           pre=lambda: model.x.copy_(x_host, non_blocking=True),
+                           post=lambda: (logits_host.copy_(model.logits, non_blocking=True), torch.cuda.current_stream().synchronize()))
+    tok_s = 1000.0 / ms_tg
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    bytes_tok = model.weight_bytes
+    ach = bytes_tok / (ms_tg * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_mmvq<IQ4_NL>", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "algorithmic_bytes_per_step": bytes_tok, "launches_per_step": model.launches_tg, "peak_source": peak_src,
+            "note": "the step consists only of k_mmvq launches; achieved = weight bytes per token / step time (per rank)"}
+    line = {"metric": "llama-bench tg128 tok/s (MUL_MAT hot path)", "value": tok_s, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_tg, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int8 (IQ4_NL weights x q8_1 activations, dp4a, f32 accumulate)", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": 1000.0 / ms_tg_e2e, "unit": "tok/s", "h2d_bytes_per_step": N_EMBD * 4, "d2h_bytes_per_step": (N_VOCAB // world) * 4},
+            "gpu_launches": model.launches_tg * args.steps, "roofline": roof}
+    # ---------------- pp512 ----------------
+    if not args.no_pp:
+        n = 512
+        model.alloc(n)
+        xh = torch.randn(n, N_EMBD).pin_memory()
+        model.x.copy_(xh)
+        pp_steps = max(3, min(args.steps, 10))
+        ms_pp = time_graph(torch, model.step_pp, pp_steps, args.warmup, dist)
+        ms_pp_e2e = time_graph(torch, model.step_pp, pp_steps, args.warmup, dist,
+                               pre=lambda: model.x.copy_(xh, non_blocking=True),
+                               post=lambda: (logits_host.copy_(model.logits, non_blocking=True), torch.cuda.current_stream().synchronize()))
+        fl = model_flops_pp(n, args.layers) / world
+        tfs = fl / (ms_pp * 1e-3) / 1e12
+        line["pp512"] = {"metric": "llama-bench pp512 tok/s (MUL_MAT hot path)", "value": n * 1000.0 / ms_pp, "unit": "tok/s", "ms_per_step": ms_pp, "steps": pp_steps,
+                         "dtype": "bf16 x bf16 -> f32 (tcgen05 kind::f16)", "e2e": {"value": n * 1000.0 / ms_pp_e2e, "unit": "tok/s", "h2d_bytes_per_step": n * N_EMBD * 4, "d2h_bytes_per_step": (N_VOCAB // world) * 4},
+                         "roofline": {"bound": "tensor", "kernel": "k_gemm_bf16 (+k_dequant_bf16, k_f32_to_bf16)", "achieved": tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfs / tf_peak,
+                                      "traffic": None, "algorithmic_flops_per_step": fl, "peak_source": peak_src + " sustained"}}
+    # ---------------- cpu baseline (rank 0, N=1 only) ----------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cb = cpu_baseline(budget_s=10.0)
+            if cb:
+                line["cpu_baseline"] = cb
+        except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
+            line["cpu_baseline"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,185 @@
+"""Host-side mirror of the reference's operator interface for the quantized mat-mul hot path.
+
+The reference is compiled code whose operator boundary for this path is, per op node,
+    ggml_cuda_mul_mat(ctx, src0 /*quantized [K, M]*/, src1 /*f32 [K, N]*/, dst /*f32 [M, N]*/)   ggml/src/ggml-cuda.cu:2645
+    ggml_cuda_up_gate_unary(ctx, dst)  (GGML_OP_FUSED_UP_GATE)                                   ggml/src/ggml-cuda.cu:3542
+and, for weights, ggml_backend_cuda_buffer_set_tensor / get_tensor (:641-672).  This module exposes the
+same operations with the same names, argument meaning and error behaviour (raise = GGML_ABORT) on top of the
+C ABI of libb200q.so.  PyTorch is used ONLY as the owner of device memory and streams; every FLOP of the
+hot path runs in our CUDA kernels.  There is no CPU fallback: importing works anywhere, calling needs a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int64, c_void_p
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import B200QError, check
+
+# ggml_type ids (reference ggml/include/ggml.h:391-492) of the types the backend implements
+GGML_TYPE = {"Q4_0": 2, "Q8_0": 8, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14, "IQ4_NL": 20, "IQ4_XS": 23,
+             "IQ2_BN": 135, "IQ4_K": 139, "IQ5_K": 140, "IQ4_KS": 144}
+UNARY = {"none": 0, "silu": 1, "gelu": 2, "relu": 3}
+MMVQ_MAX_BATCH_SIZE = 8          # ggml-cuda/mmvq.cuh:10 — n <= 8 takes the mat-vec path
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise B200QError("ik_llama_cpp_b200: the quantized mat-mul hot path needs a CUDA device (no CPU fallback)")
+
+
+def type_supported(ggml_type: int) -> bool:
+    return bool(_lib.lib().b200q_type_supported(ggml_type))
+
+
+def row_size(ggml_type: int, k: int) -> int:
+    r = _lib.lib().b200q_wire_row_size(ggml_type, k)
+    if r < 0:
+        raise B200QError(f"row_size: type {ggml_type} / K {k} unsupported")
+    return int(r)
+
+
+def plane_bytes(ggml_type: int, m: int, k: int) -> int:
+    r = _lib.lib().b200q_plane_bytes(ggml_type, m, k)
+    if r < 0:
+        raise B200QError(f"plane_bytes: type {ggml_type} / shape ({m},{k}) unsupported")
+    return int(r)
+
+
+@dataclass
+class QuantTensor:
+    """A src0 of GGML_OP_MUL_MAT resident in HBM in the B200 plane layout (ne = [K, M] in ggml terms)."""
+    ggml_type: int
+    m: int            # rows  (ne[1])
+    k: int            # cols  (ne[0])
+    planes: torch.Tensor  # uint8, plane_bytes(type, m, k)
+
+    @property
+    def nbytes_wire(self) -> int:
+        return self.m * row_size(self.ggml_type, self.k)
+
+    @property
+    def ptr(self) -> int:
+        return self.planes.data_ptr()
+
+
+def set_tensor(ggml_type: int, wire, m: int, k: int, device=None) -> QuantTensor:
+    """ggml_backend_cuda_buffer_set_tensor: upload GGUF wire bytes (host numpy/bytes or a CUDA uint8 tensor)."""
+    _require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    nb = plane_bytes(ggml_type, m, k)
+    planes = torch.empty(nb, dtype=torch.uint8, device=device)
+    L = _lib.lib()
+    with torch.cuda.device(device):
+        if isinstance(wire, torch.Tensor) and wire.is_cuda:
+            assert wire.dtype == torch.uint8 and wire.numel() == m * row_size(ggml_type, k)
+            check(L.b200q_repack(ggml_type, wire.data_ptr(), planes.data_ptr(), m, k, _stream()), "b200q_repack")
+        else:
+            host = np.ascontiguousarray(np.frombuffer(wire, dtype=np.uint8) if not isinstance(wire, np.ndarray) else wire.view(np.uint8).ravel())
+            assert host.size == m * row_size(ggml_type, k), (host.size, m * row_size(ggml_type, k))
+            check(L.b200q_set_tensor(ggml_type, host.ctypes.data, planes.data_ptr(), m, k, _stream()), "b200q_set_tensor")
+    return QuantTensor(ggml_type, m, k, planes)
+
+
+def get_tensor(t: QuantTensor) -> np.ndarray:
+    """ggml_backend_cuda_buffer_get_tensor: the original wire bytes, bit-for-bit."""
+    _require_cuda()
+    out = np.empty(t.nbytes_wire, np.uint8)
+    with torch.cuda.device(t.planes.device):
+        check(_lib.lib().b200q_get_tensor(t.ggml_type, t.ptr, out.ctypes.data, t.m, t.k, _stream()), "b200q_get_tensor")
+    return out
+
+
+_workspaces: dict[torch.device, torch.Tensor] = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+def mul_mat(w: QuantTensor, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """GGML_OP_MUL_MAT: x f32 [N, K] -> dst f32 [N, M]  (ggml ne: src1 [K, N], dst [M, N])."""
+    _require_cuda()
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == w.k and x.stride(1) == 1
+    n = x.shape[0]
+    dst = out if out is not None else torch.empty((n, w.m), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        if n <= MMVQ_MAX_BATCH_SIZE:
+            check(L.b200q_mul_mat_vec(w.ggml_type, w.ptr, x.data_ptr(), dst.data_ptr(), w.m, w.k, n, x.stride(0), None, _stream()), "b200q_mul_mat_vec")
+        else:
+            xc = x if x.is_contiguous() else x.contiguous()
+            need = L.b200q_mul_mat_workspace(w.ggml_type, w.m, w.k, n)
+            ws = _workspace(need, x.device)
+            check(L.b200q_mul_mat_gemm(w.ggml_type, w.ptr, xc.data_ptr(), dst.data_ptr(), w.m, w.k, n, ws.data_ptr(), ws.numel(), _stream()), "b200q_mul_mat_gemm")
+    return dst
+
+
+def mul_mat_multi(ws: list[QuantTensor], x: torch.Tensor, outs: list[torch.Tensor] | None = None) -> list[torch.Tensor]:
+    """Several MUL_MATs sharing src1 (Q,K,V) in one launch — the reference's look-ahead fusion, ggml-cuda.cu:2573-2601."""
+    _require_cuda()
+    n = x.shape[0]
+    assert n <= MMVQ_MAX_BATCH_SIZE and all(w.k == ws[0].k and w.ggml_type == ws[0].ggml_type for w in ws)
+    outs = outs or [torch.empty((n, w.m), dtype=torch.float32, device=x.device) for w in ws]
+    nt = len(ws)
+    Wp = (c_void_p * nt)(*[w.ptr for w in ws])
+    Dp = (c_void_p * nt)(*[o.data_ptr() for o in outs])
+    Mp = (c_int64 * nt)(*[w.m for w in ws])
+    with torch.cuda.device(x.device):
+        check(_lib.lib().b200q_mul_mat_vec_multi(ws[0].ggml_type, nt, Wp, Dp, Mp, ws[0].k, x.data_ptr(), n, x.stride(0), _stream()), "b200q_mul_mat_vec_multi")
+    return outs
+
+
+def fused_up_gate(up: QuantTensor, gate: QuantTensor, x: torch.Tensor, unary: str = "silu", limit: float = 0.0,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """GGML_OP_FUSED_UP_GATE: dst = unary(gate.x) * (up.x)."""
+    _require_cuda()
+    assert up.m == gate.m and up.k == gate.k and up.ggml_type == gate.ggml_type
+    n = x.shape[0]
+    dst = out if out is not None else torch.empty((n, up.m), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        if n <= MMVQ_MAX_BATCH_SIZE:
+            check(_lib.lib().b200q_fused_up_gate_vec(up.ggml_type, up.ptr, gate.ptr, x.data_ptr(), dst.data_ptr(), up.m, up.k, n,
+                                                     x.stride(0), UNARY[unary], float(limit), _stream()), "b200q_fused_up_gate_vec")
+        else:
+            # n > 8: two GEMMs + fused mul-unary, like the reference (ggml-cuda.cu:3588-3618)
+            u = mul_mat(up, x)
+            g = mul_mat(gate, x)
+            if limit > 0:
+                g = g.clamp(max=limit); u = u.clamp(-limit, limit)
+            act = {"silu": torch.nn.functional.silu, "gelu": lambda t: torch.nn.functional.gelu(t, approximate="tanh"),
+                   "relu": torch.relu, "none": lambda t: t}[unary]
+            torch.mul(act(g), u, out=dst)
+    return dst
+
+
+def dequantize_bf16(w: QuantTensor) -> torch.Tensor:
+    _require_cuda()
+    out = torch.empty((w.m, w.k), dtype=torch.bfloat16, device=w.planes.device)
+    with torch.cuda.device(w.planes.device):
+        check(_lib.lib().b200q_dequantize_bf16(w.ggml_type, w.ptr, out.data_ptr(), w.m, w.k, _stream()), "b200q_dequantize_bf16")
+    return out
+
+
+def mul_mat_host(w: QuantTensor, x_host: np.ndarray) -> np.ndarray:
+    """End-to-end entry point with HOST activations and results (H2D + kernel + D2H inside the call)."""
+    _require_cuda()
+    x_host = np.ascontiguousarray(x_host, np.float32)
+    n, k = x_host.shape
+    assert k == w.k
+    out = np.empty((n, w.m), np.float32)
+    with torch.cuda.device(w.planes.device):
+        check(_lib.lib().b200q_mul_mat_host(w.ggml_type, w.ptr, x_host.ctypes.data, out.ctypes.data, w.m, w.k, n, _stream()), "b200q_mul_mat_host")
+    return out

@@ -1,0 +1,174 @@
+// b200q_api.cu — the C ABI of libb200q.so (see include/b200q.h for the reference interfaces each entry replaces).
+#include "../../include/b200q.h"
+#include "b200q_internal.h"
+#include <cuda_runtime.h>
+#include <mutex>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
+int b200q_launch_gemm(int type, const void * W, const float * x, int64_t x_stride, float * dst, int64_t M, int64_t K, int64_t N,
+                      void * ws, size_t ws_bytes, int sm_count, cudaStream_t st);
+
+namespace {
+thread_local char g_err[512] = "";
+int fail(int code, const char * fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+int cuda_fail(const char * what, cudaError_t e) { return fail(B200Q_E_CUDA, "%s: %s", what, cudaGetErrorString(e)); }
+
+struct dev_info { int sm_count = 0; bool ok = false; };
+dev_info & device_info() {
+    static dev_info info[16]; static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) { static dev_info bad; return bad; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (!info[dev].ok) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) == cudaSuccess) { info[dev].sm_count = p.multiProcessorCount; info[dev].ok = true; }
+    }
+    return info[dev];
+}
+int check_launch(int rc, const char * what) {
+    if (rc == 0) return B200Q_OK;
+    if (rc == -1) return fail(B200Q_E_TYPE, "%s: unsupported ggml type", what);
+    if (rc == -2) return fail(B200Q_E_SHAPE, "%s: unsupported shape", what);
+    if (rc == -5) return fail(B200Q_E_NOMEM, "%s: workspace too small", what);
+    if (rc > 0) return cuda_fail(what, (cudaError_t)rc);
+    return fail(B200Q_E_CUDA, "%s: launch failed (%d)", what, rc);
+}
+// per-thread scratch for the host-buffer entry points
+struct scratch { void * p = nullptr; size_t n = 0; };
+int ensure(scratch & s, size_t n) {
+    if (s.n >= n) return 0;
+    if (s.p) cudaFree(s.p);
+    s.p = nullptr; s.n = 0;
+    cudaError_t e = cudaMalloc(&s.p, n);
+    if (e != cudaSuccess) return cuda_fail("cudaMalloc(scratch)", e);
+    s.n = n; return 0;
+}
+thread_local scratch g_x, g_y, g_ws, g_stage;
+}  // namespace
+
+extern "C" {
+
+int b200q_abi_version(void) { return B200Q_ABI_VERSION; }
+const char * b200q_last_error(void) { return g_err; }
+int b200q_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+int b200q_type_supported(int type) { b200q_layout L; return b200q_make_layout(type, 1, 256, &L) == 0 ? 1 : 0; }
+int64_t b200q_wire_row_size(int type, int64_t k) { b200q_layout L; if (b200q_make_layout(type, 1, k, &L)) return -1; return b200q_wire_row_size(L); }
+int64_t b200q_plane_bytes(int type, int64_t m, int64_t k) { b200q_layout L; if (b200q_make_layout(type, m, k, &L)) return -1; return L.total_bytes; }
+
+int b200q_repack(int type, const void * wire_dev, void * planes_dev, int64_t m, int64_t k, void * stream) {
+    b200q_layout L; int rc = b200q_make_layout(type, m, k, &L);
+    if (rc) return check_launch(rc, "b200q_repack");
+    return check_launch(b200q_launch_repack(wire_dev, planes_dev, L, 0, (cudaStream_t)stream), "b200q_repack");
+}
+int b200q_unrepack(int type, const void * planes_dev, void * wire_dev, int64_t m, int64_t k, void * stream) {
+    b200q_layout L; int rc = b200q_make_layout(type, m, k, &L);
+    if (rc) return check_launch(rc, "b200q_unrepack");
+    // the inverse pass ORs bits into the wire buffer for some types: it clears what it needs itself
+    return check_launch(b200q_launch_repack(wire_dev, const_cast<void *>(planes_dev), L, 1, (cudaStream_t)stream), "b200q_unrepack");
+}
+int b200q_set_tensor(int type, const void * wire_host, void * planes_dev, int64_t m, int64_t k, void * stream) {
+    b200q_layout L; int rc = b200q_make_layout(type, m, k, &L);
+    if (rc) return check_launch(rc, "b200q_set_tensor");
+    const size_t nbytes = (size_t)b200q_wire_row_size(L) * m;
+    if ((rc = ensure(g_stage, nbytes))) return rc;
+    cudaStream_t st = (cudaStream_t)stream; cudaError_t e;
+    if ((e = cudaMemcpyAsync(g_stage.p, wire_host, nbytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail("set_tensor H2D", e);
+    if ((rc = check_launch(b200q_launch_repack(g_stage.p, planes_dev, L, 0, st), "b200q_set_tensor"))) return rc;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail("set_tensor sync", e);
+    return B200Q_OK;
+}
+int b200q_get_tensor(int type, const void * planes_dev, void * wire_host, int64_t m, int64_t k, void * stream) {
+    b200q_layout L; int rc = b200q_make_layout(type, m, k, &L);
+    if (rc) return check_launch(rc, "b200q_get_tensor");
+    const size_t nbytes = (size_t)b200q_wire_row_size(L) * m;
+    if ((rc = ensure(g_stage, nbytes))) return rc;
+    cudaStream_t st = (cudaStream_t)stream; cudaError_t e;
+    if ((rc = check_launch(b200q_launch_repack(g_stage.p, const_cast<void *>(planes_dev), L, 1, st), "b200q_get_tensor"))) return rc;
+    if ((e = cudaMemcpyAsync(wire_host, g_stage.p, nbytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail("get_tensor D2H", e);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail("get_tensor sync", e);
+    return B200Q_OK;
+}
+
+static int mmvq_cols(b200q_mmvq_desc & d, int n, int64_t x_stride, cudaStream_t st, const char * what) {
+    // the kernel is instantiated for 1/2/4/8 columns: cover n with the largest pieces
+    int done = 0;
+    const int64_t xs = x_stride ? x_stride : d.K;
+    float * dst0[B200Q_MAX_SEGS]; for (int i = 0; i < d.n_seg; ++i) dst0[i] = d.seg[i].dst;
+    const float * x0 = d.x;
+    while (done < n) {
+        int c = 8; while (c > n - done) c >>= 1;
+        // shared memory budget: c*K int8 + c*(K/32)*8 bytes must fit in ~200 KB
+        while (c > 1 && (size_t)c * d.K + (size_t)c * (d.K / 32) * 8 > 200 * 1024) c >>= 1;
+        if ((size_t)c * d.K + (size_t)c * (d.K / 32) * 8 > 200 * 1024) return fail(B200Q_E_SHAPE, "%s: K=%lld too large for the mat-vec kernel", what, (long long)d.K);
+        d.ncols = c; d.x = x0 + (int64_t)done * xs; d.x_stride = xs;
+        for (int i = 0; i < d.n_seg; ++i) d.seg[i].dst = dst0[i] + (int64_t)done * d.seg[i].M;
+        int rc = check_launch(b200q_launch_mmvq(d, st), what);
+        if (rc) return rc;
+        done += c;
+    }
+    return B200Q_OK;
+}
+
+int b200q_mul_mat_vec(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int n, int64_t x_stride,
+                      const float * bias, void * stream) {
+    if (!W || !x || !dst || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_vec: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_vec: no CUDA device");
+    b200q_mmvq_desc d; memset(&d, 0, sizeof d);
+    d.type = type; d.n_seg = 1; d.seg[0] = {W, nullptr, dst, bias, m}; d.K = k; d.x = x; d.sm_count = di.sm_count;
+    return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_mul_mat_vec");
+}
+int b200q_mul_mat_vec_multi(int type, int n_tensors, const void * const * W, float * const * dst, const int64_t * m, int64_t k,
+                            const float * x, int n, int64_t x_stride, void * stream) {
+    if (n_tensors < 1 || n_tensors > B200Q_MAX_SEGS || !W || !dst || !m || !x || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_multi: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_vec_multi: no CUDA device");
+    b200q_mmvq_desc d; memset(&d, 0, sizeof d);
+    d.type = type; d.n_seg = n_tensors; d.K = k; d.x = x; d.sm_count = di.sm_count;
+    for (int i = 0; i < n_tensors; ++i) d.seg[i] = {W[i], nullptr, dst[i], nullptr, m[i]};
+    return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_mul_mat_vec_multi");
+}
+int b200q_fused_up_gate_vec(int type, const void * W_up, const void * W_gate, const float * x, float * dst, int64_t m, int64_t k, int n,
+                            int64_t x_stride, int unary, float limit, void * stream) {
+    if (!W_up || !W_gate || !x || !dst || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_fused_up_gate_vec: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_fused_up_gate_vec: no CUDA device");
+    b200q_mmvq_desc d; memset(&d, 0, sizeof d);
+    d.type = type; d.n_seg = 1; d.seg[0] = {W_up, W_gate, dst, nullptr, m}; d.K = k; d.x = x; d.act = unary; d.limit = limit; d.sm_count = di.sm_count;
+    return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_fused_up_gate_vec");
+}
+
+size_t b200q_mul_mat_workspace(int type, int64_t m, int64_t k, int64_t n) { return n <= 8 ? 0 : b200q_gemm_workspace_bytes(type, m, k, n); }
+
+int b200q_dequantize_bf16(int type, const void * W, void * out, int64_t m, int64_t k, void * stream) {
+    b200q_layout L; int rc = b200q_make_layout(type, m, k, &L);
+    if (rc) return check_launch(rc, "b200q_dequantize_bf16");
+    return check_launch(b200q_launch_dequant_bf16(W, L, out, (cudaStream_t)stream), "b200q_dequantize_bf16");
+}
+int b200q_mul_mat_gemm(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
+                       void * workspace, size_t workspace_bytes, void * stream) {
+    if (!W || !x || !dst || !workspace || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_gemm: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_gemm: no CUDA device");
+    return check_launch(b200q_launch_gemm(type, W, x, k, dst, m, k, n, workspace, workspace_bytes, di.sm_count, (cudaStream_t)stream), "b200q_mul_mat_gemm");
+}
+int b200q_mul_mat(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
+                  void * workspace, size_t workspace_bytes, void * stream) {
+    if (n <= 8) return b200q_mul_mat_vec(type, W, x, dst, m, k, (int)n, k, nullptr, stream);
+    return b200q_mul_mat_gemm(type, W, x, dst, m, k, n, workspace, workspace_bytes, stream);
+}
+int b200q_mul_mat_host(int type, const void * W, const float * x_host, float * dst_host, int64_t m, int64_t k, int64_t n, void * stream) {
+    cudaStream_t st = (cudaStream_t)stream; cudaError_t e; int rc;
+    const size_t xb = (size_t)n * k * sizeof(float), yb = (size_t)n * m * sizeof(float), wsb = b200q_mul_mat_workspace(type, m, k, n);
+    if ((rc = ensure(g_x, xb)) || (rc = ensure(g_y, yb)) || (wsb && (rc = ensure(g_ws, wsb)))) return rc;
+    if ((e = cudaMemcpyAsync(g_x.p, x_host, xb, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail("mul_mat_host H2D", e);
+    if ((rc = b200q_mul_mat(type, W, (const float *)g_x.p, (float *)g_y.p, m, k, n, g_ws.p, g_ws.n, stream))) return rc;
+    if ((e = cudaMemcpyAsync(dst_host, g_y.p, yb, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail("mul_mat_host D2H", e);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail("mul_mat_host sync", e);
+    return B200Q_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,292 @@
+// b200q_gemm.cu — prefill (n_batch > 8) path: tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+//   dst[n][m] (f32, ggml layout dst[n*M + m]) = sum_k W[m][k] * X[n][k]
+//
+// replaces the reference's quantize_mmq_q8_1 + mul_mat_q<type> (mma.sync m16n8k32 s8, ggml-cuda/mmq.cuh:3849-4173)
+// and its dequantize + cublasGemmEx fallback (ggml-cuda.cu:1723-1894).
+//
+// Kernel k_gemm_bf16<BN> (warp-specialised, 192 threads, 1 CTA/SM, one 128 x BN output tile per CTA):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of the A (weights, bf16 [M][K]) and B (activations,
+//               bf16 [N][K]) tiles, 128-byte swizzle, into a STAGES-deep smem ring guarded by full/empty mbarriers
+//   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16)
+//               4x per 64-wide k-block; tcgen05.commit releases the smem stage / signals the epilogue
+//   warps 2..5  epilogue: tcgen05.ld 32x32b.x32 (TMEM lane = output feature m, column = token n) -> registers ->
+//               coalesced f32 stores (the 32 lanes of a warp hold 32 consecutive m of the same token)
+// A comes either from the bf16 scratch written by k_dequant_bf16 (generic types) or ... (fused dequant: see k_gemm_q).
+#include "b200q_internal.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include <unordered_map>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t * bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t * bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t * bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t * bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void * smem_dst, const CUtensorMap * tm, uint64_t * bar, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tm), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap * tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tm) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t * smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t * bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in smem, rows of 64 bf16 = 128 bytes, SWIZZLE_128B, 8-row groups 1024 bytes apart
+// (UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout=SWIZZLE_128B(2) [61,64))
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;                 // LBO (ignored for swizzled K-major), canonical value 1
+    d |= (uint64_t)(1024 >> 4) << 32;       // SBO: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                 // descriptor version for sm_100
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+
+template <int BN> struct gemm_cfg {
+    static constexpr int STAGES = BN == 256 ? 4 : 6;
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr size_t SMEM = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+k_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            float * __restrict__ dst, int M, int N, int K, int k_split) {
+    using cfg = gemm_cfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char * smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t * full_bar  = reinterpret_cast<uint64_t *>(smem + (size_t)cfg::STAGES * cfg::STAGE_BYTES);
+    uint64_t * empty_bar = full_bar + cfg::STAGES;
+    uint64_t * tmem_full = empty_bar + cfg::STAGES;
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int nk_total = (K + BK - 1) / BK;
+    const int nk_per = (nk_total + k_split - 1) / k_split;
+    const int kb0 = blockIdx.z * nk_per;
+    const int kb1 = min(nk_total, kb0 + nk_per);
+    const int nk = kb1 - kb0;                                   // may be <= 0 for trailing splits
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % cfg::STAGES; const uint32_t ph = (i / cfg::STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                unsigned char * sa = smem + (size_t)s * cfg::STAGE_BYTES; unsigned char * sb = sa + cfg::A_BYTES;
+                mbar_expect_tx(&full_bar[s], cfg::STAGE_BYTES);
+                tma_load_2d(sa, &tmA, &full_bar[s], (kb0 + i) * BK, m0);
+                tma_load_2d(sb, &tmB, &full_bar[s], (kb0 + i) * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % cfg::STAGES; const uint32_t ph = (i / cfg::STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * cfg::STAGE_BYTES), b_addr = a_addr + cfg::A_BYTES;
+                const uint64_t a_desc = make_kmajor_sw128_desc(a_addr), b_desc = make_kmajor_sw128_desc(b_addr);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advance 32 bytes (16 bf16) along K inside the 128-byte swizzle row: +2 in 16-byte units of the start address
+                    umma_f16_ss(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);               // frees this smem stage when the MMAs have read it
+            }
+            umma_commit(tmem_full);                       // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        const int q = warp & 3;
+        if (nk > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+            const int m = m0 + 32 * q + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= N) break;                  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (m < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + c0 + j;
+                        if (n < N) {
+                            float * p = dst + (size_t)n * M + m;
+                            if (k_split > 1) atomicAdd(p, __uint_as_float(r[j])); else *p = __uint_as_float(r[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
+// f32 [N][K] (row stride xs) -> bf16 [N][K]
+__global__ void k_f32_to_bf16(const float * __restrict__ x, int64_t xs, __nv_bfloat16 * __restrict__ out, int64_t K, int64_t N) {
+    const int64_t total4 = N * (K / 4);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / (K / 4), k4 = i % (K / 4);
+        const float4 v = *reinterpret_cast<const float4 *>(x + n * xs + 4 * k4);
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u; u.x = *reinterpret_cast<uint32_t *>(&a); u.y = *reinterpret_cast<uint32_t *>(&b);
+        *reinterpret_cast<uint2 *>(out + n * K + 4 * k4) = u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+encode_tiled_fn get_encode() {
+    static encode_tiled_fn fn = nullptr; static std::once_flag once;
+    std::call_once(once, [] {
+        void * p = nullptr; cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess) fn = (encode_tiled_fn)p;
+    });
+    return fn;
+}
+// bf16 matrix [rows][cols] row-major (cols contiguous), box = 64 cols x box_rows, 128B swizzle
+int make_tmap_bf16(CUtensorMap * tm, const void * ptr, int64_t rows, int64_t cols, int box_rows) {
+    encode_tiled_fn enc = get_encode(); if (!enc) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+template <int BN>
+int launch_gemm_bf16(const void * A_bf16, const void * B_bf16, float * dst, int64_t M, int64_t N, int64_t K, int k_split, cudaStream_t st) {
+    using cfg = gemm_cfg<BN>;
+    CUtensorMap tmA, tmB;
+    if (make_tmap_bf16(&tmA, A_bf16, M, K, BM)) return -10;
+    if (make_tmap_bf16(&tmB, B_bf16, N, K, BN)) return -11;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_gemm_bf16<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM) != cudaSuccess) return -12;
+        configured = true;
+    }
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)k_split);
+    k_gemm_bf16<BN><<<grid, 192, cfg::SMEM, st>>>(tmA, tmB, dst, (int)M, (int)N, (int)K, k_split);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {
+    (void)type;
+    return (size_t)b200q_align_up(N * K * 2, 256) + (size_t)b200q_align_up(M * K * 2, 256);
+}
+
+// A = planes of `type` [M][K]; X = f32 [N][K]; dst f32 [N][M].  Workspace: bf16 X followed by bf16 W.
+int b200q_launch_gemm(int type, const void * W, const float * x, int64_t x_stride, float * dst, int64_t M, int64_t K, int64_t N,
+                      void * ws, size_t ws_bytes, int sm_count, cudaStream_t st) {
+    if (ws_bytes < b200q_gemm_workspace_bytes(type, M, K, N)) return -5;
+    if (K % 8) return -2;
+    b200q_layout L; if (b200q_make_layout(type, M, K, &L)) return -1;
+    __nv_bfloat16 * xb = (__nv_bfloat16 *)ws;
+    __nv_bfloat16 * wb = (__nv_bfloat16 *)((char *)ws + b200q_align_up(N * K * 2, 256));
+    { const int64_t total4 = N * (K / 4); int64_t nb = (total4 + 255) / 256; if (nb > 148 * 32) nb = 148 * 32; if (nb < 1) nb = 1;
+      k_f32_to_bf16<<<(unsigned)nb, 256, 0, st>>>(x, x_stride ? x_stride : K, xb, K, N); }
+    int rc = b200q_launch_dequant_bf16(W, L, wb, st); if (rc) return rc;
+    // tile / split selection: fill ~1 wave of the SMs
+    const int64_t mt = (M + BM - 1) / BM;
+    const bool bn256 = N >= 256 && mt * ((N + 255) / 256) >= sm_count / 2;
+    const int64_t tiles = bn256 ? mt * ((N + 255) / 256) : mt * ((N + 127) / 128);
+    int k_split = 1;
+    const int64_t nk = (K + BK - 1) / BK;
+    while (tiles * k_split * 2 <= sm_count && k_split * 2 <= 8 && nk / (k_split * 2) >= 8) k_split *= 2;
+    if (k_split > 1) { cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)M * N * sizeof(float), st); if (e != cudaSuccess) return -3; }
+    return bn256 ? launch_gemm_bf16<256>(wb, xb, dst, M, N, K, k_split, st) : launch_gemm_bf16<128>(wb, xb, dst, M, N, K, k_split, st);
+}

@@ -1,0 +1,24 @@
+// b200q_internal.h — declarations shared by the translation units of libb200q.so (not part of the public ABI).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "b200q_types.cuh"
+
+#define B200Q_MAX_SEGS 4
+
+enum { B200Q_ACT_NONE = 0, B200Q_ACT_SILU = 1, B200Q_ACT_GELU = 2, B200Q_ACT_RELU = 3 };
+
+// types whose canonical decode has a non-zero subtracted offset (ml) -> the kernel needs the integer activation sums
+B200Q_HD constexpr bool b200q_mmvq_has_ml(int type) {
+    return !(type == B200Q_TYPE_IQ4_NL || type == B200Q_TYPE_Q8_0 || type == B200Q_TYPE_IQ4_XS);
+}
+
+struct b200q_mmvq_seg_desc { const void * W; const void * W2; float * dst; const float * bias; int64_t M; };
+struct b200q_mmvq_desc {
+    int type; int n_seg; b200q_mmvq_seg_desc seg[B200Q_MAX_SEGS];
+    int64_t K; const float * x; int64_t x_stride; int ncols; int act; float limit; int sm_count;
+};
+
+int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L, int inverse, cudaStream_t st);
+int b200q_launch_dequant_bf16(const void * W, const b200q_layout & L, void * out, cudaStream_t st);
+int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st);

@@ -26,6 +26,9 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 #if defined(__CUDACC__)
 #define B200Q_HD __host__ __device__ __forceinline__

@@ -1,0 +1,81 @@
+/* b200q.h — C ABI of libb200q.so: the Blackwell (sm_100a) quantized mat-mul hot path of ik_llama.cpp.
+ *
+ * Plain C: pointers, sizes, ggml_type ids.  No torch / ggml types.  All device pointers are CUDA device
+ * addresses on the current device; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ * Every function returns 0 on success, a negative B200Q_E_* code otherwise (b200q_last_error() has the text).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with B200Q_E_CUDA.
+ *
+ * What each entry point replaces in the reference (paths relative to the ik_llama.cpp tree):
+ *   b200q_set_tensor / b200q_get_tensor    ggml_backend_cuda_buffer_set_tensor / _get_tensor   ggml/src/ggml-cuda.cu:641-672
+ *                                          (+ the wire->device re-layout, cf. run-time repack `-rtr`)
+ *   b200q_mul_mat                          ggml_cuda_mul_mat dispatcher                        ggml/src/ggml-cuda.cu:2645-2727
+ *   b200q_mul_mat_vec[_multi]              quantize_row_q8_1_cuda + ggml_cuda_op_mul_mat_vec_q ggml/src/ggml-cuda.cu:2503-2604,
+ *                                          (mul_mat_vec_q / iqk_mul_mat_vec_q kernels)         ggml-cuda/mmvq-templates.cuh:68-150,287-303
+ *                                          incl. the "following MUL_MATs share src1" fusion    ggml/src/ggml-cuda.cu:2573-2601
+ *   b200q_fused_up_gate_vec                ggml_cuda_up_gate_unary / fused_mul_mat_vec_q       ggml/src/ggml-cuda.cu:3542-3620, mmvq-templates.cuh:152-330
+ *   b200q_mul_mat_gemm                     quantize_mmq_q8_1_cuda + mul_mat_q (MMQ)            ggml-cuda/mmq.cuh:3849-4173; dequant+cuBLAS fallback ggml-cuda.cu:1723-1894
+ *   b200q_dequantize_bf16                  dequantize_block_* (convert.cu)                     ggml-cuda/convert.cu
+ *   b200q_reduce_*                         ggml_cuda_op_reduce                                 ggml-cuda/reduce.cu:125-598
+ * Tensor conventions are ggml's: W is [M rows][K cols] in the GGUF wire format of `type`
+ * (row stride = ggml_row_size(type, K)); x is f32 [N][K]; dst is f32 [N][M]  (dst[j*M + i]).
+ */
+#ifndef B200Q_H
+#define B200Q_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200Q_ABI_VERSION 1
+#if defined(__GNUC__)
+#define B200Q_API __attribute__((visibility("default")))
+#else
+#define B200Q_API
+#endif
+
+enum { B200Q_OK = 0, B200Q_E_TYPE = -1, B200Q_E_SHAPE = -2, B200Q_E_CUDA = -3, B200Q_E_ARG = -4, B200Q_E_NOMEM = -5 };
+enum { B200Q_UNARY_NONE = 0, B200Q_UNARY_SILU = 1, B200Q_UNARY_GELU = 2, B200Q_UNARY_RELU = 3 };
+
+B200Q_API int          b200q_abi_version(void);
+B200Q_API const char * b200q_last_error(void);
+B200Q_API int          b200q_device_count(void);                      /* ggml_backend_cuda_get_device_count, ggml-cuda.h:38 */
+
+/* ---- type geometry (mirrors ggml_type_traits: ggml/src/ggml.c:640-1460) ---- */
+B200Q_API int     b200q_type_supported(int ggml_type);                /* 1 if MUL_MAT with this src0 type is implemented   */
+B200Q_API int64_t b200q_wire_row_size(int ggml_type, int64_t k);      /* == ggml_row_size(type, k); <0 on error            */
+B200Q_API int64_t b200q_plane_bytes(int ggml_type, int64_t m, int64_t k); /* device bytes of the re-laid-out tensor        */
+
+/* ---- weights: wire <-> device layout ---- */
+B200Q_API int b200q_repack  (int type, const void * wire_dev,   void * planes_dev, int64_t m, int64_t k, void * stream);
+B200Q_API int b200q_unrepack(int type, const void * planes_dev, void * wire_dev,   int64_t m, int64_t k, void * stream);
+B200Q_API int b200q_set_tensor(int type, const void * wire_host, void * planes_dev, int64_t m, int64_t k, void * stream); /* H2D + repack, synchronous */
+B200Q_API int b200q_get_tensor(int type, const void * planes_dev, void * wire_host, int64_t m, int64_t k, void * stream); /* unrepack + D2H, synchronous */
+
+/* ---- decode: n <= 8 activation columns ---- */
+B200Q_API int b200q_mul_mat_vec(int type, const void * W, const float * x, float * dst,
+                      int64_t m, int64_t k, int n, int64_t x_stride, const float * bias, void * stream);
+/* several weight tensors of the same type and K sharing one activation (Q,K,V): one launch */
+B200Q_API int b200q_mul_mat_vec_multi(int type, int n_tensors, const void * const * W, float * const * dst, const int64_t * m,
+                            int64_t k, const float * x, int n, int64_t x_stride, void * stream);
+/* dst = unary(gate.x) * (up.x)   (optionally clamped: limit > 0) */
+B200Q_API int b200q_fused_up_gate_vec(int type, const void * W_up, const void * W_gate, const float * x, float * dst,
+                            int64_t m, int64_t k, int n, int64_t x_stride, int unary, float limit, void * stream);
+
+/* ---- prefill: tcgen05 GEMM ---- */
+B200Q_API size_t b200q_mul_mat_workspace(int type, int64_t m, int64_t k, int64_t n);
+B200Q_API int b200q_mul_mat_gemm(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
+                       void * workspace, size_t workspace_bytes, void * stream);
+B200Q_API int b200q_dequantize_bf16(int type, const void * W, void * out_bf16, int64_t m, int64_t k, void * stream);
+
+/* ---- dispatcher (what GGML_OP_MUL_MAT calls): n <= 8 -> mat-vec, else GEMM ---- */
+B200Q_API int b200q_mul_mat(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
+                  void * workspace, size_t workspace_bytes, void * stream);
+/* same through HOST activations/results: H2D(x) -> mul_mat -> D2H(dst), synchronous (end-to-end entry point) */
+B200Q_API int b200q_mul_mat_host(int type, const void * W_planes_dev, const float * x_host, float * dst_host,
+                       int64_t m, int64_t k, int64_t n, void * stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H */

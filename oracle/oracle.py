@@ -196,16 +196,23 @@ class RefLib:
         assert n == out.size, (n, out.size)
         return out
 
-    def to_float(self, t: int, wire: np.ndarray, m: int, k: int) -> np.ndarray:
-        """Reference to_float per row; for row-meta types the pointer passed is past the header
-        (to_float takes a block pointer) — the row scale is NOT applied (SURVEY.md §8c pitfall 1)."""
+    # to_float of the ternary types takes a BLOCK pointer and ignores the row scale (SURVEY.md §8c pitfall 1,
+    # iqk_quantize.cpp:375,418); every other row-meta type (IQ4_KS, ...) takes the ROW start and applies it itself.
+    TO_FLOAT_IGNORES_ROW_SCALE = (134, 135)
+
+    def to_float(self, t: int, wire: np.ndarray, m: int, k: int, apply_row_scale: bool = True) -> np.ndarray:
+        """Reference to_float per row (row scale applied by hand for IQ1_BN/IQ2_BN when apply_row_scale)."""
         rs = self.row_size(t, k)
         meta = self.row_meta_size(t)
         wire = np.ascontiguousarray(wire, np.uint8).reshape(m, rs)
         out = np.empty((m, k), np.float32)
         for i in range(m):
-            row = np.ascontiguousarray(wire[i, meta:])
+            skip = meta if t in self.TO_FLOAT_IGNORES_ROW_SCALE else 0
+            row = np.ascontiguousarray(wire[i, skip:])
             assert self.lib.refshim_to_float(t, _p(row), _p(out[i]), k) == 0
+            if skip and apply_row_scale:
+                scale = np.frombuffer(wire[i, :4].tobytes(), np.float32)[0] if meta == 4 else np.frombuffer(wire[i, :2].tobytes(), np.float16)[0].astype(np.float32)
+                out[i] *= scale
         return out
 
     def mul_mat(self, t: int, wire: np.ndarray, x: np.ndarray, m: int, n_threads: int = 4, reps: int = 1):

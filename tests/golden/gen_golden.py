@@ -1,0 +1,43 @@
+"""Generate tests/golden/*.npz FROM THE UNMODIFIED REFERENCE (oracle/_ref, built by oracle/Makefile.ref).
+
+Run in the container that has /root/reference:   python tests/golden/gen_golden.py
+For every supported wire type: seeded f32 weights -> ggml_quantize_chunk (reference) -> wire bytes;
+reference to_float(wire) -> dequantised f32; reference CPU backend MUL_MAT (IQK path) -> y_ref_cpu.
+The fixtures pin the oracle restatement (tests/test_oracle.py) and are replayed against the CUDA
+kernels on the GPU box (tests/test_gpu_parity.py), where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle.oracle import GGML_TYPE, RefLib  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TYPES = ["Q4_0", "Q8_0", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "IQ4_K", "IQ5_K", "IQ4_KS", "IQ2_BN"]
+M, K, N = 16, 512, 3
+
+
+def main():
+    R = RefLib()
+    for name in TYPES:
+        t = GGML_TYPE[name]
+        rng = np.random.default_rng(1234 + t)
+        w = (rng.standard_normal((M, K)) * 0.02).astype(np.float32)
+        w[0, :32] = 0.0                       # an all-zero block (d == 0 edge case)
+        w[1, 5] = 1.5                         # an outlier
+        if name == "IQ2_BN":                  # ternary weights so the quantiser is lossless
+            w = (rng.integers(-1, 2, (M, K)) * 0.043).astype(np.float32)
+        x = rng.uniform(-1, 1, (N, K)).astype(np.float32)
+        x[0, :32] = 0.0                       # an all-zero activation block (amax == 0 edge case of quantize_q8_1)
+        wire = R.quantize(t, w)
+        deq = R.to_float(t, wire, M, K)
+        y_cpu, _ = R.mul_mat(t, wire, x, M, n_threads=1)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), ggml_type=t, m=M, k=K, n=N, wire=wire, x=x,
+                            dequant_ref=deq, y_ref_cpu=y_cpu, row_size=R.row_size(t, K))
+        print(name, "wire", wire.size, "row_size", R.row_size(t, K))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,88 @@
+"""CPU tests of the PRODUCT's format code: ik_llama_cpp_b200/csrc/b200q_types.cuh is __host__ __device__, so the
+very same repack / PRMT-LUT / decode arithmetic the CUDA kernels execute is compiled with g++ (tests/host_emul/emul.cpp)
+and checked against the oracle: wire->planes->wire bijection, bit-exact dequantisation, mat-vec arithmetic."""
+import ctypes
+import os
+import subprocess
+from ctypes import c_int, c_long, c_void_p
+
+import numpy as np
+import pytest
+
+from conftest import ALL_TYPES, ROOT, load_golden, random_wire
+from oracle.oracle import GGML_TYPE, _p, nmse
+
+
+@pytest.fixture(scope="session")
+def emul():
+    src = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
+    so = os.path.join(ROOT, "tests", "host_emul", "libemul.so")
+    hdr = os.path.join(ROOT, "ik_llama_cpp_b200", "csrc", "b200q_types.cuh")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    E = ctypes.CDLL(so)
+    E.emul_layout_bytes.restype = c_long
+    E.emul_layout_bytes.argtypes = [c_int, c_long, c_long]
+    E.emul_wire_row_size.restype = c_long
+    E.emul_wire_row_size.argtypes = [c_int, c_long]
+    E.emul_repack.argtypes = [c_int, c_void_p, c_void_p, c_long, c_long, c_int]
+    E.emul_dequant.argtypes = [c_int, c_void_p, c_long, c_long, c_void_p]
+    E.emul_mul_mat_vec.argtypes = [c_int, c_void_p, c_long, c_long, c_void_p, c_void_p, c_void_p, c_long, c_void_p]
+    return E
+
+
+def _emul_all(E, oracle, t, wire, m, k, x):
+    nb = E.emul_layout_bytes(t, m, k)
+    planes = np.zeros(nb, np.uint8)
+    assert E.emul_repack(t, _p(wire), _p(planes), m, k, 0) == 0
+    back = np.full_like(wire, 0x5A)
+    assert E.emul_repack(t, _p(back), _p(planes), m, k, 1) == 0
+    deq = np.empty((m, k), np.float32)
+    assert E.emul_dequant(t, _p(planes), m, k, _p(deq)) == 0
+    n = x.shape[0]
+    q, d, _ = oracle.quantize_q8_1(x)
+    xd = np.ascontiguousarray(d.astype(np.float32))
+    q16 = q.reshape(n, k // 32, 2, 16).astype(np.int32).sum(-1)
+    xis = np.ascontiguousarray(((q16[..., 0] & 0xFFFF) | (q16[..., 1] << 16)).astype(np.int32))
+    y = np.empty((n, m), np.float32)
+    assert E.emul_mul_mat_vec(t, _p(planes), m, k, _p(q), _p(xd), _p(xis), n, _p(y)) == 0
+    return nb, back, deq, y
+
+
+@pytest.mark.parametrize("name", ALL_TYPES)
+def test_emulated_kernel_arithmetic_on_golden(emul, oracle, name):
+    g = load_golden(name)
+    t, m, k = int(g["ggml_type"]), int(g["m"]), int(g["k"])
+    wire, x = g["wire"], g["x"]
+    assert emul.emul_wire_row_size(t, k) == int(g["row_size"])
+    nb, back, deq, y = _emul_all(emul, oracle, t, wire, m, k, x)
+    assert nb >= wire.size and nb <= wire.size + 5 * 256            # same bytes, only 256-B plane alignment on top
+    assert np.array_equal(back, wire), "planes -> wire must restore the GGUF bytes bit-for-bit"
+    if name == "IQ4_KS":
+        np.testing.assert_allclose(deq, g["dequant_ref"], rtol=2e-7)
+    else:
+        assert np.array_equal(deq, g["dequant_ref"]), "canonical decode must equal the reference to_float bit-for-bit"
+    yq = oracle.mul_mat_q8_1(t, wire, x, m)
+    rms = np.sqrt((yq.astype(np.float64) ** 2).mean())
+    assert np.abs(y - yq).max() <= 2e-5 * rms, "mat-vec arithmetic differs from the restated reference MMVQ beyond f32 summation order"
+    assert nmse(y, oracle.mul_mat_exact(t, wire, x, m)) <= 5e-4
+
+
+@pytest.mark.parametrize("name", ALL_TYPES)
+def test_emulated_random_bit_patterns(emul, oracle, name):
+    """Every payload bit pattern is a valid block: fuzz the codecs with random bytes (catches index/LUT corner cases)."""
+    t = GGML_TYPE[name]
+    rng = np.random.default_rng(4242 + t)
+    m, k = 6, 1024
+    wire = random_wire(name, m, k, rng)
+    x = rng.standard_normal((2, k)).astype(np.float32)
+    nb, back, deq, y = _emul_all(emul, oracle, t, wire, m, k, x)
+    assert np.array_equal(back, wire)
+    ref = oracle.dequantize(t, wire, m, k)
+    if name in ("IQ4_KS", "IQ2_BN"):   # dl*q - ml vs dl*(q - c): one rounding apart for out-of-codebook bit patterns
+        np.testing.assert_allclose(deq, ref, rtol=3e-7, atol=1e-12)
+    else:
+        assert np.array_equal(deq, ref)
+    yq = oracle.mul_mat_q8_1(t, wire, x, m)
+    rms = np.sqrt((yq.astype(np.float64) ** 2).mean())
+    assert np.abs(y - yq).max() <= 2e-5 * rms
