@@ -37,6 +37,7 @@ def lib() -> ctypes.CDLL:
     L.b200q_abi_version.restype = i32
     L.b200q_last_error.restype = c_char_p
     L.b200q_device_count.restype = i32
+    L.b200q_set_option.argtypes = [c_char_p, i32]
     L.b200q_type_supported.argtypes = [i32]
     L.b200q_wire_row_size.restype = i64
     L.b200q_wire_row_size.argtypes = [i32, i64]

@@ -76,7 +76,7 @@ def set_tensor(ggml_type: int, wire, m: int, k: int, device=None) -> QuantTensor
     _require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     nb = plane_bytes(ggml_type, m, k)
-    planes = torch.empty(nb, dtype=torch.uint8, device=device)
+    planes = torch.zeros(nb, dtype=torch.uint8, device=device)   # alignment gaps between planes stay zero
     L = _lib.lib()
     with torch.cuda.device(device):
         if isinstance(wire, torch.Tensor) and wire.is_cuda:

@@ -5,6 +5,7 @@
 #include <mutex>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
@@ -50,12 +51,18 @@ int ensure(scratch & s, size_t n) {
     s.n = n; return 0;
 }
 thread_local scratch g_x, g_y, g_ws, g_stage;
+// programmatic dependent launch for the decode kernels (default on; B200Q_PDL=0 or b200q_set_option("pdl",0) disables)
+int & opt_pdl() { static int v = [] { const char * e = getenv("B200Q_PDL"); return e ? atoi(e) : 1; }(); return v; }
 }  // namespace
 
 extern "C" {
 
 int b200q_abi_version(void) { return B200Q_ABI_VERSION; }
 const char * b200q_last_error(void) { return g_err; }
+int b200q_set_option(const char * key, int value) {
+    if (key && !strcmp(key, "pdl")) { opt_pdl() = value; return B200Q_OK; }
+    return fail(B200Q_E_ARG, "b200q_set_option: unknown option");
+}
 int b200q_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
 int b200q_type_supported(int type) { b200q_layout L; return b200q_make_layout(type, 1, 256, &L) == 0 ? 1 : 0; }
@@ -100,6 +107,7 @@ static int mmvq_cols(b200q_mmvq_desc & d, int n, int64_t x_stride, cudaStream_t 
     // the kernel is instantiated for 1/2/4/8 columns: cover n with the largest pieces
     int done = 0;
     const int64_t xs = x_stride ? x_stride : d.K;
+    if (((uintptr_t)d.x & 15) || (xs & 3)) return fail(B200Q_E_ARG, "%s: activations must be 16-byte aligned with a row stride multiple of 4 floats", what);
     float * dst0[B200Q_MAX_SEGS]; for (int i = 0; i < d.n_seg; ++i) dst0[i] = d.seg[i].dst;
     const float * x0 = d.x;
     while (done < n) {
@@ -121,7 +129,7 @@ int b200q_mul_mat_vec(int type, const void * W, const float * x, float * dst, in
     if (!W || !x || !dst || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_vec: bad argument");
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_vec: no CUDA device");
     b200q_mmvq_desc d; memset(&d, 0, sizeof d);
-    d.type = type; d.n_seg = 1; d.seg[0] = {W, nullptr, dst, bias, m}; d.K = k; d.x = x; d.sm_count = di.sm_count;
+    d.type = type; d.n_seg = 1; d.seg[0] = {W, nullptr, dst, bias, m}; d.K = k; d.x = x; d.sm_count = di.sm_count; d.pdl = opt_pdl();
     return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_mul_mat_vec");
 }
 int b200q_mul_mat_vec_multi(int type, int n_tensors, const void * const * W, float * const * dst, const int64_t * m, int64_t k,
@@ -129,7 +137,7 @@ int b200q_mul_mat_vec_multi(int type, int n_tensors, const void * const * W, flo
     if (n_tensors < 1 || n_tensors > B200Q_MAX_SEGS || !W || !dst || !m || !x || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_multi: bad argument");
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_vec_multi: no CUDA device");
     b200q_mmvq_desc d; memset(&d, 0, sizeof d);
-    d.type = type; d.n_seg = n_tensors; d.K = k; d.x = x; d.sm_count = di.sm_count;
+    d.type = type; d.n_seg = n_tensors; d.K = k; d.x = x; d.sm_count = di.sm_count; d.pdl = opt_pdl();
     for (int i = 0; i < n_tensors; ++i) d.seg[i] = {W[i], nullptr, dst[i], nullptr, m[i]};
     return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_mul_mat_vec_multi");
 }
@@ -138,7 +146,7 @@ int b200q_fused_up_gate_vec(int type, const void * W_up, const void * W_gate, co
     if (!W_up || !W_gate || !x || !dst || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_fused_up_gate_vec: bad argument");
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_fused_up_gate_vec: no CUDA device");
     b200q_mmvq_desc d; memset(&d, 0, sizeof d);
-    d.type = type; d.n_seg = 1; d.seg[0] = {W_up, W_gate, dst, nullptr, m}; d.K = k; d.x = x; d.act = unary; d.limit = limit; d.sm_count = di.sm_count;
+    d.type = type; d.n_seg = 1; d.seg[0] = {W_up, W_gate, dst, nullptr, m}; d.K = k; d.x = x; d.act = unary; d.limit = limit; d.sm_count = di.sm_count; d.pdl = opt_pdl();
     return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_fused_up_gate_vec");
 }
 

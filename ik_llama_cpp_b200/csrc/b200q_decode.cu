@@ -42,7 +42,7 @@ __global__ void k_dequant_bf16(const uint8_t * __restrict__ W, b200q_layout L, _
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = i / n32, it = i % n32;
         b200q_item I; b200q_canon C;
-        b200q_load_item<TYPE>(I, W, L, row, it);
+        b200q_load_item<TYPE>(I, b200q_planes_from(W, L), row, it);
         b200q_decode_item<TYPE>(I, it, C);
         float f[32];
         b200q_canon_to_float<b200q_traits<TYPE>::HAS_B>(C, f);
@@ -61,8 +61,8 @@ __global__ void k_dequant_bf16(const uint8_t * __restrict__ W, b200q_layout L, _
 // decode mat-vec
 // ------------------------------------------------------------------------------------------------
 struct mmvq_seg {               // one weight tensor of a multi-tensor launch (Q,K,V share the activation)
-    const uint8_t * W;          // plane base
-    const uint8_t * W2;         // second tensor (gate) for the fused up/gate mode, else nullptr
+    b200q_planes    P;          // resolved plane pointers
+    b200q_planes    P2;         // second tensor (gate) for the fused up/gate mode
     float *         dst;        // [ncols][M] f32 (ggml: dst[j*M + i])
     const float *   bias;       // optional [M]
     int64_t         M;
@@ -77,7 +77,6 @@ struct mmvq_args {
     int64_t      x_stride;
     int          act;           // B200Q_ACT_* for the up/gate mode
     float        limit;         // clamp for swiglu variants (0 = none)
-    b200q_layout L;             // geometry (M of the layout is per-segment; only offsets that do not depend on M are used here)
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -93,30 +92,50 @@ __device__ __forceinline__ float act_apply(int act, float g) {
         default: return g;
     }
 }
+// programmatic dependent launch (no-ops unless the launch carries the PDL attribute)
+__device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Quantise ncols activation columns into shared memory (q8_1 semantics of ggml-cuda/quantize.cu:13-47):
 //   d = amax/127 ; q = amax == 0 ? 0 : roundf(x/d) ; d kept as float(half(d)) ; isum = packed int16 sums of q over each 16.
+// Cooperative and vectorised: a thread owns 8 consecutive floats (two LDG.128), 4 adjacent lanes own one 32-block.
 template <int NCOLS>
 __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x, int64_t x_stride, int64_t K,
                                                    int8_t * sq, float * sd, int * sis) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int n32 = (int)(K / 32);
-    for (int b = warp; b < n32 * NCOLS; b += nwarps) {
-        const int col = b / n32, blk = b % n32;
-        const float v = __ldg(x + col * x_stride + (int64_t)blk * 32 + lane);
-        float amax = fabsf(v);
+    const int nch = (int)(K / 8), total = nch * NCOLS, n32 = (int)(K / 32);
+    for (int base = 0; base < total; base += blockDim.x) {
+        const int c = base + threadIdx.x;
+        const bool valid = c < total;
+        const int col = valid ? c / nch : 0, ch = valid ? c % nch : 0;
+        float v[8];
+        if (valid) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8));
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+        }
+        float amax = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
         const float d = amax / 127.0f;
-        const int q = amax == 0.0f ? 0 : (int)roundf(__fdiv_rn(v, d));
-        int s = q;
+        int q[8]; int s = 0;
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // sum within each 16-lane half
-        const int s_hi = __shfl_sync(0xffffffffu, s, 16);
-        sq[(size_t)col * K + blk * 32 + lane] = (int8_t)q;
-        if (lane == 0) {
-            sd[col * n32 + blk]  = __half2float(__float2half_rn(d));
-            sis[col * n32 + blk] = (s & 0xFFFF) | (s_hi << 16);
+        for (int j = 0; j < 8; ++j) { q[j] = amax == 0.0f ? 0 : (int)roundf(__fdiv_rn(v[j], d)); s += q[j]; }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);                       // sum over 16 weights (2 lanes)
+        const int s_hi = __shfl_down_sync(0xffffffffu, s, 2);          // the second 16 of the 32-block
+        if (valid) {
+            int2 pk;
+            pk.x = (q[0] & 0xFF) | ((q[1] & 0xFF) << 8) | ((q[2] & 0xFF) << 16) | ((q[3] & 0xFF) << 24);
+            pk.y = (q[4] & 0xFF) | ((q[5] & 0xFF) << 8) | ((q[6] & 0xFF) << 16) | ((q[7] & 0xFF) << 24);
+            *reinterpret_cast<int2 *>(sq + (size_t)col * K + (size_t)ch * 8) = pk;
+            if ((ch & 3) == 0) {
+                sd[col * n32 + (ch >> 2)]  = __half2float(__float2half_rn(d));
+                sis[col * n32 + (ch >> 2)] = (s & 0xFFFF) | (s_hi << 16);
+            }
         }
     }
 }
@@ -137,15 +156,21 @@ __device__ __forceinline__ void item_dot(const b200q_canon & C, const int8_t * s
             s1 = b200q_dp4a(C.vb[4], x1.x, s1); s1 = b200q_dp4a(C.vb[5], x1.y, s1); s1 = b200q_dp4a(C.vb[6], x1.z, s1); s1 = b200q_dp4a(C.vb[7], x1.w, s1);
         }
         const float d8 = sd[c * n32 + it];
-        float t = C.dl[0] * (float)s0 + C.dl[1] * (float)s1;
+        float t;
+        if (b200q_split16(TYPE)) t = C.dl[0] * (float)s0 + C.dl[1] * (float)s1;
+        else                     t = C.dl[0] * (float)(s0 + s1);
         if (b200q_mmvq_has_ml(TYPE)) {
             const int is = sis[c * n32 + it];
-            t -= C.ml[0] * (float)(int)(short)(is & 0xFFFF) + C.ml[1] * (float)(is >> 16);
+            if (b200q_split16(TYPE)) t -= C.ml[0] * (float)(int)(short)(is & 0xFFFF) + C.ml[1] * (float)(is >> 16);
+            else                     t -= C.ml[0] * (float)((int)(short)(is & 0xFFFF) + (is >> 16));
         }
         acc[c] = fmaf(d8, t, acc[c]);
     }
 }
 
+// One CTA per SM (512 threads = 16 warps, <= 64 registers): leaves half of the SM for the NEXT kernel of the graph,
+// which under programmatic dependent launch is already resident, has its first weight batch in flight and is parked
+// in griddepcontrol.wait while this one drains.
 template <int TYPE, int NCOLS, bool UPGATE>
 __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_args a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,35 +179,48 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
     float *  sd = reinterpret_cast<float *>(smem_raw + (size_t)NCOLS * K);
     int *    sis = reinterpret_cast<int *>(sd + NCOLS * n32);
 
-    quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis);
-    __syncthreads();
-
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, tw = (int64_t)gridDim.x * nwarps;
     constexpr int U = UPGATE ? 2 : 4;
 
-    for (int64_t grow = gw; grow < a.M_total; grow += tw) {
-        int s = 0;
+    auto locate = [&](int64_t grow, int & s, int64_t & row) {
+        s = 0;
 #pragma unroll
         for (int i = 1; i < B200Q_MAX_SEGS; ++i) if (i < a.n_seg && grow >= a.seg[i].row0) s = i;
-        const mmvq_seg & sg = a.seg[s];
-        const int64_t row = grow - sg.row0;
-        b200q_layout L = a.L; L.M = sg.M;
-        // plane offsets depend on M: recompute (cheap integer math; identical to b200q_make_layout)
-        { int64_t off = 0;
-#pragma unroll
-          for (int p = 0; p < B200Q_MAX_PLANES; ++p) if (p < L.n_planes) { L.plane_off[p] = off; const int64_t n = L.plane_per_row[p] ? L.M : L.M * L.nb; off = b200q_align_up(off + n * L.plane_bytes[p], 256); } }
+        row = grow - a.seg[s].row0;
+    };
 
+    // (1) weights do not depend on the previous kernel: get the first batch of this warp's first row in flight now
+    b200q_item I[U], J[U];
+    int64_t grow = gw;
+    if (grow < a.M_total) {
+        int s; int64_t row; locate(grow, s, row);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = lane + 32 * u;
+            if (it < n32) { b200q_load_item<TYPE>(I[u], a.seg[s].P, row, it); if (UPGATE) b200q_load_item<TYPE>(J[u], a.seg[s].P2, row, it); }
+        }
+    }
+    pdl_trigger();                       // let the next kernel of the stream/graph become resident
+    // (2) the activations are produced by the previous kernel
+    pdl_wait();
+    quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis);
+    __syncthreads();
+
+    for (; grow < a.M_total; grow += tw) {
+        int s; int64_t row; locate(grow, s, row);
+        const mmvq_seg & sg = a.seg[s];
         float acc[NCOLS], acc2[NCOLS];
 #pragma unroll
         for (int c = 0; c < NCOLS; ++c) { acc[c] = 0.0f; acc2[c] = 0.0f; }
 
         for (int it0 = lane; it0 < n32; it0 += 32 * U) {
-            b200q_item I[U], J[U];
+            if (it0 != lane || grow != gw) {          // the very first batch is already in registers
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int it = it0 + 32 * u;
-                if (it < n32) { b200q_load_item<TYPE>(I[u], sg.W, L, row, it); if (UPGATE) b200q_load_item<TYPE>(J[u], sg.W2, L, row, it); }
+                for (int u = 0; u < U; ++u) {
+                    const int it = it0 + 32 * u;
+                    if (it < n32) { b200q_load_item<TYPE>(I[u], sg.P, row, it); if (UPGATE) b200q_load_item<TYPE>(J[u], sg.P2, row, it); }
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -234,27 +272,30 @@ int b200q_launch_dequant_bf16(const void * W, const b200q_layout & L, void * out
 }
 
 template <int TYPE, int NCOLS, bool UPGATE>
-static int launch_mmvq_t(const mmvq_args & a, int sm_count, cudaStream_t st) {
+static int launch_mmvq_t(const mmvq_args & a, int sm_count, bool pdl, cudaStream_t st) {
     const size_t smem = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8;
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
         if (cudaFuncSetAttribute(k_mmvq<TYPE, NCOLS, UPGATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
         configured = smem;
     }
-    // one warp per row; size the CTA so that the grid covers the SMs about twice (prologue cost is per CTA)
+    // one warp per row, one CTA per SM; shrink the CTA when there are fewer rows than warps
     int nwarps = 16;
-    while (nwarps > 4 && a.M_total < (int64_t)sm_count * 2 * nwarps) nwarps >>= 1;
+    while (nwarps > 2 && a.M_total <= (int64_t)sm_count * (nwarps / 2)) nwarps >>= 1;
     int64_t grid = (a.M_total + nwarps - 1) / nwarps;
-    const int64_t max_grid = (int64_t)sm_count * (smem > 100 * 1024 ? 1 : 2) * (16 / nwarps);
-    if (grid > max_grid) grid = max_grid;
+    if (grid > sm_count) grid = sm_count;
     if (grid < 1) grid = 1;
-    k_mmvq<TYPE, NCOLS, UPGATE><<<(unsigned)grid, nwarps * 32, smem, st>>>(a);
-    return (int)cudaGetLastError();
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(nwarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, k_mmvq<TYPE, NCOLS, UPGATE>, a);
 }
 
 template <int TYPE>
-static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_count, cudaStream_t st) {
-#define CASE(N) case N: return upgate ? launch_mmvq_t<TYPE, N, true>(a, sm_count, st) : launch_mmvq_t<TYPE, N, false>(a, sm_count, st);
+static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_count, bool pdl, cudaStream_t st) {
+#define CASE(N) case N: return upgate ? launch_mmvq_t<TYPE, N, true>(a, sm_count, pdl, st) : launch_mmvq_t<TYPE, N, false>(a, sm_count, pdl, st);
     switch (ncols) { CASE(1) CASE(2) CASE(4) CASE(8) default: return -2; }
 #undef CASE
 }
@@ -262,16 +303,17 @@ static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_
 int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
     mmvq_args a; memset(&a, 0, sizeof a);
     if (d.n_seg < 1 || d.n_seg > B200Q_MAX_SEGS || d.ncols < 1 || d.ncols > 8) return -2;
-    if (b200q_make_layout(d.type, d.seg[0].M, d.K, &a.L)) return -1;
     int64_t r0 = 0;
     for (int i = 0; i < d.n_seg; ++i) {
-        a.seg[i].W = (const uint8_t *)d.seg[i].W; a.seg[i].W2 = (const uint8_t *)d.seg[i].W2; a.seg[i].dst = d.seg[i].dst;
-        a.seg[i].bias = d.seg[i].bias; a.seg[i].M = d.seg[i].M; a.seg[i].row0 = r0; r0 += d.seg[i].M;
+        b200q_layout L; const int rc = b200q_make_layout(d.type, d.seg[i].M, d.K, &L); if (rc) return rc;
+        a.seg[i].P = b200q_planes_from((const uint8_t *)d.seg[i].W, L);
+        if (d.seg[i].W2) a.seg[i].P2 = b200q_planes_from((const uint8_t *)d.seg[i].W2, L);
+        a.seg[i].dst = d.seg[i].dst; a.seg[i].bias = d.seg[i].bias; a.seg[i].M = d.seg[i].M; a.seg[i].row0 = r0; r0 += d.seg[i].M;
     }
     a.n_seg = d.n_seg; a.M_total = r0; a.K = d.K; a.x = d.x; a.x_stride = d.x_stride ? d.x_stride : d.K; a.act = d.act; a.limit = d.limit;
     const bool upgate = d.seg[0].W2 != nullptr;
     switch (d.type) {
-#define X(T) case T: return launch_mmvq_type<T>(a, d.ncols, upgate, d.sm_count, st);
+#define X(T) case T: return launch_mmvq_type<T>(a, d.ncols, upgate, d.sm_count, d.pdl != 0, st);
         B200Q_FOR_TYPES(X)
 #undef X
         default: return -1;

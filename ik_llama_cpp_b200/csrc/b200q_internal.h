@@ -12,11 +12,15 @@ enum { B200Q_ACT_NONE = 0, B200Q_ACT_SILU = 1, B200Q_ACT_GELU = 2, B200Q_ACT_REL
 B200Q_HD constexpr bool b200q_mmvq_has_ml(int type) {
     return !(type == B200Q_TYPE_IQ4_NL || type == B200Q_TYPE_Q8_0 || type == B200Q_TYPE_IQ4_XS);
 }
+// types whose two 16-weight halves of an item carry different scales / offsets
+B200Q_HD constexpr bool b200q_split16(int type) {
+    return type == B200Q_TYPE_Q6_K || type == B200Q_TYPE_IQ4_K || type == B200Q_TYPE_IQ5_K;
+}
 
 struct b200q_mmvq_seg_desc { const void * W; const void * W2; float * dst; const float * bias; int64_t M; };
 struct b200q_mmvq_desc {
     int type; int n_seg; b200q_mmvq_seg_desc seg[B200Q_MAX_SEGS];
-    int64_t K; const float * x; int64_t x_stride; int ncols; int act; float limit; int sm_count;
+    int64_t K; const float * x; int64_t x_stride; int ncols; int act; float limit; int sm_count; int pdl;
 };
 
 int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L, int inverse, cudaStream_t st);

@@ -57,7 +57,8 @@ B200Q_HD int b200q_dp4a(int a, int b, int c) {
 // PTX prmt.b32 (default mode): selector nibble = {bit3: replicate sign of the selected byte, bits0-2: byte index in {a,b}}
 B200Q_HD uint32_t b200q_prmt(uint32_t a, uint32_t b, uint32_t s) {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(a, b, s);
+    // NOT __byte_perm(): the intrinsic masks the selector with 0x7777, which removes the sign-replicate mode we rely on
+    uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s)); return r;
 #else
     uint64_t ab = ((uint64_t)b << 32) | a; uint32_t r = 0;
     for (int i = 0; i < 4; ++i) {
@@ -420,40 +421,51 @@ B200Q_HD uint32_t b200q_ld2(const uint8_t * p) {
 #endif
 }
 
+// resolved plane pointers of one tensor (computed once per tensor on the host / once per kernel)
+struct b200q_planes { const uint8_t * p[B200Q_MAX_PLANES]; int64_t nb; int64_t n32; };
+B200Q_HD b200q_planes b200q_planes_from(const uint8_t * base, const b200q_layout & L) {
+    b200q_planes P; for (int i = 0; i < B200Q_MAX_PLANES; ++i) P.p[i] = base + L.plane_off[i];
+    P.nb = L.nb; P.n32 = L.K / 32; return P;
+}
+
 // item index `it` counts 32-weight items along the row: it in [0, K/32)
 template <int TYPE>
-B200Q_HD void b200q_load_item(b200q_item & I, const uint8_t * base, const b200q_layout & L, int64_t row, int64_t it) {
-    const int64_t n32 = L.K / 32;
+B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, int64_t row, int64_t it) {
+    const int64_t n32 = P.n32, nb = P.nb;
     if (TYPE == B200Q_TYPE_IQ4_NL || TYPE == B200Q_TYPE_Q4_0) {
-        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
-        I.m[0] = b200q_ld2(base + L.plane_off[1] + (row * n32 + it) * 2);
+        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        I.m[0] = b200q_ld2(P.p[1] + (row * n32 + it) * 2);
     } else if (TYPE == B200Q_TYPE_Q8_0) {
-        const uint8_t * p = base + L.plane_off[0] + (row * n32 + it) * 32;
+        const uint8_t * p = P.p[0] + (row * n32 + it) * 32;
         b200q_ld16(I.q, p); b200q_ld16(I.q + 4, p + 16);
-        I.m[0] = b200q_ld2(base + L.plane_off[1] + (row * n32 + it) * 2);
+        I.m[0] = b200q_ld2(P.p[1] + (row * n32 + it) * 2);
     } else if (TYPE == B200Q_TYPE_Q4_K || TYPE == B200Q_TYPE_IQ4_K) {
-        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
-        b200q_ld16(I.m, base + L.plane_off[1] + (row * L.nb + it / 8) * 16);
+        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        b200q_ld16(I.m, P.p[1] + (row * nb + it / 8) * 16);
     } else if (TYPE == B200Q_TYPE_Q5_K || TYPE == B200Q_TYPE_IQ5_K) {
-        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
-        I.h[0] = b200q_ld4(base + L.plane_off[1] + (row * n32 + it) * 4);
-        b200q_ld16(I.m, base + L.plane_off[2] + (row * L.nb + it / 8) * 16);
+        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        I.h[0] = b200q_ld4(P.p[1] + (row * n32 + it) * 4);
+        b200q_ld16(I.m, P.p[2] + (row * nb + it / 8) * 16);
     } else if (TYPE == B200Q_TYPE_Q6_K) {
-        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
-        b200q_ld8(I.h, base + L.plane_off[1] + (row * n32 + it) * 8);
-        I.m[0] = b200q_ld2(base + L.plane_off[2] + (row * n32 + it) * 2);     // two int8 scales of this item
-        I.m[1] = b200q_ld2(base + L.plane_off[3] + (row * L.nb + it / 8) * 2); // d
+        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        b200q_ld8(I.h, P.p[1] + (row * n32 + it) * 8);
+        I.m[0] = b200q_ld2(P.p[2] + (row * n32 + it) * 2);     // two int8 scales of this item
+        I.m[1] = b200q_ld2(P.p[3] + (row * nb + it / 8) * 2);  // d
     } else if (TYPE == B200Q_TYPE_IQ4_XS) {
-        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
-        b200q_ld8(I.m, base + L.plane_off[1] + (row * L.nb + it / 8) * 8);
+        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        b200q_ld8(I.m, P.p[1] + (row * nb + it / 8) * 8);
     } else if (TYPE == B200Q_TYPE_IQ4_KS) {
-        b200q_ld16(I.q, base + L.plane_off[0] + (row * n32 + it) * 16);
-        I.m[0] = (uint32_t)(base + L.plane_off[1] + (row * L.nb + it / 8) * 8)[it % 8];
-        uint32_t r = b200q_ld4(base + L.plane_off[2] + row * 4); memcpy(&I.rs, &r, 4);
-    } else if (TYPE == B200Q_TYPE_IQ2_BN) {           // 64 weights per wire block: item = half a block (8 bytes of the 16: see decode)
-        b200q_ld16(I.q, base + L.plane_off[0] + (row * L.nb + it / 2) * 16);
-        uint32_t r = b200q_ld4(base + L.plane_off[1] + row * 4); memcpy(&I.rs, &r, 4);
+        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        I.m[0] = (uint32_t)(P.p[1] + (row * nb + it / 8) * 8)[it % 8];
+        uint32_t r = b200q_ld4(P.p[2] + row * 4); memcpy(&I.rs, &r, 4);
+    } else if (TYPE == B200Q_TYPE_IQ2_BN) {           // 64 weights per wire block: item = half a block (see decode)
+        b200q_ld16(I.q, P.p[0] + (row * nb + it / 2) * 16);
+        uint32_t r = b200q_ld4(P.p[1] + row * 4); memcpy(&I.rs, &r, 4);
     }
+}
+template <int TYPE>
+B200Q_HD void b200q_load_item(b200q_item & I, const uint8_t * base, const b200q_layout & L, int64_t row, int64_t it) {
+    b200q_load_item<TYPE>(I, b200q_planes_from(base, L), row, it);
 }
 
 template <int TYPE>

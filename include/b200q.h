@@ -39,6 +39,7 @@ enum { B200Q_UNARY_NONE = 0, B200Q_UNARY_SILU = 1, B200Q_UNARY_GELU = 2, B200Q_U
 
 B200Q_API int          b200q_abi_version(void);
 B200Q_API const char * b200q_last_error(void);
+B200Q_API int          b200q_set_option(const char * key, int value);   /* "pdl": programmatic dependent launch of the decode kernels (cf. the "-cuda k=v" string of ggml_backend_cuda_init, ggml-cuda.cu:5339) */
 B200Q_API int          b200q_device_count(void);                      /* ggml_backend_cuda_get_device_count, ggml-cuda.h:38 */
 
 /* ---- type geometry (mirrors ggml_type_traits: ggml/src/ggml.c:640-1460) ---- */
