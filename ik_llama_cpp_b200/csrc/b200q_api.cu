@@ -52,6 +52,7 @@ int ensure(scratch & s, size_t n) {
 }
 thread_local scratch g_x, g_y, g_ws, g_stage;
 // programmatic dependent launch for the decode kernels (default on; B200Q_PDL=0 or b200q_set_option("pdl",0) disables)
+int & opt_ring() { static int v = [] { const char * e = getenv("B200Q_RING"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_pdl() { static int v = [] { const char * e = getenv("B200Q_PDL"); return e ? atoi(e) : 1; }(); return v; }
 }  // namespace
 
@@ -61,6 +62,7 @@ int b200q_abi_version(void) { return B200Q_ABI_VERSION; }
 const char * b200q_last_error(void) { return g_err; }
 int b200q_set_option(const char * key, int value) {
     if (key && !strcmp(key, "pdl")) { opt_pdl() = value; return B200Q_OK; }
+    if (key && !strcmp(key, "ring")) { opt_ring() = value; return B200Q_OK; }
     return fail(B200Q_E_ARG, "b200q_set_option: unknown option");
 }
 int b200q_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
@@ -129,7 +131,7 @@ int b200q_mul_mat_vec(int type, const void * W, const float * x, float * dst, in
     if (!W || !x || !dst || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_vec: bad argument");
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_vec: no CUDA device");
     b200q_mmvq_desc d; memset(&d, 0, sizeof d);
-    d.type = type; d.n_seg = 1; d.seg[0] = {W, nullptr, dst, bias, m}; d.K = k; d.x = x; d.sm_count = di.sm_count; d.pdl = opt_pdl();
+    d.type = type; d.n_seg = 1; d.seg[0] = {W, nullptr, dst, bias, m}; d.K = k; d.x = x; d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = opt_ring();
     return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_mul_mat_vec");
 }
 int b200q_mul_mat_vec_multi(int type, int n_tensors, const void * const * W, float * const * dst, const int64_t * m, int64_t k,
@@ -137,7 +139,7 @@ int b200q_mul_mat_vec_multi(int type, int n_tensors, const void * const * W, flo
     if (n_tensors < 1 || n_tensors > B200Q_MAX_SEGS || !W || !dst || !m || !x || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_multi: bad argument");
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_vec_multi: no CUDA device");
     b200q_mmvq_desc d; memset(&d, 0, sizeof d);
-    d.type = type; d.n_seg = n_tensors; d.K = k; d.x = x; d.sm_count = di.sm_count; d.pdl = opt_pdl();
+    d.type = type; d.n_seg = n_tensors; d.K = k; d.x = x; d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = opt_ring();
     for (int i = 0; i < n_tensors; ++i) d.seg[i] = {W[i], nullptr, dst[i], nullptr, m[i]};
     return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_mul_mat_vec_multi");
 }
@@ -146,7 +148,7 @@ int b200q_fused_up_gate_vec(int type, const void * W_up, const void * W_gate, co
     if (!W_up || !W_gate || !x || !dst || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_fused_up_gate_vec: bad argument");
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_fused_up_gate_vec: no CUDA device");
     b200q_mmvq_desc d; memset(&d, 0, sizeof d);
-    d.type = type; d.n_seg = 1; d.seg[0] = {W_up, W_gate, dst, nullptr, m}; d.K = k; d.x = x; d.act = unary; d.limit = limit; d.sm_count = di.sm_count; d.pdl = opt_pdl();
+    d.type = type; d.n_seg = 1; d.seg[0] = {W_up, W_gate, dst, nullptr, m}; d.K = k; d.x = x; d.act = unary; d.limit = limit; d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = opt_ring();
     return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_fused_up_gate_vec");
 }
 

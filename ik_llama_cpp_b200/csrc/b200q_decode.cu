@@ -205,8 +205,8 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
     // (2) the activations are produced by the previous kernel
     pdl_wait();
     quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis);
-    __syncthreads();
-
+    __shared__ uint32_t kv_slot[128];
+    const b200q_kv4 T = b200q_kv4_init_via_smem(kv_slot);     // includes the __syncthreads() that publishes the activations
     for (; grow < a.M_total; grow += tw) {
         int s; int64_t row; locate(grow, s, row);
         const mmvq_seg & sg = a.seg[s];
@@ -227,9 +227,9 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
                 const int it = it0 + 32 * u;
                 if (it < n32) {
                     b200q_canon C;
-                    b200q_decode_item<TYPE>(I[u], it, C);
+                    b200q_decode_item<TYPE>(I[u], it, C, T);
                     item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc);
-                    if (UPGATE) { b200q_decode_item<TYPE>(J[u], it, C); item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc2); }
+                    if (UPGATE) { b200q_decode_item<TYPE>(J[u], it, C, T); item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc2); }
                 }
             }
         }
@@ -242,6 +242,195 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
                 v = act_apply(a.act, g) * v;
             } else if (sg.bias) v += sg.bias[row];
             if (lane == 0) sg.dst[(int64_t)c * sg.M + row] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode mat-vec, TMA-ring variant (the default): weights are streamed HBM -> shared memory by cp.async.bulk (1-D TMA)
+// into warp-private rings, decoupled from registers and from the data dependency on the previous kernel.
+//   * every warp owns S stages; a stage holds one SEGMENT (<= 128 items = 4096 weights) of one row of one tensor:
+//     one bulk copy per plane (rows are contiguous inside a plane), completion on a per-stage mbarrier (expect_tx);
+//   * lane 0 refills a stage as soon as the warp has consumed it, so W*S*stage bytes (~74 KB/SM) stay in flight —
+//     tools/membench.cu: 64 KB/SM of 2 KB bulk copies stream at 7.29 TB/s, LDG with 16 warps x 4 loads at 6.3 TB/s;
+//   * the first S units of every warp are issued BEFORE griddepcontrol.wait: under programmatic dependent launch the
+//     next mat-vec of the graph is already resident (one 512-thread CTA per SM leaves room for a second) and has its
+//     ring full when the previous kernel finishes; only the activation quantisation is on the dependent path.
+// ------------------------------------------------------------------------------------------------
+#define B200Q_SEG_ITEMS 128
+struct ring_geom {
+    int n_planes;                 // block planes staged through the ring (the per-row scale plane is read directly)
+    int b8[4];                    // bytes per 8 items (256 weights) of plane p
+    int seg_off[4];               // byte offset of plane p inside a stage
+    int stage_bytes;              // 16-byte aligned
+    int n_stages;                 // S
+    int row_plane;                // index of the per-row plane in b200q_planes::p, or -1
+};
+struct mmvq_ring_args {
+    mmvq_args  a;
+    ring_geom  g;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rb_init(uint64_t * bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar))); }
+__device__ __forceinline__ void rb_expect(uint64_t * bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rb_wait(uint64_t * bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tRW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra RD_%=;\n\tbra RW_%=;\n\tRD_%=:\n\t}"
+                 ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
+
+// Warp 0 = producer (lane l streams the units of consumer warp l), warps 1..NCW = consumers (one output row at a time).
+template <int TYPE, int NCOLS, bool UPGATE>
+__global__ void __launch_bounds__(512, 2) k_mmvq_ring(const mmvq_ring_args ra) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const mmvq_args & a = ra.a; const ring_geom & g = ra.g;
+    const int64_t K = a.K; const int n32 = (int)(K / 32), n8 = n32 / 8;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ncw = (blockDim.x >> 5) - 1;     // consumer warps
+    const int S = g.n_stages;
+    // smem carve-up: [ring: ncw*S stages][full barriers ncw*S][empty barriers ncw*S][x: sq | sd | sis]
+    unsigned char * ring0 = smem_raw;
+    uint64_t * full0  = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ncw * S * g.stage_bytes);
+    uint64_t * empty0 = full0 + ncw * S;
+    unsigned char * xbase = reinterpret_cast<unsigned char *>(empty0 + ncw * S);
+    int8_t * sq = reinterpret_cast<int8_t *>(xbase);
+    float *  sd = reinterpret_cast<float *>(xbase + (size_t)NCOLS * K);
+    int *    sis = reinterpret_cast<int *>(sd + NCOLS * n32);
+
+    const int64_t tw = (int64_t)gridDim.x * ncw;                 // consumer warps in the grid
+    const int nseg = (n32 + B200Q_SEG_ITEMS - 1) / B200Q_SEG_ITEMS;
+    constexpr int NT = UPGATE ? 2 : 1;                           // tensors per row (up, gate)
+    auto units_of = [&](int64_t gw) -> int64_t { return a.M_total > gw ? ((a.M_total - gw + tw - 1) / tw) * NT * nseg : 0; };
+    auto locate = [&](int64_t grow, int & s, int64_t & row) {
+        s = 0;
+#pragma unroll
+        for (int i = 1; i < B200Q_MAX_SEGS; ++i) if (i < a.n_seg && grow >= a.seg[i].row0) s = i;
+        row = grow - a.seg[s].row0;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < ncw * S; ++i) { rb_init(&full0[i]); rb_init(&empty0[i]); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---------------- producer state (warp 0, lane = consumer warp index) ----------------
+    const int64_t pgw = (int64_t)blockIdx.x * ncw + lane;        // global consumer-warp id served by this lane
+    const int64_t p_units = (warp == 0 && lane < ncw) ? units_of(pgw) : 0;
+    int64_t pu = 0, pj = 0; int pt = 0, psg = 0;
+    auto produce_one = [&]() {                                    // issue unit pu of consumer warp `lane`
+        const int st = (int)(pu % S);
+        uint64_t * fb = &full0[lane * S + st];
+        int s; int64_t row; locate(pgw + pj * tw, s, row);
+        const b200q_planes & P = (UPGATE && pt == 1) ? a.seg[s].P2 : a.seg[s].P;
+        const int g8 = min(B200Q_SEG_ITEMS, n32 - psg * B200Q_SEG_ITEMS) >> 3;
+        unsigned char * dstb = ring0 + ((size_t)lane * S + st) * g.stage_bytes;
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) if (p < g.n_planes) bytes += (uint32_t)(g8 * g.b8[p]);
+        rb_expect(fb, bytes);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) if (p < g.n_planes)
+            bulk_g2s(dstb + g.seg_off[p], P.p[p] + ((int64_t)row * n8 + (int64_t)psg * (B200Q_SEG_ITEMS / 8)) * g.b8[p], (uint32_t)(g8 * g.b8[p]), fb);
+        ++pu; if (++psg == nseg) { psg = 0; if (++pt == NT) { pt = 0; ++pj; } }
+    };
+    // (1) weights do not depend on the previous kernel: fill the ring before waiting for it
+    if (warp == 0) { for (int s = 0; s < S; ++s) if (pu < p_units) produce_one(); }
+    pdl_trigger();                       // the next kernel of the stream/graph may become resident and fill ITS ring
+    pdl_wait();                          // (2) the activations are produced by the previous kernel
+    quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis);
+    __shared__ uint32_t kv_slot[128];
+    const b200q_kv4 T = b200q_kv4_init_via_smem(kv_slot);        // includes the __syncthreads() that publishes the activations
+
+    if (warp == 0) {
+        // ---------------- producer: refill a stage as soon as its consumer has released it ----------------
+        while (pu < p_units) {
+            const int st = (int)(pu % S);
+            rb_wait(&empty0[lane * S + st], (uint32_t)(((pu / S) & 1) ^ 1));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            produce_one();
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int cw = warp - 1;
+    const int64_t gw = (int64_t)blockIdx.x * ncw + cw;
+    const int64_t n_units = units_of(gw);
+    unsigned char * ring = ring0 + (size_t)cw * S * g.stage_bytes;
+    uint64_t * fullb = full0 + cw * S, * emptyb = empty0 + cw * S;
+    float acc[NCOLS], upv[NCOLS];
+    int64_t j = 0; int t = 0, sg = 0;
+    int cs = 0; int64_t crow = 0; float rs0 = 0.0f, rs1 = 0.0f;
+    int st = 0; uint32_t parity = 0;
+    for (int64_t u = 0; u < n_units; ++u) {
+        if (sg == 0) {
+#pragma unroll
+            for (int c = 0; c < NCOLS; ++c) acc[c] = 0.0f;
+            if (t == 0) {
+                locate(gw + j * tw, cs, crow);
+                if (b200q_row_plane(TYPE) >= 0) {              // per-row scale straight from global memory
+                    rs0 = __ldg(reinterpret_cast<const float *>(a.seg[cs].P.p[b200q_row_plane(TYPE)]) + crow);
+                    if (UPGATE) rs1 = __ldg(reinterpret_cast<const float *>(a.seg[cs].P2.p[b200q_row_plane(TYPE)]) + crow);
+                }
+            }
+        }
+        const int items = min(B200Q_SEG_ITEMS, n32 - sg * B200Q_SEG_ITEMS);
+        b200q_planes SP;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) SP.p[p] = ring + (size_t)st * g.stage_bytes + g.seg_off[p < g.n_planes ? p : 0];
+        SP.p[4] = nullptr; SP.nb = 0; SP.n32 = 0;
+        const float rs = (UPGATE && t == 1) ? rs1 : rs0;
+        rb_wait(&fullb[st], parity);
+        if (items == B200Q_SEG_ITEMS) {
+#pragma unroll
+            for (int i = 0; i < B200Q_SEG_ITEMS / 32; ++i) {
+                const int itl = lane + 32 * i;
+                b200q_item I; b200q_canon C;
+                b200q_load_item<TYPE, b200q_ld_plain, false, int>(I, SP, 0, itl);
+                I.rs = rs;
+                b200q_decode_item<TYPE>(I, itl, C, T);
+                item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, sg * B200Q_SEG_ITEMS + itl, acc);
+            }
+        } else {
+            for (int itl = lane; itl < items; itl += 32) {
+                b200q_item I; b200q_canon C;
+                b200q_load_item<TYPE, b200q_ld_plain, false, int>(I, SP, 0, itl);
+                I.rs = rs;
+                b200q_decode_item<TYPE>(I, itl, C, T);
+                item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, sg * B200Q_SEG_ITEMS + itl, acc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) rb_arrive(&emptyb[st]);                  // stage may be overwritten by the producer
+        if (++st == S) { st = 0; parity ^= 1; }
+        if (++sg == nseg) {
+            sg = 0;
+            const mmvq_seg & sgm = a.seg[cs];
+            if (UPGATE && t == 0) {
+#pragma unroll
+                for (int c = 0; c < NCOLS; ++c) upv[c] = warp_sum(acc[c]);       // up . x
+                t = 1;
+            } else {
+#pragma unroll
+                for (int c = 0; c < NCOLS; ++c) {
+                    float v = warp_sum(acc[c]);
+                    if (UPGATE) {                                                 // v = gate . x
+                        float up = upv[c];
+                        if (a.limit > 0.0f) { v = fminf(v, a.limit); up = fminf(fmaxf(up, -a.limit), a.limit); }
+                        v = act_apply(a.act, v) * up;
+                    } else if (sgm.bias) v += sgm.bias[crow];
+                    if (lane == 0) sgm.dst[(int64_t)c * sgm.M + crow] = v;
+                }
+                t = 0; ++j;
+            }
         }
     }
 }
@@ -293,8 +482,66 @@ static int launch_mmvq_t(const mmvq_args & a, int sm_count, bool pdl, cudaStream
     return (int)cudaLaunchKernelEx(&cfg, k_mmvq<TYPE, NCOLS, UPGATE>, a);
 }
 
+// ring geometry for a type; returns false if the planes cannot be bulk-copied (alignment) -> LDG kernel
+static bool make_ring_geom(int type, int64_t K, ring_geom & g) {
+    b200q_layout L; if (b200q_make_layout(type, 1, K, &L)) return false;
+    if (K % 256) return false;
+    const int64_t n8 = K / 256;
+    memset(&g, 0, sizeof g); g.row_plane = -1;
+    int off = 0, np = 0;
+    for (int p = 0; p < L.n_planes; ++p) {
+        if (L.plane_per_row[p]) { g.row_plane = p; continue; }
+        if (p != np) return false;                       // block planes must come first (they do for every type)
+        const int b8 = L.plane_bytes[p] * 256 / L.qk;
+        if (b8 <= 0 || (n8 * b8) % 16) return false;     // every row/segment start must be 16-byte aligned
+        g.b8[np] = b8; g.seg_off[np] = off; off += (int)b200q_align_up((B200Q_SEG_ITEMS / 8) * b8, 16); ++np;
+    }
+    g.n_planes = np; g.stage_bytes = (int)b200q_align_up(off, 128);
+    return np > 0 && np <= 4;
+}
+
+template <int TYPE, int NCOLS, bool UPGATE>
+static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, cudaStream_t st) {
+    mmvq_ring_args ra; ra.a = a; ra.g = g0;
+    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8;
+    const size_t budget = 112 * 1024;                   // two CTAs (this kernel + the next one under PDL) per SM
+    int ncw = 15, S = 0;                                // consumer warps (+1 producer warp)
+    for (;;) {
+        const size_t per_stage = (size_t)ncw * (ra.g.stage_bytes + 16);
+        S = xbytes + 64 < budget ? (int)((budget - xbytes - 64) / per_stage) : 0;
+        if (S >= 2 || ncw == 3) break;
+        ncw = (ncw + 1) / 2 - 1;                        // 15 -> 7 -> 3
+    }
+    if (S < 2) return -100;                              // does not fit: caller falls back to the LDG kernel
+    if (S > 4) S = 4;
+    while (ncw > 3 && a.M_total <= (int64_t)sm_count * ((ncw + 1) / 2 - 1)) ncw = (ncw + 1) / 2 - 1;
+    ra.g.n_stages = S;
+    const size_t smem = (size_t)ncw * S * (ra.g.stage_bytes + 16) + xbytes + 64;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
+        configured = true;
+    }
+    int64_t grid = (a.M_total + ncw - 1) / ncw;
+    if (grid > sm_count) grid = sm_count;
+    if (grid < 1) grid = 1;
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((ncw + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return (int)cudaLaunchKernelEx(&cfg, k_mmvq_ring<TYPE, NCOLS, UPGATE>, ra);
+}
+
 template <int TYPE>
-static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_count, bool pdl, cudaStream_t st) {
+static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_count, bool pdl, bool ring, cudaStream_t st) {
+    ring_geom g;
+    if (ring && ncols <= 2 && make_ring_geom(TYPE, a.K, g)) {
+        int rc;
+        if (ncols == 1) rc = upgate ? launch_mmvq_ring_t<TYPE, 1, true>(a, g, sm_count, pdl, st) : launch_mmvq_ring_t<TYPE, 1, false>(a, g, sm_count, pdl, st);
+        else            rc = upgate ? launch_mmvq_ring_t<TYPE, 2, true>(a, g, sm_count, pdl, st) : launch_mmvq_ring_t<TYPE, 2, false>(a, g, sm_count, pdl, st);
+        if (rc != -100) return rc;
+    }
 #define CASE(N) case N: return upgate ? launch_mmvq_t<TYPE, N, true>(a, sm_count, pdl, st) : launch_mmvq_t<TYPE, N, false>(a, sm_count, pdl, st);
     switch (ncols) { CASE(1) CASE(2) CASE(4) CASE(8) default: return -2; }
 #undef CASE
@@ -313,7 +560,7 @@ int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
     a.n_seg = d.n_seg; a.M_total = r0; a.K = d.K; a.x = d.x; a.x_stride = d.x_stride ? d.x_stride : d.K; a.act = d.act; a.limit = d.limit;
     const bool upgate = d.seg[0].W2 != nullptr;
     switch (d.type) {
-#define X(T) case T: return launch_mmvq_type<T>(a, d.ncols, upgate, d.sm_count, d.pdl != 0, st);
+#define X(T) case T: return launch_mmvq_type<T>(a, d.ncols, upgate, d.sm_count, d.pdl != 0, d.ring != 0, st);
         B200Q_FOR_TYPES(X)
 #undef X
         default: return -1;

@@ -20,7 +20,7 @@ B200Q_HD constexpr bool b200q_split16(int type) {
 struct b200q_mmvq_seg_desc { const void * W; const void * W2; float * dst; const float * bias; int64_t M; };
 struct b200q_mmvq_desc {
     int type; int n_seg; b200q_mmvq_seg_desc seg[B200Q_MAX_SEGS];
-    int64_t K; const float * x; int64_t x_stride; int ncols; int act; float limit; int sm_count; int pdl;
+    int64_t K; const float * x; int64_t x_stride; int ncols; int act; float limit; int sm_count; int pdl; int ring;
 };
 
 int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L, int inverse, cudaStream_t st);

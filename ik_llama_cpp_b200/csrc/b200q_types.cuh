@@ -329,13 +329,33 @@ struct b200q_canon {        // 32 weights
 #define B200Q_KV4_B0 0x271A0E02u   /*  1+1, 13+1, 25+1, 38+1 */
 #define B200Q_KV4_B1 0x725A4636u   /* 53+1, 69+1, 89+1,113+1 */
 
-B200Q_HD void b200q_lut4(uint32_t q, int & a_lo, int & b_lo, int & a_hi, int & b_hi) {
+// The four table words are passed in registers (struct b200q_kv4): written as literals the compiler re-materialises
+// a constant->register move in front of every PRMT (16 extra instructions per 32 weights in the mat-vec inner loop).
+struct b200q_kv4 { uint32_t a0, a1, b0, b1; };
+B200Q_HD b200q_kv4 b200q_kv4_init() {
+    b200q_kv4 t; t.a0 = B200Q_KV4_A0; t.a1 = B200Q_KV4_A1; t.b0 = B200Q_KV4_B0; t.b1 = B200Q_KV4_B1; return t;
+}
+#if defined(__CUDACC__)
+// Same values, but laundered through shared memory at a LANE-DEPENDENT address, so that ptxas can neither fold them
+// (constants get a UR->R move in front of every PRMT) nor keep them in uniform registers (same move): they stay in
+// four ordinary registers for the whole kernel.  `slot` = 128 words of smem; call from all threads (has a __syncthreads()).
+__device__ __forceinline__ b200q_kv4 b200q_kv4_init_via_smem(volatile uint32_t * slot) {
+    if (threadIdx.x < 32) {
+        slot[threadIdx.x * 4 + 0] = B200Q_KV4_A0; slot[threadIdx.x * 4 + 1] = B200Q_KV4_A1;
+        slot[threadIdx.x * 4 + 2] = B200Q_KV4_B0; slot[threadIdx.x * 4 + 3] = B200Q_KV4_B1;
+    }
+    __syncthreads();
+    const int l = threadIdx.x & 31;
+    b200q_kv4 t; t.a0 = slot[l * 4 + 0]; t.a1 = slot[l * 4 + 1]; t.b0 = slot[l * 4 + 2]; t.b1 = slot[l * 4 + 3]; return t;
+}
+#endif
+B200Q_HD void b200q_lut4(const b200q_kv4 & t, uint32_t q, int & a_lo, int & b_lo, int & a_hi, int & b_hi) {
     // q: 8 nibbles (L-order: nibble j = weight j).  lo = weights 0..3, hi = weights 4..7.
     const uint32_t qx = q ^ 0x88888888u;
-    a_lo = (int)b200q_prmt(B200Q_KV4_A0, B200Q_KV4_A1, q);
-    b_lo = (int)b200q_prmt(B200Q_KV4_B0, B200Q_KV4_B1, qx);
-    a_hi = (int)b200q_prmt(B200Q_KV4_A0, B200Q_KV4_A1, q >> 16);
-    b_hi = (int)b200q_prmt(B200Q_KV4_B0, B200Q_KV4_B1, qx >> 16);
+    a_lo = (int)b200q_prmt(t.a0, t.a1, q);
+    b_lo = (int)b200q_prmt(t.b0, t.b1, qx);
+    a_hi = (int)b200q_prmt(t.a0, t.a1, q >> 16);
+    b_hi = (int)b200q_prmt(t.b0, t.b1, qx >> 16);
 }
 
 // byte i (0..15) of a 4-word register group, without dynamic register indexing
@@ -389,38 +409,48 @@ struct b200q_item {
     float    rs;       // row scale (types with a row header)
 };
 
-#if defined(__CUDACC__)
-#define B200Q_LDG128(dst, ptr) { const uint4 _t = __ldg(reinterpret_cast<const uint4 *>(ptr)); (dst)[0] = _t.x; (dst)[1] = _t.y; (dst)[2] = _t.z; (dst)[3] = _t.w; }
+#if !defined(__CUDACC__)
+struct uint4 { uint32_t x, y, z, w; }; struct uint2 { uint32_t x, y; };
 #endif
-B200Q_HD void b200q_ld16(uint32_t * dst, const uint8_t * p) {
+// load policies: GLOBAL = read-only data path (ld.global.nc), PLAIN = ordinary loads (shared-memory stages, host emulation)
+struct b200q_ld_global {
+    static B200Q_HD void ld16(uint32_t * dst, const uint8_t * p) {
 #if defined(__CUDA_ARCH__)
-    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p)); dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p)); dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
 #else
-    memcpy(dst, p, 16);
+        memcpy(dst, p, 16);
 #endif
-}
-B200Q_HD void b200q_ld8(uint32_t * dst, const uint8_t * p) {
+    }
+    static B200Q_HD void ld8(uint32_t * dst, const uint8_t * p) {
 #if defined(__CUDA_ARCH__)
-    const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p)); dst[0] = t.x; dst[1] = t.y;
+        const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p)); dst[0] = t.x; dst[1] = t.y;
 #else
-    memcpy(dst, p, 8);
+        memcpy(dst, p, 8);
 #endif
-}
-B200Q_HD uint32_t b200q_ld4(const uint8_t * p) {
+    }
+    static B200Q_HD uint32_t ld4(const uint8_t * p) {
 #if defined(__CUDA_ARCH__)
-    return __ldg(reinterpret_cast<const uint32_t *>(p));
+        return __ldg(reinterpret_cast<const uint32_t *>(p));
 #else
-    uint32_t v; memcpy(&v, p, 4); return v;
+        uint32_t v; memcpy(&v, p, 4); return v;
 #endif
-}
-B200Q_HD uint32_t b200q_ld2(const uint8_t * p) {
+    }
+    static B200Q_HD uint32_t ld2(const uint8_t * p) {
 #if defined(__CUDA_ARCH__)
-    return __ldg(reinterpret_cast<const uint16_t *>(p));
+        return __ldg(reinterpret_cast<const uint16_t *>(p));
 #else
-    uint16_t v; memcpy(&v, p, 2); return v;
+        uint16_t v; memcpy(&v, p, 2); return v;
 #endif
-}
-
+    }
+    static B200Q_HD uint32_t ld1(const uint8_t * p) { return *p; }
+};
+struct b200q_ld_plain {
+    static B200Q_HD void ld16(uint32_t * dst, const uint8_t * p) { const uint4 t = *reinterpret_cast<const uint4 *>(p); dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w; }
+    static B200Q_HD void ld8(uint32_t * dst, const uint8_t * p)  { const uint2 t = *reinterpret_cast<const uint2 *>(p); dst[0] = t.x; dst[1] = t.y; }
+    static B200Q_HD uint32_t ld4(const uint8_t * p) { return *reinterpret_cast<const uint32_t *>(p); }
+    static B200Q_HD uint32_t ld2(const uint8_t * p) { return *reinterpret_cast<const uint16_t *>(p); }
+    static B200Q_HD uint32_t ld1(const uint8_t * p) { return *p; }
+};
 // resolved plane pointers of one tensor (computed once per tensor on the host / once per kernel)
 struct b200q_planes { const uint8_t * p[B200Q_MAX_PLANES]; int64_t nb; int64_t n32; };
 B200Q_HD b200q_planes b200q_planes_from(const uint8_t * base, const b200q_layout & L) {
@@ -428,51 +458,55 @@ B200Q_HD b200q_planes b200q_planes_from(const uint8_t * base, const b200q_layout
     P.nb = L.nb; P.n32 = L.K / 32; return P;
 }
 
-// item index `it` counts 32-weight items along the row: it in [0, K/32)
-template <int TYPE>
-B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, int64_t row, int64_t it) {
-    const int64_t n32 = P.n32, nb = P.nb;
+// item index `it` counts 32-weight items along the row: it in [0, K/32).  LD = load policy; ROWPLANE = also fetch the
+// per-row scale (the smem-ring kernel passes stage-relative planes with row = 0 and fetches the row scale itself).
+template <class T> struct b200q_ident { typedef T type; };
+template <int TYPE, class LD = b200q_ld_global, bool ROWPLANE = true, class IDX = int64_t>
+B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, typename b200q_ident<IDX>::type row, typename b200q_ident<IDX>::type it) {
+    const IDX n32 = (IDX)P.n32, nb = (IDX)P.nb;
     if (TYPE == B200Q_TYPE_IQ4_NL || TYPE == B200Q_TYPE_Q4_0) {
-        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
-        I.m[0] = b200q_ld2(P.p[1] + (row * n32 + it) * 2);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        I.m[0] = LD::ld2(P.p[1] + (row * n32 + it) * 2);
     } else if (TYPE == B200Q_TYPE_Q8_0) {
         const uint8_t * p = P.p[0] + (row * n32 + it) * 32;
-        b200q_ld16(I.q, p); b200q_ld16(I.q + 4, p + 16);
-        I.m[0] = b200q_ld2(P.p[1] + (row * n32 + it) * 2);
+        LD::ld16(I.q, p); LD::ld16(I.q + 4, p + 16);
+        I.m[0] = LD::ld2(P.p[1] + (row * n32 + it) * 2);
     } else if (TYPE == B200Q_TYPE_Q4_K || TYPE == B200Q_TYPE_IQ4_K) {
-        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
-        b200q_ld16(I.m, P.p[1] + (row * nb + it / 8) * 16);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        LD::ld16(I.m, P.p[1] + (row * nb + it / 8) * 16);
     } else if (TYPE == B200Q_TYPE_Q5_K || TYPE == B200Q_TYPE_IQ5_K) {
-        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
-        I.h[0] = b200q_ld4(P.p[1] + (row * n32 + it) * 4);
-        b200q_ld16(I.m, P.p[2] + (row * nb + it / 8) * 16);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        I.h[0] = LD::ld4(P.p[1] + (row * n32 + it) * 4);
+        LD::ld16(I.m, P.p[2] + (row * nb + it / 8) * 16);
     } else if (TYPE == B200Q_TYPE_Q6_K) {
-        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
-        b200q_ld8(I.h, P.p[1] + (row * n32 + it) * 8);
-        I.m[0] = b200q_ld2(P.p[2] + (row * n32 + it) * 2);     // two int8 scales of this item
-        I.m[1] = b200q_ld2(P.p[3] + (row * nb + it / 8) * 2);  // d
+        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        LD::ld8(I.h, P.p[1] + (row * n32 + it) * 8);
+        I.m[0] = LD::ld2(P.p[2] + (row * n32 + it) * 2);     // two int8 scales of this item
+        I.m[1] = LD::ld2(P.p[3] + (row * nb + it / 8) * 2);  // d
     } else if (TYPE == B200Q_TYPE_IQ4_XS) {
-        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
-        b200q_ld8(I.m, P.p[1] + (row * nb + it / 8) * 8);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        LD::ld8(I.m, P.p[1] + (row * nb + it / 8) * 8);
     } else if (TYPE == B200Q_TYPE_IQ4_KS) {
-        b200q_ld16(I.q, P.p[0] + (row * n32 + it) * 16);
-        I.m[0] = (uint32_t)(P.p[1] + (row * nb + it / 8) * 8)[it % 8];
-        uint32_t r = b200q_ld4(P.p[2] + row * 4); memcpy(&I.rs, &r, 4);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        I.m[0] = LD::ld1(P.p[1] + (row * nb + it / 8) * 8 + it % 8);
+        if (ROWPLANE) { uint32_t r = LD::ld4(P.p[2] + row * 4); memcpy(&I.rs, &r, 4); }
     } else if (TYPE == B200Q_TYPE_IQ2_BN) {           // 64 weights per wire block: item = half a block (see decode)
-        b200q_ld16(I.q, P.p[0] + (row * nb + it / 2) * 16);
-        uint32_t r = b200q_ld4(P.p[1] + row * 4); memcpy(&I.rs, &r, 4);
+        LD::ld16(I.q, P.p[0] + (row * nb + it / 2) * 16);
+        if (ROWPLANE) { uint32_t r = LD::ld4(P.p[1] + row * 4); memcpy(&I.rs, &r, 4); }
     }
 }
 template <int TYPE>
 B200Q_HD void b200q_load_item(b200q_item & I, const uint8_t * base, const b200q_layout & L, int64_t row, int64_t it) {
     b200q_load_item<TYPE>(I, b200q_planes_from(base, L), row, it);
 }
+// index of the per-row plane of a type (-1 if none)
+B200Q_HD constexpr int b200q_row_plane(int type) { return type == B200Q_TYPE_IQ4_KS ? 2 : (type == B200Q_TYPE_IQ2_BN ? 1 : -1); }
 
 template <int TYPE>
-B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & C) {
+B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & C, const b200q_kv4 & T) {
     if (TYPE == B200Q_TYPE_IQ4_NL) {
         const float d = b200q_h2f((uint16_t)I.m[0]);
-        for (int w = 0; w < 4; ++w) b200q_lut4(I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
+        for (int w = 0; w < 4; ++w) b200q_lut4(T, I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
         C.dl[0] = C.dl[1] = d; C.ml[0] = C.ml[1] = 0.0f;
     } else if (TYPE == B200Q_TYPE_Q4_0) {
         const float d = b200q_h2f((uint16_t)I.m[0]);
@@ -505,20 +539,20 @@ B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & 
         const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const uint32_t sh = I.m[0] >> 16; const int ib = (int)(it % 8);
         const uint32_t sl = (I.m[1] >> (8 * (ib / 2) + 4 * (ib % 2))) & 0xF;   // scales_l[ib/2] nibble ib%2
         const int ls = (int)(sl | (((sh >> (2 * ib)) & 3) << 4)) - 32;
-        for (int w = 0; w < 4; ++w) b200q_lut4(I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
+        for (int w = 0; w < 4; ++w) b200q_lut4(T, I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
         C.dl[0] = C.dl[1] = d * ls; C.ml[0] = C.ml[1] = 0.0f;
     } else if (TYPE == B200Q_TYPE_IQ4_K) {            // meta {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]}
         const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const int ib = (int)(it % 8);
         const uint32_t extra = (I.m[0] >> 16) >> (2 * ib);
         const uint32_t h = b200q_byte(I.m, 4 + ib / 2) >> (4 * (ib % 2)); const uint32_t sl = b200q_byte(I.m, 8 + ib);
         const int ls1 = (int)((sl & 0xF) | ((h << 4) & 0x30)) - 32, ls2 = (int)((sl >> 4) | ((h << 2) & 0x30)) - 32;
-        for (int w = 0; w < 4; ++w) b200q_lut4(I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
+        for (int w = 0; w < 4; ++w) b200q_lut4(T, I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
         C.dl[0] = d * ls1; C.dl[1] = d * ls2;
         C.ml[0] = (extra & 1) ? -4.0f * C.dl[0] : 0.0f; C.ml[1] = (extra & 2) ? -4.0f * C.dl[1] : 0.0f;   // iq4k_values[16+i] = kvalues[i] + 4
     } else if (TYPE == B200Q_TYPE_IQ4_KS) {           // m[0] = scale byte of this 32-block
         const uint32_t s = I.m[0];
         const float dl = I.rs * (float)((int)(s & 254) - 127);
-        for (int w = 0; w < 4; ++w) b200q_lut4(I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
+        for (int w = 0; w < 4; ++w) b200q_lut4(T, I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
         C.dl[0] = C.dl[1] = dl; C.ml[0] = C.ml[1] = (s & 1) ? -4.0f * dl : 0.0f;
     } else if (TYPE == B200Q_TYPE_IQ5_K) {            // meta {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]}
         // item s: c = s/2 (64-chunk), second = s%2.  Weights 0..15 of the item use scale dl(2*second) and extra bit (2*second),
@@ -550,6 +584,9 @@ B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & 
         C.dl[0] = C.dl[1] = I.rs; C.ml[0] = C.ml[1] = I.rs;      // w = rs*(q-1)
     }
 }
+
+template <int TYPE>
+B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & C) { b200q_decode_item<TYPE>(I, it, C, b200q_kv4_init()); }
 
 // Dequantise canonical item to 32 floats (used by the bf16 dequantiser and by host tests)
 template <bool HAS_B>
