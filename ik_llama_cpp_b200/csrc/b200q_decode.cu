@@ -18,6 +18,7 @@
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------------
 // repack
@@ -288,7 +289,7 @@ __device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t 
 __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
 
 // Warp 0 = producer (lane l streams the units of consumer warp l), warps 1..NCW = consumers (one output row at a time).
-template <int TYPE, int NCOLS, bool UPGATE>
+template <int TYPE, int NCOLS, bool UPGATE, bool MULTI>
 __global__ void __launch_bounds__(512, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const mmvq_args & a = ra.a; const ring_geom & g = ra.g;
@@ -309,10 +310,12 @@ __global__ void __launch_bounds__(512, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     constexpr int NT = UPGATE ? 2 : 1;                           // tensors per row (up, gate)
     auto units_of = [&](int64_t gw) -> int64_t { return a.M_total > gw ? ((a.M_total - gw + tw - 1) / tw) * NT * nseg : 0; };
     auto locate = [&](int64_t grow, int & s, int64_t & row) {
-        s = 0;
+        s = 0; row = grow;
+        if (MULTI) {
 #pragma unroll
-        for (int i = 1; i < B200Q_MAX_SEGS; ++i) if (i < a.n_seg && grow >= a.seg[i].row0) s = i;
-        row = grow - a.seg[s].row0;
+            for (int i = 1; i < B200Q_MAX_SEGS; ++i) if (i < a.n_seg && grow >= a.seg[i].row0) s = i;
+            row = grow - a.seg[s].row0;
+        }
     };
 
     if (threadIdx.x == 0) {
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(512, 2) k_mmvq_ring(const mmvq_ring_args ra) {
         const int st = (int)(pu % S);
         uint64_t * fb = &full0[lane * S + st];
         int s; int64_t row; locate(pgw + pj * tw, s, row);
-        const b200q_planes & P = (UPGATE && pt == 1) ? a.seg[s].P2 : a.seg[s].P;
+        const b200q_planes & P = (UPGATE && pt == 1) ? a.seg[MULTI ? s : 0].P2 : a.seg[MULTI ? s : 0].P;
         const int g8 = min(B200Q_SEG_ITEMS, n32 - psg * B200Q_SEG_ITEMS) >> 3;
         unsigned char * dstb = ring0 + ((size_t)lane * S + st) * g.stage_bytes;
         uint32_t bytes = 0;
@@ -377,8 +380,8 @@ __global__ void __launch_bounds__(512, 2) k_mmvq_ring(const mmvq_ring_args ra) {
             if (t == 0) {
                 locate(gw + j * tw, cs, crow);
                 if (b200q_row_plane(TYPE) >= 0) {              // per-row scale straight from global memory
-                    rs0 = __ldg(reinterpret_cast<const float *>(a.seg[cs].P.p[b200q_row_plane(TYPE)]) + crow);
-                    if (UPGATE) rs1 = __ldg(reinterpret_cast<const float *>(a.seg[cs].P2.p[b200q_row_plane(TYPE)]) + crow);
+                    rs0 = __ldg(reinterpret_cast<const float *>(a.seg[MULTI ? cs : 0].P.p[b200q_row_plane(TYPE)]) + crow);
+                    if (UPGATE) rs1 = __ldg(reinterpret_cast<const float *>(a.seg[MULTI ? cs : 0].P2.p[b200q_row_plane(TYPE)]) + crow);
                 }
             }
         }
@@ -413,7 +416,7 @@ __global__ void __launch_bounds__(512, 2) k_mmvq_ring(const mmvq_ring_args ra) {
         if (++st == S) { st = 0; parity ^= 1; }
         if (++sg == nseg) {
             sg = 0;
-            const mmvq_seg & sgm = a.seg[cs];
+            const mmvq_seg & sgm = a.seg[MULTI ? cs : 0];
             if (UPGATE && t == 0) {
 #pragma unroll
                 for (int c = 0; c < NCOLS; ++c) upv[c] = warp_sum(acc[c]);       // up . x
@@ -500,8 +503,8 @@ static bool make_ring_geom(int type, int64_t K, ring_geom & g) {
     return np > 0 && np <= 4;
 }
 
-template <int TYPE, int NCOLS, bool UPGATE>
-static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, cudaStream_t st) {
+template <int TYPE, int NCOLS, bool UPGATE, bool MULTI>
+static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
     mmvq_ring_args ra; ra.a = a; ra.g = g0;
     const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8;
     const size_t budget = 112 * 1024;                   // two CTAs (this kernel + the next one under PDL) per SM
@@ -519,18 +522,18 @@ static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_
     const size_t smem = (size_t)ncw * S * (ra.g.stage_bytes + 16) + xbytes + 64;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
+        if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
         configured = true;
     }
     int64_t grid = (a.M_total + ncw - 1) / ncw;
-    if (grid > sm_count) grid = sm_count;
+    if (grid > (int64_t)sm_count * ctas_per_sm) grid = (int64_t)sm_count * ctas_per_sm;
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((ncw + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, k_mmvq_ring<TYPE, NCOLS, UPGATE>, ra);
+    return (int)cudaLaunchKernelEx(&cfg, k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI>, ra);
 }
 
 template <int TYPE>
@@ -538,8 +541,11 @@ static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_
     ring_geom g;
     if (ring && ncols <= 2 && make_ring_geom(TYPE, a.K, g)) {
         int rc;
-        if (ncols == 1) rc = upgate ? launch_mmvq_ring_t<TYPE, 1, true>(a, g, sm_count, pdl, st) : launch_mmvq_ring_t<TYPE, 1, false>(a, g, sm_count, pdl, st);
-        else            rc = upgate ? launch_mmvq_ring_t<TYPE, 2, true>(a, g, sm_count, pdl, st) : launch_mmvq_ring_t<TYPE, 2, false>(a, g, sm_count, pdl, st);
+        static const int cps = [] { const char * e = getenv("B200Q_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
+        const bool multi = a.n_seg > 1;
+        if (upgate) rc = ncols == 1 ? launch_mmvq_ring_t<TYPE, 1, true, false>(a, g, sm_count, pdl, cps, st) : launch_mmvq_ring_t<TYPE, 2, true, false>(a, g, sm_count, pdl, cps, st);
+        else if (multi) rc = ncols == 1 ? launch_mmvq_ring_t<TYPE, 1, false, true>(a, g, sm_count, pdl, cps, st) : launch_mmvq_ring_t<TYPE, 2, false, true>(a, g, sm_count, pdl, cps, st);
+        else rc = ncols == 1 ? launch_mmvq_ring_t<TYPE, 1, false, false>(a, g, sm_count, pdl, cps, st) : launch_mmvq_ring_t<TYPE, 2, false, false>(a, g, sm_count, pdl, cps, st);
         if (rc != -100) return rc;
     }
 #define CASE(N) case N: return upgate ? launch_mmvq_t<TYPE, N, true>(a, sm_count, pdl, st) : launch_mmvq_t<TYPE, N, false>(a, sm_count, pdl, st);
