@@ -122,16 +122,21 @@ __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x,
         for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
         amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+        // q = rint(x * (127/amax)): one division per block instead of one per element.  Differs from the reference's
+        // roundf(x / d) only for products within 1 ulp of a rounding tie (p ~ 1e-5 per element, 1 LSB); the oracle
+        // restates exactly this arithmetic (oracle_quantize_q8_1_b200) next to the reference's (oracle_quantize_q8_1).
         const float d = amax / 127.0f;
-        int q[8]; int s = 0;
+        const float inv = amax > 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
+        int q[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { q[j] = amax == 0.0f ? 0 : (int)roundf(__fdiv_rn(v[j], d)); s += q[j]; }
+        for (int j = 0; j < 8; ++j) q[j] = __float2int_rn(__fmul_rn(v[j], inv));
+        int2 pk;
+        pk.x = (int)__byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+        pk.y = (int)__byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+        int s = __dp4a(pk.x, 0x01010101, __dp4a(pk.y, 0x01010101, 0));
         s += __shfl_xor_sync(0xffffffffu, s, 1);                       // sum over 16 weights (2 lanes)
         const int s_hi = __shfl_down_sync(0xffffffffu, s, 2);          // the second 16 of the 32-block
         if (valid) {
-            int2 pk;
-            pk.x = (q[0] & 0xFF) | ((q[1] & 0xFF) << 8) | ((q[2] & 0xFF) << 16) | ((q[3] & 0xFF) << 24);
-            pk.y = (q[4] & 0xFF) | ((q[5] & 0xFF) << 8) | ((q[6] & 0xFF) << 16) | ((q[7] & 0xFF) << 24);
             *reinterpret_cast<int2 *>(sq + (size_t)col * K + (size_t)ch * 8) = pk;
             if ((ch & 3) == 0) {
                 sd[col * n32 + (ch >> 2)]  = __half2float(__float2half_rn(d));
@@ -288,128 +293,143 @@ __device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t 
 
 __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
 
-// Warp 0 = producer (lane l streams the units of consumer warp l), warps 1..NCW = consumers (one output row at a time).
+// Warp 0 = producer (lane l streams the units of consumer warp l), warps 1..NCW = consumers.
+// A unit is one SEGMENT (<= 128 items) of a PAIR of adjacent output rows of one tensor: the two rows share every
+// activation load and all loop bookkeeping, and give the scheduler two independent dependency chains.
 template <int TYPE, int NCOLS, bool UPGATE, bool MULTI>
-__global__ void __launch_bounds__(512, 2) k_mmvq_ring(const mmvq_ring_args ra) {
+__global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const mmvq_args & a = ra.a; const ring_geom & g = ra.g;
-    const int64_t K = a.K; const int n32 = (int)(K / 32), n8 = n32 / 8;
+    const int K = (int)a.K, n32 = K / 32, n8 = n32 / 8;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ncw = (blockDim.x >> 5) - 1;     // consumer warps
     const int S = g.n_stages;
-    // smem carve-up: [ring: ncw*S stages][full barriers ncw*S][empty barriers ncw*S][x: sq | sd | sis]
+    const int row_stage = g.stage_bytes, pair_stage = 2 * row_stage;
+    // smem carve-up: [ring: ncw*S pair-stages][full barriers ncw*S][empty barriers ncw*S][kv table 128 words][x: sq | sd | sis]
     unsigned char * ring0 = smem_raw;
-    uint64_t * full0  = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ncw * S * g.stage_bytes);
+    uint64_t * full0  = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ncw * S * pair_stage);
     uint64_t * empty0 = full0 + ncw * S;
-    unsigned char * xbase = reinterpret_cast<unsigned char *>(empty0 + ncw * S);
+    uint32_t * kv_slot = reinterpret_cast<uint32_t *>(empty0 + ncw * S);
+    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128);
     int8_t * sq = reinterpret_cast<int8_t *>(xbase);
     float *  sd = reinterpret_cast<float *>(xbase + (size_t)NCOLS * K);
     int *    sis = reinterpret_cast<int *>(sd + NCOLS * n32);
 
-    const int64_t tw = (int64_t)gridDim.x * ncw;                 // consumer warps in the grid
+    const int tw = (int)gridDim.x * ncw;                          // consumer warps in the grid
     const int nseg = (n32 + B200Q_SEG_ITEMS - 1) / B200Q_SEG_ITEMS;
-    constexpr int NT = UPGATE ? 2 : 1;                           // tensors per row (up, gate)
-    auto units_of = [&](int64_t gw) -> int64_t { return a.M_total > gw ? ((a.M_total - gw + tw - 1) / tw) * NT * nseg : 0; };
-    auto locate = [&](int64_t grow, int & s, int64_t & row) {
+    constexpr int NT = UPGATE ? 2 : 1;                            // tensors per row (up, gate)
+    const int n_pairs = (int)((a.M_total + 1) / 2);               // pair p = rows 2p, 2p+1 (segments have even row counts)
+    auto units_of = [&](int gw) -> int { return n_pairs > gw ? ((n_pairs - gw + tw - 1) / tw) * NT * nseg : 0; };
+    auto locate = [&](int grow, int & s, int & row) {
         s = 0; row = grow;
         if (MULTI) {
 #pragma unroll
-            for (int i = 1; i < B200Q_MAX_SEGS; ++i) if (i < a.n_seg && grow >= a.seg[i].row0) s = i;
-            row = grow - a.seg[s].row0;
+            for (int i = 1; i < B200Q_MAX_SEGS; ++i) if (i < a.n_seg && grow >= (int)a.seg[i].row0) s = i;
+            row = grow - (int)a.seg[s].row0;
         }
     };
 
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < ncw * S; ++i) { rb_init(&full0[i]); rb_init(&empty0[i]); }
+    if (threadIdx.x < 32) {
+        for (int i = lane; i < ncw * S; i += 32) { rb_init(&full0[i]); rb_init(&empty0[i]); }
+        kv_slot[lane * 4 + 0] = B200Q_KV4_A0; kv_slot[lane * 4 + 1] = B200Q_KV4_A1; kv_slot[lane * 4 + 2] = B200Q_KV4_B0; kv_slot[lane * 4 + 3] = B200Q_KV4_B1;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
     }
-    __syncthreads();
 
     // ---------------- producer state (warp 0, lane = consumer warp index) ----------------
-    const int64_t pgw = (int64_t)blockIdx.x * ncw + lane;        // global consumer-warp id served by this lane
-    const int64_t p_units = (warp == 0 && lane < ncw) ? units_of(pgw) : 0;
-    int64_t pu = 0, pj = 0; int pt = 0, psg = 0;
-    auto produce_one = [&]() {                                    // issue unit pu of consumer warp `lane`
-        const int st = (int)(pu % S);
-        uint64_t * fb = &full0[lane * S + st];
-        int s; int64_t row; locate(pgw + pj * tw, s, row);
-        const b200q_planes & P = (UPGATE && pt == 1) ? a.seg[MULTI ? s : 0].P2 : a.seg[MULTI ? s : 0].P;
+    const int pgw = (int)blockIdx.x * ncw + lane;                 // global consumer-warp id served by this lane
+    const int p_units = (warp == 0 && lane < ncw) ? units_of(pgw) : 0;
+    int pu = 0, pj = 0, pt = 0, psg = 0, pst = 0;
+    auto produce_one = [&]() {                                    // issue unit pu of consumer warp `lane` into stage pst
+        uint64_t * fb = &full0[lane * S + pst];
+        int s, row; locate(2 * (pgw + pj * tw), s, row);
+        const mmvq_seg & sgm = a.seg[MULTI ? s : 0];
+        const b200q_planes & P = (UPGATE && pt == 1) ? sgm.P2 : sgm.P;
         const int g8 = min(B200Q_SEG_ITEMS, n32 - psg * B200Q_SEG_ITEMS) >> 3;
-        unsigned char * dstb = ring0 + ((size_t)lane * S + st) * g.stage_bytes;
+        const bool two = row + 1 < (int)sgm.M;
+        unsigned char * dstb = ring0 + ((size_t)lane * S + pst) * pair_stage;
         uint32_t bytes = 0;
 #pragma unroll
         for (int p = 0; p < 4; ++p) if (p < g.n_planes) bytes += (uint32_t)(g8 * g.b8[p]);
-        rb_expect(fb, bytes);
+        rb_expect(fb, two ? 2 * bytes : bytes);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) if (p < g.n_planes)
-            bulk_g2s(dstb + g.seg_off[p], P.p[p] + ((int64_t)row * n8 + (int64_t)psg * (B200Q_SEG_ITEMS / 8)) * g.b8[p], (uint32_t)(g8 * g.b8[p]), fb);
-        ++pu; if (++psg == nseg) { psg = 0; if (++pt == NT) { pt = 0; ++pj; } }
+        for (int p = 0; p < 4; ++p) if (p < g.n_planes) {
+            const uint8_t * src = P.p[p] + ((int64_t)row * n8 + (int64_t)psg * (B200Q_SEG_ITEMS / 8)) * g.b8[p];
+            bulk_g2s(dstb + g.seg_off[p], src, (uint32_t)(g8 * g.b8[p]), fb);
+            if (two) bulk_g2s(dstb + row_stage + g.seg_off[p], src + (int64_t)n8 * g.b8[p], (uint32_t)(g8 * g.b8[p]), fb);
+        }
+        ++pu; if (++pst == S) pst = 0;
+        if (++psg == nseg) { psg = 0; if (++pt == NT) { pt = 0; ++pj; } }
     };
     // (1) weights do not depend on the previous kernel: fill the ring before waiting for it
     if (warp == 0) { for (int s = 0; s < S; ++s) if (pu < p_units) produce_one(); }
     pdl_trigger();                       // the next kernel of the stream/graph may become resident and fill ITS ring
     pdl_wait();                          // (2) the activations are produced by the previous kernel
     quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis);
-    __shared__ uint32_t kv_slot[128];
-    const b200q_kv4 T = b200q_kv4_init_via_smem(kv_slot);        // includes the __syncthreads() that publishes the activations
+    __syncthreads();                     // publishes barriers, kv table and activations
 
     if (warp == 0) {
         // ---------------- producer: refill a stage as soon as its consumer has released it ----------------
+        uint32_t epar = 1;               // parity to wait for on the empty barrier of stage pst (first pass: S units already issued)
+        int k = 0;
         while (pu < p_units) {
-            const int st = (int)(pu % S);
-            rb_wait(&empty0[lane * S + st], (uint32_t)(((pu / S) & 1) ^ 1));
+            rb_wait(&empty0[lane * S + pst], epar ^ 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             produce_one();
+            if (++k == S) { k = 0; epar ^= 1; }
         }
         return;
     }
 
     // ---------------- consumers ----------------
+    b200q_kv4 T; T.a0 = kv_slot[lane * 4 + 0]; T.a1 = kv_slot[lane * 4 + 1]; T.b0 = kv_slot[lane * 4 + 2]; T.b1 = kv_slot[lane * 4 + 3];
     const int cw = warp - 1;
-    const int64_t gw = (int64_t)blockIdx.x * ncw + cw;
-    const int64_t n_units = units_of(gw);
-    unsigned char * ring = ring0 + (size_t)cw * S * g.stage_bytes;
+    const int gw = (int)blockIdx.x * ncw + cw;
+    const int n_units = units_of(gw);
+    unsigned char * ring = ring0 + (size_t)cw * S * pair_stage;
     uint64_t * fullb = full0 + cw * S, * emptyb = empty0 + cw * S;
-    float acc[NCOLS], upv[NCOLS];
-    int64_t j = 0; int t = 0, sg = 0;
-    int cs = 0; int64_t crow = 0; float rs0 = 0.0f, rs1 = 0.0f;
+    float acc0[NCOLS], acc1[NCOLS], up0[NCOLS], up1[NCOLS];
+    int j = 0, t = 0, sg = 0;
+    int cs = 0, crow = 0; float rs[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
     int st = 0; uint32_t parity = 0;
-    for (int64_t u = 0; u < n_units; ++u) {
+    for (int u = 0; u < n_units; ++u) {
         if (sg == 0) {
 #pragma unroll
-            for (int c = 0; c < NCOLS; ++c) acc[c] = 0.0f;
+            for (int c = 0; c < NCOLS; ++c) { acc0[c] = 0.0f; acc1[c] = 0.0f; }
             if (t == 0) {
-                locate(gw + j * tw, cs, crow);
-                if (b200q_row_plane(TYPE) >= 0) {              // per-row scale straight from global memory
-                    rs0 = __ldg(reinterpret_cast<const float *>(a.seg[MULTI ? cs : 0].P.p[b200q_row_plane(TYPE)]) + crow);
-                    if (UPGATE) rs1 = __ldg(reinterpret_cast<const float *>(a.seg[MULTI ? cs : 0].P2.p[b200q_row_plane(TYPE)]) + crow);
+                locate(2 * (gw + j * tw), cs, crow);
+                if (b200q_row_plane(TYPE) >= 0) {              // per-row scales straight from global memory
+                    const mmvq_seg & sgm = a.seg[MULTI ? cs : 0];
+                    const int r1 = min(crow + 1, (int)sgm.M - 1);
+                    rs[0][0] = __ldg(reinterpret_cast<const float *>(sgm.P.p[b200q_row_plane(TYPE)]) + crow);
+                    rs[0][1] = __ldg(reinterpret_cast<const float *>(sgm.P.p[b200q_row_plane(TYPE)]) + r1);
+                    if (UPGATE) { rs[1][0] = __ldg(reinterpret_cast<const float *>(sgm.P2.p[b200q_row_plane(TYPE)]) + crow);
+                                  rs[1][1] = __ldg(reinterpret_cast<const float *>(sgm.P2.p[b200q_row_plane(TYPE)]) + r1); }
                 }
             }
         }
         const int items = min(B200Q_SEG_ITEMS, n32 - sg * B200Q_SEG_ITEMS);
-        b200q_planes SP;
+        b200q_planes SP0, SP1;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) SP.p[p] = ring + (size_t)st * g.stage_bytes + g.seg_off[p < g.n_planes ? p : 0];
-        SP.p[4] = nullptr; SP.nb = 0; SP.n32 = 0;
-        const float rs = (UPGATE && t == 1) ? rs1 : rs0;
+        for (int p = 0; p < 4; ++p) { SP0.p[p] = ring + (size_t)st * pair_stage + g.seg_off[p < g.n_planes ? p : 0]; SP1.p[p] = SP0.p[p] + row_stage; }
+        SP0.p[4] = SP1.p[4] = nullptr; SP0.nb = SP1.nb = 0; SP0.n32 = SP1.n32 = 0;
+        const float rsa = rs[UPGATE ? t : 0][0], rsb = rs[UPGATE ? t : 0][1];
         rb_wait(&fullb[st], parity);
+        auto do_item = [&](int itl) {
+            b200q_item I0, I1; b200q_canon C;
+            b200q_load_item<TYPE, b200q_ld_plain, false, int>(I0, SP0, 0, itl);
+            b200q_load_item<TYPE, b200q_ld_plain, false, int>(I1, SP1, 0, itl);
+            I0.rs = rsa; I1.rs = rsb;
+            const int it = sg * B200Q_SEG_ITEMS + itl;
+            b200q_decode_item<TYPE>(I0, itl, C, T);
+            item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc0);
+            b200q_decode_item<TYPE>(I1, itl, C, T);
+            item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc1);
+        };
         if (items == B200Q_SEG_ITEMS) {
 #pragma unroll
-            for (int i = 0; i < B200Q_SEG_ITEMS / 32; ++i) {
-                const int itl = lane + 32 * i;
-                b200q_item I; b200q_canon C;
-                b200q_load_item<TYPE, b200q_ld_plain, false, int>(I, SP, 0, itl);
-                I.rs = rs;
-                b200q_decode_item<TYPE>(I, itl, C, T);
-                item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, sg * B200Q_SEG_ITEMS + itl, acc);
-            }
+            for (int i = 0; i < B200Q_SEG_ITEMS / 32; ++i) do_item(lane + 32 * i);
         } else {
-            for (int itl = lane; itl < items; itl += 32) {
-                b200q_item I; b200q_canon C;
-                b200q_load_item<TYPE, b200q_ld_plain, false, int>(I, SP, 0, itl);
-                I.rs = rs;
-                b200q_decode_item<TYPE>(I, itl, C, T);
-                item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, sg * B200Q_SEG_ITEMS + itl, acc);
-            }
+            for (int itl = lane; itl < items; itl += 32) do_item(itl);
         }
         __syncwarp();
         if (lane == 0) rb_arrive(&emptyb[st]);                  // stage may be overwritten by the producer
@@ -419,18 +439,24 @@ __global__ void __launch_bounds__(512, 2) k_mmvq_ring(const mmvq_ring_args ra) {
             const mmvq_seg & sgm = a.seg[MULTI ? cs : 0];
             if (UPGATE && t == 0) {
 #pragma unroll
-                for (int c = 0; c < NCOLS; ++c) upv[c] = warp_sum(acc[c]);       // up . x
+                for (int c = 0; c < NCOLS; ++c) { up0[c] = acc0[c]; up1[c] = acc1[c]; }      // up . x (still per-lane partials)
                 t = 1;
             } else {
+                const bool two = crow + 1 < (int)sgm.M;
 #pragma unroll
                 for (int c = 0; c < NCOLS; ++c) {
-                    float v = warp_sum(acc[c]);
-                    if (UPGATE) {                                                 // v = gate . x
-                        float up = upv[c];
-                        if (a.limit > 0.0f) { v = fminf(v, a.limit); up = fminf(fmaxf(up, -a.limit), a.limit); }
-                        v = act_apply(a.act, v) * up;
-                    } else if (sgm.bias) v += sgm.bias[crow];
-                    if (lane == 0) sgm.dst[(int64_t)c * sgm.M + crow] = v;
+                    // four (two) independent butterfly chains interleave in the pipeline
+                    float v0 = acc0[c], v1 = acc1[c], u0 = UPGATE ? up0[c] : 0.0f, u1 = UPGATE ? up1[c] : 0.0f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                        if (UPGATE) { u0 += __shfl_xor_sync(0xffffffffu, u0, o); u1 += __shfl_xor_sync(0xffffffffu, u1, o); }
+                    }
+                    if (UPGATE) {                                                 // v = gate . x, u = up . x
+                        if (a.limit > 0.0f) { v0 = fminf(v0, a.limit); u0 = fminf(fmaxf(u0, -a.limit), a.limit); v1 = fminf(v1, a.limit); u1 = fminf(fmaxf(u1, -a.limit), a.limit); }
+                        v0 = act_apply(a.act, v0) * u0; v1 = act_apply(a.act, v1) * u1;
+                    } else if (sgm.bias) { v0 += sgm.bias[crow]; if (two) v1 += sgm.bias[crow + 1]; }
+                    if (lane == 0) { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
                 }
                 t = 0; ++j;
             }
@@ -506,26 +532,30 @@ static bool make_ring_geom(int type, int64_t K, ring_geom & g) {
 template <int TYPE, int NCOLS, bool UPGATE, bool MULTI>
 static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
     mmvq_ring_args ra; ra.a = a; ra.g = g0;
-    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8;
-    const size_t budget = 112 * 1024;                   // two CTAs (this kernel + the next one under PDL) per SM
-    int ncw = 15, S = 0;                                // consumer warps (+1 producer warp)
+    for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
+    if (a.M_total >= (int64_t)1 << 30) return -100;
+    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512;
+    const size_t budget = 112 * 1024;                   // two CTAs per SM (same kernel, or this one + the next under PDL)
+    const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
+    int ncw = 11, S = 0;                                // consumer warps (+1 producer warp)
     for (;;) {
-        const size_t per_stage = (size_t)ncw * (ra.g.stage_bytes + 16);
+        const size_t per_stage = (size_t)ncw * (pair_stage + 16);
         S = xbytes + 64 < budget ? (int)((budget - xbytes - 64) / per_stage) : 0;
         if (S >= 2 || ncw == 3) break;
-        ncw = (ncw + 1) / 2 - 1;                        // 15 -> 7 -> 3
+        ncw = ncw > 7 ? 7 : 3;
     }
     if (S < 2) return -100;                              // does not fit: caller falls back to the LDG kernel
     if (S > 4) S = 4;
-    while (ncw > 3 && a.M_total <= (int64_t)sm_count * ((ncw + 1) / 2 - 1)) ncw = (ncw + 1) / 2 - 1;
+    const int64_t n_pairs = (a.M_total + 1) / 2;
+    while (ncw > 3 && n_pairs <= (int64_t)sm_count * (ncw > 7 ? 7 : 3)) ncw = ncw > 7 ? 7 : 3;
     ra.g.n_stages = S;
-    const size_t smem = (size_t)ncw * S * (ra.g.stage_bytes + 16) + xbytes + 64;
+    const size_t smem = (size_t)ncw * S * (pair_stage + 16) + xbytes + 64;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
         configured = true;
     }
-    int64_t grid = (a.M_total + ncw - 1) / ncw;
+    int64_t grid = (n_pairs + ncw - 1) / ncw;
     if (grid > (int64_t)sm_count * ctas_per_sm) grid = (int64_t)sm_count * ctas_per_sm;
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);

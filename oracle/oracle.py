@@ -71,6 +71,8 @@ class Oracle:
         L.oracle_quantize_q8_1.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]
         L.oracle_mul_mat_exact.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64]
         L.oracle_mul_mat_q8_1.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64]
+        L.oracle_mul_mat_q8_1_b200.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64]
+        L.oracle_quantize_q8_1_b200.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_void_p]
         L.oracle_h2f.restype = c_float
         L.oracle_h2f.argtypes = [c_uint16]
         L.oracle_f2h.restype = c_uint16
@@ -112,14 +114,25 @@ class Oracle:
         assert self.lib.oracle_mul_mat_exact(t, _p(wire), _p(x), _p(out), m, k, n) == 0
         return out
 
-    def mul_mat_q8_1(self, t: int, wire: np.ndarray, x: np.ndarray, m: int) -> np.ndarray:
+    def mul_mat_q8_1(self, t: int, wire: np.ndarray, x: np.ndarray, m: int, variant: str = "reference") -> np.ndarray:
+        """dequant(W) . dequant_q8_1(x) in f64.  variant="reference": quantize_q8_1 exactly as ggml-cuda/quantize.cu;
+        variant="b200": the product's quantiser (one division per block, round-half-even)."""
         x = np.ascontiguousarray(x, np.float32)
         n, k = x.shape
         wire = np.ascontiguousarray(wire, np.uint8)
         assert wire.size == m * self.row_size(t, k)
         out = np.empty((n, m), np.float32)
-        assert self.lib.oracle_mul_mat_q8_1(t, _p(wire), _p(x), _p(out), m, k, n) == 0
+        fn = self.lib.oracle_mul_mat_q8_1 if variant == "reference" else self.lib.oracle_mul_mat_q8_1_b200
+        assert fn(t, _p(wire), _p(x), _p(out), m, k, n) == 0
         return out
+
+    def quantize_q8_1_b200(self, x: np.ndarray):
+        x = np.ascontiguousarray(x, np.float32)
+        n, k = x.shape
+        q = np.empty((n, k), np.int8)
+        d = np.empty((n, k // 32), np.uint16)
+        assert self.lib.oracle_quantize_q8_1_b200(_p(x), n, k, _p(q), _p(d)) == 0
+        return q, d.view(np.float16)
 
 
 def _cpu_flags() -> set[str]:

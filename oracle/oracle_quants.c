@@ -279,6 +279,22 @@ ORACLE_API int oracle_quantize_q8_1(const float * x, int64_t n, int64_t k, int8_
     return 0;
 }
 
+// The product's variant of the activation quantiser (ik_llama_cpp_b200/csrc/b200q_decode.cu quantize_x_to_smem):
+//   d = amax/127 (stored as half), inv = 127/amax, q = rint(x*inv) (round-half-even), i.e. one division per block
+// instead of the reference's roundf(x/d) per element.  Identical except at rounding ties (p ~ 1e-5 per element).
+// Restated so that kernel-vs-oracle checks can be held to f32 summation-order accuracy.
+ORACLE_API int oracle_quantize_q8_1_b200(const float * x, int64_t n, int64_t k, int8_t * q, uint16_t * d_bits) {
+    if (k % 32) return -1;
+    for (int64_t r = 0; r < n; ++r) for (int64_t b = 0; b < k / 32; ++b) {
+        const float * xb = x + r * k + b * 32; float amax = 0.0f;
+        for (int j = 0; j < 32; ++j) { const float a = fabsf(xb[j]); if (a > amax) amax = a; }
+        const float d = amax / 127.0f; const float inv = amax > 0.0f ? 127.0f / amax : 0.0f;
+        for (int j = 0; j < 32; ++j) { const float p = xb[j] * inv; q[r * k + b * 32 + j] = (int8_t)lrintf(p); }
+        d_bits[r * (k / 32) + b] = f2h(d);
+    }
+    return 0;
+}
+
 // dst[n][m] (f32) = exact f64 dot of dequant(W) rows with x columns.  W: m wire rows, x: f32 [n][k].
 ORACLE_API int oracle_mul_mat_exact(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n) {
     const int64_t rs = oracle_row_size(type, k); if (rs < 0) return -1;
@@ -291,11 +307,15 @@ ORACLE_API int oracle_mul_mat_exact(int type, const uint8_t * W, const float * x
 }
 
 // dst[n][m] = the value the reference's MMVQ kernels compute up to f32 summation order (see header).
-ORACLE_API int oracle_mul_mat_q8_1(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n) {
+static int mul_mat_q8_impl(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n, int variant);
+ORACLE_API int oracle_mul_mat_q8_1(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n) { return mul_mat_q8_impl(type, W, x, dst, m, k, n, 0); }
+// same with the product's quantiser variant (see oracle_quantize_q8_1_b200)
+ORACLE_API int oracle_mul_mat_q8_1_b200(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n) { return mul_mat_q8_impl(type, W, x, dst, m, k, n, 1); }
+static int mul_mat_q8_impl(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n, int variant) {
     const int64_t rs = oracle_row_size(type, k); if (rs < 0 || k % 32) return -1;
     int8_t * q = (int8_t *)malloc((size_t)n * k); uint16_t * db = (uint16_t *)malloc(sizeof(uint16_t) * n * (k / 32)); uint16_t * sb = (uint16_t *)malloc(sizeof(uint16_t) * n * (k / 32));
     float * xq = (float *)malloc(sizeof(float) * n * k); float * w = (float *)malloc(sizeof(float) * k);
-    oracle_quantize_q8_1(x, n, k, q, db, sb);
+    if (variant) oracle_quantize_q8_1_b200(x, n, k, q, db); else oracle_quantize_q8_1(x, n, k, q, db, sb);
     for (int64_t j = 0; j < n; ++j) for (int64_t l = 0; l < k; ++l) xq[j * k + l] = h2f(db[j * (k / 32) + l / 32]) * q[j * k + l];
     int rc = 0;
     for (int64_t i = 0; i < m && !rc; ++i) {

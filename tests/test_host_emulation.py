@@ -40,7 +40,7 @@ def _emul_all(E, oracle, t, wire, m, k, x):
     deq = np.empty((m, k), np.float32)
     assert E.emul_dequant(t, _p(planes), m, k, _p(deq)) == 0
     n = x.shape[0]
-    q, d, _ = oracle.quantize_q8_1(x)
+    q, d = oracle.quantize_q8_1_b200(x)
     xd = np.ascontiguousarray(d.astype(np.float32))
     q16 = q.reshape(n, k // 32, 2, 16).astype(np.int32).sum(-1)
     xis = np.ascontiguousarray(((q16[..., 0] & 0xFFFF) | (q16[..., 1] << 16)).astype(np.int32))
@@ -62,7 +62,7 @@ def test_emulated_kernel_arithmetic_on_golden(emul, oracle, name):
         np.testing.assert_allclose(deq, g["dequant_ref"], rtol=2e-7)
     else:
         assert np.array_equal(deq, g["dequant_ref"]), "canonical decode must equal the reference to_float bit-for-bit"
-    yq = oracle.mul_mat_q8_1(t, wire, x, m)
+    yq = oracle.mul_mat_q8_1(t, wire, x, m, variant="b200")
     rms = np.sqrt((yq.astype(np.float64) ** 2).mean())
     assert np.abs(y - yq).max() <= 2e-5 * rms, "mat-vec arithmetic differs from the restated reference MMVQ beyond f32 summation order"
     assert nmse(y, oracle.mul_mat_exact(t, wire, x, m)) <= 5e-4
@@ -83,6 +83,6 @@ def test_emulated_random_bit_patterns(emul, oracle, name):
         np.testing.assert_allclose(deq, ref, rtol=3e-7, atol=1e-12)
     else:
         assert np.array_equal(deq, ref)
-    yq = oracle.mul_mat_q8_1(t, wire, x, m)
+    yq = oracle.mul_mat_q8_1(t, wire, x, m, variant="b200")
     rms = np.sqrt((yq.astype(np.float64) ** 2).mean())
     assert np.abs(y - yq).max() <= 2e-5 * rms

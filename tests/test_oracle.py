@@ -52,6 +52,17 @@ def test_quantize_q8_1_restatement(oracle):
     np.testing.assert_allclose(s.astype(np.float32), xb.sum(-1), rtol=2e-3, atol=1e-3)
 
 
+def test_b200_quantizer_variant_vs_reference_variant(oracle):
+    """The product's quantiser (one division per block, rint) must agree with the reference's (roundf(x/d)) except at ties."""
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((8, 4096)).astype(np.float32)
+    q0, d0, _ = oracle.quantize_q8_1(x)
+    q1, d1 = oracle.quantize_q8_1_b200(x)
+    assert np.array_equal(d0, d1)
+    diff = np.abs(q0.astype(np.int32) - q1.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3
+
+
 def test_half_conversions(oracle):
     hs = np.arange(0, 65536, 7, dtype=np.uint16)
     f = np.array([oracle.lib.oracle_h2f(int(h)) for h in hs], np.float32)
