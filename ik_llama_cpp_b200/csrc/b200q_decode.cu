@@ -102,10 +102,10 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // Cooperative and vectorised: a thread owns 8 consecutive floats (two LDG.128), 4 adjacent lanes own one 32-block.
 template <int NCOLS>
 __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x, int64_t x_stride, int64_t K,
-                                                   int8_t * sq, float * sd, int * sis) {
+                                                   int8_t * sq, float * sd, int * sis, int tid, int nthreads) {
     const int nch = (int)(K / 8), total = nch * NCOLS, n32 = (int)(K / 32);
-    for (int base = 0; base < total; base += blockDim.x) {
-        const int c = base + threadIdx.x;
+    for (int base = 0; base < total; base += nthreads) {
+        const int c = base + tid;
         const bool valid = c < total;
         const int col = valid ? c / nch : 0, ch = valid ? c % nch : 0;
         float v[8];
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
     pdl_trigger();                       // let the next kernel of the stream/graph become resident
     // (2) the activations are produced by the previous kernel
     pdl_wait();
-    quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis);
+    quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis, threadIdx.x, blockDim.x);
     __shared__ uint32_t kv_slot[128];
     const b200q_kv4 T = b200q_kv4_init_via_smem(kv_slot);     // includes the __syncthreads() that publishes the activations
     for (; grow < a.M_total; grow += tw) {
@@ -309,16 +309,20 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     uint64_t * full0  = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ncw * S * pair_stage);
     uint64_t * empty0 = full0 + ncw * S;
     uint32_t * kv_slot = reinterpret_cast<uint32_t *>(empty0 + ncw * S);
-    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128);
+    int * pair_id = reinterpret_cast<int *>(kv_slot + 128);       // [ncw*S] pair index streamed into each stage (-1 = end)
+    int * next_pair = pair_id + 60;                               // CTA-wide claim counter
+    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128 + 64);
     int8_t * sq = reinterpret_cast<int8_t *>(xbase);
     float *  sd = reinterpret_cast<float *>(xbase + (size_t)NCOLS * K);
     int *    sis = reinterpret_cast<int *>(sd + NCOLS * n32);
 
-    const int tw = (int)gridDim.x * ncw;                          // consumer warps in the grid
     const int nseg = (n32 + B200Q_SEG_ITEMS - 1) / B200Q_SEG_ITEMS;
     constexpr int NT = UPGATE ? 2 : 1;                            // tensors per row (up, gate)
     const int n_pairs = (int)((a.M_total + 1) / 2);               // pair p = rows 2p, 2p+1 (segments have even row counts)
-    auto units_of = [&](int gw) -> int { return n_pairs > gw ? ((n_pairs - gw + tw - 1) / tw) * NT * nseg : 0; };
+    // static split of the pairs over CTAs (+-1 pair), dynamic claiming inside the CTA: the producer lane of a consumer
+    // warp takes the next pair from a shared counter whenever that warp's ring has room, so warps never idle on a
+    // coarse static remainder (2.2 pairs/warp for the FFN up/gate shape would otherwise mean 3 for some, 2 for others)
+    const int c0 = (int)(((int64_t)n_pairs * blockIdx.x) / gridDim.x), c1 = (int)(((int64_t)n_pairs * (blockIdx.x + 1)) / gridDim.x);
     auto locate = [&](int grow, int & s, int & row) {
         s = 0; row = grow;
         if (MULTI) {
@@ -331,17 +335,19 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     if (threadIdx.x < 32) {
         for (int i = lane; i < ncw * S; i += 32) { rb_init(&full0[i]); rb_init(&empty0[i]); }
         kv_slot[lane * 4 + 0] = B200Q_KV4_A0; kv_slot[lane * 4 + 1] = B200Q_KV4_A1; kv_slot[lane * 4 + 2] = B200Q_KV4_B0; kv_slot[lane * 4 + 3] = B200Q_KV4_B1;
+        if (lane == 0) *next_pair = c0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
     }
 
     // ---------------- producer state (warp 0, lane = consumer warp index) ----------------
-    const int pgw = (int)blockIdx.x * ncw + lane;                 // global consumer-warp id served by this lane
-    const int p_units = (warp == 0 && lane < ncw) ? units_of(pgw) : 0;
-    int pu = 0, pj = 0, pt = 0, psg = 0, pst = 0;
-    auto produce_one = [&]() {                                    // issue unit pu of consumer warp `lane` into stage pst
+    int pcur = -1, pt = 0, psg = 0, pst = 0, pu = 0; bool pdone = !(warp == 0 && lane < ncw);
+    auto produce_one = [&]() {                                    // issue the next unit of consumer warp `lane` into stage pst
         uint64_t * fb = &full0[lane * S + pst];
-        int s, row; locate(2 * (pgw + pj * tw), s, row);
+        if (pt == 0 && psg == 0) { pcur = atomicAdd(next_pair, 1); if (pcur >= c1) pcur = -1; }
+        pair_id[lane * S + pst] = pcur;
+        if (pcur < 0) { rb_arrive(fb); pdone = true; return; }   // sentinel: nothing left for this consumer
+        int s, row; locate(2 * pcur, s, row);
         const mmvq_seg & sgm = a.seg[MULTI ? s : 0];
         const b200q_planes & P = (UPGATE && pt == 1) ? sgm.P2 : sgm.P;
         const int g8 = min(B200Q_SEG_ITEMS, n32 - psg * B200Q_SEG_ITEMS) >> 3;
@@ -358,20 +364,20 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
             if (two) bulk_g2s(dstb + row_stage + g.seg_off[p], src + (int64_t)n8 * g.b8[p], (uint32_t)(g8 * g.b8[p]), fb);
         }
         ++pu; if (++pst == S) pst = 0;
-        if (++psg == nseg) { psg = 0; if (++pt == NT) { pt = 0; ++pj; } }
+        if (++psg == nseg) { psg = 0; if (++pt == NT) pt = 0; }
     };
     // (1) weights do not depend on the previous kernel: fill the ring before waiting for it
-    if (warp == 0) { for (int s = 0; s < S; ++s) if (pu < p_units) produce_one(); }
+    if (warp == 0) { for (int s = 0; s < S; ++s) if (!pdone) produce_one(); }
     pdl_trigger();                       // the next kernel of the stream/graph may become resident and fill ITS ring
     pdl_wait();                          // (2) the activations are produced by the previous kernel
-    quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis);
+    if (warp != 0) quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis, threadIdx.x - 32, blockDim.x - 32);
     __syncthreads();                     // publishes barriers, kv table and activations
 
     if (warp == 0) {
         // ---------------- producer: refill a stage as soon as its consumer has released it ----------------
-        uint32_t epar = 1;               // parity to wait for on the empty barrier of stage pst (first pass: S units already issued)
+        uint32_t epar = 1;               // first pass over the ring: the S initial units are already issued
         int k = 0;
-        while (pu < p_units) {
+        while (!pdone) {
             rb_wait(&empty0[lane * S + pst], epar ^ 1);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             produce_one();
@@ -383,20 +389,21 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     // ---------------- consumers ----------------
     b200q_kv4 T; T.a0 = kv_slot[lane * 4 + 0]; T.a1 = kv_slot[lane * 4 + 1]; T.b0 = kv_slot[lane * 4 + 2]; T.b1 = kv_slot[lane * 4 + 3];
     const int cw = warp - 1;
-    const int gw = (int)blockIdx.x * ncw + cw;
-    const int n_units = units_of(gw);
     unsigned char * ring = ring0 + (size_t)cw * S * pair_stage;
     uint64_t * fullb = full0 + cw * S, * emptyb = empty0 + cw * S;
     float acc0[NCOLS], acc1[NCOLS], up0[NCOLS], up1[NCOLS];
-    int j = 0, t = 0, sg = 0;
+    int t = 0, sg = 0;
     int cs = 0, crow = 0; float rs[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
     int st = 0; uint32_t parity = 0;
-    for (int u = 0; u < n_units; ++u) {
+    for (;;) {
+        rb_wait(&fullb[st], parity);
+        const int pid = pair_id[cw * S + st];
+        if (pid < 0) break;
         if (sg == 0) {
 #pragma unroll
             for (int c = 0; c < NCOLS; ++c) { acc0[c] = 0.0f; acc1[c] = 0.0f; }
             if (t == 0) {
-                locate(2 * (gw + j * tw), cs, crow);
+                locate(2 * pid, cs, crow);
                 if (b200q_row_plane(TYPE) >= 0) {              // per-row scales straight from global memory
                     const mmvq_seg & sgm = a.seg[MULTI ? cs : 0];
                     const int r1 = min(crow + 1, (int)sgm.M - 1);
@@ -413,7 +420,6 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
         for (int p = 0; p < 4; ++p) { SP0.p[p] = ring + (size_t)st * pair_stage + g.seg_off[p < g.n_planes ? p : 0]; SP1.p[p] = SP0.p[p] + row_stage; }
         SP0.p[4] = SP1.p[4] = nullptr; SP0.nb = SP1.nb = 0; SP0.n32 = SP1.n32 = 0;
         const float rsa = rs[UPGATE ? t : 0][0], rsb = rs[UPGATE ? t : 0][1];
-        rb_wait(&fullb[st], parity);
         auto do_item = [&](int itl) {
             b200q_item I0, I1; b200q_canon C;
             b200q_load_item<TYPE, b200q_ld_plain, false, int>(I0, SP0, 0, itl);
@@ -458,7 +464,7 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
                     } else if (sgm.bias) { v0 += sgm.bias[crow]; if (two) v1 += sgm.bias[crow + 1]; }
                     if (lane == 0) { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
                 }
-                t = 0; ++j;
+                t = 0;
             }
         }
     }
@@ -534,7 +540,7 @@ static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_
     mmvq_ring_args ra; ra.a = a; ra.g = g0;
     for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
     if (a.M_total >= (int64_t)1 << 30) return -100;
-    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512;
+    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 256;
     const size_t budget = 112 * 1024;                   // two CTAs per SM (same kernel, or this one + the next under PDL)
     const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
     int ncw = 11, S = 0;                                // consumer warps (+1 producer warp)
