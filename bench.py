@@ -130,6 +130,8 @@ class Model:
         self.h = f(n, N_EMBD); self.a = f(n, N_FF // tp); self.x2 = f(n, N_EMBD); self.logits = f(1, N_VOCAB // tp)
         self.u = f(n, N_FF // tp) if n > 8 else None
         self.g = f(n, N_FF // tp) if n > 8 else None
+        b = lambda *s: t.empty(s, dtype=t.bfloat16, device="cuda")
+        self.xb, self.qb, self.hb, self.ab = (b(n, N_EMBD), b(n, N_EMBD // tp), b(n, N_EMBD), b(n, N_FF // tp)) if n > 8 else (None,) * 4
 
     def allreduce(self, t):
         if self.tp > 1:
@@ -151,11 +153,15 @@ class Model:
         be, t = self.be, self.torch
         x = self.x
         for L in self.layers:
-            be.mul_mat(L["wq"], x, out=self.q); be.mul_mat(L["wk"], x, out=self.kk); be.mul_mat(L["wv"], x, out=self.v)
-            be.mul_mat(L["wo"], self.q, out=self.h); self.allreduce(self.h)
-            be.mul_mat(L["up"], self.h, out=self.u); be.mul_mat(L["gate"], self.h, out=self.g)
+            be.convert_activations(x, self.xb)          # f32 -> bf16 once per distinct activation (shared by Q,K,V)
+            be.mul_mat(L["wq"], x, out=self.q, x_bf16=self.xb); be.mul_mat(L["wk"], x, out=self.kk, x_bf16=self.xb); be.mul_mat(L["wv"], x, out=self.v, x_bf16=self.xb)
+            be.convert_activations(self.q, self.qb)
+            be.mul_mat(L["wo"], self.q, out=self.h, x_bf16=self.qb); self.allreduce(self.h)
+            be.convert_activations(self.h, self.hb)
+            be.mul_mat(L["up"], self.h, out=self.u, x_bf16=self.hb); be.mul_mat(L["gate"], self.h, out=self.g, x_bf16=self.hb)
             t.mul(t.nn.functional.silu(self.g), self.u, out=self.a)         # glue, not the hot path
-            be.mul_mat(L["down"], self.a, out=self.x2); self.allreduce(self.x2)
+            be.convert_activations(self.a, self.ab)
+            be.mul_mat(L["down"], self.a, out=self.x2, x_bf16=self.ab); self.allreduce(self.x2)
             x = self.x2
         be.mul_mat(self.head, x[-1:], out=self.logits)
 
@@ -323,7 +329,7 @@ def main():
         tfs = fl / (ms_pp * 1e-3) / 1e12
         line["pp512"] = {"metric": "llama-bench pp512 tok/s (MUL_MAT hot path)", "value": n * 1000.0 / ms_pp, "unit": "tok/s", "ms_per_step": ms_pp, "steps": pp_steps,
                          "dtype": "bf16 x bf16 -> f32 (tcgen05 kind::f16)", "e2e": {"value": n * 1000.0 / ms_pp_e2e, "unit": "tok/s", "h2d_bytes_per_step": n * N_EMBD * 4, "d2h_bytes_per_step": (N_VOCAB // world) * 4},
-                         "roofline": {"bound": "tensor", "kernel": "k_gemm_bf16 (+k_dequant_bf16, k_f32_to_bf16)", "achieved": tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfs / tf_peak,
+                         "roofline": {"bound": "tensor", "kernel": "k_gemm_q<IQ4_NL> (fused dequant + tcgen05; + k_f32_to_bf16)", "achieved": tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfs / tf_peak,
                                       "traffic": None, "algorithmic_flops_per_step": fl, "peak_source": peak_src + " sustained"}}
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu:

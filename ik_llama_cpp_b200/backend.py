@@ -109,15 +109,32 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return ws
 
 
-def mul_mat(w: QuantTensor, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
-    """GGML_OP_MUL_MAT: x f32 [N, K] -> dst f32 [N, M]  (ggml ne: src1 [K, N], dst [M, N])."""
+def convert_activations(x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """f32 [N, K] -> bf16 [N, K] once, for several prefill MUL_MATs that share src1 (Q,K,V / up,gate)."""
+    _require_cuda()
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    n, k = x.shape
+    xb = out if out is not None else torch.empty((n, k), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().b200q_convert_f32_bf16(x.data_ptr(), x.stride(0), xb.data_ptr(), k, n, _stream()), "b200q_convert_f32_bf16")
+    return xb
+
+
+def mul_mat(w: QuantTensor, x: torch.Tensor, out: torch.Tensor | None = None, x_bf16: torch.Tensor | None = None) -> torch.Tensor:
+    """GGML_OP_MUL_MAT: x f32 [N, K] -> dst f32 [N, M]  (ggml ne: src1 [K, N], dst [M, N]).
+    x_bf16: optional result of convert_activations(x) (prefill only) to skip the per-call conversion."""
     _require_cuda()
     assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == w.k and x.stride(1) == 1
     n = x.shape[0]
     dst = out if out is not None else torch.empty((n, w.m), dtype=torch.float32, device=x.device)
     L = _lib.lib()
     with torch.cuda.device(x.device):
-        if n <= MMVQ_MAX_BATCH_SIZE:
+        if n > MMVQ_MAX_BATCH_SIZE and x_bf16 is not None:
+            assert x_bf16.dtype == torch.bfloat16 and x_bf16.shape == x.shape and x_bf16.is_contiguous()
+            need = w.m * w.k * 2 + 256
+            ws = _workspace(need, x.device)
+            check(L.b200q_mul_mat_gemm_bf16(w.ggml_type, w.ptr, x_bf16.data_ptr(), dst.data_ptr(), w.m, w.k, n, ws.data_ptr(), ws.numel(), _stream()), "b200q_mul_mat_gemm_bf16")
+        elif n <= MMVQ_MAX_BATCH_SIZE:
             check(L.b200q_mul_mat_vec(w.ggml_type, w.ptr, x.data_ptr(), dst.data_ptr(), w.m, w.k, n, x.stride(0), None, _stream()), "b200q_mul_mat_vec")
         else:
             xc = x if x.is_contiguous() else x.contiguous()

@@ -10,7 +10,10 @@
 
 size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
 int b200q_launch_gemm(int type, const void * W, const float * x, int64_t x_stride, float * dst, int64_t M, int64_t K, int64_t N,
-                      void * ws, size_t ws_bytes, int sm_count, cudaStream_t st);
+                      void * ws, size_t ws_bytes, int sm_count, int fused, cudaStream_t st);
+int b200q_launch_gemm_bf16x(int type, const void * W, const void * xb, float * dst, int64_t M, int64_t K, int64_t N,
+                            void * wscratch, size_t ws_bytes, int sm_count, int fused, cudaStream_t st);
+int b200q_launch_f32_to_bf16(const float * x, int64_t x_stride, void * out, int64_t K, int64_t N, cudaStream_t st);
 
 namespace {
 thread_local char g_err[512] = "";
@@ -53,6 +56,7 @@ int ensure(scratch & s, size_t n) {
 thread_local scratch g_x, g_y, g_ws, g_stage;
 // programmatic dependent launch for the decode kernels (default on; B200Q_PDL=0 or b200q_set_option("pdl",0) disables)
 int & opt_ring() { static int v = [] { const char * e = getenv("B200Q_RING"); return e ? atoi(e) : 1; }(); return v; }
+int & opt_fused() { static int v = [] { const char * e = getenv("B200Q_FUSED_GEMM"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_pdl() { static int v = [] { const char * e = getenv("B200Q_PDL"); return e ? atoi(e) : 1; }(); return v; }
 }  // namespace
 
@@ -63,6 +67,7 @@ const char * b200q_last_error(void) { return g_err; }
 int b200q_set_option(const char * key, int value) {
     if (key && !strcmp(key, "pdl")) { opt_pdl() = value; return B200Q_OK; }
     if (key && !strcmp(key, "ring")) { opt_ring() = value; return B200Q_OK; }
+    if (key && !strcmp(key, "fused_gemm")) { opt_fused() = value; return B200Q_OK; }
     return fail(B200Q_E_ARG, "b200q_set_option: unknown option");
 }
 int b200q_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
@@ -163,7 +168,17 @@ int b200q_mul_mat_gemm(int type, const void * W, const float * x, float * dst, i
                        void * workspace, size_t workspace_bytes, void * stream) {
     if (!W || !x || !dst || !workspace || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_gemm: bad argument");
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_gemm: no CUDA device");
-    return check_launch(b200q_launch_gemm(type, W, x, k, dst, m, k, n, workspace, workspace_bytes, di.sm_count, (cudaStream_t)stream), "b200q_mul_mat_gemm");
+    return check_launch(b200q_launch_gemm(type, W, x, k, dst, m, k, n, workspace, workspace_bytes, di.sm_count, opt_fused(), (cudaStream_t)stream), "b200q_mul_mat_gemm");
+}
+int b200q_convert_f32_bf16(const float * x, int64_t x_stride, void * out_bf16, int64_t k, int64_t n, void * stream) {
+    if (!x || !out_bf16 || n < 1) return fail(B200Q_E_ARG, "b200q_convert_f32_bf16: bad argument");
+    return check_launch(b200q_launch_f32_to_bf16(x, x_stride, out_bf16, k, n, (cudaStream_t)stream), "b200q_convert_f32_bf16");
+}
+int b200q_mul_mat_gemm_bf16(int type, const void * W, const void * x_bf16, float * dst, int64_t m, int64_t k, int64_t n,
+                            void * workspace, size_t workspace_bytes, void * stream) {
+    if (!W || !x_bf16 || !dst || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_gemm_bf16: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_gemm_bf16: no CUDA device");
+    return check_launch(b200q_launch_gemm_bf16x(type, W, x_bf16, dst, m, k, n, workspace, workspace_bytes, di.sm_count, opt_fused(), (cudaStream_t)stream), "b200q_mul_mat_gemm_bf16");
 }
 int b200q_mul_mat(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
                   void * workspace, size_t workspace_bytes, void * stream) {

@@ -286,6 +286,12 @@ __device__ __forceinline__ void rb_wait(uint64_t * bar, uint32_t parity) {
     asm volatile("{\n\t.reg .pred p;\n\tRW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra RD_%=;\n\tbra RW_%=;\n\tRD_%=:\n\t}"
                  ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ bool rb_test(uint64_t * bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
@@ -375,13 +381,19 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
 
     if (warp == 0) {
         // ---------------- producer: refill a stage as soon as its consumer has released it ----------------
+        // All lanes poll their consumer's empty barrier with a NON-blocking test_wait and stay converged: a lane parked in a
+        // blocking try_wait would stall the refills of the other ten consumers that share this warp.
         uint32_t epar = 1;               // first pass over the ring: the S initial units are already issued
         int k = 0;
-        while (!pdone) {
-            rb_wait(&empty0[lane * S + pst], epar ^ 1);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            produce_one();
-            if (++k == S) { k = 0; epar ^= 1; }
+        while (__any_sync(0xffffffffu, !pdone)) {
+            bool ready = false;
+            if (!pdone) ready = rb_test(&empty0[lane * S + pst], epar ^ 1);
+            if (ready) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                produce_one();
+                if (++k == S) { k = 0; epar ^= 1; }
+            }
+            if (!__any_sync(0xffffffffu, ready)) __nanosleep(64);
         }
         return;
     }

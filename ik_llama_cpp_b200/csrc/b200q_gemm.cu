@@ -208,6 +208,182 @@ k_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 1) tmem_dealloc(tmem_base, BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused prefill kernel: the A operand is dequantised INSIDE the kernel (no bf16 weight scratch in HBM).
+//   warp 0      TMA producer: (a) packed weight planes of a 128-row x 256-weight block (low-bit plane 128 B/row with
+//               SWIZZLE_128B, scale/meta plane 16 B/row) into a 2-deep RAW ring, (b) bf16 activation tiles into the B ring
+//   warp 1      MMA issuer (tcgen05.mma kind::f16, M=128, N=BN, K=16), A and B from shared memory
+//   warps 2..5  thread = one weight row: canonical decode (PRMT-LUT / mask) of 2 items per 64-wide k-block ->
+//               bf16(dl*q - ml) -> the 128-byte K-major SWIZZLE_128B row of the A stage; after the main loop the same
+//               warps run the epilogue (their warp%4 is their TMEM lane quadrant)
+// Pipelines: raw_full/raw_empty (TMA <-> dequant), a_full/a_empty (dequant <-> MMA), b_full/b_empty (TMA <-> MMA),
+// tmem_full (MMA -> epilogue).  Generic-proxy smem writes of the dequant warps are published to the tensor core with
+// fence.proxy.async before the a_full arrive.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RAW_K = 256;                       // weights per row per raw stage (= 8 items, 4 MMA k-blocks)
+
+template <int BN> struct gemmq_cfg {
+    static constexpr int A_STAGES = 3, B_STAGES = 3, RAW_STAGES = 2;
+    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static constexpr int RAW_P0 = BM * 128, RAW_P1 = BM * 16, RAW_BYTES = RAW_P0 + RAW_P1;     // low-bit plane | meta plane
+    static constexpr size_t SMEM = 1024 + (size_t)A_STAGES * A_BYTES + (size_t)B_STAGES * B_BYTES + (size_t)RAW_STAGES * RAW_BYTES + 256;
+};
+
+__device__ __forceinline__ void mbar_arrive_plain(uint64_t * bar) { mbar_arrive(bar); }
+
+template <int TYPE, int BN>
+__global__ void __launch_bounds__(192, 1)
+k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ CUtensorMap tmB,
+         float * __restrict__ dst, int M, int N, int K, int k_split) {
+    using cfg = gemmq_cfg<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char * smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char * sA = smem;
+    unsigned char * sB = sA + (size_t)cfg::A_STAGES * cfg::A_BYTES;
+    unsigned char * sR = sB + (size_t)cfg::B_STAGES * cfg::B_BYTES;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(sR + (size_t)cfg::RAW_STAGES * cfg::RAW_BYTES);
+    uint64_t * a_full = bars, * a_empty = a_full + cfg::A_STAGES, * b_full = a_empty + cfg::A_STAGES, * b_empty = b_full + cfg::B_STAGES;
+    uint64_t * raw_full = b_empty + cfg::B_STAGES, * raw_empty = raw_full + cfg::RAW_STAGES, * tmem_full = raw_empty + cfg::RAW_STAGES;
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // K is walked in raw blocks of 256 weights; split-K over blockIdx.z in units of raw blocks
+    const int nr_total = (K + RAW_K - 1) / RAW_K;
+    const int nr_per = (nr_total + k_split - 1) / k_split;
+    const int rb0 = blockIdx.z * nr_per, rb1 = min(nr_total, rb0 + nr_per);
+    const int nr = rb1 - rb0;                                   // raw blocks of this CTA (may be <= 0)
+    const int kb_begin = rb0 * (RAW_K / BK);
+    const int kb_end = min((K + BK - 1) / BK, rb1 * (RAW_K / BK));
+    const int nk = kb_end - kb_begin;                           // 64-wide MMA k-blocks of this CTA
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cfg::A_STAGES; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < cfg::B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < cfg::RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmP0); tma_prefetch_desc(&tmP1); tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // interleave: one raw block, then its (up to) four B tiles
+            int ib = 0;
+            for (int r = 0; r < nr; ++r) {
+                const int rs = r % cfg::RAW_STAGES; const uint32_t rph = (r / cfg::RAW_STAGES) & 1;
+                mbar_wait(&raw_empty[rs], rph ^ 1);
+                unsigned char * raw = sR + (size_t)rs * cfg::RAW_BYTES;
+                mbar_expect_tx(&raw_full[rs], cfg::RAW_BYTES);
+                tma_load_2d(raw, &tmP0, &raw_full[rs], (rb0 + r) * 128, m0);               // bytes along the row
+                tma_load_2d(raw + cfg::RAW_P0, &tmP1, &raw_full[rs], (rb0 + r) * 16, m0);
+                for (int q = 0; q < RAW_K / BK && ib < nk; ++q, ++ib) {
+                    const int s = ib % cfg::B_STAGES; const uint32_t ph = (ib / cfg::B_STAGES) & 1;
+                    mbar_wait(&b_empty[s], ph ^ 1);
+                    mbar_expect_tx(&b_full[s], cfg::B_BYTES);
+                    tma_load_2d(sB + (size_t)s * cfg::B_BYTES, &tmB, &b_full[s], (kb_begin + ib) * BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            for (int i = 0; i < nk; ++i) {
+                const int sa = i % cfg::A_STAGES; const uint32_t pa = (i / cfg::A_STAGES) & 1;
+                const int sb = i % cfg::B_STAGES; const uint32_t pb = (i / cfg::B_STAGES) & 1;
+                mbar_wait(&a_full[sa], pa);
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
+                const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(sA + (size_t)sa * cfg::A_BYTES));
+                const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(sB + (size_t)sb * cfg::B_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_f16_ss(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&a_empty[sa]);
+                umma_commit(&b_empty[sb]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // ---------------- dequant warps (then epilogue) ----------------
+        const int q4 = warp & 3;                                  // TMEM lane quadrant == row quadrant of the tile
+        const int row = 32 * q4 + lane;                           // row of the tile owned by this thread
+        const b200q_kv4 T = b200q_kv4_init();
+        int ia = 0;
+        for (int r = 0; r < nr; ++r) {
+            const int rs = r % cfg::RAW_STAGES; const uint32_t rph = (r / cfg::RAW_STAGES) & 1;
+            mbar_wait(&raw_full[rs], rph);
+            const unsigned char * raw = sR + (size_t)rs * cfg::RAW_BYTES;
+            b200q_planes SP; SP.p[0] = raw; SP.p[1] = raw + cfg::RAW_P0; SP.p[2] = SP.p[3] = SP.p[4] = nullptr; SP.n32 = 8; SP.nb = 1;
+            for (int q = 0; q < RAW_K / BK && ia < nk; ++q, ++ia) {
+                const int sa = ia % cfg::A_STAGES; const uint32_t pa = (ia / cfg::A_STAGES) & 1;
+                mbar_wait(&a_empty[sa], pa ^ 1);
+                unsigned char * arow = sA + (size_t)sa * cfg::A_BYTES + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {                     // two items = 64 weights of this row
+                    const int it = 2 * q + h;
+                    b200q_item I; b200q_canon C;
+                    b200q_load_item<TYPE, b200q_ld_plain, false, int, true>(I, SP, row, it);
+                    b200q_decode_item<TYPE>(I, it, C, T);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {                 // 4 chunks of 8 weights (16 bytes of bf16)
+                        uint32_t o[4];
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {             // weights e = 8c + 2p, 8c + 2p + 1
+                            const int e = 8 * c + 2 * p;
+                            const int w = (8 * c) / 4 + p / 2;    // word of va/vb holding them
+                            const int sh = 16 * (p & 1);
+                            int q0 = (int)(int8_t)(C.va[w] >> sh), q1 = (int)(int8_t)(C.va[w] >> (sh + 8));
+                            if (b200q_traits<TYPE>::HAS_B) { q0 += (int)(int8_t)(C.vb[w] >> sh); q1 += (int)(int8_t)(C.vb[w] >> (sh + 8)); }
+                            const float f0 = fmaf(C.dl[e / 16], (float)q0, -C.ml[e / 16]), f1 = fmaf(C.dl[e / 16], (float)q1, -C.ml[e / 16]);
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
+                            o[p] = *reinterpret_cast<uint32_t *>(&b2);
+                        }
+                        const int chunk = (4 * h + c) ^ (row & 7);
+                        *reinterpret_cast<uint4 *>(arow + chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                }
+                fence_proxy_async();                              // make the generic-proxy writes visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[sa]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[rs]);
+        }
+        // ---------------- epilogue ----------------
+        if (nk > 0) {
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+            const int m = m0 + row;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                if (n0 + c0 >= N) break;
+                uint32_t rr[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)c0, rr);
+                tmem_ld_wait();
+                if (m < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = n0 + c0 + j;
+                        if (n < N) {
+                            float * p = dst + (size_t)n * M + m;
+                            if (k_split > 1) atomicAdd(p, __uint_as_float(rr[j])); else *p = __uint_as_float(rr[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN);
+}
+
 // f32 [N][K] (row stride xs) -> bf16 [N][K]
 __global__ void k_f32_to_bf16(const float * __restrict__ x, int64_t xs, __nv_bfloat16 * __restrict__ out, int64_t K, int64_t N) {
     const int64_t total4 = N * (K / 4);
@@ -262,6 +438,42 @@ int launch_gemm_bf16(const void * A_bf16, const void * B_bf16, float * dst, int6
     return (int)cudaGetLastError();
 }
 
+
+// uint8 matrix [rows][row_bytes] (row_bytes contiguous), box = box_bytes x box_rows
+int make_tmap_u8(CUtensorMap * tm, const void * ptr, int64_t rows, int64_t row_bytes, int box_bytes, int box_rows, bool swizzle128) {
+    encode_tiled_fn enc = get_encode(); if (!enc) return -1;
+    cuuint64_t dims[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_bytes, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+// types whose planes are {16 B / item low bits, 16 B / 256 weights of scales+meta}: IQ4_NL/Q4_0 (8 halfs), Q4_K, IQ4_K
+constexpr bool gemmq_supported(int type) {
+    return type == B200Q_TYPE_IQ4_NL || type == B200Q_TYPE_Q4_0 || type == B200Q_TYPE_Q4_K || type == B200Q_TYPE_IQ4_K;
+}
+
+template <int TYPE, int BN>
+int launch_gemm_q(const void * W, const b200q_layout & L, const void * B_bf16, float * dst, int64_t M, int64_t N, int64_t K, int k_split, cudaStream_t st) {
+    using cfg = gemmq_cfg<BN>;
+    CUtensorMap tmP0, tmP1, tmB;
+    const int64_t p1_row = (K / 256) * 16;
+    if (make_tmap_u8(&tmP0, (const char *)W + L.plane_off[0], M, K / 2, 128, BM, true)) return -10;
+    if (make_tmap_u8(&tmP1, (const char *)W + L.plane_off[1], M, p1_row, 16, BM, false)) return -13;
+    if (make_tmap_bf16(&tmB, B_bf16, N, K, BN)) return -11;
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(k_gemm_q<TYPE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM) != cudaSuccess) return -12;
+        configured = true;
+    }
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)k_split);
+    k_gemm_q<TYPE, BN><<<grid, 192, cfg::SMEM, st>>>(tmP0, tmP1, tmB, dst, (int)M, (int)N, (int)K, k_split);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {
@@ -270,23 +482,47 @@ size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {
 }
 
 // A = planes of `type` [M][K]; X = f32 [N][K]; dst f32 [N][M].  Workspace: bf16 X followed by bf16 W.
-int b200q_launch_gemm(int type, const void * W, const float * x, int64_t x_stride, float * dst, int64_t M, int64_t K, int64_t N,
-                      void * ws, size_t ws_bytes, int sm_count, cudaStream_t st) {
-    if (ws_bytes < b200q_gemm_workspace_bytes(type, M, K, N)) return -5;
+int b200q_launch_f32_to_bf16(const float * x, int64_t x_stride, void * out, int64_t K, int64_t N, cudaStream_t st) {
+    if (K % 4) return -2;
+    const int64_t total4 = N * (K / 4); int64_t nb = (total4 + 255) / 256; if (nb > 148 * 32) nb = 148 * 32; if (nb < 1) nb = 1;
+    k_f32_to_bf16<<<(unsigned)nb, 256, 0, st>>>(x, x_stride ? x_stride : K, (__nv_bfloat16 *)out, K, N);
+    return (int)cudaGetLastError();
+}
+
+// A = planes of `type` [M][K]; X = bf16 [N][K] (already converted); dst f32 [N][M].  ws: bf16 W scratch for the unfused path.
+int b200q_launch_gemm_bf16x(int type, const void * W, const void * xb, float * dst, int64_t M, int64_t K, int64_t N,
+                            void * wscratch, size_t ws_bytes, int sm_count, int fused, cudaStream_t st) {
     if (K % 8) return -2;
     b200q_layout L; if (b200q_make_layout(type, M, K, &L)) return -1;
-    __nv_bfloat16 * xb = (__nv_bfloat16 *)ws;
-    __nv_bfloat16 * wb = (__nv_bfloat16 *)((char *)ws + b200q_align_up(N * K * 2, 256));
-    { const int64_t total4 = N * (K / 4); int64_t nb = (total4 + 255) / 256; if (nb > 148 * 32) nb = 148 * 32; if (nb < 1) nb = 1;
-      k_f32_to_bf16<<<(unsigned)nb, 256, 0, st>>>(x, x_stride ? x_stride : K, xb, K, N); }
-    int rc = b200q_launch_dequant_bf16(W, L, wb, st); if (rc) return rc;
     // tile / split selection: fill ~1 wave of the SMs
     const int64_t mt = (M + BM - 1) / BM;
     const bool bn256 = N >= 256 && mt * ((N + 255) / 256) >= sm_count / 2;
     const int64_t tiles = bn256 ? mt * ((N + 255) / 256) : mt * ((N + 127) / 128);
+    const bool use_fused = fused && gemmq_supported(type) && K % 256 == 0;
     int k_split = 1;
-    const int64_t nk = (K + BK - 1) / BK;
-    while (tiles * k_split * 2 <= sm_count && k_split * 2 <= 8 && nk / (k_split * 2) >= 8) k_split *= 2;
+    const int64_t nk = use_fused ? K / 256 : (K + BK - 1) / BK;
+    const int64_t min_per = use_fused ? 2 : 8;
+    while (tiles * k_split * 2 <= sm_count && k_split * 2 <= 8 && nk / (k_split * 2) >= min_per) k_split *= 2;
     if (k_split > 1) { cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)M * N * sizeof(float), st); if (e != cudaSuccess) return -3; }
-    return bn256 ? launch_gemm_bf16<256>(wb, xb, dst, M, N, K, k_split, st) : launch_gemm_bf16<128>(wb, xb, dst, M, N, K, k_split, st);
+    if (use_fused) {
+        switch (type) {
+#define GQ(T) case T: return bn256 ? launch_gemm_q<T, 256>(W, L, xb, dst, M, N, K, k_split, st) : launch_gemm_q<T, 128>(W, L, xb, dst, M, N, K, k_split, st);
+            GQ(B200Q_TYPE_IQ4_NL) GQ(B200Q_TYPE_Q4_0) GQ(B200Q_TYPE_Q4_K) GQ(B200Q_TYPE_IQ4_K)
+#undef GQ
+            default: break;
+        }
+    }
+    if (ws_bytes < (size_t)b200q_align_up(M * K * 2, 256)) return -5;
+    int rc = b200q_launch_dequant_bf16(W, L, wscratch, st); if (rc) return rc;
+    return bn256 ? launch_gemm_bf16<256>(wscratch, xb, dst, M, N, K, k_split, st) : launch_gemm_bf16<128>(wscratch, xb, dst, M, N, K, k_split, st);
+}
+
+// A = planes of `type` [M][K]; X = f32 [N][K]; dst f32 [N][M].  Workspace: bf16 X followed by bf16 W (unfused path only).
+int b200q_launch_gemm(int type, const void * W, const float * x, int64_t x_stride, float * dst, int64_t M, int64_t K, int64_t N,
+                      void * ws, size_t ws_bytes, int sm_count, int fused, cudaStream_t st) {
+    if (ws_bytes < b200q_gemm_workspace_bytes(type, M, K, N)) return -5;
+    void * xb = ws;
+    void * wb = (char *)ws + b200q_align_up(N * K * 2, 256);
+    int rc = b200q_launch_f32_to_bf16(x, x_stride, xb, K, N, st); if (rc) return rc;
+    return b200q_launch_gemm_bf16x(type, W, xb, dst, M, K, N, wb, ws_bytes - (size_t)b200q_align_up(N * K * 2, 256), sm_count, fused, st);
 }

@@ -461,33 +461,36 @@ B200Q_HD b200q_planes b200q_planes_from(const uint8_t * base, const b200q_layout
 // item index `it` counts 32-weight items along the row: it in [0, K/32).  LD = load policy; ROWPLANE = also fetch the
 // per-row scale (the smem-ring kernel passes stage-relative planes with row = 0 and fetches the row scale itself).
 template <class T> struct b200q_ident { typedef T type; };
-template <int TYPE, class LD = b200q_ld_global, bool ROWPLANE = true, class IDX = int64_t>
-B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, typename b200q_ident<IDX>::type row, typename b200q_ident<IDX>::type it) {
+// SWZ: plane 0 is a TMA SWIZZLE_128B tile of 8 items (128 bytes) per row: 16-byte chunk c of row r sits at chunk c ^ (r & 7).
+template <int TYPE, class LD = b200q_ld_global, bool ROWPLANE = true, class IDX = int64_t, bool SWZ = false>
+B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, typename b200q_ident<IDX>::type row, typename b200q_ident<IDX>::type it_) {
     const IDX n32 = (IDX)P.n32, nb = (IDX)P.nb;
+    const IDX it = it_;
+    const IDX it0 = SWZ ? (IDX)(it_ ^ (row & 7)) : it_;      // index used for the low-bit plane only
     if (TYPE == B200Q_TYPE_IQ4_NL || TYPE == B200Q_TYPE_Q4_0) {
-        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         I.m[0] = LD::ld2(P.p[1] + (row * n32 + it) * 2);
     } else if (TYPE == B200Q_TYPE_Q8_0) {
         const uint8_t * p = P.p[0] + (row * n32 + it) * 32;
         LD::ld16(I.q, p); LD::ld16(I.q + 4, p + 16);
         I.m[0] = LD::ld2(P.p[1] + (row * n32 + it) * 2);
     } else if (TYPE == B200Q_TYPE_Q4_K || TYPE == B200Q_TYPE_IQ4_K) {
-        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         LD::ld16(I.m, P.p[1] + (row * nb + it / 8) * 16);
     } else if (TYPE == B200Q_TYPE_Q5_K || TYPE == B200Q_TYPE_IQ5_K) {
-        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         I.h[0] = LD::ld4(P.p[1] + (row * n32 + it) * 4);
         LD::ld16(I.m, P.p[2] + (row * nb + it / 8) * 16);
     } else if (TYPE == B200Q_TYPE_Q6_K) {
-        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         LD::ld8(I.h, P.p[1] + (row * n32 + it) * 8);
         I.m[0] = LD::ld2(P.p[2] + (row * n32 + it) * 2);     // two int8 scales of this item
         I.m[1] = LD::ld2(P.p[3] + (row * nb + it / 8) * 2);  // d
     } else if (TYPE == B200Q_TYPE_IQ4_XS) {
-        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         LD::ld8(I.m, P.p[1] + (row * nb + it / 8) * 8);
     } else if (TYPE == B200Q_TYPE_IQ4_KS) {
-        LD::ld16(I.q, P.p[0] + (row * n32 + it) * 16);
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         I.m[0] = LD::ld1(P.p[1] + (row * nb + it / 8) * 8 + it % 8);
         if (ROWPLANE) { uint32_t r = LD::ld4(P.p[2] + row * 4); memcpy(&I.rs, &r, 4); }
     } else if (TYPE == B200Q_TYPE_IQ2_BN) {           // 64 weights per wire block: item = half a block (see decode)

@@ -144,6 +144,29 @@ def test_gemm_vs_oracle(be, oracle, ref_or_none, name, n):
     assert e <= 2e-5, f"{name} n={n}: NMSE {e}"          # ours: bf16 inputs, f32 accumulate
 
 
+@pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K", "Q6_K"])
+def test_gemm_shared_activation_and_unfused_path(be, oracle, name):
+    """convert_activations once + _bf16 entry point; fused (in-kernel dequant) and unfused (bf16 scratch) kernels agree."""
+    import ik_llama_cpp_b200 as pkg
+    t = GGML_TYPE[name]
+    m, k, n = 256, 768, 40
+    wire = make_wire(oracle, name, m, k, seed=91 + t)
+    x = np.random.default_rng(17).standard_normal((n, k)).astype(np.float32)
+    w = be.set_tensor(t, wire, m, k)
+    xg = torch.from_numpy(x).cuda()
+    xb = be.convert_activations(xg)
+    assert torch.equal(xb, xg.to(torch.bfloat16))
+    exact = oracle.mul_mat_exact(t, wire, x, m)
+    y1 = be.mul_mat(w, xg, x_bf16=xb).cpu().numpy()
+    pkg.lib().b200q_set_option(b"fused_gemm", 0)
+    try:
+        y0 = be.mul_mat(w, xg, x_bf16=xb).cpu().numpy()
+    finally:
+        pkg.lib().b200q_set_option(b"fused_gemm", 1)
+    assert nmse(y1, exact) <= 2e-5 and nmse(y0, exact) <= 2e-5
+    assert nmse(y1, y0) <= 1e-9          # same bf16 operands, same MMA order
+
+
 def test_gemm_llama_shape_properties(be, oracle):
     """pp512 shape 4096x4096x512: GEMM path must agree with the mat-vec path column by column (two independent kernels)
     within their documented noise, and with the oracle on a sample of columns."""
