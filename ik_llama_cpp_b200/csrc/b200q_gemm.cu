@@ -221,21 +221,48 @@ k_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 // fence.proxy.async before the a_full arrive.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int RAW_K = 256;                       // weights per row per raw stage (= 8 items, 4 MMA k-blocks)
+constexpr int DQ_WARPS = 8;                      // dequant / epilogue warps (warps 2..9)
 
-template <int BN> struct gemmq_cfg {
-    static constexpr int A_STAGES = 3, B_STAGES = 3, RAW_STAGES = 2;
+// NB = number of 256-column accumulators (BN = 256*NB), or BN = 128 when NB == 0
+template <int NB> struct gemmq_cfg {
+    static constexpr int BN = NB == 0 ? 128 : 256 * NB;
+    static constexpr int A_STAGES = 3, B_STAGES = NB == 2 ? 2 : 3, RAW_STAGES = 2;
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int RAW_P0 = BM * 128, RAW_P1 = BM * 16, RAW_BYTES = RAW_P0 + RAW_P1;     // low-bit plane | meta plane
+    static constexpr int TMEM_COLS = BN;
     static constexpr size_t SMEM = 1024 + (size_t)A_STAGES * A_BYTES + (size_t)B_STAGES * B_BYTES + (size_t)RAW_STAGES * RAW_BYTES + 256;
 };
 
-__device__ __forceinline__ void mbar_arrive_plain(uint64_t * bar) { mbar_arrive(bar); }
+// carry-less per-byte add of two packed int8x4 (the A/B halves of the sign-fill LUT)
+__device__ __forceinline__ uint32_t vadd4_wrap(uint32_t a, uint32_t b) {
+    return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u);
+}
+// signed int8 lane J of a word already XOR-ed with 0x80808080 (biased by +128) -> float(v), exact:
+// place the byte under the exponent of 2^23 and subtract 2^23 + 128
+template <int J> __device__ __forceinline__ float biased_byte_to_float(uint32_t wb) {
+    const uint32_t bits = __byte_perm(wb, 0x4B000000u, 0x7650 + J);       // {byte J, 0x00, 0x00, 0x4B}
+    return __uint_as_float(bits) - 8388736.0f;
+}
 
-template <int TYPE, int BN>
-__global__ void __launch_bounds__(192, 1)
+// Fused prefill kernel: the A operand is dequantised INSIDE the kernel (no bf16 weight scratch in HBM).
+//   warp 0      TMA producer: (a) packed weight planes of a 128-row x 256-weight block (low-bit plane 128 B/row with
+//               SWIZZLE_128B, scale/meta plane 16 B/row) into a 2-deep RAW ring, (b) bf16 activation tiles into the B ring
+//   warp 1      MMA issuer: tcgen05.mma kind::f16, M=128, N=256 (or 128), K=16; with NB=2 the SAME dequantised A stage feeds two
+//               accumulators (512 TMEM columns = 512 tokens), so every weight is decoded once per 512 tokens
+//   warps 2..9  thread = (weight row, 32-weight item): canonical decode (PRMT-LUT / mask) -> exact int8->f32 via the 2^23
+//               exponent trick -> bf16(dl*q - ml) -> its 64 bytes of the 128-byte K-major SWIZZLE_128B row of the A stage;
+//               after the main loop the same warps run the epilogue (warp%4 = TMEM lane quadrant, warp/4 = column half)
+// Pipelines: raw_full/raw_empty (TMA <-> dequant), a_full/a_empty (dequant <-> MMA), b_full/b_empty (TMA <-> MMA),
+// tmem_full (MMA -> epilogue).  Generic-proxy smem writes of the dequant warps are published to the tensor core with
+// fence.proxy.async before the a_full arrive.
+template <int TYPE, int NB>
+__global__ void __launch_bounds__(64 + 32 * DQ_WARPS, 1)
 k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ CUtensorMap tmB,
          float * __restrict__ dst, int M, int N, int K, int k_split) {
-    using cfg = gemmq_cfg<BN>;
+    using cfg = gemmq_cfg<NB>;
+    constexpr int BN = cfg::BN;
+    constexpr int MMA_N = NB == 0 ? 128 : 256;
+    constexpr int N_ACC = NB == 0 ? 1 : NB;
     extern __shared__ unsigned char smem_raw[];
     unsigned char * smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char * sA = smem;
@@ -258,14 +285,14 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
     const int nk = kb_end - kb_begin;                           // 64-wide MMA k-blocks of this CTA
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < cfg::A_STAGES; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < cfg::A_STAGES; ++s) { mbar_init(&a_full[s], DQ_WARPS); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < cfg::B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < cfg::RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+        for (int s = 0; s < cfg::RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], DQ_WARPS); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmP0); tma_prefetch_desc(&tmP1); tma_prefetch_desc(&tmB);
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    if (warp == 1) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -273,7 +300,6 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
 
     if (warp == 0) {
         if (lane == 0) {
-            // interleave: one raw block, then its (up to) four B tiles
             int ib = 0;
             for (int r = 0; r < nr; ++r) {
                 const int rs = r % cfg::RAW_STAGES; const uint32_t rph = (r / cfg::RAW_STAGES) & 1;
@@ -286,13 +312,15 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
                     const int s = ib % cfg::B_STAGES; const uint32_t ph = (ib / cfg::B_STAGES) & 1;
                     mbar_wait(&b_empty[s], ph ^ 1);
                     mbar_expect_tx(&b_full[s], cfg::B_BYTES);
-                    tma_load_2d(sB + (size_t)s * cfg::B_BYTES, &tmB, &b_full[s], (kb_begin + ib) * BK, n0);
+#pragma unroll
+                    for (int j = 0; j < N_ACC; ++j)
+                        tma_load_2d(sB + (size_t)s * cfg::B_BYTES + (size_t)j * MMA_N * BK * 2, &tmB, &b_full[s], (kb_begin + ib) * BK, n0 + j * MMA_N);
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            constexpr uint32_t idesc = make_idesc_bf16(BM, MMA_N);
             for (int i = 0; i < nk; ++i) {
                 const int sa = i % cfg::A_STAGES; const uint32_t pa = (i / cfg::A_STAGES) & 1;
                 const int sb = i % cfg::B_STAGES; const uint32_t pb = (i / cfg::B_STAGES) & 1;
@@ -300,18 +328,23 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
                 mbar_wait(&b_full[sb], pb);
                 tc_fence_after();
                 const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(sA + (size_t)sa * cfg::A_BYTES));
-                const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(sB + (size_t)sb * cfg::B_BYTES));
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                    umma_f16_ss(tmem_base, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                for (int j = 0; j < N_ACC; ++j) {
+                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(sB + (size_t)sb * cfg::B_BYTES + (size_t)j * MMA_N * BK * 2));
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_f16_ss(tmem_base + (uint32_t)(j * MMA_N), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
                 umma_commit(&a_empty[sa]);
                 umma_commit(&b_empty[sb]);
             }
             umma_commit(tmem_full);
         }
     } else {
-        // ---------------- dequant warps (then epilogue) ----------------
-        const int q4 = warp & 3;                                  // TMEM lane quadrant == row quadrant of the tile
+        // ---------------- dequant warps (then epilogue): thread = (row, item half) ----------------
+        const int dq = warp - 2;                                  // 0..7
+        const int q4 = warp & 3;                                  // TMEM lane quadrant of this warp (hardware rule: warp % 4)
+        const int half = dq >> 2;                                 // which 32-weight item of each 64-wide k-block / which column half in the epilogue
         const int row = 32 * q4 + lane;                           // row of the tile owned by this thread
         const b200q_kv4 T = b200q_kv4_init();
         int ia = 0;
@@ -322,31 +355,29 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
             b200q_planes SP; SP.p[0] = raw; SP.p[1] = raw + cfg::RAW_P0; SP.p[2] = SP.p[3] = SP.p[4] = nullptr; SP.n32 = 8; SP.nb = 1;
             for (int q = 0; q < RAW_K / BK && ia < nk; ++q, ++ia) {
                 const int sa = ia % cfg::A_STAGES; const uint32_t pa = (ia / cfg::A_STAGES) & 1;
+                // decode before waiting for the A slot: the raw data is already there
+                const int it = 2 * q + half;
+                b200q_item I; b200q_canon C;
+                b200q_load_item<TYPE, b200q_ld_plain, false, int, true>(I, SP, row, it);
+                b200q_decode_item<TYPE>(I, it, C, T);
+                uint32_t o[16];
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {                     // word w = weights 4w..4w+3
+                    uint32_t v = (uint32_t)C.va[w];
+                    if (b200q_traits<TYPE>::HAS_B) v = vadd4_wrap(v, (uint32_t)C.vb[w]);
+                    v ^= 0x80808080u;                             // bias +128 -> unsigned bytes
+                    const float dl = C.dl[w / 4], ml = C.ml[w / 4];
+                    const float f0 = fmaf(biased_byte_to_float<0>(v), dl, -ml), f1 = fmaf(biased_byte_to_float<1>(v), dl, -ml);
+                    const float f2 = fmaf(biased_byte_to_float<2>(v), dl, -ml), f3 = fmaf(biased_byte_to_float<3>(v), dl, -ml);
+                    __nv_bfloat162 b01 = __floats2bfloat162_rn(f0, f1), b23 = __floats2bfloat162_rn(f2, f3);
+                    o[2 * w] = *reinterpret_cast<uint32_t *>(&b01); o[2 * w + 1] = *reinterpret_cast<uint32_t *>(&b23);
+                }
                 mbar_wait(&a_empty[sa], pa ^ 1);
                 unsigned char * arow = sA + (size_t)sa * cfg::A_BYTES + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {                     // two items = 64 weights of this row
-                    const int it = 2 * q + h;
-                    b200q_item I; b200q_canon C;
-                    b200q_load_item<TYPE, b200q_ld_plain, false, int, true>(I, SP, row, it);
-                    b200q_decode_item<TYPE>(I, it, C, T);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {                 // 4 chunks of 8 weights (16 bytes of bf16)
-                        uint32_t o[4];
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {             // weights e = 8c + 2p, 8c + 2p + 1
-                            const int e = 8 * c + 2 * p;
-                            const int w = (8 * c) / 4 + p / 2;    // word of va/vb holding them
-                            const int sh = 16 * (p & 1);
-                            int q0 = (int)(int8_t)(C.va[w] >> sh), q1 = (int)(int8_t)(C.va[w] >> (sh + 8));
-                            if (b200q_traits<TYPE>::HAS_B) { q0 += (int)(int8_t)(C.vb[w] >> sh); q1 += (int)(int8_t)(C.vb[w] >> (sh + 8)); }
-                            const float f0 = fmaf(C.dl[e / 16], (float)q0, -C.ml[e / 16]), f1 = fmaf(C.dl[e / 16], (float)q1, -C.ml[e / 16]);
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
-                            o[p] = *reinterpret_cast<uint32_t *>(&b2);
-                        }
-                        const int chunk = (4 * h + c) ^ (row & 7);
-                        *reinterpret_cast<uint4 *>(arow + chunk * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-                    }
+                for (int c = 0; c < 4; ++c) {
+                    const int chunk = (4 * half + c) ^ (row & 7);
+                    *reinterpret_cast<uint4 *>(arow + chunk * 16) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
                 }
                 fence_proxy_async();                              // make the generic-proxy writes visible to the tensor core
                 __syncwarp();
@@ -355,13 +386,14 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
             __syncwarp();
             if (lane == 0) mbar_arrive(&raw_empty[rs]);
         }
-        // ---------------- epilogue ----------------
+        // ---------------- epilogue: quadrant q4, column half `half` ----------------
         if (nk > 0) {
             mbar_wait(tmem_full, 0);
             tc_fence_after();
             const int m = m0 + row;
+            constexpr int COLS_PER = BN / 2;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = half * COLS_PER; c0 < (half + 1) * COLS_PER; c0 += 32) {
                 if (n0 + c0 >= N) break;
                 uint32_t rr[32];
                 tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)c0, rr);
@@ -381,7 +413,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, BN);
+    if (warp == 1) tmem_dealloc(tmem_base, cfg::TMEM_COLS);
 }
 
 // f32 [N][K] (row stride xs) -> bf16 [N][K]
@@ -456,21 +488,21 @@ constexpr bool gemmq_supported(int type) {
     return type == B200Q_TYPE_IQ4_NL || type == B200Q_TYPE_Q4_0 || type == B200Q_TYPE_Q4_K || type == B200Q_TYPE_IQ4_K;
 }
 
-template <int TYPE, int BN>
+template <int TYPE, int NB>
 int launch_gemm_q(const void * W, const b200q_layout & L, const void * B_bf16, float * dst, int64_t M, int64_t N, int64_t K, int k_split, cudaStream_t st) {
-    using cfg = gemmq_cfg<BN>;
+    using cfg = gemmq_cfg<NB>;
     CUtensorMap tmP0, tmP1, tmB;
     const int64_t p1_row = (K / 256) * 16;
     if (make_tmap_u8(&tmP0, (const char *)W + L.plane_off[0], M, K / 2, 128, BM, true)) return -10;
     if (make_tmap_u8(&tmP1, (const char *)W + L.plane_off[1], M, p1_row, 16, BM, false)) return -13;
-    if (make_tmap_bf16(&tmB, B_bf16, N, K, BN)) return -11;
+    if (make_tmap_bf16(&tmB, B_bf16, N, K, NB == 0 ? 128 : 256)) return -11;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_gemm_q<TYPE, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM) != cudaSuccess) return -12;
+        if (cudaFuncSetAttribute(k_gemm_q<TYPE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM) != cudaSuccess) return -12;
         configured = true;
     }
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)k_split);
-    k_gemm_q<TYPE, BN><<<grid, 192, cfg::SMEM, st>>>(tmP0, tmP1, tmB, dst, (int)M, (int)N, (int)K, k_split);
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + cfg::BN - 1) / cfg::BN), (unsigned)k_split);
+    k_gemm_q<TYPE, NB><<<grid, 64 + 32 * DQ_WARPS, cfg::SMEM, st>>>(tmP0, tmP1, tmB, dst, (int)M, (int)N, (int)K, k_split);
     return (int)cudaGetLastError();
 }
 
@@ -481,7 +513,7 @@ size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {
     return (size_t)b200q_align_up(N * K * 2, 256) + (size_t)b200q_align_up(M * K * 2, 256);
 }
 
-// A = planes of `type` [M][K]; X = f32 [N][K]; dst f32 [N][M].  Workspace: bf16 X followed by bf16 W.
+// f32 [N][K] -> bf16 [N][K] (shared by the mat-muls that consume the same activation)
 int b200q_launch_f32_to_bf16(const float * x, int64_t x_stride, void * out, int64_t K, int64_t N, cudaStream_t st) {
     if (K % 4) return -2;
     const int64_t total4 = N * (K / 4); int64_t nb = (total4 + 255) / 256; if (nb > 148 * 32) nb = 148 * 32; if (nb < 1) nb = 1;
@@ -494,24 +526,32 @@ int b200q_launch_gemm_bf16x(int type, const void * W, const void * xb, float * d
                             void * wscratch, size_t ws_bytes, int sm_count, int fused, cudaStream_t st) {
     if (K % 8) return -2;
     b200q_layout L; if (b200q_make_layout(type, M, K, &L)) return -1;
-    // tile / split selection: fill ~1 wave of the SMs
     const int64_t mt = (M + BM - 1) / BM;
-    const bool bn256 = N >= 256 && mt * ((N + 255) / 256) >= sm_count / 2;
-    const int64_t tiles = bn256 ? mt * ((N + 255) / 256) : mt * ((N + 127) / 128);
     const bool use_fused = fused && gemmq_supported(type) && K % 256 == 0;
-    int k_split = 1;
-    const int64_t nk = use_fused ? K / 256 : (K + BK - 1) / BK;
-    const int64_t min_per = use_fused ? 2 : 8;
-    while (tiles * k_split * 2 <= sm_count && k_split * 2 <= 8 && nk / (k_split * 2) >= min_per) k_split *= 2;
-    if (k_split > 1) { cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)M * N * sizeof(float), st); if (e != cudaSuccess) return -3; }
     if (use_fused) {
+        // one CTA dequantises a 128-row block once for up to 512 tokens (two 256-column accumulators in TMEM);
+        // split-K (f32 atomics) fills the SMs when there are few row blocks
+        const int nb = N > 256 ? 2 : (N > 128 ? 1 : 0);
+        const int bn = nb == 0 ? 128 : 256 * nb;
+        const int64_t tiles = mt * ((N + bn - 1) / bn);
+        int k_split = 1;
+        const int64_t nr = K / 256;
+        while (tiles * k_split * 2 <= sm_count && k_split * 2 <= 16 && nr / (k_split * 2) >= 2) k_split *= 2;
+        if (k_split > 1) { cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)M * N * sizeof(float), st); if (e != cudaSuccess) return -3; }
         switch (type) {
-#define GQ(T) case T: return bn256 ? launch_gemm_q<T, 256>(W, L, xb, dst, M, N, K, k_split, st) : launch_gemm_q<T, 128>(W, L, xb, dst, M, N, K, k_split, st);
+#define GQ(T) case T: return nb == 2 ? launch_gemm_q<T, 2>(W, L, xb, dst, M, N, K, k_split, st) : nb == 1 ? launch_gemm_q<T, 1>(W, L, xb, dst, M, N, K, k_split, st) : launch_gemm_q<T, 0>(W, L, xb, dst, M, N, K, k_split, st);
             GQ(B200Q_TYPE_IQ4_NL) GQ(B200Q_TYPE_Q4_0) GQ(B200Q_TYPE_Q4_K) GQ(B200Q_TYPE_IQ4_K)
 #undef GQ
             default: break;
         }
     }
+    // unfused: bf16 weight scratch + plain bf16 GEMM; tile / split selection: fill ~1 wave of the SMs
+    const bool bn256 = N >= 256 && mt * ((N + 255) / 256) >= sm_count / 2;
+    const int64_t tiles = bn256 ? mt * ((N + 255) / 256) : mt * ((N + 127) / 128);
+    int k_split = 1;
+    const int64_t nk = (K + BK - 1) / BK;
+    while (tiles * k_split * 2 <= sm_count && k_split * 2 <= 8 && nk / (k_split * 2) >= 8) k_split *= 2;
+    if (k_split > 1) { cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)M * N * sizeof(float), st); if (e != cudaSuccess) return -3; }
     if (ws_bytes < (size_t)b200q_align_up(M * K * 2, 256)) return -5;
     int rc = b200q_launch_dequant_bf16(W, L, wscratch, st); if (rc) return rc;
     return bn256 ? launch_gemm_bf16<256>(wscratch, xb, dst, M, N, K, k_split, st) : launch_gemm_bf16<128>(wscratch, xb, dst, M, N, K, k_split, st);
