@@ -260,7 +260,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cb = cpu_baseline(n_threads=os.cpu_count(), budget_s=20.0)
+        # "all the host threads it can use": the reference's spin-barrier thread pool collapses when oversubscribed
+        # (SURVEY.md §8c pitfall 4), so calibrate the thread count on a short sample and keep the fastest
+        ncpu = os.cpu_count() or 8
+        cands = sorted({max(1, ncpu), max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 16), min(ncpu, 8)}, reverse=True)
+        best = None
+        for nt in cands:
+            c = cpu_baseline(n_threads=nt, budget_s=2.5)
+            if c and (best is None or c["value"] > best[1]["value"]):
+                best = (nt, c)
+        cb = cpu_baseline(n_threads=best[0], budget_s=12.0) if best else None
+        if cb:
+            cb["sample"] += f"; thread count calibrated over {cands} (logical CPUs: {ncpu})"
         if cb is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference CPU build) not present"}))
             return 0

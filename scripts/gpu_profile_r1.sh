@@ -1,0 +1,17 @@
+#!/bin/bash
+# round-1 evidence: full test suite, bench (+ reference arm), ncu launch list and full captures of the two hot kernels
+mkdir -p gpurun_out; rm -f gpurun_out/summary.txt
+nvidia-smi -L > gpurun_out/gpu.txt; lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" >> gpurun_out/gpu.txt
+timeout -k 5 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/t_all.log 2>&1
+echo "tests rc=$?" >> gpurun_out/summary.txt
+timeout -k 5 600 python bench.py --steps 20 --warmup 3 > gpurun_out/BENCH_r1_ours.json 2> gpurun_out/bench_ours.err
+echo "bench rc=$?" >> gpurun_out/summary.txt
+timeout -k 5 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/BENCH_r1_reference.json 2> gpurun_out/bench_ref.err
+echo "bench ref rc=$?" >> gpurun_out/summary.txt
+timeout -k 5 500 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1
+echo "ncu launches rc=$?" >> gpurun_out/summary.txt
+timeout -k 5 500 ncu --set full --clock-control none --import-source on -k regex:k_mmvq_ring -s 20 -c 4 -o gpurun_out/prof_mmvq_r1 python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu --no-pp > gpurun_out/ncu_mmvq.log 2>&1
+echo "ncu mmvq rc=$?" >> gpurun_out/summary.txt
+timeout -k 5 500 ncu --set full --clock-control none --import-source on -k regex:k_gemm_q -s 14 -c 7 -o gpurun_out/prof_gemmq_r1 python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_gemm.log 2>&1
+echo "ncu gemm rc=$?" >> gpurun_out/summary.txt
+cat gpurun_out/summary.txt; tail -3 gpurun_out/t_all.log; cut -c1-1200 gpurun_out/BENCH_r1_ours.json; echo; cut -c1-600 gpurun_out/BENCH_r1_reference.json

@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""Turn ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
+usage: summarize_ncu.py launches <csv> <out.md> | full <ncu-rep> <out.md>"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_op_hmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max", "sm__cycles_active.avg",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_sector_hit_rate.pct"]
+
+
+def launches(path, out):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    total = 0.0
+    for row in csv.DictReader(lines):
+        name = re.sub(r"\(.*", "", row["Kernel Name"])[:64]
+        v = float(row["Metric Value"].replace(",", ""))
+        agg.setdefault((name, row.get("Grid Size", ""), row.get("Block Size", "")), []).append(v)
+        total += v
+    with open(out, "w") as f:
+        f.write(f"# ncu launch list ({path}) — gpu__time_duration per launch, cold-cache & serialised: compare SHARES\n\n")
+        f.write("| kernel | grid | block | launches | mean µs | total ms | share |\n|---|---|---|---:|---:|---:|---:|\n")
+        for (name, g, b), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+            f.write(f"| `{name}` | {g} | {b} | {len(v)} | {sum(v)/len(v)/1e3:.2f} | {sum(v)/1e6:.3f} | {100*sum(v)/total:.1f}% |\n")
+
+
+def full(path, out):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(out, "w") as f:
+        f.write(f"# ncu --set full summary of {path}\n\n")
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+            f.write(f"## {d.get('Kernel Name','?')[:110]}  grid {d.get('Grid Size')} block {d.get('Block Size')}\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in KEEP:
+                if k in d:
+                    f.write(f"| {k} | {d[k]} | {units[hdr.index(k)]} |\n")
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
