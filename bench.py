@@ -121,6 +121,10 @@ class Model:
                 down=mk(N_EMBD, N_FF // tp, s_f * 4)))
         self.head = mk(N_VOCAB // tp, N_EMBD, s_e)
         self.launches_tg = n_layer * 4 + 1
+        self.reducer = None
+        if tp > 1 and os.environ.get("B200Q_NCCL_REDUCE", "0") != "1":
+            self.reducer = be.NvlsReducer(512 * N_EMBD)
+            self.launches_tg += 2 * n_layer if self.reducer.ok else 0
         self.weight_bytes = sum(t.nbytes_wire for L in self.layers for t in L.values()) + self.head.nbytes_wire
 
     def alloc(self, n):
@@ -135,8 +139,11 @@ class Model:
 
     def allreduce(self, t):
         if self.tp > 1:
-            import torch.distributed as dist
-            dist.all_reduce(t)
+            if self.reducer is not None:
+                self.reducer.all_reduce(t)          # our NVLS kernel (falls back to NCCL without multicast support)
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(t)
 
     def step_tg(self):
         be = self.be
@@ -253,7 +260,7 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    config = {"workload": "Llama-3-8B pure IQ4_NL, llama-bench tg128 (n_batch=1) / pp512 (n_ubatch=512): all MUL_MAT nodes in graph order",
+    config = {"reduce": "b200q NVLS kernel" if world > 1 and os.environ.get("B200Q_NCCL_REDUCE", "0") != "1" else ("nccl" if world > 1 else "none"), "workload": "Llama-3-8B pure IQ4_NL, llama-bench tg128 (n_batch=1) / pp512 (n_ubatch=512): all MUL_MAT nodes in graph order",
               "n_layer": args.layers, "l2_policy": "inputs larger than L2 (4.2 GB of weights streamed per step)",
               "parallelism": f"tp{world}" if world > 1 else "none"}
 
@@ -291,6 +298,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.manual_seed(0)
 

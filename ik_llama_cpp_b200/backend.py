@@ -200,3 +200,48 @@ def mul_mat_host(w: QuantTensor, x_host: np.ndarray) -> np.ndarray:
     with torch.cuda.device(w.planes.device):
         check(_lib.lib().b200q_mul_mat_host(w.ggml_type, w.ptr, x_host.ctypes.data, out.ctypes.data, w.m, w.k, n, _stream()), "b200q_mul_mat_host")
     return out
+
+
+class NvlsReducer:
+    """GGML_OP_REDUCE (sum) across the ranks of a torch.distributed group with the in-tree NVLS kernel (b200q_reduce_sum_nvls).
+    Symmetric memory + multicast mapping come from torch.distributed._symmetric_memory (plumbing); the reduction itself is
+    our kernel: multimem.red into the switch, flag, acquire-spin, copy-out.  Falls back to NCCL all_reduce when the
+    platform has no multicast support."""
+
+    def __init__(self, max_elems: int, group=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.dist = dist
+        self.group = group or dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.stride = (max_elems + 3) // 4 * 4
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.ok = False
+        try:
+            self.buf = symm.empty(2 * self.stride + 64, dtype=torch.float32, device=dev)
+            self.hdl = symm.rendezvous(self.buf, self.group)
+            self.mc = int(self.hdl.multicast_ptr) if self.hdl.has_multicast_support else 0
+            if self.mc:
+                self.buf.zero_()
+                self.local = self.buf.data_ptr()
+                self.flag_off = 2 * self.stride * 4
+                self.state = torch.zeros(8, dtype=torch.int32, device=dev)      # [0] seq counter, [4] cta counter
+                torch.cuda.synchronize()
+                self.hdl.barrier()
+                self.ok = True
+        except Exception as e:  # no symmetric memory / multicast on this platform
+            self.err = repr(e)
+        if not self.ok:
+            self.mc = 0
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum over ranks of a contiguous f32 tensor."""
+        if not self.ok or t.numel() > self.stride:
+            self.dist.all_reduce(t, group=self.group)
+            return t
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        L = _lib.lib()
+        check(L.b200q_reduce_sum_nvls(t.data_ptr(), t.data_ptr(), t.numel(), self.mc, self.local, self.stride,
+                                      self.mc + self.flag_off, self.local + self.flag_off, self.world,
+                                      self.state.data_ptr(), self.state.data_ptr() + 16, _stream()), "b200q_reduce_sum_nvls")
+        return t

@@ -1,0 +1,261 @@
+// ggml_b200_backend.cpp — the drop-in boundary at the ggml-backend level.
+//
+// Implements the reference's backend vtable (struct ggml_backend_i, ggml/src/ggml-backend-impl.h:81-130) and buffer vtables
+// (:18-51) on top of libb200q.so, and exports the C symbols of ggml/include/ggml-cuda.h:24-46 under their original names.
+// graph_compute owns the hot path: GGML_OP_MUL_MAT on block-quantized src0 and GGML_OP_FUSED_UP_GATE.  Every other op is
+// reported as unsupported (supports_op == false): this library is the quantized-mat-mul backend, the pass-through kernels
+// (norm, rope, attention ...) that a full llama graph needs are outside SURVEY §8a and are the documented next step.
+// Compiled against the reference's headers where they lie (-I/root/reference/ggml/include -I.../ggml/src); nothing is copied.
+#include "ggml.h"
+#include "ggml-backend.h"
+#include "ggml-backend-impl.h"
+#include "ggml-cuda.h"      // the reference's own header: the prototypes this library implements
+#include "b200q.h"
+
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#define B200_MAX_DEVICES 16
+
+static ggml_log_callback g_log_cb = nullptr; static void * g_log_ud = nullptr;
+static void b200_log(enum ggml_log_level lvl, const char * fmt, ...) {
+    char buf[512]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (g_log_cb) g_log_cb(lvl, buf, g_log_ud); else fputs(buf, stderr);
+}
+// abort-on-error convention of the reference (CUDA_CHECK -> GGML_ABORT, ggml-cuda.cu:135-145)
+#define B200_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { b200_log(GGML_LOG_LEVEL_ERROR, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); GGML_ABORT("CUDA error"); } } while (0)
+#define B200Q_CHECK(x) do { int rc_ = (x); if (rc_ != 0) { b200_log(GGML_LOG_LEVEL_ERROR, "b200q error %d: %s at %s:%d\n", rc_, b200q_last_error(), __FILE__, __LINE__); GGML_ABORT("b200q error"); } } while (0)
+
+// ------------------------------------------------------------------------------------------------------------------
+// buffers
+// ------------------------------------------------------------------------------------------------------------------
+struct b200_buft_ctx { int device; std::string name; };
+struct b200_buffer_ctx { int device; void * base; };
+
+static bool b200_tensor_is_repacked(const ggml_tensor * t) {
+    // quantized weight matrices are stored in the plane layout (ik_llama_cpp_b200/csrc/b200q_types.cuh)
+    return ggml_is_quantized(t->type) && b200q_type_supported(t->type) && ggml_is_contiguous(t) && t->view_src == nullptr;
+}
+
+GGML_CALL static const char * b200_buffer_get_name(ggml_backend_buffer_t) { return "B200"; }
+GGML_CALL static bool b200_buffer_is_ours(ggml_backend_buffer_t b) { return b->iface.get_name == b200_buffer_get_name; }   // identity idiom of ggml-cuda.cu:607-609
+GGML_CALL static void b200_buffer_free(ggml_backend_buffer_t buffer) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *)buffer->context; cudaSetDevice(c->device); cudaFree(c->base); delete c;
+}
+GGML_CALL static void * b200_buffer_get_base(ggml_backend_buffer_t buffer) { return ((b200_buffer_ctx *)buffer->context)->base; }
+GGML_CALL static void b200_buffer_init_tensor(ggml_backend_buffer_t, ggml_tensor *) {}
+GGML_CALL static void b200_buffer_memset_tensor(ggml_backend_buffer_t buffer, ggml_tensor * t, uint8_t v, size_t off, size_t size) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *)buffer->context; B200_CUDA_CHECK(cudaSetDevice(c->device));
+    B200_CUDA_CHECK(cudaMemsetAsync((char *)t->data + off, v, size, cudaStreamPerThread)); B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamPerThread));
+}
+GGML_CALL static void b200_buffer_set_tensor(ggml_backend_buffer_t buffer, ggml_tensor * t, const void * data, size_t off, size_t size) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *)buffer->context; B200_CUDA_CHECK(cudaSetDevice(c->device));
+    if (b200_tensor_is_repacked(t)) {
+        GGML_ASSERT(off == 0 && size == ggml_nbytes(t) && "quantized tensors are uploaded whole (they are re-laid-out on the device)");
+        B200Q_CHECK(b200q_set_tensor(t->type, data, t->data, ggml_nrows(t), t->ne[0], cudaStreamPerThread));
+        return;
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync((char *)t->data + off, data, size, cudaMemcpyHostToDevice, cudaStreamPerThread));
+    B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamPerThread));
+}
+GGML_CALL static void b200_buffer_get_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * t, void * data, size_t off, size_t size) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *)buffer->context; B200_CUDA_CHECK(cudaSetDevice(c->device));
+    if (b200_tensor_is_repacked(t)) {
+        GGML_ASSERT(off == 0 && size == ggml_nbytes(t));
+        B200Q_CHECK(b200q_get_tensor(t->type, t->data, data, ggml_nrows(t), t->ne[0], cudaStreamPerThread));   // original GGUF bytes, bit-for-bit
+        return;
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(data, (const char *)t->data + off, size, cudaMemcpyDeviceToHost, cudaStreamPerThread));
+    B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamPerThread));
+}
+static size_t b200_alloc_size(const ggml_tensor * t) {
+    size_t n = ggml_nbytes(t);
+    if (b200_tensor_is_repacked(t)) { const int64_t pb = b200q_plane_bytes(t->type, ggml_nrows(t), t->ne[0]); if (pb > (int64_t)n) n = (size_t)pb; }
+    return n;
+}
+GGML_CALL static bool b200_buffer_cpy_tensor(ggml_backend_buffer_t buffer, const ggml_tensor * src, ggml_tensor * dst) {
+    if (!src->buffer || !b200_buffer_is_ours(src->buffer)) return false;       // host sources go through set_tensor
+    b200_buffer_ctx * c = (b200_buffer_ctx *)buffer->context; B200_CUDA_CHECK(cudaSetDevice(c->device));
+    B200_CUDA_CHECK(cudaMemcpyAsync(dst->data, src->data, b200_alloc_size(src), cudaMemcpyDeviceToDevice, cudaStreamPerThread));
+    B200_CUDA_CHECK(cudaStreamSynchronize(cudaStreamPerThread));
+    return true;
+}
+GGML_CALL static void b200_buffer_clear(ggml_backend_buffer_t buffer, uint8_t v) {
+    b200_buffer_ctx * c = (b200_buffer_ctx *)buffer->context; B200_CUDA_CHECK(cudaSetDevice(c->device));
+    B200_CUDA_CHECK(cudaMemset(c->base, v, buffer->size));
+}
+static const ggml_backend_buffer_i b200_buffer_iface = {
+    /* get_name */ b200_buffer_get_name, /* free_buffer */ b200_buffer_free, /* get_base */ b200_buffer_get_base, /* init_tensor */ b200_buffer_init_tensor,
+    /* memset_tensor */ b200_buffer_memset_tensor, /* set_tensor */ b200_buffer_set_tensor, /* get_tensor */ b200_buffer_get_tensor,
+    /* cpy_tensor */ b200_buffer_cpy_tensor, /* clear */ b200_buffer_clear, /* reset */ nullptr,
+};
+
+GGML_CALL static const char * b200_buft_get_name(ggml_backend_buffer_type_t buft) { return ((b200_buft_ctx *)buft->context)->name.c_str(); }
+GGML_CALL static ggml_backend_buffer_t b200_buft_alloc(ggml_backend_buffer_type_t buft, size_t size) {
+    b200_buft_ctx * bc = (b200_buft_ctx *)buft->context;
+    if (cudaSetDevice(bc->device) != cudaSuccess) return nullptr;
+    void * p = nullptr; size = size < 1 ? 1 : size;
+    if (cudaMalloc(&p, size) != cudaSuccess) { cudaGetLastError(); b200_log(GGML_LOG_LEVEL_ERROR, "%s: allocating %.2f MiB on device %d failed\n", __func__, size / 1048576.0, bc->device); return nullptr; }
+    return ggml_backend_buffer_init(buft, b200_buffer_iface, new b200_buffer_ctx{bc->device, p}, size);
+}
+GGML_CALL static size_t b200_buft_alignment(ggml_backend_buffer_type_t) { return 256; }     // plane offsets are 256-byte aligned
+GGML_CALL static size_t b200_buft_alloc_size(ggml_backend_buffer_type_t, const ggml_tensor * t) { return b200_alloc_size(t); }
+GGML_CALL static bool b200_buft_is_host(ggml_backend_buffer_type_t) { return false; }
+static const ggml_backend_buffer_type_i b200_buft_iface = { b200_buft_get_name, b200_buft_alloc, b200_buft_alignment, /* get_max_size */ nullptr, b200_buft_alloc_size, b200_buft_is_host };
+
+// pinned host buffer type (ggml-cuda.cu:1408-1520)
+GGML_CALL static const char * b200_host_buffer_name(ggml_backend_buffer_t) { return "B200_Host"; }
+GGML_CALL static void b200_host_buffer_free(ggml_backend_buffer_t buffer) { cudaFreeHost(buffer->context); }
+GGML_CALL static const char * b200_host_buft_name(ggml_backend_buffer_type_t) { return "B200_Host"; }
+GGML_CALL static ggml_backend_buffer_t b200_host_buft_alloc(ggml_backend_buffer_type_t buft, size_t size) {
+    void * p = nullptr;
+    if (cudaMallocHost(&p, size < 1 ? 1 : size) != cudaSuccess) { cudaGetLastError(); return ggml_backend_buft_alloc_buffer(ggml_backend_cpu_buffer_type(), size); }
+    ggml_backend_buffer_t b = ggml_backend_cpu_buffer_from_ptr(p, size);
+    b->buft = buft; b->iface.get_name = b200_host_buffer_name; b->iface.free_buffer = b200_host_buffer_free;
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backend
+// ------------------------------------------------------------------------------------------------------------------
+struct b200_backend_ctx {
+    int device; std::string name; cudaStream_t stream = nullptr; void * ws = nullptr; size_t ws_size = 0; const void * model = nullptr;
+    void * workspace(size_t n) {
+        if (n > ws_size) { if (ws) { cudaStreamSynchronize(stream); cudaFree(ws); } B200_CUDA_CHECK(cudaMalloc(&ws, n)); ws_size = n; }
+        return ws;
+    }
+};
+static ggml_guid_t b200_guid() { static ggml_guid g = {0xb2, 0x00, 0x51, 0x0a, 0x71, 0x63, 0x67, 0x65, 0x6e, 0x30, 0x35, 0x2d, 0x71, 0x6d, 0x6d, 0x01}; return &g; }
+
+GGML_CALL static const char * b200_backend_name(ggml_backend_t b) { return ((b200_backend_ctx *)b->context)->name.c_str(); }
+GGML_CALL static void b200_backend_free(ggml_backend_t b) {
+    b200_backend_ctx * c = (b200_backend_ctx *)b->context; cudaSetDevice(c->device);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (c->ws) cudaFree(c->ws);
+    delete c; delete b;
+}
+GGML_CALL static ggml_backend_buffer_type_t b200_backend_default_buft(ggml_backend_t b) { return ggml_backend_cuda_buffer_type(((b200_backend_ctx *)b->context)->device); }
+GGML_CALL static void b200_backend_synchronize(ggml_backend_t b) { b200_backend_ctx * c = (b200_backend_ctx *)b->context; B200_CUDA_CHECK(cudaSetDevice(c->device)); B200_CUDA_CHECK(cudaStreamSynchronize(c->stream)); }
+
+static int32_t b200_op_param_i32(const ggml_tensor * t, int i) { int32_t v; memcpy(&v, (const char *)t->op_params + i * sizeof(int32_t), sizeof v); return v; }
+static int b200_unary(int ggml_unary) {
+    switch (ggml_unary) { case GGML_UNARY_OP_SILU: return B200Q_UNARY_SILU; case GGML_UNARY_OP_GELU: return B200Q_UNARY_GELU; case GGML_UNARY_OP_RELU: return B200Q_UNARY_RELU; default: return -1; }
+}
+static bool b200_can_mul_mat(const ggml_tensor * w, const ggml_tensor * x, const ggml_tensor * dst) {
+    return w && x && ggml_is_quantized(w->type) && b200q_type_supported(w->type) && ggml_is_contiguous(w) && w->ne[2] * w->ne[3] == 1 &&
+           x->type == GGML_TYPE_F32 && ggml_is_contiguous(x) && x->ne[2] * x->ne[3] == 1 && dst->type == GGML_TYPE_F32 && ggml_is_contiguous(dst) &&
+           w->ne[0] == x->ne[0] && w->ne[0] % 256 == 0;
+}
+GGML_CALL static bool b200_backend_supports_op(ggml_backend_t, const ggml_tensor * op) {
+    switch (op->op) {
+        case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE: return true;
+        case GGML_OP_MUL_MAT: return b200_can_mul_mat(op->src[0], op->src[1], op);
+        case GGML_OP_FUSED_UP_GATE:
+            return op->src[0] && op->src[1] && op->src[0]->type == op->src[1]->type && b200_can_mul_mat(op->src[0], op->src[2], op) &&
+                   b200_can_mul_mat(op->src[1], op->src[2], op) && op->src[2]->ne[1] <= 8 && b200_unary(b200_op_param_i32(op, 0)) >= 0;
+        default: return false;     // no silent CPU detour inside graph_compute: unsupported ops are refused up front
+    }
+}
+GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t b, ggml_cgraph * cgraph) {
+    b200_backend_ctx * c = (b200_backend_ctx *)b->context; B200_CUDA_CHECK(cudaSetDevice(c->device));
+    for (int i = 0; i < cgraph->n_nodes; ++i) {
+        ggml_tensor * node = cgraph->nodes[i];
+        switch (node->op) {
+            case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE: break;
+            case GGML_OP_MUL_MAT: {
+                const ggml_tensor * w = node->src[0]; const ggml_tensor * x = node->src[1];
+                GGML_ASSERT(b200_can_mul_mat(w, x, node));
+                const int64_t m = w->ne[1], k = w->ne[0], n = x->ne[1];
+                const size_t need = b200q_mul_mat_workspace(w->type, m, k, n);
+                void * ws = need ? c->workspace(need) : nullptr;
+                B200Q_CHECK(b200q_mul_mat(w->type, w->data, (const float *)x->data, (float *)node->data, m, k, n, ws, need, c->stream));
+            } break;
+            case GGML_OP_FUSED_UP_GATE: {
+                const ggml_tensor * up = node->src[0]; const ggml_tensor * gate = node->src[1]; const ggml_tensor * x = node->src[2];
+                float limit = 0.0f; memcpy(&limit, (const char *)node->op_params + sizeof(int32_t), sizeof(float));
+                B200Q_CHECK(b200q_fused_up_gate_vec(up->type, up->data, gate->data, (const float *)x->data, (float *)node->data, up->ne[1], up->ne[0],
+                                                    (int)x->ne[1], x->ne[0], b200_unary(b200_op_param_i32(node, 0)), limit, c->stream));
+            } break;
+            default:
+                b200_log(GGML_LOG_LEVEL_ERROR, "%s: op %s not supported by the B200 quantized-mat-mul backend\n", __func__, ggml_op_name(node->op));
+                return GGML_STATUS_FAILED;
+        }
+    }
+    return GGML_STATUS_SUCCESS;     // asynchronous w.r.t. the host, like ggml_backend_cuda_graph_compute (ggml-cuda.cu:4687)
+}
+GGML_CALL static bool b200_backend_supports_buft(ggml_backend_t b, ggml_backend_buffer_type_t buft) {
+    if (buft->iface.get_name != b200_buft_get_name) return false;
+    return ((b200_buft_ctx *)buft->context)->device == ((b200_backend_ctx *)b->context)->device;
+}
+GGML_CALL static bool b200_backend_offload_op(ggml_backend_t, const ggml_tensor *) { return false; }
+
+static const ggml_backend_i b200_backend_iface = {
+    /* get_name */ b200_backend_name, /* free */ b200_backend_free, /* get_default_buffer_type */ b200_backend_default_buft,
+    /* set_tensor_async */ nullptr, /* get_tensor_async */ nullptr, /* cpy_tensor_async */ nullptr, /* synchronize */ b200_backend_synchronize,
+    /* graph_plan_create */ nullptr, /* graph_plan_free */ nullptr, /* graph_plan_update */ nullptr, /* graph_plan_compute */ nullptr,
+    /* graph_compute */ b200_backend_graph_compute, /* supports_op */ b200_backend_supports_op, /* supports_buft */ b200_backend_supports_buft,
+    /* offload_op */ b200_backend_offload_op, /* event_new */ nullptr, /* event_free */ nullptr, /* event_record */ nullptr, /* event_wait */ nullptr, /* event_synchronize */ nullptr,
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// exported C ABI (names and meaning of ggml/include/ggml-cuda.h:24-46)
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+GGML_API GGML_CALL int ggml_backend_cuda_get_device_count(void) { int n = b200q_device_count(); return n > B200_MAX_DEVICES ? B200_MAX_DEVICES : n; }
+GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_cuda_buffer_type(int device) {
+    static std::mutex mu; std::lock_guard<std::mutex> lk(mu);
+    static ggml_backend_buffer_type types[B200_MAX_DEVICES]; static bool init = false;
+    if (device < 0 || device >= ggml_backend_cuda_get_device_count()) return nullptr;
+    if (!init) { for (int i = 0; i < B200_MAX_DEVICES; ++i) types[i] = { b200_buft_iface, new b200_buft_ctx{i, "B200" + std::to_string(i)} }; init = true; }
+    return &types[device];
+}
+GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_cuda_split_buffer_type(const float *) {
+    // one process per GPU in this design: the tensor-parallel shards are ordinary device tensors of each rank (ik_llama_cpp_b200/tp.py);
+    // the single-process multi-device split buffer of the reference (ggml-cuda.cu:805-1406) maps onto device 0's buffer type here
+    return ggml_backend_cuda_buffer_type(0);
+}
+GGML_API GGML_CALL ggml_backend_buffer_type_t ggml_backend_cuda_host_buffer_type(void) {
+    static ggml_backend_buffer_type t = { { b200_host_buft_name, b200_host_buft_alloc, ggml_backend_cpu_buffer_type()->iface.get_alignment, nullptr,
+                                            ggml_backend_cpu_buffer_type()->iface.get_alloc_size, ggml_backend_cpu_buffer_type()->iface.is_host }, nullptr };
+    return &t;
+}
+GGML_API GGML_CALL void ggml_backend_cuda_get_device_description(int device, char * description, size_t n) {
+    cudaDeviceProp p; if (cudaGetDeviceProperties(&p, device) == cudaSuccess) snprintf(description, n, "%s", p.name); else snprintf(description, n, "unknown");
+}
+GGML_API GGML_CALL void ggml_backend_cuda_get_device_memory(int device, size_t * free_, size_t * total) {
+    cudaSetDevice(device); if (cudaMemGetInfo(free_, total) != cudaSuccess) { *free_ = 0; *total = 0; }
+}
+GGML_API GGML_CALL bool ggml_backend_cuda_register_host_buffer(void * buffer, size_t size) { return cudaHostRegister(buffer, size, cudaHostRegisterPortable | cudaHostRegisterReadOnly) == cudaSuccess; }
+GGML_API GGML_CALL void ggml_backend_cuda_unregister_host_buffer(void * buffer) { cudaHostUnregister(buffer); }
+GGML_API GGML_CALL void ggml_backend_cuda_log_set_callback(ggml_log_callback cb, void * ud) { g_log_cb = cb; g_log_ud = ud; }
+GGML_API GGML_CALL void ggml_backend_cuda_invalidate_graphs(const void *) {}     // no cached CUDA graphs inside this backend
+GGML_API GGML_CALL bool ggml_backend_is_cuda(ggml_backend_t backend) { return backend != nullptr && ggml_guid_matches(backend->guid, b200_guid()); }
+GGML_API GGML_CALL ggml_backend_t ggml_backend_cuda_init(int device, const void * params, const void * model) {
+    if (device < 0 || device >= ggml_backend_cuda_get_device_count()) { b200_log(GGML_LOG_LEVEL_ERROR, "%s: invalid device %d\n", __func__, device); return nullptr; }
+    if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+    if (params) {   // "k=v,k=v" like ggml_cuda_parse_params (ggml-cuda.cu:5339-5389); unknown keys are ignored like unknown features
+        std::string s((const char *)params); size_t pos = 0;
+        while (pos < s.size()) {
+            size_t e = s.find(',', pos); if (e == std::string::npos) e = s.size();
+            std::string kv = s.substr(pos, e - pos); size_t eq = kv.find('=');
+            if (eq != std::string::npos) b200q_set_option(kv.substr(0, eq).c_str(), atoi(kv.c_str() + eq + 1));
+            pos = e + 1;
+        }
+    }
+    b200_backend_ctx * c = new b200_backend_ctx{device, "B200" + std::to_string(device)}; c->model = model;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+    return new ggml_backend{ b200_guid(), b200_backend_iface, c };
+}
+GGML_CALL static ggml_backend_t b200_reg_init(const char *, void * user_data) { return ggml_backend_cuda_init((int)(intptr_t)user_data, nullptr, nullptr); }
+GGML_API GGML_CALL int ggml_backend_cuda_reg_devices(void) {
+    const int n = ggml_backend_cuda_get_device_count();
+    for (int i = 0; i < n; ++i) { char name[64]; snprintf(name, sizeof name, "B200%d", i); ggml_backend_register(name, b200_reg_init, ggml_backend_cuda_buffer_type(i), (void *)(intptr_t)i); }
+    return n;
+}
+}

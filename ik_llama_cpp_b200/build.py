@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200q.so")
 OBJDIR = os.path.join(HERE, "_obj")
-SOURCES = ["b200q_decode.cu", "b200q_gemm.cu", "b200q_api.cu"]
+SOURCES = ["b200q_decode.cu", "b200q_gemm.cu", "b200q_reduce.cu", "b200q_api.cu"]
 HEADERS = ["b200q_types.cuh", "b200q_internal.h", os.path.join("..", "..", "include", "b200q.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -54,5 +54,50 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+PLUG_SRC = os.path.join(HERE, "backend_plug", "ggml_b200_backend.cpp")
+PLUG_LIB = os.path.join(HERE, "libggml_b200.so")
+REFERENCE_ROOT = "/root/reference"
+
+
+def build_backend_plug(force: bool = False, verbose: bool = False) -> str | None:
+    """libggml_b200.so: the ggml-backend vtable + ggml-cuda.h symbols on top of libb200q.so.  It is compiled against the
+    reference's headers where they lie, so it can only be (re)built where /root/reference exists; the GPU box gets the prebuilt file.
+    It links against the reference's own ggml (oracle/_ref/libggml_ref_avx2.so, built by oracle/Makefile.ref) for ggml_* symbols."""
+    if not os.path.isdir(REFERENCE_ROOT):
+        return PLUG_LIB if os.path.exists(PLUG_LIB) else None
+    ref_lib = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libggml_ref_avx2.so")
+    if not os.path.exists(ref_lib):
+        return None
+    if force or _stale(PLUG_LIB, [PLUG_SRC, LIB, os.path.join(os.path.dirname(HERE), "include", "b200q.h")]):
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", PLUG_LIB, PLUG_SRC,
+               f"-I{REFERENCE_ROOT}/ggml/include", f"-I{REFERENCE_ROOT}/ggml/src", f"-I{os.path.join(os.path.dirname(HERE), 'include')}",
+               "-I/usr/local/cuda/include", "-DGGML_SHARED", "-DGGML_USE_CUDA", f"-L{HERE}", "-lb200q", ref_lib,
+               "-L/usr/local/cuda/lib64", "-lcudart_static", "-ldl", "-lrt", "-lpthread", "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,$ORIGIN/../oracle/_ref"]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return PLUG_LIB
+
+
+def build_backend_ops_test(force: bool = False) -> str | None:
+    """tests/backend_ops/test_mul_mat_backend: test-backend-ops semantics through the real ggml-backend API."""
+    root = os.path.dirname(HERE)
+    exe = os.path.join(root, "tests", "backend_ops", "test_mul_mat_backend")
+    src = exe + ".cpp"
+    if not os.path.isdir(REFERENCE_ROOT):
+        return exe if os.path.exists(exe) else None
+    plug = build_backend_plug(force)
+    ref_lib = os.path.join(root, "oracle", "_ref", "libggml_ref_avx2.so")
+    if plug is None:
+        return None
+    if force or _stale(exe, [src, plug]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, src, f"-I{REFERENCE_ROOT}/ggml/include", f"-I{REFERENCE_ROOT}/ggml/src",
+                               plug, ref_lib, os.path.join(HERE, "libb200q.so"), "-lpthread", "-ldl",
+                               "-Wl,-rpath,$ORIGIN/../../ik_llama_cpp_b200", "-Wl,-rpath,$ORIGIN/../../oracle/_ref"])
+    return exe
+
+
 if __name__ == "__main__":
     print(build_native(force="--force" in sys.argv, verbose=True))
+    print(build_backend_plug(force="--force" in sys.argv, verbose=True))
+    print(build_backend_ops_test(force="--force" in sys.argv))

@@ -73,6 +73,14 @@ B200Q_API int b200q_mul_mat_gemm_bf16(int type, const void * W, const void * x_b
                             void * workspace /* bf16 [m][k] scratch, only for types without a fused kernel */, size_t workspace_bytes, void * stream);
 B200Q_API int b200q_dequantize_bf16(int type, const void * W, void * out_bf16, int64_t m, int64_t k, void * stream);
 
+/* ---- GGML_OP_REDUCE (sum) for the row-parallel mat-muls of split-mode-graph: NVLS all-reduce in ONE kernel ----
+ * One process per GPU; the reduction buffers live in symmetric memory: `mc_base` / `mc_flag` = multicast (NVLS) addresses,
+ * `local_base` / `local_flag` = this rank's own mapping of the same allocation.  Two parity buffers of `parity_stride` floats
+ * alternate (base + parity*stride); the parity and the flag target come from the device counter `seq_counter` (rank-local,
+ * zero-initialised), so the call has constant arguments and can be captured in a CUDA graph.  `cta_counter`: rank-local u32, zero. */
+B200Q_API int b200q_reduce_sum_nvls(const float * in, float * out, int64_t n, void * mc_base, void * local_base, int64_t parity_stride,
+                          void * mc_flag, const void * local_flag, uint32_t world_size, void * seq_counter, void * cta_counter, void * stream);
+
 /* ---- dispatcher (what GGML_OP_MUL_MAT calls): n <= 8 -> mat-vec, else GEMM ---- */
 B200Q_API int b200q_mul_mat(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
                   void * workspace, size_t workspace_bytes, void * stream);

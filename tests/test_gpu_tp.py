@@ -1,0 +1,80 @@
+"""Multi-GPU tests (need >= 2 B200s; skipped on a 1-GPU box): the in-tree NVLS all-reduce kernel vs the exact sum, eager and
+replayed from a CUDA graph, and the row-parallel mat-vec + reduce against the unsharded oracle result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NCCL_DEBUG="WARN")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from conftest import random_wire
+        from ik_llama_cpp_b200 import backend as be, tp
+        from oracle.oracle import GGML_TYPE, Oracle
+        red = be.NvlsReducer(512 * 4096)
+        res = {"rank": rank, "nvls": red.ok, "why": getattr(red, "err", "")}
+        if red.ok:
+            # integer-valued floats: the f32 sum is exact in any order
+            for n in (4096, 4100, 512 * 4096):
+                for it in range(3):
+                    t = torch.full((n,), float(rank + 1 + it), device="cuda") + torch.arange(n, device="cuda") % 7
+                    red.all_reduce(t)
+                    exp = sum(float(r + 1 + it) for r in range(world)) + world * (torch.arange(n, device="cuda") % 7)
+                    assert torch.equal(t, exp.float()), (n, it)
+            # CUDA-graph replay: constant launch arguments, parity/target from the device counter
+            x = torch.zeros(4096, device="cuda"); y = torch.empty_like(x)
+            s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                y.copy_(x); red.all_reduce(y)
+            torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                y.copy_(x); red.all_reduce(y); y.mul_(0.5); red.all_reduce(y)
+            for it in range(4):
+                x.fill_(float(rank + it)); g.replay(); torch.cuda.synchronize()
+                inner = sum(float(r + it) for r in range(world))
+                assert torch.equal(y, torch.full_like(y, inner * 0.5 * world)), it
+            res["graph"] = True
+        # row-parallel (K-split) mat-vec + reduce == unsharded result
+        t = GGML_TYPE["IQ4_NL"]; m, k = 256, 2048
+        rng = np.random.default_rng(9)
+        wire = random_wire("IQ4_NL", m, k, rng)
+        x = rng.standard_normal((1, k)).astype(np.float32)
+        shard, ks, k0 = tp.shard_cols(wire, t, m, k, world, rank, granularity=256)
+        w = be.set_tensor(t, shard, m, ks)
+        part = be.mul_mat(w, torch.from_numpy(np.ascontiguousarray(x[:, k0:k0 + ks])).cuda())
+        red.all_reduce(part)
+        ref = Oracle().mul_mat_exact(t, wire, x, m)
+        err = float(((part.cpu().numpy() - ref) ** 2).sum() / (ref ** 2).sum())
+        assert err <= 5e-4, err
+        res["tp_nmse"] = err
+        q.put(res)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nvls_allreduce_and_row_parallel_matvec_world2():
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    print(res)
+    assert all(r["tp_nmse"] <= 5e-4 for r in res)
