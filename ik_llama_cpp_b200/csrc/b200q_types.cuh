@@ -38,7 +38,7 @@
 
 // ggml_type ids (reference ggml/include/ggml.h:391-492)
 enum b200q_type : int {
-    B200Q_TYPE_Q4_0 = 2, B200Q_TYPE_Q8_0 = 8, B200Q_TYPE_Q4_K = 12, B200Q_TYPE_Q5_K = 13, B200Q_TYPE_Q6_K = 14,
+    B200Q_TYPE_Q4_0 = 2, B200Q_TYPE_Q4_1 = 3, B200Q_TYPE_Q5_0 = 6, B200Q_TYPE_Q5_1 = 7, B200Q_TYPE_Q6_0 = 133, B200Q_TYPE_Q8_0 = 8, B200Q_TYPE_Q4_K = 12, B200Q_TYPE_Q5_K = 13, B200Q_TYPE_Q6_K = 14,
     B200Q_TYPE_IQ4_NL = 20, B200Q_TYPE_IQ4_XS = 23, B200Q_TYPE_IQ2_BN = 135, B200Q_TYPE_IQ4_K = 139,
     B200Q_TYPE_IQ5_K = 140, B200Q_TYPE_IQ4_KS = 144,
 };
@@ -114,6 +114,10 @@ inline int b200q_make_layout(int type, int64_t M, int64_t K, b200q_layout * L) {
         case B200Q_TYPE_IQ4_NL: set(32,  18, 0, 2, 16, 2, 0, 0, -1); break;   // qs | d
         case B200Q_TYPE_Q4_0:   set(32,  18, 0, 2, 16, 2, 0, 0, -1); break;   // qs | d
         case B200Q_TYPE_Q8_0:   set(32,  34, 0, 2, 32, 2, 0, 0, -1); break;   // qs | d
+        case B200Q_TYPE_Q4_1:   set(32,  20, 0, 2, 16, 4, 0, 0, -1); break;   // qs | {d,m}
+        case B200Q_TYPE_Q5_0:   set(32,  22, 0, 3, 16, 4, 2, 0, -1); break;   // qs | qh | d
+        case B200Q_TYPE_Q5_1:   set(32,  24, 0, 3, 16, 4, 4, 0, -1); break;   // qs | qh | {d,m}
+        case B200Q_TYPE_Q6_0:   set(32,  26, 0, 3, 16, 8, 2, 0, -1); break;   // qs | qh(2 bits) | d
         case B200Q_TYPE_Q4_K:   set(256, 144, 0, 2, 128, 16, 0, 0, -1); break; // qs | {d,dmin,scales[12]}
         case B200Q_TYPE_Q5_K:   set(256, 176, 0, 3, 128, 32, 16, 0, -1); break; // qs | qh | {d,dmin,scales[12]}
         case B200Q_TYPE_Q6_K:   set(256, 210, 0, 4, 128, 64, 16, 2, -1); break; // ql | qh | scales[16] | d
@@ -204,6 +208,40 @@ B200Q_HD void b200q_repack_block(const b200q_layout & L, const uint8_t * wire, u
         } else {
             if (lut) b200q_unpack_nib_L(pq, idx); else b200q_unpack_nib_A(pq, idx);
             for (int j = 0; j < 16; ++j) w[2 + j] = (uint8_t)(idx[j] | (idx[j + 16] << 4));
+            w[0] = pd[0]; w[1] = pd[1];
+        }
+    } break;
+    case B200Q_TYPE_Q4_1: {                            // {half d, m; u8 qs[16]}   (ggml-common.h: block_q4_1)
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * pd = b200q_plane_ptr(dst, L, 1, row, blk);
+        if (!inverse) { for (int j = 0; j < 16; ++j) { idx[j] = w[4 + j] & 0xF; idx[j + 16] = w[4 + j] >> 4; } b200q_pack_nib_A(idx, pq); for (int j = 0; j < 4; ++j) pd[j] = w[j]; }
+        else { b200q_unpack_nib_A(pq, idx); for (int j = 0; j < 16; ++j) w[4 + j] = (uint8_t)(idx[j] | (idx[j + 16] << 4)); for (int j = 0; j < 4; ++j) w[j] = pd[j]; }
+    } break;
+    case B200Q_TYPE_Q5_0: case B200Q_TYPE_Q5_1: {      // {half d; [half m;] u8 qh[4]; u8 qs[16]}: qh bit e = 5th bit of element e
+        const int hd = L.type == B200Q_TYPE_Q5_1 ? 4 : 2;
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * ph = b200q_plane_ptr(dst, L, 1, row, blk); uint8_t * pd = b200q_plane_ptr(dst, L, 2, row, blk);
+        if (!inverse) {
+            uint32_t qh; memcpy(&qh, w + hd, 4);
+            for (int j = 0; j < 16; ++j) { idx[j] = w[hd + 4 + j] & 0xF; idx[j + 16] = w[hd + 4 + j] >> 4; }
+            for (int e = 0; e < 32; ++e) hb[e] = (qh >> e) & 1;
+            b200q_pack_nib_A(idx, pq); uint32_t q = b200q_pack_hb(hb); memcpy(ph, &q, 4); for (int j = 0; j < hd; ++j) pd[j] = w[j];
+        } else {
+            b200q_unpack_nib_A(pq, idx); uint32_t q; memcpy(&q, ph, 4); b200q_unpack_hb(q, hb);
+            uint32_t qh = 0; for (int e = 0; e < 32; ++e) qh |= (uint32_t)hb[e] << e;
+            memcpy(w + hd, &qh, 4); for (int j = 0; j < 16; ++j) w[hd + 4 + j] = (uint8_t)(idx[j] | (idx[j + 16] << 4)); for (int j = 0; j < hd; ++j) w[j] = pd[j];
+        }
+    } break;
+    case B200Q_TYPE_Q6_0: {                            // {half d; u8 qh[8]; u8 qs[16]}  (ggml-quants.c:1675-1695)
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * ph = b200q_plane_ptr(dst, L, 1, row, blk); uint8_t * pd = b200q_plane_ptr(dst, L, 2, row, blk);
+        if (!inverse) {
+            for (int j = 0; j < 16; ++j) {
+                idx[j] = w[10 + j] & 0xF; idx[j + 16] = w[10 + j] >> 4;
+                const uint8_t h = w[2 + j % 8] >> (4 * (j / 8)); hb[j] = h & 3; hb[j + 16] = (h >> 2) & 3;
+            }
+            b200q_pack_nib_A(idx, pq); uint32_t U[2]; b200q_pack_h2(hb, U); memcpy(ph, U, 8); pd[0] = w[0]; pd[1] = w[1];
+        } else {
+            b200q_unpack_nib_A(pq, idx); uint32_t U[2]; memcpy(U, ph, 8); b200q_unpack_h2(U, hb);
+            for (int j = 0; j < 8; ++j) w[2 + j] = 0;
+            for (int j = 0; j < 16; ++j) { w[10 + j] = (uint8_t)(idx[j] | (idx[j + 16] << 4)); w[2 + j % 8] |= (uint8_t)((hb[j] | (hb[j + 16] << 2)) << (4 * (j / 8))); }
             w[0] = pd[0]; w[1] = pd[1];
         }
     } break;
@@ -392,6 +430,10 @@ template <int TYPE> struct b200q_traits;
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_NL, true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q4_0,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q8_0,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q4_1,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q5_0,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q5_1,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q6_0,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q4_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q5_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q6_K,  false, 32)
@@ -470,6 +512,17 @@ B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, typename b
     if (TYPE == B200Q_TYPE_IQ4_NL || TYPE == B200Q_TYPE_Q4_0) {
         LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         I.m[0] = LD::ld2(P.p[1] + (row * n32 + it) * 2);
+    } else if (TYPE == B200Q_TYPE_Q4_1) {
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
+        I.m[0] = LD::ld4(P.p[1] + (row * n32 + it) * 4);
+    } else if (TYPE == B200Q_TYPE_Q5_0 || TYPE == B200Q_TYPE_Q5_1) {
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
+        I.h[0] = LD::ld4(P.p[1] + (row * n32 + it) * 4);
+        I.m[0] = TYPE == B200Q_TYPE_Q5_1 ? LD::ld4(P.p[2] + (row * n32 + it) * 4) : LD::ld2(P.p[2] + (row * n32 + it) * 2);
+    } else if (TYPE == B200Q_TYPE_Q6_0) {
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
+        LD::ld8(I.h, P.p[1] + (row * n32 + it) * 8);
+        I.m[0] = LD::ld2(P.p[2] + (row * n32 + it) * 2);
     } else if (TYPE == B200Q_TYPE_Q8_0) {
         const uint8_t * p = P.p[0] + (row * n32 + it) * 32;
         LD::ld16(I.q, p); LD::ld16(I.q + 4, p + 16);
@@ -515,6 +568,25 @@ B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & 
         const float d = b200q_h2f((uint16_t)I.m[0]);
         for (int w = 0; w < 4; ++w) { C.va[2 * w] = (int)(I.q[w] & 0x0F0F0F0Fu); C.va[2 * w + 1] = (int)((I.q[w] >> 4) & 0x0F0F0F0Fu); }
         C.dl[0] = C.dl[1] = d; C.ml[0] = C.ml[1] = 8.0f * d;
+    } else if (TYPE == B200Q_TYPE_Q4_1 || TYPE == B200Q_TYPE_Q5_0 || TYPE == B200Q_TYPE_Q5_1) {
+        // Q4_1: w = d*q + m ; Q5_0: w = d*(q5 - 16) ; Q5_1: w = d*q5 + m      (ggml-quants.c:1601-1673)
+        const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF));
+        for (int w = 0; w < 4; ++w) {
+            uint32_t lo = I.q[w] & 0x0F0F0F0Fu, hi = (I.q[w] >> 4) & 0x0F0F0F0Fu;
+            if (TYPE != B200Q_TYPE_Q4_1) { lo |= (I.h[0] << (4 - w)) & 0x10101010u; hi |= (I.h[0] >> w) & 0x10101010u; }
+            C.va[2 * w] = (int)lo; C.va[2 * w + 1] = (int)hi;
+        }
+        C.dl[0] = C.dl[1] = d;
+        C.ml[0] = C.ml[1] = TYPE == B200Q_TYPE_Q5_0 ? 16.0f * d : -b200q_h2f((uint16_t)(I.m[0] >> 16));
+    } else if (TYPE == B200Q_TYPE_Q6_0) {
+        const float d = b200q_h2f((uint16_t)I.m[0]);
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t U = I.h[w / 2]; const int f0 = 2 * (w % 2), f1 = f0 + 1;
+            uint32_t lo = I.q[w] & 0x0F0F0F0Fu, hi = (I.q[w] >> 4) & 0x0F0F0F0Fu;
+            lo |= ((U >> (2 * f0)) & 0x03030303u) << 4; hi |= ((U >> (2 * f1)) & 0x03030303u) << 4;
+            C.va[2 * w] = (int)lo; C.va[2 * w + 1] = (int)hi;
+        }
+        C.dl[0] = C.dl[1] = d; C.ml[0] = C.ml[1] = 32.0f * d;
     } else if (TYPE == B200Q_TYPE_Q8_0) {
         const float d = b200q_h2f((uint16_t)I.m[0]);
         for (int w = 0; w < 8; ++w) C.va[w] = (int)I.q[w];
