@@ -106,43 +106,54 @@ template <int NCOLS>
 __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x, int64_t x_stride, int64_t K,
                                                    int8_t * sq, float * sd, int * sis, int tid, int nthreads) {
     const int nch = (int)(K / 8), total = nch * NCOLS, n32 = (int)(K / 32);
-    for (int base = 0; base < total; base += nthreads) {
-        const int c = base + tid;
-        const bool valid = c < total;
-        const int col = valid ? c / nch : 0, ch = valid ? c % nch : 0;
-        float v[8];
-        if (valid) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8));
-            const float4 b = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+    constexpr int B = 4;                                   // chunks per thread per batch: 8 independent LDG.128 in flight, so the
+                                                           // activation vector costs 1 (K=4096) .. 2 (K=14336) L2 round trips, not 2 .. 6
+    for (int base = 0; base < total; base += nthreads * B) {
+        float4 va[B], vb[B];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+        for (int u = 0; u < B; ++u) {
+            const int c = base + u * nthreads + tid;
+            int col = 0, ch = c < total ? c : 0;
+            if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
+            if (c < total) {
+                va[u] = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8));
+                vb[u] = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
+            } else { va[u] = make_float4(0.f, 0.f, 0.f, 0.f); vb[u] = va[u]; }
         }
-        float amax = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-        // q = rint(x * (127/amax)): one division per block instead of one per element.  Differs from the reference's
-        // roundf(x / d) only for products within 1 ulp of a rounding tie (p ~ 1e-5 per element, 1 LSB); the oracle
-        // restates exactly this arithmetic (oracle_quantize_q8_1_b200) next to the reference's (oracle_quantize_q8_1).
-        const float d = amax / 127.0f;
-        const float inv = amax > 0.0f ? __fdiv_rn(127.0f, amax) : 0.0f;
-        int q[8];
+        for (int u = 0; u < B; ++u) {
+            const int c = base + u * nthreads + tid;
+            if (base + u * nthreads >= total) break;       // warp-uniform: the whole batch slot is past the end
+            const bool valid = c < total;
+            int col = 0, ch = valid ? c : 0;
+            if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
+            const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+            float amax = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) q[j] = __float2int_rn(__fmul_rn(v[j], inv));
-        int2 pk;
-        pk.x = (int)__byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
-        pk.y = (int)__byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
-        int s = __dp4a(pk.x, 0x01010101, __dp4a(pk.y, 0x01010101, 0));
-        s += __shfl_xor_sync(0xffffffffu, s, 1);                       // sum over 16 weights (2 lanes)
-        const int s_hi = __shfl_down_sync(0xffffffffu, s, 2);          // the second 16 of the 32-block
-        if (valid) {
-            *reinterpret_cast<int2 *>(sq + (size_t)col * K + (size_t)ch * 8) = pk;
-            if ((ch & 3) == 0) {
-                sd[col * n32 + (ch >> 2)]  = __half2float(__float2half_rn(d));
-                sis[col * n32 + (ch >> 2)] = (s & 0xFFFF) | (s_hi << 16);
+            for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            // d = amax/127 exactly as the reference; q = rint(x * (1/d)) with a correctly rounded reciprocal: one division and one
+            // reciprocal per block instead of one division per element.  Differs from the reference's roundf(x / d) only for
+            // products within 1 ulp of a rounding tie (p ~ 1e-5 per element, 1 LSB); the oracle restates exactly this arithmetic
+            // (oracle_quantize_q8_1_b200) next to the reference's (oracle_quantize_q8_1).
+            const float d = __fdiv_rn(amax, 127.0f);
+            const float inv = d > 0.0f ? __frcp_rn(d) : 0.0f;
+            int q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = max(-127, min(127, __float2int_rn(__fmul_rn(v[j], inv))));
+            int2 pk;
+            pk.x = (int)__byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+            pk.y = (int)__byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+            int s = __dp4a(pk.x, 0x01010101, __dp4a(pk.y, 0x01010101, 0));
+            s += __shfl_xor_sync(0xffffffffu, s, 1);                       // sum over 16 weights (2 lanes)
+            const int s_hi = __shfl_down_sync(0xffffffffu, s, 2);          // the second 16 of the 32-block
+            if (valid) {
+                *reinterpret_cast<int2 *>(sq + (size_t)col * K + (size_t)ch * 8) = pk;
+                if ((ch & 3) == 0) {
+                    sd[col * n32 + (ch >> 2)]  = __half2float(__float2half_rn(d));
+                    sis[col * n32 + (ch >> 2)] = (s & 0xFFFF) | (s_hi << 16);
+                }
             }
         }
     }
@@ -304,7 +315,9 @@ __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarri
 // Warp 0 = producer (lane l streams the units of consumer warp l), warps 1..NCW = consumers.
 // A unit is one SEGMENT (<= 128 items) of a PAIR of adjacent output rows of one tensor: the two rows share every
 // activation load and all loop bookkeeping, and give the scheduler two independent dependency chains.
-template <int TYPE, int NCOLS, bool UPGATE, bool MULTI>
+// PAIR = false: single-row units (used when there are fewer row pairs than warps in the grid: small matrices are latency-bound,
+// more and shorter units win there); the second half of every pair-stage is then simply unused.
+template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR>
 __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const mmvq_args & a = ra.a; const ring_geom & g = ra.g;
@@ -326,7 +339,8 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
 
     const int nseg = (n32 + B200Q_SEG_ITEMS - 1) / B200Q_SEG_ITEMS;
     constexpr int NT = UPGATE ? 2 : 1;                            // tensors per row (up, gate)
-    const int n_pairs = (int)((a.M_total + 1) / 2);               // pair p = rows 2p, 2p+1 (segments have even row counts)
+    constexpr int RPU = PAIR ? 2 : 1;                             // rows per unit
+    const int n_pairs = (int)((a.M_total + RPU - 1) / RPU);       // unit p = rows RPU*p (.. +1) (segments have even row counts)
     // static split of the pairs over CTAs (+-1 pair), dynamic claiming inside the CTA: the producer lane of a consumer
     // warp takes the next pair from a shared counter whenever that warp's ring has room, so warps never idle on a
     // coarse static remainder (2.2 pairs/warp for the FFN up/gate shape would otherwise mean 3 for some, 2 for others)
@@ -356,11 +370,11 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
         if (pt == 0 && psg == 0) { pcur = atomicAdd(next_pair, 1); if (pcur >= c1) pcur = -1; }
         pair_id[lane * S + pst] = pcur;
         if (pcur < 0) { rb_arrive(fb); pdone = true; return; }   // sentinel: nothing left for this consumer
-        int s, row; locate(2 * pcur, s, row);
+        int s, row; locate(RPU * pcur, s, row);
         const mmvq_seg & sgm = a.seg[MULTI ? s : 0];
         const b200q_planes & P = (UPGATE && pt == 1) ? sgm.P2 : sgm.P;
         const int g8 = min(B200Q_SEG_ITEMS, n32 - psg * B200Q_SEG_ITEMS) >> 3;
-        const bool two = row + 1 < (int)sgm.M;
+        const bool two = PAIR && row + 1 < (int)sgm.M;
         unsigned char * dstb = ring0 + ((size_t)lane * S + pst) * pair_stage;
         uint32_t bytes = 0;
 #pragma unroll
@@ -420,7 +434,7 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
 #pragma unroll
             for (int c = 0; c < NCOLS; ++c) { acc0[c] = 0.0f; acc1[c] = 0.0f; }
             if (t == 0) {
-                locate(2 * pid, cs, crow);
+                locate(RPU * pid, cs, crow);
                 if (b200q_row_plane(TYPE) >= 0) {              // per-row scales straight from global memory
                     const mmvq_seg & sgm = a.seg[MULTI ? cs : 0];
                     const int r1 = min(crow + 1, (int)sgm.M - 1);
@@ -440,13 +454,12 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
         auto do_item = [&](int itl) {
             b200q_item I0, I1; b200q_canon C;
             b200q_load_item<TYPE, b200q_ld_plain, false, int>(I0, SP0, 0, itl);
-            b200q_load_item<TYPE, b200q_ld_plain, false, int>(I1, SP1, 0, itl);
+            if (PAIR) b200q_load_item<TYPE, b200q_ld_plain, false, int>(I1, SP1, 0, itl);
             I0.rs = rsa; I1.rs = rsb;
             const int it = sg * B200Q_SEG_ITEMS + itl;
             b200q_decode_item<TYPE>(I0, itl, C, T);
             item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc0);
-            b200q_decode_item<TYPE>(I1, itl, C, T);
-            item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc1);
+            if (PAIR) { b200q_decode_item<TYPE>(I1, itl, C, T); item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc1); }
         };
         if (items == B200Q_SEG_ITEMS) {
 #pragma unroll
@@ -465,15 +478,15 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
                 for (int c = 0; c < NCOLS; ++c) { up0[c] = acc0[c]; up1[c] = acc1[c]; }      // up . x (still per-lane partials)
                 t = 1;
             } else {
-                const bool two = crow + 1 < (int)sgm.M;
+                const bool two = PAIR && crow + 1 < (int)sgm.M;
 #pragma unroll
                 for (int c = 0; c < NCOLS; ++c) {
                     // four (two) independent butterfly chains interleave in the pipeline
                     float v0 = acc0[c], v1 = acc1[c], u0 = UPGATE ? up0[c] : 0.0f, u1 = UPGATE ? up1[c] : 0.0f;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
-                        v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-                        if (UPGATE) { u0 += __shfl_xor_sync(0xffffffffu, u0, o); u1 += __shfl_xor_sync(0xffffffffu, u1, o); }
+                        v0 += __shfl_xor_sync(0xffffffffu, v0, o); if (PAIR) v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                        if (UPGATE) { u0 += __shfl_xor_sync(0xffffffffu, u0, o); if (PAIR) u1 += __shfl_xor_sync(0xffffffffu, u1, o); }
                     }
                     if (UPGATE) {                                                 // v = gate . x, u = up . x
                         if (a.limit > 0.0f) { v0 = fminf(v0, a.limit); u0 = fminf(fmaxf(u0, -a.limit), a.limit); v1 = fminf(v1, a.limit); u1 = fminf(fmaxf(u1, -a.limit), a.limit); }
@@ -554,8 +567,8 @@ static bool make_ring_geom(int type, int64_t K, ring_geom & g) {
     return np > 0 && np <= 4;
 }
 
-template <int TYPE, int NCOLS, bool UPGATE, bool MULTI>
-static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
+template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR>
+static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
     mmvq_ring_args ra; ra.a = a; ra.g = g0;
     for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
     if (a.M_total >= (int64_t)1 << 30) return -100;
@@ -571,13 +584,13 @@ static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_
     }
     if (S < 2) return -100;                              // does not fit: caller falls back to the LDG kernel
     if (S > 4) S = 4;
-    const int64_t n_pairs = (a.M_total + 1) / 2;
+    const int64_t n_pairs = PAIR ? (a.M_total + 1) / 2 : a.M_total;
     while (ncw > 3 && n_pairs <= (int64_t)sm_count * (ncw > 7 ? 7 : 3)) ncw = ncw > 7 ? 7 : 3;
     ra.g.n_stages = S;
     const size_t smem = (size_t)ncw * S * (pair_stage + 16) + xbytes + 64;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
+        if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
         configured = true;
     }
     int64_t grid = (n_pairs + ncw - 1) / ncw;
@@ -588,7 +601,16 @@ static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI>, ra);
+    return (int)cudaLaunchKernelEx(&cfg, k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR>, ra);
+}
+
+template <int TYPE, int NCOLS, bool UPGATE, bool MULTI>
+static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
+    // row pairs amortise the activation loads; single rows give more, shorter units when the matrix is small
+    static const int force = [] { const char * e = getenv("B200Q_PAIR"); return e ? atoi(e) : -1; }();
+    const bool pair = force >= 0 ? force != 0 : true;      // measured: pairs win for every Llama-3-8B shape (679 vs 628 tok/s)
+    return pair ? launch_mmvq_ring_tp<TYPE, NCOLS, UPGATE, MULTI, true>(a, g0, sm_count, pdl, ctas_per_sm, st)
+                : launch_mmvq_ring_tp<TYPE, NCOLS, UPGATE, MULTI, false>(a, g0, sm_count, pdl, ctas_per_sm, st);
 }
 
 template <int TYPE>

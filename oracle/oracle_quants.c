@@ -280,7 +280,7 @@ ORACLE_API int oracle_quantize_q8_1(const float * x, int64_t n, int64_t k, int8_
 }
 
 // The product's variant of the activation quantiser (ik_llama_cpp_b200/csrc/b200q_decode.cu quantize_x_to_smem):
-//   d = amax/127 (stored as half), inv = 127/amax, q = rint(x*inv) (round-half-even), i.e. one division per block
+//   d = amax/127 (stored as half), inv = 1/d (correctly rounded), q = clamp(rint(x*inv), +-127) (round-half-even), i.e. one division + one reciprocal per block
 // instead of the reference's roundf(x/d) per element.  Identical except at rounding ties (p ~ 1e-5 per element).
 // Restated so that kernel-vs-oracle checks can be held to f32 summation-order accuracy.
 ORACLE_API int oracle_quantize_q8_1_b200(const float * x, int64_t n, int64_t k, int8_t * q, uint16_t * d_bits) {
@@ -288,8 +288,8 @@ ORACLE_API int oracle_quantize_q8_1_b200(const float * x, int64_t n, int64_t k, 
     for (int64_t r = 0; r < n; ++r) for (int64_t b = 0; b < k / 32; ++b) {
         const float * xb = x + r * k + b * 32; float amax = 0.0f;
         for (int j = 0; j < 32; ++j) { const float a = fabsf(xb[j]); if (a > amax) amax = a; }
-        const float d = amax / 127.0f; const float inv = amax > 0.0f ? 127.0f / amax : 0.0f;
-        for (int j = 0; j < 32; ++j) { const float p = xb[j] * inv; q[r * k + b * 32 + j] = (int8_t)lrintf(p); }
+        const float d = amax / 127.0f; const float inv = d > 0.0f ? 1.0f / d : 0.0f;      // correctly rounded reciprocal == __frcp_rn
+        for (int j = 0; j < 32; ++j) { const float p = xb[j] * inv; long qi = lrintf(p); if (qi > 127) qi = 127; if (qi < -127) qi = -127; q[r * k + b * 32 + j] = (int8_t)qi; }
         d_bits[r * (k / 32) + b] = f2h(d);
     }
     return 0;
