@@ -161,13 +161,12 @@ class Model:
         x = self.x
         for L in self.layers:
             be.convert_activations(x, self.xb)          # f32 -> bf16 once per distinct activation (shared by Q,K,V)
-            be.mul_mat(L["wq"], x, out=self.q, x_bf16=self.xb); be.mul_mat(L["wk"], x, out=self.kk, x_bf16=self.xb); be.mul_mat(L["wv"], x, out=self.v, x_bf16=self.xb)
+            be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v], x_bf16=self.xb)      # one launch
             be.convert_activations(self.q, self.qb)
             be.mul_mat(L["wo"], self.q, out=self.h, x_bf16=self.qb); self.allreduce(self.h)
             be.convert_activations(self.h, self.hb)
-            be.mul_mat(L["up"], self.h, out=self.u, x_bf16=self.hb); be.mul_mat(L["gate"], self.h, out=self.g, x_bf16=self.hb)
-            t.mul(t.nn.functional.silu(self.g), self.u, out=self.a)         # glue, not the hot path
-            be.convert_activations(self.a, self.ab)
+            # FUSED_UP_GATE (n > 8): up GEMM, gate GEMM with silu(gate)*up in its epilogue; it also emits the bf16 operand of ffn_down
+            be.fused_up_gate(L["up"], L["gate"], self.h, "silu", out=self.a, x_bf16=self.hb, out_bf16=self.ab)
             be.mul_mat(L["down"], self.a, out=self.x2, x_bf16=self.ab); self.allreduce(self.x2)
             x = self.x2
         be.mul_mat(self.head, x[-1:], out=self.logits)

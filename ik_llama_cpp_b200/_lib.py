@@ -54,6 +54,14 @@ def lib() -> ctypes.CDLL:
     L.b200q_dequantize_bf16.argtypes = [i32, vp, vp, i64, i64, vp]
     L.b200q_convert_f32_bf16.argtypes = [vp, i64, vp, i64, i64, vp]
     L.b200q_mul_mat_gemm_bf16.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp, c_size_t, vp]
+    L.b200q_mul_mat_gemm_multi_bf16.argtypes = [i32, i32, vp, vp, vp, i64, vp, i64, vp, c_size_t, vp]
+    L.b200q_fused_up_gate_gemm_bf16.argtypes = [i32, vp, vp, vp, vp, vp, i64, i64, i64, i32, c_float, vp, c_size_t, vp]
+    L.b200q_mul_mat_multi_workspace.restype = c_size_t
+    L.b200q_mul_mat_multi_workspace.argtypes = [i32, i32, vp, i64, i64]
+    L.b200q_mul_mat_multi.argtypes = [i32, i32, vp, vp, vp, i64, vp, i64, vp, c_size_t, vp]
+    L.b200q_fused_up_gate_workspace.restype = c_size_t
+    L.b200q_fused_up_gate_workspace.argtypes = [i32, i64, i64, i64]
+    L.b200q_fused_up_gate.argtypes = [i32, vp, vp, vp, vp, i64, i64, i64, i32, c_float, vp, c_size_t, vp]
     L.b200q_reduce_sum_nvls.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, ctypes.c_uint32, vp, vp, vp]
     L.b200q_mul_mat.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp, c_size_t, vp]
     L.b200q_mul_mat_host.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp]

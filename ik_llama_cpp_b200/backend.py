@@ -144,41 +144,66 @@ def mul_mat(w: QuantTensor, x: torch.Tensor, out: torch.Tensor | None = None, x_
     return dst
 
 
-def mul_mat_multi(ws: list[QuantTensor], x: torch.Tensor, outs: list[torch.Tensor] | None = None) -> list[torch.Tensor]:
-    """Several MUL_MATs sharing src1 (Q,K,V) in one launch — the reference's look-ahead fusion, ggml-cuda.cu:2573-2601."""
+def mul_mat_multi(ws: list[QuantTensor], x: torch.Tensor, outs: list[torch.Tensor] | None = None,
+                  x_bf16: torch.Tensor | None = None) -> list[torch.Tensor]:
+    """Several MUL_MATs sharing src1 (Q,K,V) in one launch — the reference's look-ahead fusion, ggml-cuda.cu:2573-2601.
+    n <= 8: one mat-vec launch over the row segments; n > 8: one GEMM launch over the row tiles of all tensors."""
     _require_cuda()
     n = x.shape[0]
-    assert n <= MMVQ_MAX_BATCH_SIZE and all(w.k == ws[0].k and w.ggml_type == ws[0].ggml_type for w in ws)
+    assert all(w.k == ws[0].k and w.ggml_type == ws[0].ggml_type for w in ws) and x.shape[1] == ws[0].k
     outs = outs or [torch.empty((n, w.m), dtype=torch.float32, device=x.device) for w in ws]
     nt = len(ws)
     Wp = (c_void_p * nt)(*[w.ptr for w in ws])
     Dp = (c_void_p * nt)(*[o.data_ptr() for o in outs])
     Mp = (c_int64 * nt)(*[w.m for w in ws])
+    L = _lib.lib()
     with torch.cuda.device(x.device):
-        check(_lib.lib().b200q_mul_mat_vec_multi(ws[0].ggml_type, nt, Wp, Dp, Mp, ws[0].k, x.data_ptr(), n, x.stride(0), _stream()), "b200q_mul_mat_vec_multi")
+        if n <= MMVQ_MAX_BATCH_SIZE:
+            check(L.b200q_mul_mat_vec_multi(ws[0].ggml_type, nt, Wp, Dp, Mp, ws[0].k, x.data_ptr(), n, x.stride(0), _stream()), "b200q_mul_mat_vec_multi")
+        elif x_bf16 is not None:
+            assert x_bf16.dtype == torch.bfloat16 and x_bf16.shape == x.shape and x_bf16.is_contiguous()
+            wsb = _workspace(max(w.m for w in ws) * ws[0].k * 2 + 256, x.device)
+            check(L.b200q_mul_mat_gemm_multi_bf16(ws[0].ggml_type, nt, Wp, Dp, Mp, ws[0].k, x_bf16.data_ptr(), n, wsb.data_ptr(), wsb.numel(), _stream()),
+                  "b200q_mul_mat_gemm_multi_bf16")
+        else:
+            xc = x if x.is_contiguous() else x.contiguous()
+            need = L.b200q_mul_mat_multi_workspace(ws[0].ggml_type, nt, Mp, ws[0].k, n)
+            wsb = _workspace(need, x.device)
+            check(L.b200q_mul_mat_multi(ws[0].ggml_type, nt, Wp, Dp, Mp, ws[0].k, xc.data_ptr(), n, wsb.data_ptr(), wsb.numel(), _stream()), "b200q_mul_mat_multi")
     return outs
 
 
 def fused_up_gate(up: QuantTensor, gate: QuantTensor, x: torch.Tensor, unary: str = "silu", limit: float = 0.0,
-                  out: torch.Tensor | None = None) -> torch.Tensor:
-    """GGML_OP_FUSED_UP_GATE: dst = unary(gate.x) * (up.x)."""
+                  out: torch.Tensor | None = None, x_bf16: torch.Tensor | None = None, out_bf16: torch.Tensor | None = None) -> torch.Tensor:
+    """GGML_OP_FUSED_UP_GATE: dst = unary(gate.x) * (up.x).
+    n <= 8: one mat-vec launch; n > 8: two GEMMs with the mul-unary in the gate GEMM's epilogue (the reference runs two MMQs +
+    ggml_fused_mul_unary, ggml-cuda.cu:3588-3618).  x_bf16 / out_bf16 (prefill only): reuse an already converted activation /
+    also emit the bf16 operand of the following ffn_down MUL_MAT."""
     _require_cuda()
     assert up.m == gate.m and up.k == gate.k and up.ggml_type == gate.ggml_type
     n = x.shape[0]
     dst = out if out is not None else torch.empty((n, up.m), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
     with torch.cuda.device(x.device):
         if n <= MMVQ_MAX_BATCH_SIZE:
-            check(_lib.lib().b200q_fused_up_gate_vec(up.ggml_type, up.ptr, gate.ptr, x.data_ptr(), dst.data_ptr(), up.m, up.k, n,
-                                                     x.stride(0), UNARY[unary], float(limit), _stream()), "b200q_fused_up_gate_vec")
+            check(L.b200q_fused_up_gate_vec(up.ggml_type, up.ptr, gate.ptr, x.data_ptr(), dst.data_ptr(), up.m, up.k, n,
+                                            x.stride(0), UNARY[unary], float(limit), _stream()), "b200q_fused_up_gate_vec")
+        elif x_bf16 is not None or out_bf16 is not None:
+            xb = x_bf16 if x_bf16 is not None else convert_activations(x)
+            assert xb.dtype == torch.bfloat16 and xb.shape == x.shape and xb.is_contiguous()
+            if out_bf16 is not None:
+                assert out_bf16.dtype == torch.bfloat16 and out_bf16.shape == dst.shape and out_bf16.is_contiguous()
+            need = (up.m * n * 4 + 255) // 256 * 256 + up.m * up.k * 2 + 256
+            ws = _workspace(need, x.device)
+            check(L.b200q_fused_up_gate_gemm_bf16(up.ggml_type, up.ptr, gate.ptr, xb.data_ptr(), dst.data_ptr(),
+                                                  out_bf16.data_ptr() if out_bf16 is not None else None, up.m, up.k, n,
+                                                  UNARY[unary], float(limit), ws.data_ptr(), ws.numel(), _stream()), "b200q_fused_up_gate_gemm_bf16")
         else:
-            # n > 8: two GEMMs + fused mul-unary, like the reference (ggml-cuda.cu:3588-3618)
-            u = mul_mat(up, x)
-            g = mul_mat(gate, x)
-            if limit > 0:
-                g = g.clamp(max=limit); u = u.clamp(-limit, limit)
-            act = {"silu": torch.nn.functional.silu, "gelu": lambda t: torch.nn.functional.gelu(t, approximate="tanh"),
-                   "relu": torch.relu, "none": lambda t: t}[unary]
-            torch.mul(act(g), u, out=dst)
+            xc = x if x.is_contiguous() else x.contiguous()
+            need = L.b200q_fused_up_gate_workspace(up.ggml_type, up.m, up.k, n)
+            ws = _workspace(need, x.device)
+            check(L.b200q_fused_up_gate(up.ggml_type, up.ptr, gate.ptr, xc.data_ptr(), dst.data_ptr(), up.m, up.k, n,
+                                        UNARY[unary], float(limit), ws.data_ptr(), ws.numel(), _stream()), "b200q_fused_up_gate")
     return dst
 
 

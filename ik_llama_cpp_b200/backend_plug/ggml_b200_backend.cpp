@@ -150,7 +150,7 @@ static int b200_unary(int ggml_unary) {
 static bool b200_can_mul_mat(const ggml_tensor * w, const ggml_tensor * x, const ggml_tensor * dst) {
     return w && x && ggml_is_quantized(w->type) && b200q_type_supported(w->type) && ggml_is_contiguous(w) && w->ne[2] * w->ne[3] == 1 &&
            x->type == GGML_TYPE_F32 && ggml_is_contiguous(x) && x->ne[2] * x->ne[3] == 1 && dst->type == GGML_TYPE_F32 && ggml_is_contiguous(dst) &&
-           w->ne[0] == x->ne[0] && w->ne[0] % 256 == 0;
+           w->ne[0] == x->ne[0] && w->ne[0] % ggml_blck_size(w->type) == 0 && w->ne[0] % 32 == 0;
 }
 GGML_CALL static bool b200_backend_supports_op(ggml_backend_t, const ggml_tensor * op) {
     switch (op->op) {
@@ -158,7 +158,8 @@ GGML_CALL static bool b200_backend_supports_op(ggml_backend_t, const ggml_tensor
         case GGML_OP_MUL_MAT: return b200_can_mul_mat(op->src[0], op->src[1], op);
         case GGML_OP_FUSED_UP_GATE:
             return op->src[0] && op->src[1] && op->src[0]->type == op->src[1]->type && b200_can_mul_mat(op->src[0], op->src[2], op) &&
-                   b200_can_mul_mat(op->src[1], op->src[2], op) && op->src[2]->ne[1] <= 8 && b200_unary(b200_op_param_i32(op, 0)) >= 0;
+                   b200_can_mul_mat(op->src[1], op->src[2], op) && b200_unary(b200_op_param_i32(op, 0)) >= 0 &&
+                   (op->src[2]->ne[1] <= 8 || (op->src[0]->ne[1] * op->src[2]->ne[1]) % 4 == 0);
         default: return false;     // no silent CPU detour inside graph_compute: unsupported ops are refused up front
     }
 }
@@ -172,15 +173,34 @@ GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t b, g
                 const ggml_tensor * w = node->src[0]; const ggml_tensor * x = node->src[1];
                 GGML_ASSERT(b200_can_mul_mat(w, x, node));
                 const int64_t m = w->ne[1], k = w->ne[0], n = x->ne[1];
-                const size_t need = b200q_mul_mat_workspace(w->type, m, k, n);
-                void * ws = need ? c->workspace(need) : nullptr;
-                B200Q_CHECK(b200q_mul_mat(w->type, w->data, (const float *)x->data, (float *)node->data, m, k, n, ws, need, c->stream));
+                // look-ahead fusion of ggml_cuda_mul_mat_q (ggml-cuda.cu:2573-2601): following MUL_MAT nodes that share src1 (Q,K,V)
+                // and the weight type join this launch; every node's data is still written
+                const void * W[3] = {w->data}; float * D[3] = {(float *)node->data}; int64_t M[3] = {m}; int nt = 1;
+                while (nt < 3 && i + 1 < cgraph->n_nodes) {
+                    const ggml_tensor * nx = cgraph->nodes[i + 1];
+                    if (nx->op != GGML_OP_MUL_MAT || nx->src[1] != x || !nx->src[0] || nx->src[0]->type != w->type || !b200_can_mul_mat(nx->src[0], x, nx)) break;
+                    if (n <= 8 && (nx->src[0]->ne[1] & 1)) break;            // the multi-tensor mat-vec walks row pairs
+                    W[nt] = nx->src[0]->data; D[nt] = (float *)nx->data; M[nt] = nx->src[0]->ne[1]; ++nt; ++i;
+                }
+                if (nt > 1 && (n > 8 || !(m & 1))) {
+                    const size_t need = b200q_mul_mat_multi_workspace(w->type, nt, M, k, n);
+                    void * ws = need ? c->workspace(need) : nullptr;
+                    B200Q_CHECK(b200q_mul_mat_multi(w->type, nt, W, D, M, k, (const float *)x->data, n, ws, need, c->stream));
+                } else {
+                    for (int j = 0; j < nt; ++j) {
+                        const size_t need = b200q_mul_mat_workspace(w->type, M[j], k, n);
+                        void * ws = need ? c->workspace(need) : nullptr;
+                        B200Q_CHECK(b200q_mul_mat(w->type, W[j], (const float *)x->data, D[j], M[j], k, n, ws, need, c->stream));
+                    }
+                }
             } break;
             case GGML_OP_FUSED_UP_GATE: {
                 const ggml_tensor * up = node->src[0]; const ggml_tensor * gate = node->src[1]; const ggml_tensor * x = node->src[2];
                 float limit = 0.0f; memcpy(&limit, (const char *)node->op_params + sizeof(int32_t), sizeof(float));
-                B200Q_CHECK(b200q_fused_up_gate_vec(up->type, up->data, gate->data, (const float *)x->data, (float *)node->data, up->ne[1], up->ne[0],
-                                                    (int)x->ne[1], x->ne[0], b200_unary(b200_op_param_i32(node, 0)), limit, c->stream));
+                const size_t need = b200q_fused_up_gate_workspace(up->type, up->ne[1], up->ne[0], x->ne[1]);
+                void * ws = need ? c->workspace(need) : nullptr;
+                B200Q_CHECK(b200q_fused_up_gate(up->type, up->data, gate->data, (const float *)x->data, (float *)node->data, up->ne[1], up->ne[0],
+                                                x->ne[1], b200_unary(b200_op_param_i32(node, 0)), limit, ws, need, c->stream));
             } break;
             default:
                 b200_log(GGML_LOG_LEVEL_ERROR, "%s: op %s not supported by the B200 quantized-mat-mul backend\n", __func__, ggml_op_name(node->op));

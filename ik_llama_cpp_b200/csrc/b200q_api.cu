@@ -8,12 +8,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
-int b200q_launch_gemm(int type, const void * W, const float * x, int64_t x_stride, float * dst, int64_t M, int64_t K, int64_t N,
-                      void * ws, size_t ws_bytes, int sm_count, int fused, cudaStream_t st);
-int b200q_launch_gemm_bf16x(int type, const void * W, const void * xb, float * dst, int64_t M, int64_t K, int64_t N,
-                            void * wscratch, size_t ws_bytes, int sm_count, int fused, cudaStream_t st);
-int b200q_launch_f32_to_bf16(const float * x, int64_t x_stride, void * out, int64_t K, int64_t N, cudaStream_t st);
 int b200q_launch_allreduce_nvls(const float * in, float * out, int64_t n, void * mc_base, void * local_base, int64_t stride,
                                 void * mc_flag, const void * local_flag, uint32_t world, void * seq, void * cta_counter, int sm_count, cudaStream_t st);
 
@@ -58,6 +52,7 @@ int ensure(scratch & s, size_t n) {
 thread_local scratch g_x, g_y, g_ws, g_stage;
 // programmatic dependent launch for the decode kernels (default on; B200Q_PDL=0 or b200q_set_option("pdl",0) disables)
 int & opt_ring() { static int v = [] { const char * e = getenv("B200Q_RING"); return e ? atoi(e) : 1; }(); return v; }
+int & opt_fuse_epi() { static int v = [] { const char * e = getenv("B200Q_FUSE_EPILOGUE"); return e ? atoi(e) : 0; }(); return v; }
 int & opt_fused() { static int v = [] { const char * e = getenv("B200Q_FUSED_GEMM"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_pdl() { static int v = [] { const char * e = getenv("B200Q_PDL"); return e ? atoi(e) : 1; }(); return v; }
 }  // namespace
@@ -70,6 +65,7 @@ int b200q_set_option(const char * key, int value) {
     if (key && !strcmp(key, "pdl")) { opt_pdl() = value; return B200Q_OK; }
     if (key && !strcmp(key, "ring")) { opt_ring() = value; return B200Q_OK; }
     if (key && !strcmp(key, "fused_gemm")) { opt_fused() = value; return B200Q_OK; }
+    if (key && !strcmp(key, "fuse_epilogue")) { opt_fuse_epi() = value; return B200Q_OK; }
     return fail(B200Q_E_ARG, "b200q_set_option: unknown option");
 }
 int b200q_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
@@ -189,6 +185,73 @@ int b200q_mul_mat_gemm_bf16(int type, const void * W, const void * x_bf16, float
     if (!W || !x_bf16 || !dst || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_gemm_bf16: bad argument");
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_gemm_bf16: no CUDA device");
     return check_launch(b200q_launch_gemm_bf16x(type, W, x_bf16, dst, m, k, n, workspace, workspace_bytes, di.sm_count, opt_fused(), (cudaStream_t)stream), "b200q_mul_mat_gemm_bf16");
+}
+int b200q_mul_mat_gemm_multi_bf16(int type, int n_tensors, const void * const * W, float * const * dst, const int64_t * m, int64_t k,
+                                  const void * x_bf16, int64_t n, void * workspace, size_t workspace_bytes, void * stream) {
+    if (n_tensors < 1 || n_tensors > 3 || !W || !dst || !m || !x_bf16 || n < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_gemm_multi_bf16: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_gemm_multi_bf16: no CUDA device");
+    b200q_gemm_multi d; memset(&d, 0, sizeof d);
+    d.type = type; d.n_seg = n_tensors; d.K = k; d.N = n; d.xb = x_bf16;
+    for (int i = 0; i < n_tensors; ++i) { if (!W[i] || !dst[i] || m[i] <= 0) return fail(B200Q_E_ARG, "b200q_mul_mat_gemm_multi_bf16: bad tensor %d", i); d.W[i] = W[i]; d.dst[i] = dst[i]; d.M[i] = m[i]; }
+    return check_launch(b200q_launch_gemm_multi_bf16x(d, workspace, workspace_bytes, di.sm_count, opt_fused(), (cudaStream_t)stream), "b200q_mul_mat_gemm_multi_bf16");
+}
+size_t b200q_mul_mat_multi_workspace(int type, int n_tensors, const int64_t * m, int64_t k, int64_t n) {
+    if (n <= 8 || !m) return 0;
+    int64_t mm = 0; for (int i = 0; i < n_tensors; ++i) mm = m[i] > mm ? m[i] : mm;
+    return b200q_gemm_workspace_bytes(type, mm, k, n);
+}
+int b200q_mul_mat_multi(int type, int n_tensors, const void * const * W, float * const * dst, const int64_t * m, int64_t k,
+                        const float * x, int64_t n, void * workspace, size_t workspace_bytes, void * stream) {
+    if (n <= 8) return b200q_mul_mat_vec_multi(type, n_tensors, W, dst, m, k, x, (int)n, k, stream);
+    if (!x || !workspace || workspace_bytes < b200q_mul_mat_multi_workspace(type, n_tensors, m, k, n)) return fail(B200Q_E_ARG, "b200q_mul_mat_multi: bad argument / workspace too small");
+    int rc = b200q_convert_f32_bf16(x, k, workspace, k, n, stream); if (rc) return rc;
+    const size_t off = (size_t)b200q_align_up(n * k * 2, 256);
+    return b200q_mul_mat_gemm_multi_bf16(type, n_tensors, W, dst, m, k, workspace, n, (char *)workspace + off, workspace_bytes - off, stream);
+}
+
+size_t b200q_fused_up_gate_workspace(int type, int64_t m, int64_t k, int64_t n) {
+    if (n <= 8) return 0;
+    return (size_t)b200q_align_up(n * k * 2, 256) + (size_t)b200q_align_up(m * n * 4, 256) + (size_t)b200q_align_up(m * k * 2, 256) + 0 * (size_t)type;
+}
+// x already bf16 [n][k]; workspace >= align(m*n*4) + align(m*k*2)
+int b200q_fused_up_gate_gemm_bf16(int type, const void * W_up, const void * W_gate, const void * x_bf16, float * dst, void * dst_bf16,
+                                  int64_t m, int64_t k, int64_t n, int unary, float limit, void * workspace, size_t workspace_bytes, void * stream) {
+    if (!W_up || !W_gate || !x_bf16 || !dst || !workspace || m <= 0 || n < 1) return fail(B200Q_E_ARG, "b200q_fused_up_gate_gemm_bf16: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_fused_up_gate_gemm_bf16: no CUDA device");
+    const size_t up_bytes = (size_t)b200q_align_up(m * n * 4, 256);
+    if (workspace_bytes < up_bytes) return fail(B200Q_E_ARG, "b200q_fused_up_gate_gemm_bf16: workspace too small");
+    float * up_res = (float *)workspace; void * wsc = (char *)workspace + up_bytes; const size_t wsc_bytes = workspace_bytes - up_bytes;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (!b200q_gemm_epilogue_fusable(type, m, k, n, di.sm_count, opt_fused() && opt_fuse_epi() ? 2 : 0)) {
+        // default: up and gate as the two segments of ONE launch (up -> workspace, gate -> dst), then the unary-mul tail in place
+        b200q_gemm_multi d; memset(&d, 0, sizeof d);
+        d.type = type; d.n_seg = 2; d.W[0] = W_up; d.dst[0] = up_res; d.M[0] = m; d.W[1] = W_gate; d.dst[1] = dst; d.M[1] = m; d.K = k; d.N = n; d.xb = x_bf16;
+        rc = check_launch(b200q_launch_gemm_multi_bf16x(d, wsc, wsc_bytes, di.sm_count, opt_fused(), st), "b200q_fused_up_gate_gemm_bf16(up,gate)");
+        if (rc) return rc;
+        return check_launch(b200q_launch_mul_unary(dst, up_res, dst, dst_bf16, m * n, unary, limit, st), "b200q_fused_up_gate_gemm_bf16(unary)");
+    }
+    rc = check_launch(b200q_launch_gemm_bf16x(type, W_up, x_bf16, up_res, m, k, n, wsc, wsc_bytes, di.sm_count, opt_fused(), st), "b200q_fused_up_gate_gemm_bf16(up)");
+    if (rc) return rc;
+    if (b200q_gemm_epilogue_fusable(type, m, k, n, di.sm_count, opt_fused() && opt_fuse_epi() ? 2 : 0)) {
+        // gate GEMM whose epilogue applies unary(gate) * up and (optionally) emits the bf16 operand of ffn_down
+        b200q_gemm_multi d; memset(&d, 0, sizeof d);
+        d.type = type; d.n_seg = 1; d.W[0] = W_gate; d.dst[0] = dst; d.mul[0] = up_res; d.dst_bf[0] = dst_bf16; d.M[0] = m; d.K = k; d.N = n; d.xb = x_bf16;
+        d.act = unary; d.limit = limit;
+        return check_launch(b200q_launch_gemm_multi_bf16x(d, wsc, wsc_bytes, di.sm_count, opt_fused(), st), "b200q_fused_up_gate_gemm_bf16(gate)");
+    }
+    rc = check_launch(b200q_launch_gemm_bf16x(type, W_gate, x_bf16, dst, m, k, n, wsc, wsc_bytes, di.sm_count, opt_fused(), st), "b200q_fused_up_gate_gemm_bf16(gate)");
+    if (rc) return rc;
+    return check_launch(b200q_launch_mul_unary(dst, up_res, dst, dst_bf16, m * n, unary, limit, st), "b200q_fused_up_gate_gemm_bf16(unary)");
+}
+int b200q_fused_up_gate(int type, const void * W_up, const void * W_gate, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
+                        int unary, float limit, void * workspace, size_t workspace_bytes, void * stream) {
+    if (n <= 8) return b200q_fused_up_gate_vec(type, W_up, W_gate, x, dst, m, k, (int)n, k, unary, limit, stream);
+    if (!x || !workspace || workspace_bytes < b200q_fused_up_gate_workspace(type, m, k, n)) return fail(B200Q_E_ARG, "b200q_fused_up_gate: bad argument / workspace too small");
+    if ((m * n) % 4) return fail(B200Q_E_SHAPE, "b200q_fused_up_gate: m*n must be a multiple of 4");
+    int rc = b200q_convert_f32_bf16(x, k, workspace, k, n, stream); if (rc) return rc;
+    const size_t off = (size_t)b200q_align_up(n * k * 2, 256);
+    return b200q_fused_up_gate_gemm_bf16(type, W_up, W_gate, workspace, dst, nullptr, m, k, n, unary, limit, (char *)workspace + off, workspace_bytes - off, stream);
 }
 int b200q_mul_mat(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
                   void * workspace, size_t workspace_bytes, void * stream) {

@@ -17,6 +17,9 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <climits>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 
@@ -233,6 +236,27 @@ template <int NB> struct gemmq_cfg {
     static constexpr size_t SMEM = 1024 + (size_t)A_STAGES * A_BYTES + (size_t)B_STAGES * B_BYTES + (size_t)RAW_STAGES * RAW_BYTES + 256;
 };
 
+// Up to GEMMQ_MAX_SEGS weight tensors that share the activation tile (Q,K,V: the reference's look-ahead fusion,
+// ggml-cuda.cu:2573-2601) are covered by ONE launch: blockIdx.x walks the concatenated 128-row tiles of all segments.
+// Epilogue options per segment (only with k_split == 1): mul != nullptr -> dst = act(clamp(acc)) * clamp(mul[n][m])
+// (the gate half of GGML_OP_FUSED_UP_GATE for n > 8, ggml-cuda.cu:3588-3618), dst_bf != nullptr -> bf16 copy of dst
+// (the activation operand of the next MUL_MAT, saves its f32 -> bf16 pass).
+constexpr int GEMMQ_MAX_SEGS = 3;
+struct gemmq_seg { float * dst; const float * mul; __nv_bfloat16 * dst_bf; int M; int tile0; };
+struct gemmq_args {
+    CUtensorMap tmP0[GEMMQ_MAX_SEGS], tmP1[GEMMQ_MAX_SEGS], tmB;
+    gemmq_seg seg[GEMMQ_MAX_SEGS];
+    int n_seg, N, K, k_split, act; float limit;
+};
+__device__ __forceinline__ float gemm_act_apply(int act, float g) {
+    switch (act) {
+        case B200Q_ACT_SILU: return __fdividef(g, 1.0f + __expf(-g));       // |rel err| ~1e-6: far below the bf16 operand noise of this path
+        case B200Q_ACT_GELU: { const float c = 0.79788456080286535587989211986876f, a = 0.044715f; return 0.5f * g * (1.0f + tanhf(c * g * (1.0f + a * g * g))); }
+        case B200Q_ACT_RELU: return fmaxf(g, 0.0f);
+        default: return g;
+    }
+}
+
 // carry-less per-byte add of two packed int8x4 (the A/B halves of the sign-fill LUT)
 __device__ __forceinline__ uint32_t vadd4_wrap(uint32_t a, uint32_t b) {
     return ((a & 0x7f7f7f7fu) + (b & 0x7f7f7f7fu)) ^ ((a ^ b) & 0x80808080u);
@@ -257,9 +281,14 @@ template <int J> __device__ __forceinline__ float biased_byte_to_float(uint32_t 
 // fence.proxy.async before the a_full arrive.
 template <int TYPE, int NB>
 __global__ void __launch_bounds__(64 + 32 * DQ_WARPS, 1)
-k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUtensorMap tmP1, const __grid_constant__ CUtensorMap tmB,
-         float * __restrict__ dst, int M, int N, int K, int k_split) {
+k_gemm_q(const __grid_constant__ gemmq_args a) {
     using cfg = gemmq_cfg<NB>;
+    int sg = 0;
+#pragma unroll
+    for (int s = 1; s < GEMMQ_MAX_SEGS; ++s) if (s < a.n_seg && (int)blockIdx.x >= a.seg[s].tile0) sg = s;
+    const CUtensorMap * tmP0 = &a.tmP0[sg], * tmP1 = &a.tmP1[sg], * tmB = &a.tmB;
+    float * __restrict__ dst = a.seg[sg].dst; const float * __restrict__ mul = a.seg[sg].mul; __nv_bfloat16 * __restrict__ dst_bf = a.seg[sg].dst_bf;
+    const int M = a.seg[sg].M, N = a.N, K = a.K, k_split = a.k_split;
     constexpr int BN = cfg::BN;
     constexpr int MMA_N = NB == 0 ? 128 : 256;
     constexpr int N_ACC = NB == 0 ? 1 : NB;
@@ -274,7 +303,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
     uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int m0 = ((int)blockIdx.x - a.seg[sg].tile0) * BM, n0 = blockIdx.y * BN;
     // K is walked in raw blocks of 256 weights; split-K over blockIdx.z in units of raw blocks
     const int nr_total = (K + RAW_K - 1) / RAW_K;
     const int nr_per = (nr_total + k_split - 1) / k_split;
@@ -290,7 +319,7 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
         for (int s = 0; s < cfg::RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], DQ_WARPS); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
-        tma_prefetch_desc(&tmP0); tma_prefetch_desc(&tmP1); tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(tmP0); tma_prefetch_desc(tmP1); tma_prefetch_desc(tmB);
     }
     if (warp == 1) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
     tc_fence_before();
@@ -306,15 +335,15 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
                 mbar_wait(&raw_empty[rs], rph ^ 1);
                 unsigned char * raw = sR + (size_t)rs * cfg::RAW_BYTES;
                 mbar_expect_tx(&raw_full[rs], cfg::RAW_BYTES);
-                tma_load_2d(raw, &tmP0, &raw_full[rs], (rb0 + r) * 128, m0);               // bytes along the row
-                tma_load_2d(raw + cfg::RAW_P0, &tmP1, &raw_full[rs], (rb0 + r) * 16, m0);
+                tma_load_2d(raw, tmP0, &raw_full[rs], (rb0 + r) * 128, m0);                // bytes along the row
+                tma_load_2d(raw + cfg::RAW_P0, tmP1, &raw_full[rs], (rb0 + r) * 16, m0);
                 for (int q = 0; q < RAW_K / BK && ib < nk; ++q, ++ib) {
                     const int s = ib % cfg::B_STAGES; const uint32_t ph = (ib / cfg::B_STAGES) & 1;
                     mbar_wait(&b_empty[s], ph ^ 1);
                     mbar_expect_tx(&b_full[s], cfg::B_BYTES);
 #pragma unroll
                     for (int j = 0; j < N_ACC; ++j)
-                        tma_load_2d(sB + (size_t)s * cfg::B_BYTES + (size_t)j * MMA_N * BK * 2, &tmB, &b_full[s], (kb_begin + ib) * BK, n0 + j * MMA_N);
+                        tma_load_2d(sB + (size_t)s * cfg::B_BYTES + (size_t)j * MMA_N * BK * 2, tmB, &b_full[s], (kb_begin + ib) * BK, n0 + j * MMA_N);
                 }
             }
         }
@@ -392,20 +421,63 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
             tc_fence_after();
             const int m = m0 + row;
             constexpr int COLS_PER = BN / 2;
+            const int c_begin = half * COLS_PER, c_end = min((half + 1) * COLS_PER, N - n0);
+            const bool mrow = m < M;
+            if (k_split > 1 || (mul == nullptr && dst_bf == nullptr)) {
 #pragma unroll 1
-            for (int c0 = half * COLS_PER; c0 < (half + 1) * COLS_PER; c0 += 32) {
-                if (n0 + c0 >= N) break;
-                uint32_t rr[32];
-                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)c0, rr);
-                tmem_ld_wait();
-                if (m < M) {
+                for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                    uint32_t rr[32];
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)c0, rr);
+                    tmem_ld_wait();
+                    if (mrow) {
+                        if (k_split > 1) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { const int n = n0 + c0 + j; if (n < N) atomicAdd(dst + (size_t)n * M + m, __uint_as_float(rr[j])); }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { const int n = n0 + c0 + j; if (n < N) dst[(size_t)n * M + m] = __uint_as_float(rr[j]); }
+                        }
+                    }
+                }
+            } else {
+                // fused unary-mul (+ bf16 copy): the `mul` operand of chunk c+1 is fetched (32 loads in flight per thread) while
+                // chunk c is computed, so the L2 latency hides behind the activation math
+                const float lim = a.limit; const int act = a.act;
+                float u[32], un[32];
+                auto fetch = [&](float (&dstu)[32], int c0) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) { const int n = n0 + c0 + j; dstu[j] = (mul != nullptr && mrow && c0 < c_end && n < N) ? __ldg(mul + (size_t)n * M + m) : 1.0f; }
+                };
+                auto finish = [&](const uint32_t (&rr)[32], const float (&uu)[32], int c0) {
+                    if (!mrow) return;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int n = n0 + c0 + j;
                         if (n < N) {
-                            float * p = dst + (size_t)n * M + m;
-                            if (k_split > 1) atomicAdd(p, __uint_as_float(rr[j])); else *p = __uint_as_float(rr[j]);
+                            float v = __uint_as_float(rr[j]);
+                            if (mul != nullptr) {
+                                float w = uu[j];
+                                if (lim > 0.0f) { v = fminf(v, lim); w = fminf(fmaxf(w, -lim), lim); }
+                                v = gemm_act_apply(act, v) * w;
+                            }
+                            dst[(size_t)n * M + m] = v;
+                            if (dst_bf != nullptr) dst_bf[(size_t)n * M + m] = __float2bfloat16_rn(v);
                         }
+                    }
+                };
+                fetch(u, c_begin);
+#pragma unroll 1
+                for (int c0 = c_begin; c0 < c_end; c0 += 64) {
+                    uint32_t rr[32];
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)c0, rr);
+                    fetch(un, c0 + 32);
+                    tmem_ld_wait();
+                    finish(rr, u, c0);
+                    if (c0 + 32 < c_end) {
+                        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)(c0 + 32), rr);
+                        fetch(u, c0 + 64);
+                        tmem_ld_wait();
+                        finish(rr, un, c0 + 32);
                     }
                 }
             }
@@ -414,6 +486,26 @@ k_gemm_q(const __grid_constant__ CUtensorMap tmP0, const __grid_constant__ CUten
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, cfg::TMEM_COLS);
+}
+
+// dst = act(clamp(gate)) * clamp(up) elementwise (the reference's ggml_fused_mul_unary after two MMQs, ggml-cuda.cu:3588-3618);
+// gate may alias dst; optional bf16 copy for the following MUL_MAT
+__global__ void k_mul_unary(const float * __restrict__ gate, const float * __restrict__ up, float * __restrict__ dst, __nv_bfloat16 * __restrict__ dst_bf,
+                            int64_t total4, int act, float lim) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 g = reinterpret_cast<const float4 *>(gate)[i]; float4 u = reinterpret_cast<const float4 *>(up)[i];
+        if (lim > 0.0f) {
+            g.x = fminf(g.x, lim); g.y = fminf(g.y, lim); g.z = fminf(g.z, lim); g.w = fminf(g.w, lim);
+            u.x = fminf(fmaxf(u.x, -lim), lim); u.y = fminf(fmaxf(u.y, -lim), lim); u.z = fminf(fmaxf(u.z, -lim), lim); u.w = fminf(fmaxf(u.w, -lim), lim);
+        }
+        float4 r; r.x = gemm_act_apply(act, g.x) * u.x; r.y = gemm_act_apply(act, g.y) * u.y; r.z = gemm_act_apply(act, g.z) * u.z; r.w = gemm_act_apply(act, g.w) * u.w;
+        reinterpret_cast<float4 *>(dst)[i] = r;
+        if (dst_bf != nullptr) {
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(r.x, r.y), b1 = __floats2bfloat162_rn(r.z, r.w);
+            uint2 o; o.x = *reinterpret_cast<uint32_t *>(&b0); o.y = *reinterpret_cast<uint32_t *>(&b1);
+            reinterpret_cast<uint2 *>(dst_bf)[i] = o;
+        }
+    }
 }
 
 // f32 [N][K] (row stride xs) -> bf16 [N][K]
@@ -489,24 +581,69 @@ constexpr bool gemmq_supported(int type) {
 }
 
 template <int TYPE, int NB>
-int launch_gemm_q(const void * W, const b200q_layout & L, const void * B_bf16, float * dst, int64_t M, int64_t N, int64_t K, int k_split, cudaStream_t st) {
+int launch_gemm_q(const b200q_gemm_multi & d, int k_split, cudaStream_t st) {
     using cfg = gemmq_cfg<NB>;
-    CUtensorMap tmP0, tmP1, tmB;
-    const int64_t p1_row = (K / 256) * 16;
-    if (make_tmap_u8(&tmP0, (const char *)W + L.plane_off[0], M, K / 2, 128, BM, true)) return -10;
-    if (make_tmap_u8(&tmP1, (const char *)W + L.plane_off[1], M, p1_row, 16, BM, false)) return -13;
-    if (make_tmap_bf16(&tmB, B_bf16, N, K, NB == 0 ? 128 : 256)) return -11;
+    gemmq_args a; memset(&a, 0, sizeof a);
+    const int64_t p1_row = (d.K / 256) * 16;
+    int tiles = 0;
+    for (int i = 0; i < d.n_seg; ++i) {
+        b200q_layout L; if (b200q_make_layout(TYPE, d.M[i], d.K, &L)) return -1;
+        if (make_tmap_u8(&a.tmP0[i], (const char *)d.W[i] + L.plane_off[0], d.M[i], d.K / 2, 128, BM, true)) return -10;
+        if (make_tmap_u8(&a.tmP1[i], (const char *)d.W[i] + L.plane_off[1], d.M[i], p1_row, 16, BM, false)) return -13;
+        a.seg[i].dst = d.dst[i]; a.seg[i].mul = d.mul[i]; a.seg[i].dst_bf = (__nv_bfloat16 *)d.dst_bf[i]; a.seg[i].M = (int)d.M[i]; a.seg[i].tile0 = tiles;
+        tiles += (int)((d.M[i] + BM - 1) / BM);
+    }
+    if (make_tmap_bf16(&a.tmB, d.xb, d.N, d.K, NB == 0 ? 128 : 256)) return -11;
+    a.n_seg = d.n_seg; a.N = (int)d.N; a.K = (int)d.K; a.k_split = k_split; a.act = d.act; a.limit = d.limit;
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(k_gemm_q<TYPE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM) != cudaSuccess) return -12;
         configured = true;
     }
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + cfg::BN - 1) / cfg::BN), (unsigned)k_split);
-    k_gemm_q<TYPE, NB><<<grid, 64 + 32 * DQ_WARPS, cfg::SMEM, st>>>(tmP0, tmP1, tmB, dst, (int)M, (int)N, (int)K, k_split);
+    dim3 grid((unsigned)tiles, (unsigned)((d.N + cfg::BN - 1) / cfg::BN), (unsigned)k_split);
+    k_gemm_q<TYPE, NB><<<grid, 64 + 32 * DQ_WARPS, cfg::SMEM, st>>>(a);
     return (int)cudaGetLastError();
 }
 
+// split-K factor of the fused kernel: minimise waves x (raw blocks per CTA + fixed cost), the fixed cost (pipeline fill,
+// TMEM round trip, epilogue) being worth ~4 raw blocks; split-K pays memset + f32 atomics
+int gemmq_choose_split(int64_t tiles, int64_t nr, int sm_count, bool allow_split) {
+    if (!allow_split) return 1;
+    static const int forced = [] { const char * e = getenv("B200Q_GEMM_SPLIT"); return e ? atoi(e) : 0; }();      // experiments only
+    if (forced > 0) return forced <= nr ? forced : (int)nr;
+    int best = 1; int64_t best_cost = INT64_MAX;
+    for (int ks = 1; ks <= 16 && ks <= nr; ++ks) {
+        const int64_t per = (nr + ks - 1) / ks;
+        if (ks > 1 && per * (ks - 1) >= nr) continue;                 // an empty split
+        const int64_t waves = (tiles * ks + sm_count - 1) / sm_count;
+        const int64_t cost = waves * (per + 4) + (ks > 1 ? 2 : 0);
+        if (cost < best_cost) { best_cost = cost; best = ks; }
+    }
+    return best;
+}
+
 }  // namespace
+
+// elementwise tail of GGML_OP_FUSED_UP_GATE for n > 8 when it cannot ride in the gate GEMM's epilogue
+int b200q_launch_mul_unary(const float * gate, const float * up, float * dst, void * dst_bf16, int64_t total, int act, float limit, cudaStream_t st) {
+    if (total % 4) return -2;
+    int64_t nb = (total / 4 + 255) / 256; if (nb > 148 * 16) nb = 148 * 16; if (nb < 1) nb = 1;
+    k_mul_unary<<<(unsigned)nb, 256, 0, st>>>(gate, up, dst, (__nv_bfloat16 *)dst_bf16, total / 4, act, limit);
+    return (int)cudaGetLastError();
+}
+
+// would the fused kernel run this shape without split-K (so that a non-linear epilogue can be fused)?
+int b200q_gemm_epilogue_fusable(int type, int64_t M, int64_t K, int64_t N, int sm_count, int fused) {
+    if (!(fused && gemmq_supported(type) && K % 256 == 0)) return 0;
+    // Measured (scripts/pp_breakdown.py, Llama-3-8B up/gate, 512 tokens): gate GEMM with the unary-mul in its epilogue 98 us vs
+    // plain gate GEMM 60 us + k_mul_unary 20 us: the grid is a single wave, every CTA reaches its epilogue at the same time and the
+    // extra loads are fully exposed.  The fused epilogue therefore stays opt-in until the kernel is persistent (epilogue of tile i
+    // under the main loop of tile i+1): option "fuse_epilogue" / B200Q_FUSE_EPILOGUE=1 (passed here as fused == 2).
+    if (fused < 2) return 0;
+    const int bn = N > 256 ? 512 : (N > 128 ? 256 : 128);
+    const int64_t tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    return gemmq_choose_split(tiles, K / 256, sm_count, true) == 1;
+}
 
 size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {
     (void)type;
@@ -521,40 +658,55 @@ int b200q_launch_f32_to_bf16(const float * x, int64_t x_stride, void * out, int6
     return (int)cudaGetLastError();
 }
 
-// A = planes of `type` [M][K]; X = bf16 [N][K] (already converted); dst f32 [N][M].  ws: bf16 W scratch for the unfused path.
-int b200q_launch_gemm_bf16x(int type, const void * W, const void * xb, float * dst, int64_t M, int64_t K, int64_t N,
-                            void * wscratch, size_t ws_bytes, int sm_count, int fused, cudaStream_t st) {
-    if (K % 8) return -2;
-    b200q_layout L; if (b200q_make_layout(type, M, K, &L)) return -1;
-    const int64_t mt = (M + BM - 1) / BM;
+// n_seg weight tensors of one type and K sharing X = bf16 [N][K] (already converted); dst[i] f32 [N][M_i].
+// wscratch: bf16 W scratch (max M_i x K) for the unfused path.
+int b200q_launch_gemm_multi_bf16x(const b200q_gemm_multi & d, void * wscratch, size_t ws_bytes, int sm_count, int fused, cudaStream_t st) {
+    if (d.K % 8) return -2;
+    if (d.n_seg < 1 || d.n_seg > GEMMQ_MAX_SEGS) return -2;
+    const int type = d.type; const int64_t K = d.K, N = d.N;
+    bool epi = false; for (int i = 0; i < d.n_seg; ++i) epi = epi || d.mul[i] || d.dst_bf[i];
     const bool use_fused = fused && gemmq_supported(type) && K % 256 == 0;
     if (use_fused) {
         // one CTA dequantises a 128-row block once for up to 512 tokens (two 256-column accumulators in TMEM);
         // split-K (f32 atomics) fills the SMs when there are few row blocks
         const int nb = N > 256 ? 2 : (N > 128 ? 1 : 0);
         const int bn = nb == 0 ? 128 : 256 * nb;
+        int64_t mt = 0; for (int i = 0; i < d.n_seg; ++i) mt += (d.M[i] + BM - 1) / BM;
         const int64_t tiles = mt * ((N + bn - 1) / bn);
-        int k_split = 1;
-        const int64_t nr = K / 256;
-        while (tiles * k_split * 2 <= sm_count && k_split * 2 <= 16 && nr / (k_split * 2) >= 2) k_split *= 2;
-        if (k_split > 1) { cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)M * N * sizeof(float), st); if (e != cudaSuccess) return -3; }
+        const int k_split = gemmq_choose_split(tiles, K / 256, sm_count, !epi);
+        if (k_split > 1) for (int i = 0; i < d.n_seg; ++i) { cudaError_t e = cudaMemsetAsync(d.dst[i], 0, (size_t)d.M[i] * N * sizeof(float), st); if (e != cudaSuccess) return -3; }
         switch (type) {
-#define GQ(T) case T: return nb == 2 ? launch_gemm_q<T, 2>(W, L, xb, dst, M, N, K, k_split, st) : nb == 1 ? launch_gemm_q<T, 1>(W, L, xb, dst, M, N, K, k_split, st) : launch_gemm_q<T, 0>(W, L, xb, dst, M, N, K, k_split, st);
+#define GQ(T) case T: return nb == 2 ? launch_gemm_q<T, 2>(d, k_split, st) : nb == 1 ? launch_gemm_q<T, 1>(d, k_split, st) : launch_gemm_q<T, 0>(d, k_split, st);
             GQ(B200Q_TYPE_IQ4_NL) GQ(B200Q_TYPE_Q4_0) GQ(B200Q_TYPE_Q4_K) GQ(B200Q_TYPE_IQ4_K)
 #undef GQ
             default: break;
         }
     }
-    // unfused: bf16 weight scratch + plain bf16 GEMM; tile / split selection: fill ~1 wave of the SMs
-    const bool bn256 = N >= 256 && mt * ((N + 255) / 256) >= sm_count / 2;
-    const int64_t tiles = bn256 ? mt * ((N + 255) / 256) : mt * ((N + 127) / 128);
-    int k_split = 1;
-    const int64_t nk = (K + BK - 1) / BK;
-    while (tiles * k_split * 2 <= sm_count && k_split * 2 <= 8 && nk / (k_split * 2) >= 8) k_split *= 2;
-    if (k_split > 1) { cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)M * N * sizeof(float), st); if (e != cudaSuccess) return -3; }
-    if (ws_bytes < (size_t)b200q_align_up(M * K * 2, 256)) return -5;
-    int rc = b200q_launch_dequant_bf16(W, L, wscratch, st); if (rc) return rc;
-    return bn256 ? launch_gemm_bf16<256>(wscratch, xb, dst, M, N, K, k_split, st) : launch_gemm_bf16<128>(wscratch, xb, dst, M, N, K, k_split, st);
+    if (epi) return -6;     // the generic path has no fused epilogue: callers use b200q_launch_mul_unary
+    // unfused: bf16 weight scratch + plain bf16 GEMM per tensor; tile / split selection: fill ~1 wave of the SMs
+    for (int i = 0; i < d.n_seg; ++i) {
+        const int64_t M = d.M[i];
+        b200q_layout L; if (b200q_make_layout(type, M, K, &L)) return -1;
+        const int64_t mt = (M + BM - 1) / BM;
+        const bool bn256 = N >= 256 && mt * ((N + 255) / 256) >= sm_count / 2;
+        const int64_t tiles = bn256 ? mt * ((N + 255) / 256) : mt * ((N + 127) / 128);
+        int k_split = 1;
+        const int64_t nk = (K + BK - 1) / BK;
+        while (tiles * k_split * 2 <= sm_count && k_split * 2 <= 8 && nk / (k_split * 2) >= 8) k_split *= 2;
+        if (k_split > 1) { cudaError_t e = cudaMemsetAsync(d.dst[i], 0, (size_t)M * N * sizeof(float), st); if (e != cudaSuccess) return -3; }
+        if (ws_bytes < (size_t)b200q_align_up(M * K * 2, 256)) return -5;
+        int rc = b200q_launch_dequant_bf16(d.W[i], L, wscratch, st); if (rc) return rc;
+        rc = bn256 ? launch_gemm_bf16<256>(wscratch, d.xb, d.dst[i], M, N, K, k_split, st) : launch_gemm_bf16<128>(wscratch, d.xb, d.dst[i], M, N, K, k_split, st);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int b200q_launch_gemm_bf16x(int type, const void * W, const void * xb, float * dst, int64_t M, int64_t K, int64_t N,
+                            void * wscratch, size_t ws_bytes, int sm_count, int fused, cudaStream_t st) {
+    b200q_gemm_multi d; memset(&d, 0, sizeof d);
+    d.type = type; d.n_seg = 1; d.W[0] = W; d.dst[0] = dst; d.M[0] = M; d.K = K; d.N = N; d.xb = xb;
+    return b200q_launch_gemm_multi_bf16x(d, wscratch, ws_bytes, sm_count, fused, st);
 }
 
 // A = planes of `type` [M][K]; X = f32 [N][K]; dst f32 [N][M].  Workspace: bf16 X followed by bf16 W (unfused path only).

@@ -26,3 +26,18 @@ struct b200q_mmvq_desc {
 int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L, int inverse, cudaStream_t st);
 int b200q_launch_dequant_bf16(const void * W, const b200q_layout & L, void * out, cudaStream_t st);
 int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st);
+
+// prefill: up to 3 weight tensors of one type / K that share the bf16 activation operand xb [N][K]
+struct b200q_gemm_multi {
+    int type; int n_seg; const void * W[3]; float * dst[3]; const float * mul[3]; void * dst_bf[3]; int64_t M[3];
+    int64_t K, N; const void * xb; int act; float limit;
+};
+size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N);
+int b200q_launch_gemm(int type, const void * W, const float * x, int64_t x_stride, float * dst, int64_t M, int64_t K, int64_t N,
+                      void * ws, size_t ws_bytes, int sm_count, int fused, cudaStream_t st);
+int b200q_launch_gemm_bf16x(int type, const void * W, const void * xb, float * dst, int64_t M, int64_t K, int64_t N,
+                            void * wscratch, size_t ws_bytes, int sm_count, int fused, cudaStream_t st);
+int b200q_launch_gemm_multi_bf16x(const b200q_gemm_multi & d, void * wscratch, size_t ws_bytes, int sm_count, int fused, cudaStream_t st);
+int b200q_launch_mul_unary(const float * gate, const float * up, float * dst, void * dst_bf16, int64_t total, int act, float limit, cudaStream_t st);
+int b200q_gemm_epilogue_fusable(int type, int64_t M, int64_t K, int64_t N, int sm_count, int fused);
+int b200q_launch_f32_to_bf16(const float * x, int64_t x_stride, void * out, int64_t K, int64_t N, cudaStream_t st);

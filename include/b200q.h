@@ -72,6 +72,15 @@ B200Q_API int b200q_convert_f32_bf16(const float * x, int64_t x_stride, void * o
 B200Q_API int b200q_mul_mat_gemm_bf16(int type, const void * W, const void * x_bf16, float * dst, int64_t m, int64_t k, int64_t n,
                             void * workspace /* bf16 [m][k] scratch, only for types without a fused kernel */, size_t workspace_bytes, void * stream);
 B200Q_API int b200q_dequantize_bf16(int type, const void * W, void * out_bf16, int64_t m, int64_t k, void * stream);
+/* several MUL_MATs of one type / K that share src1, n > 8 (the look-ahead fusion of ggml_cuda_mul_mat_q, ggml-cuda.cu:2573-2601):
+ * ONE launch walks the row tiles of up to 3 tensors (Q,K,V) */
+B200Q_API int b200q_mul_mat_gemm_multi_bf16(int type, int n_tensors, const void * const * W, float * const * dst, const int64_t * m, int64_t k,
+                                  const void * x_bf16, int64_t n, void * workspace, size_t workspace_bytes, void * stream);
+/* GGML_OP_FUSED_UP_GATE for n > 8 (ggml_cuda_up_gate_unary, ggml-cuda.cu:3588-3618: two MMQ + ggml_fused_mul_unary): the unary-mul
+ * rides in the epilogue of the gate GEMM; dst_bf16 (optional, may be NULL) receives a bf16 copy = the operand of ffn_down.
+ * workspace >= align256(m*n*4) + align256(m*k*2) */
+B200Q_API int b200q_fused_up_gate_gemm_bf16(int type, const void * W_up, const void * W_gate, const void * x_bf16, float * dst, void * dst_bf16,
+                                  int64_t m, int64_t k, int64_t n, int unary, float limit, void * workspace, size_t workspace_bytes, void * stream);
 
 /* ---- GGML_OP_REDUCE (sum) for the row-parallel mat-muls of split-mode-graph: NVLS all-reduce in ONE kernel ----
  * One process per GPU; the reduction buffers live in symmetric memory: `mc_base` / `mc_flag` = multicast (NVLS) addresses,
@@ -84,6 +93,13 @@ B200Q_API int b200q_reduce_sum_nvls(const float * in, float * out, int64_t n, vo
 /* ---- dispatcher (what GGML_OP_MUL_MAT calls): n <= 8 -> mat-vec, else GEMM ---- */
 B200Q_API int b200q_mul_mat(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
                   void * workspace, size_t workspace_bytes, void * stream);
+/* any-n variants of the multi-tensor and fused up/gate ops with f32 activations (what the graph nodes carry) */
+B200Q_API size_t b200q_mul_mat_multi_workspace(int type, int n_tensors, const int64_t * m, int64_t k, int64_t n);
+B200Q_API int b200q_mul_mat_multi(int type, int n_tensors, const void * const * W, float * const * dst, const int64_t * m, int64_t k,
+                        const float * x, int64_t n, void * workspace, size_t workspace_bytes, void * stream);
+B200Q_API size_t b200q_fused_up_gate_workspace(int type, int64_t m, int64_t k, int64_t n);
+B200Q_API int b200q_fused_up_gate(int type, const void * W_up, const void * W_gate, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
+                        int unary, float limit, void * workspace, size_t workspace_bytes, void * stream);
 /* same through HOST activations/results: H2D(x) -> mul_mat -> D2H(dst), synchronous (end-to-end entry point) */
 B200Q_API int b200q_mul_mat_host(int type, const void * W_planes_dev, const float * x_host, float * dst_host,
                        int64_t m, int64_t k, int64_t n, void * stream);

@@ -82,6 +82,52 @@ static int run_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, int64
     return ok ? 0 : 1;
 }
 
+// Q,K,V-style graph: three MUL_MAT nodes that share src1, computed in ONE ggml_backend_graph_compute so that the backend's
+// look-ahead fusion (ggml-cuda.cu:2573-2601) is exercised; every node's data is checked against the f64 dot on to_float weights
+static int run_qkv_case(ggml_backend_t be, ggml_type type, int64_t k, int64_t n, unsigned seed) {
+    const int64_t ms[3] = {512, 128, 128};
+    ggml_init_params ip = { ggml_tensor_overhead() * 16 + ggml_graph_overhead(), nullptr, true };
+    ggml_context * ctx = ggml_init(ip);
+    ggml_tensor * w[3], * out[3];
+    ggml_tensor * b = ggml_new_tensor_2d(ctx, GGML_TYPE_F32, k, n);
+    ggml_cgraph * gf = ggml_new_graph(ctx);
+    for (int i = 0; i < 3; ++i) { w[i] = ggml_new_tensor_2d(ctx, type, k, ms[i]); out[i] = ggml_mul_mat(ctx, w[i], b); ggml_build_forward_expand(gf, out[i]); }
+    ggml_backend_buffer_t buf = ggml_backend_alloc_ctx_tensors(ctx, be);
+    if (!buf) { printf("  alloc failed\n"); return 1; }
+    std::mt19937 rng(seed);
+    std::vector<float> xf(n * k), ones(k, 1.0f);
+    std::vector<std::vector<float>> wdeq(3);
+    ggml_type_traits_t tt = ggml_internal_get_type_traits(type);
+    const size_t rs = ggml_row_size(type, k);
+    for (int i = 0; i < 3; ++i) {
+        std::vector<float> wf(ms[i] * k); fill_uniform(wf, rng);
+        if (type == GGML_TYPE_IQ2_BN) for (auto & x : wf) x = 0.37f * (float)((int)std::floor((x + 1.f) * 1.5f) - 1);
+        std::vector<uint8_t> wq(rs * ms[i]);
+        ggml_quantize_chunk(type, wf.data(), wq.data(), 0, ms[i], k, ggml_quantize_requires_imatrix(type) ? ones.data() : nullptr, nullptr);
+        ggml_backend_tensor_set(w[i], wq.data(), 0, wq.size());
+        wdeq[i].resize(ms[i] * k);
+        for (int64_t r = 0; r < ms[i]; ++r) {
+            const uint8_t * row = wq.data() + r * rs;
+            if (type == GGML_TYPE_IQ2_BN) { float sc; memcpy(&sc, row, 4); tt.to_float(row + 4, wdeq[i].data() + r * k, k); for (int64_t l = 0; l < k; ++l) wdeq[i][r * k + l] *= sc; }
+            else tt.to_float(row, wdeq[i].data() + r * k, k);
+        }
+    }
+    fill_uniform(xf, rng);
+    ggml_backend_tensor_set(b, xf.data(), 0, xf.size() * sizeof(float));
+    if (ggml_backend_graph_compute(be, gf) != GGML_STATUS_SUCCESS) { printf("  graph_compute failed\n"); return 1; }
+    double worst = 0;
+    for (int i = 0; i < 3; ++i) {
+        std::vector<float> y(ms[i] * n), ref(ms[i] * n);
+        ggml_backend_tensor_get(out[i], y.data(), 0, y.size() * sizeof(float));
+        for (int64_t j = 0; j < n; ++j) for (int64_t r = 0; r < ms[i]; ++r) { double acc = 0; for (int64_t l = 0; l < k; ++l) acc += (double)wdeq[i][r * k + l] * xf[j * k + l]; ref[j * ms[i] + r] = (float)acc; }
+        const double e = nmse(y.data(), ref.data(), y.size()); if (e > worst) worst = e;
+    }
+    const bool ok = worst <= 5e-4;
+    printf("  %-8s 3x MUL_MAT sharing src1 (fused launch) k=%lld n=%lld: worst NMSE vs f64(to_float) %.3g -> %s\n", ggml_type_name(type), (long long)k, (long long)n, worst, ok ? "OK" : "FAIL");
+    ggml_backend_buffer_free(buf); ggml_free(ctx);
+    return ok ? 0 : 1;
+}
+
 int main(int argc, char ** argv) {
     const bool quick = argc > 1 && !strcmp(argv[1], "quick");
     ggml_backend_t be = ggml_backend_cuda_init(0, "pdl=1", nullptr);
@@ -99,6 +145,12 @@ int main(int argc, char ** argv) {
         if (quick) continue;
         for (int64_t n : {2, 8, 16, 32, 512}) fails += run_case(be, cpu, t, 512, 1024, n, false, ++seed);
         fails += run_case(be, cpu, t, 768, 2048, 1, true, ++seed);
+        fails += run_case(be, cpu, t, 768, 1024, 64, true, ++seed);               // FUSED_UP_GATE, n > 8: GEMMs + unary-mul epilogue
+        for (int64_t n : {1, 64}) fails += run_qkv_case(be, t, 1024, n, ++seed);
+    }
+    if (!quick) {   // bitnet shapes: K = 3200 is not a multiple of 256
+        for (int64_t n : {1, 4, 32}) fails += run_case(be, cpu, GGML_TYPE_IQ2_BN, 640, 3200, n, false, ++seed);
+        for (int64_t n : {1, 32}) fails += run_case(be, cpu, GGML_TYPE_Q4_0, 256, 160, n, false, ++seed);
     }
     printf("%s: %d failures\n", fails ? "FAILED" : "PASSED", fails);
     ggml_backend_free(be); ggml_backend_free(cpu);

@@ -88,6 +88,27 @@ def test_mat_vec_vs_oracle(be, oracle, ref_or_none, name, n):
     assert nmse(y, oracle.mul_mat_exact(t, wire, x, m)) <= 5e-4
 
 
+@pytest.mark.parametrize("name,k", [("IQ2_BN", 3200), ("IQ2_BN", 8640), ("Q4_0", 160), ("IQ4_NL", 96), ("Q8_0", 224), ("Q5_1", 1056)])
+@pytest.mark.parametrize("n", [1, 3, 32])
+def test_k_not_multiple_of_256(be, oracle, name, k, n):
+    """bitnet-b1.58 rows (K = 3200 / 8640 = 50 / 135 IQ2_BN blocks) and short 32-weight-block rows:
+    the TMA ring needs K % 256 == 0, these shapes take the LDG mat-vec / the zero-filled last GEMM k-block."""
+    t = GGML_TYPE[name]
+    m = 130
+    wire = make_wire(oracle, name, m, k, seed=300 + n)
+    x = np.random.default_rng(50 + n).standard_normal((n, k)).astype(np.float32)
+    w = be.set_tensor(t, wire, m, k)
+    assert np.array_equal(be.get_tensor(w), np.frombuffer(wire, np.uint8))
+    y = be.mul_mat(w, torch.from_numpy(x).cuda()).cpu().numpy()
+    exact = oracle.mul_mat_exact(t, wire, x, m)
+    if n <= 8:
+        yq = oracle.mul_mat_q8_1(t, wire, x, m, variant="b200")
+        assert np.abs(y - yq).max() <= 2e-5 * rms(yq)
+        assert nmse(y, exact) <= 5e-4
+    else:
+        assert nmse(y, exact) <= 2e-5
+
+
 @pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K", "Q6_K", "IQ5_K"])
 def test_mat_vec_llama_shapes(be, oracle, ref_or_none, name):
     """BASELINE config 1: MUL_MAT 4096x4096 n=1 (and the 14336-wide FFN shape) at full size."""
@@ -165,6 +186,68 @@ def test_gemm_shared_activation_and_unfused_path(be, oracle, name):
         pkg.lib().b200q_set_option(b"fused_gemm", 1)
     assert nmse(y1, exact) <= 2e-5 and nmse(y0, exact) <= 2e-5
     assert nmse(y1, y0) <= 1e-9          # same bf16 operands, same MMA order
+
+
+@pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K", "Q6_K"])
+@pytest.mark.parametrize("n", [40, 512])
+def test_gemm_multi_tensor_launch_qkv(be, oracle, name, n):
+    """n > 8 look-ahead fusion: Q,K,V in ONE GEMM launch (row tiles of three tensors, ragged M) == three single launches."""
+    t = GGML_TYPE[name]
+    k = 1024
+    ms = [512, 128, 200]
+    wires = [make_wire(oracle, name, m, k, seed=120 + i) for i, m in enumerate(ms)]
+    ws = [be.set_tensor(t, wire, m, k) for wire, m in zip(wires, ms)]
+    x = np.random.default_rng(21).standard_normal((n, k)).astype(np.float32)
+    xg = torch.from_numpy(x).cuda()
+    xb = be.convert_activations(xg)
+    outs_b = be.mul_mat_multi(ws, xg, x_bf16=xb)
+    outs_f = be.mul_mat_multi(ws, xg)                        # f32 activations: conversion inside the call
+    for w, wire, m, ob, of in zip(ws, wires, ms, outs_b, outs_f):
+        single = be.mul_mat(w, xg, x_bf16=xb).cpu().numpy()
+        assert nmse(ob.cpu().numpy(), single) <= 1e-9       # same operands; only the split-K summation order may differ
+        assert nmse(of.cpu().numpy(), single) <= 1e-9
+        cols = [0, n // 2, n - 1]
+        assert nmse(ob.cpu().numpy()[cols], oracle.mul_mat_exact(t, wire, x[cols], m)) <= 2e-5
+
+
+@pytest.mark.parametrize("name,m,k", [("IQ4_NL", 1000, 256), ("IQ4_NL", 384, 1024), ("Q4_K", 1000, 256), ("Q6_K", 384, 1024), ("IQ2_BN", 256, 512)])
+@pytest.mark.parametrize("unary,limit", [("silu", 0.0), ("gelu", 0.0), ("relu", 0.0), ("silu", 1.5)])
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_fused_up_gate_gemm(be, oracle, name, m, k, unary, limit, fuse):
+    """GGML_OP_FUSED_UP_GATE for n > 8.  fuse=1 with k=256 (split-K 1): unary-mul inside the gate GEMM's epilogue; everything else:
+    gate GEMM + k_mul_unary.  Checked against act(gate.x)*(up.x) from the plain GEMM entry point and the oracle."""
+    t = GGML_TYPE[name]
+    n = 70
+    wu, wg = make_wire(oracle, name, m, k, seed=131), make_wire(oracle, name, m, k, seed=132)
+    up, gate = be.set_tensor(t, wu, m, k), be.set_tensor(t, wg, m, k)
+    x = np.random.default_rng(23).standard_normal((n, k)).astype(np.float32) * 2
+    xg = torch.from_numpy(x).cuda()
+    xb = be.convert_activations(xg)
+    ybf = torch.empty((n, m), dtype=torch.bfloat16, device="cuda")
+    import ik_llama_cpp_b200 as pkg
+    pkg.lib().b200q_set_option(b"fuse_epilogue", fuse)       # 1: unary-mul inside the gate GEMM's epilogue (opt-in), 0: k_mul_unary tail
+    try:
+        y = be.fused_up_gate(up, gate, xg, unary=unary, limit=limit, x_bf16=xb, out_bf16=ybf)
+        y2 = be.fused_up_gate(up, gate, xg, unary=unary, limit=limit)           # f32 activations, no bf16 copy
+    finally:
+        pkg.lib().b200q_set_option(b"fuse_epilogue", 0)
+    u, g = be.mul_mat(up, xg, x_bf16=xb).double(), be.mul_mat(gate, xg, x_bf16=xb).double()
+    if limit > 0:
+        g = g.clamp(max=limit); u = u.clamp(-limit, limit)
+    act = {"silu": lambda v: v / (1 + torch.exp(-v)), "gelu": lambda v: 0.5 * v * (1 + torch.tanh(0.79788456080286535588 * v * (1 + 0.044715 * v * v))),
+           "relu": lambda v: v.clamp(min=0)}[unary]
+    ref = (act(g) * u)
+    scale = float(ref.pow(2).mean().sqrt())
+    assert float((y.double() - ref).abs().max()) <= 2e-5 * scale
+    assert float((y2.double() - ref).abs().max()) <= 2e-5 * scale
+    assert torch.equal(ybf, y.to(torch.bfloat16))
+    # and against exact math on a few tokens (bf16-operand noise only)
+    cols = [0, 33, 69]
+    ue, ge = oracle.mul_mat_exact(t, wu, x[cols], m).astype(np.float64), oracle.mul_mat_exact(t, wg, x[cols], m).astype(np.float64)
+    if limit > 0:
+        ge = np.minimum(ge, limit); ue = np.clip(ue, -limit, limit)
+    acte = {"silu": ge / (1 + np.exp(-ge)), "gelu": 0.5 * ge * (1 + np.tanh(0.79788456080286535588 * ge * (1 + 0.044715 * ge * ge))), "relu": np.maximum(ge, 0)}[unary]
+    assert nmse(y[cols].cpu().numpy(), acte * ue) <= (2e-4 if limit == 0 else 1e-3)     # the clamp saturates most outputs: sign flips of tiny values dominate
 
 
 def test_gemm_llama_shape_properties(be, oracle):
