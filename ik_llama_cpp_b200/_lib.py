@@ -7,7 +7,8 @@ import re
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p, POINTER
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200q.so")
+# B200Q_LIB_PATH: tuning experiments only (a variant of the same library built with other -D knobs, scripts/build_variant.sh)
+LIB_PATH = os.environ.get("B200Q_LIB_PATH") or os.path.join(HERE, "libb200q.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "b200q.h")
 
 

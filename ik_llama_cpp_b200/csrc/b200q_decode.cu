@@ -276,7 +276,13 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
 //     next mat-vec of the graph is already resident (one 512-thread CTA per SM leaves room for a second) and has its
 //     ring full when the previous kernel finishes; only the activation quantisation is on the dependent path.
 // ------------------------------------------------------------------------------------------------
-#define B200Q_SEG_ITEMS 128
+#ifndef B200Q_SEG_ITEMS
+#define B200Q_SEG_ITEMS 128          // items (of 32 weights) per row per ring stage; tuning knob, see experiments/README.md
+#endif
+#ifndef B200Q_MAX_STAGES
+#define B200Q_MAX_STAGES 4
+#endif
+#define B200Q_PAIR_SLOTS 124         // ncw * S stage descriptors (+ the claim counter) fit the 128-int slot table
 struct ring_geom {
     int n_planes;                 // block planes staged through the ring (the per-row scale plane is read directly)
     int b8[4];                    // bytes per 8 items (256 weights) of plane p
@@ -331,8 +337,8 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     uint64_t * empty0 = full0 + ncw * S;
     uint32_t * kv_slot = reinterpret_cast<uint32_t *>(empty0 + ncw * S);
     int * pair_id = reinterpret_cast<int *>(kv_slot + 128);       // [ncw*S] pair index streamed into each stage (-1 = end)
-    int * next_pair = pair_id + 60;                               // CTA-wide claim counter
-    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128 + 64);
+    int * next_pair = pair_id + B200Q_PAIR_SLOTS;                 // CTA-wide claim counter
+    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128 + 128);
     int8_t * sq = reinterpret_cast<int8_t *>(xbase);
     float *  sd = reinterpret_cast<float *>(xbase + (size_t)NCOLS * K);
     int *    sis = reinterpret_cast<int *>(sd + NCOLS * n32);
@@ -572,7 +578,7 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     mmvq_ring_args ra; ra.a = a; ra.g = g0;
     for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
     if (a.M_total >= (int64_t)1 << 30) return -100;
-    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 256;
+    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 512;
     const size_t budget = 112 * 1024;                   // two CTAs per SM (same kernel, or this one + the next under PDL)
     const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
     int ncw = 11, S = 0;                                // consumer warps (+1 producer warp)
@@ -583,9 +589,10 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
         ncw = ncw > 7 ? 7 : 3;
     }
     if (S < 2) return -100;                              // does not fit: caller falls back to the LDG kernel
-    if (S > 4) S = 4;
+    if (S > B200Q_MAX_STAGES) S = B200Q_MAX_STAGES;
     const int64_t n_pairs = PAIR ? (a.M_total + 1) / 2 : a.M_total;
     while (ncw > 3 && n_pairs <= (int64_t)sm_count * (ncw > 7 ? 7 : 3)) ncw = ncw > 7 ? 7 : 3;
+    while (ncw * S > B200Q_PAIR_SLOTS) --S;
     ra.g.n_stages = S;
     const size_t smem = (size_t)ncw * S * (pair_stage + 16) + xbytes + 64;
     static bool configured = false;
