@@ -122,9 +122,11 @@ class Model:
         self.head = mk(N_VOCAB // tp, N_EMBD, s_e)
         self.launches_tg = n_layer * 4 + 1
         self.reducer = None
+        self.fused_tp = False
         if tp > 1 and os.environ.get("B200Q_NCCL_REDUCE", "0") != "1":
             self.reducer = be.NvlsReducer(512 * N_EMBD)
-            self.launches_tg += 2 * n_layer if self.reducer.ok else 0
+            self.fused_tp = self.reducer.ok and os.environ.get("B200Q_TP_FUSED", "1") == "1"
+            self.launches_tg += 2 * n_layer if (self.reducer.ok and not self.fused_tp) else 0
         self.weight_bytes = sum(t.nbytes_wire for L in self.layers for t in L.values()) + self.head.nbytes_wire
 
     def alloc(self, n):
@@ -145,8 +147,23 @@ class Model:
                 import torch.distributed as dist
                 dist.all_reduce(t)
 
+    def step_tg_fused_tp(self):
+        """tp > 1: the two GGML_OP_REDUCE per layer are fused into the mat-vec kernels (multimem.red from the wo / ffn_down epilogue,
+        flag wait in the prologue of the next mat-vec): 4 launches per layer like the single-GPU graph, no reduce kernel."""
+        be, r = self.be, self.reducer
+        first = True
+        for L in self.layers:
+            be.mul_mat_vec_tp([L["wq"], L["wk"], L["wv"]], self.x if first else None, [self.q, self.kk, self.v], r, reduce_in=not first)
+            be.mul_mat_vec_tp([L["wo"]], self.q, None, r, reduce_out=True)
+            be.mul_mat_vec_tp([L["up"]], None, [self.a], r, reduce_in=True, gate=L["gate"], unary="silu")
+            be.mul_mat_vec_tp([L["down"]], self.a, None, r, reduce_out=True)
+            first = False
+        be.mul_mat_vec_tp([self.head], None, [self.logits], r, reduce_in=True)
+
     def step_tg(self):
         be = self.be
+        if self.tp > 1 and self.fused_tp:
+            return self.step_tg_fused_tp()
         x = self.x
         for L in self.layers:
             be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v])
@@ -302,6 +319,8 @@ def main():
     torch.manual_seed(0)
 
     model = Model(be, torch, args.layers, tp=world, rank=rank)
+    if model.fused_tp:
+        config["reduce"] = "fused into the mat-vec kernels (multimem.red from the wo/ffn_down epilogue, flag wait in the next prologue); pp512: b200q NVLS kernel"
     # ---------------- tg128 ----------------
     model.alloc(1)
     x_host = torch.randn(1, N_EMBD).pin_memory()

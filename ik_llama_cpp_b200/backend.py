@@ -227,6 +227,33 @@ def mul_mat_host(w: QuantTensor, x_host: np.ndarray) -> np.ndarray:
     return out
 
 
+class NvlsComm(ctypes.Structure):
+    """struct b200q_nvls_comm of include/b200q.h"""
+    _fields_ = [("mc_base", c_void_p), ("local_base", c_void_p), ("parity_stride", c_int64), ("mc_flag", c_void_p), ("local_flag", c_void_p),
+                ("world_size", ctypes.c_uint32), ("seq_counter", c_void_p), ("cta_counter", c_void_p)]
+
+
+def mul_mat_vec_tp(ws: list[QuantTensor], x: torch.Tensor | None, outs: list[torch.Tensor] | None, reducer: "NvlsReducer",
+                   reduce_in: bool = False, reduce_out: bool = False, gate: QuantTensor | None = None, unary: str = "silu", limit: float = 0.0):
+    """Tensor-parallel decode (n = 1) with GGML_OP_REDUCE fused into the mat-vec kernels (b200q_mul_mat_vec_tp).
+    reduce_out: the partial rows are summed across ranks inside the NVSwitch into the reducer's buffer (outs may be None);
+    reduce_in:  the activations are the result of the previous reduce_out launch (x may be None)."""
+    _require_cuda()
+    nt = len(ws)
+    assert all(w.k == ws[0].k and w.ggml_type == ws[0].ggml_type for w in ws)
+    if x is not None:
+        assert x.is_cuda and x.dtype == torch.float32 and x.shape == (1, ws[0].k) and x.is_contiguous()
+    Wp = (c_void_p * nt)(*[w.ptr for w in ws])
+    Dp = (c_void_p * nt)(*[o.data_ptr() for o in outs]) if outs is not None else None
+    Mp = (c_int64 * nt)(*[w.m for w in ws])
+    dev = ws[0].planes.device
+    with torch.cuda.device(dev):
+        check(_lib.lib().b200q_mul_mat_vec_tp(ws[0].ggml_type, nt, Wp, gate.ptr if gate is not None else None, Dp, Mp, ws[0].k,
+                                              x.data_ptr() if x is not None else None, UNARY[unary], float(limit),
+                                              ctypes.byref(reducer.comm()), int(reduce_in), int(reduce_out), _stream()), "b200q_mul_mat_vec_tp")
+    return outs
+
+
 class NvlsReducer:
     """GGML_OP_REDUCE (sum) across the ranks of a torch.distributed group with the in-tree NVLS kernel (b200q_reduce_sum_nvls).
     Symmetric memory + multicast mapping come from torch.distributed._symmetric_memory (plumbing); the reduction itself is
@@ -258,6 +285,21 @@ class NvlsReducer:
             self.err = repr(e)
         if not self.ok:
             self.mc = 0
+
+    def comm(self):
+        """ctypes b200q_nvls_comm for the fused tensor-parallel mat-vec (b200q_mul_mat_vec_tp)."""
+        assert self.ok
+        if not hasattr(self, "_comm"):
+            self._comm = NvlsComm(self.mc, self.local, self.stride, self.mc + self.flag_off, self.local + self.flag_off, self.world,
+                                  self.state.data_ptr(), self.state.data_ptr() + 16)
+        return self._comm
+
+    def reduced_view(self, n: int, use: int = -1) -> torch.Tensor:
+        """This rank's copy of the buffer written by the latest (use = -1) fused reduce: debugging / tests only (synchronises)."""
+        torch.cuda.synchronize()
+        seq = int(self.state[0].item())
+        par = (seq + use) & 1
+        return self.buf[par * self.stride: par * self.stride + n].clone()
 
     def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         """In-place sum over ranks of a contiguous f32 tensor."""

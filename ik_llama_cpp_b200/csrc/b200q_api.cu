@@ -155,6 +155,25 @@ int b200q_fused_up_gate_vec(int type, const void * W_up, const void * W_gate, co
     return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_fused_up_gate_vec");
 }
 
+int b200q_mul_mat_vec_tp(int type, int n_tensors, const void * const * W, const void * W_gate, float * const * dst, const int64_t * m,
+                         int64_t k, const float * x, int unary, float limit, const b200q_nvls_comm * comm, int reduce_in, int reduce_out, void * stream) {
+    if (n_tensors < 1 || n_tensors > B200Q_MAX_SEGS || !W || !m || (W_gate && n_tensors != 1)) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_tp: bad argument");
+    if ((reduce_in || reduce_out) && (!comm || !comm->mc_base || !comm->local_base || !comm->mc_flag || !comm->local_flag || !comm->seq_counter || !comm->cta_counter || comm->world_size < 2))
+        return fail(B200Q_E_ARG, "b200q_mul_mat_vec_tp: incomplete communicator");
+    if (!reduce_in && !x) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_tp: x is NULL");
+    if (!reduce_out && !dst) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_tp: dst is NULL");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_vec_tp: no CUDA device");
+    b200q_mmvq_desc d; memset(&d, 0, sizeof d);
+    d.type = type; d.n_seg = n_tensors; d.K = k; d.x = x; d.x_stride = k; d.ncols = 1; d.act = unary; d.limit = limit; d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = 1;
+    for (int i = 0; i < n_tensors; ++i) d.seg[i] = {W[i], i == 0 ? W_gate : nullptr, dst ? dst[i] : nullptr, nullptr, m[i]};
+    if (comm) {
+        d.tp.mc_base = (float *)comm->mc_base; d.tp.local_base = (float *)comm->local_base; d.tp.stride = comm->parity_stride;
+        d.tp.mc_flag = (uint32_t *)comm->mc_flag; d.tp.local_flag = (const uint32_t *)comm->local_flag; d.tp.world = comm->world_size;
+        d.tp.seq = (uint32_t *)comm->seq_counter; d.tp.cta_counter = (uint32_t *)comm->cta_counter; d.tp.in = reduce_in != 0; d.tp.out = reduce_out != 0;
+    }
+    return check_launch(b200q_launch_mmvq(d, (cudaStream_t)stream), "b200q_mul_mat_vec_tp");
+}
+
 int b200q_reduce_sum_nvls(const float * in, float * out, int64_t n, void * mc_base, void * local_base, int64_t parity_stride,
                           void * mc_flag, const void * local_flag, uint32_t world_size, void * seq_counter, void * cta_counter, void * stream) {
     if (!in || !out || !mc_base || !local_base || !mc_flag || !local_flag || !seq_counter || !cta_counter || world_size < 2) return fail(B200Q_E_ARG, "b200q_reduce_sum_nvls: bad argument");

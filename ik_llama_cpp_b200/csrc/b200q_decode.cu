@@ -78,6 +78,7 @@ struct mmvq_args {
     int64_t      x_stride;
     int          act;           // B200Q_ACT_* for the up/gate mode
     float        limit;         // clamp for swiglu variants (0 = none)
+    b200q_tp_comm tp;           // tensor-parallel decode: GGML_OP_REDUCE fused into the mat-vec (tp.in / tp.out), see k_mmvq_ring
     unsigned long long * trace; // optional phase timestamps (b200q_debug_trace): [slot][4] = entry, after griddepcontrol.wait, prologue done, last consumer done
 };
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -102,7 +103,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // Quantise ncols activation columns into shared memory (q8_1 semantics of ggml-cuda/quantize.cu:13-47):
 //   d = amax/127 ; q = amax == 0 ? 0 : roundf(x/d) ; d kept as float(half(d)) ; isum = packed int16 sums of q over each 16.
 // Cooperative and vectorised: a thread owns 8 consecutive floats (two LDG.128), 4 adjacent lanes own one 32-block.
-template <int NCOLS>
+template <int NCOLS, bool COHERENT = false>
 __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x, int64_t x_stride, int64_t K,
                                                    int8_t * sq, float * sd, int * sis, int tid, int nthreads) {
     const int nch = (int)(K / 8), total = nch * NCOLS, n32 = (int)(K / 32);
@@ -116,8 +117,9 @@ __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x,
             int col = 0, ch = c < total ? c : 0;
             if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
             if (c < total) {
-                va[u] = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8));
-                vb[u] = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
+                // COHERENT: the vector was written through the NVLS multicast mapping by other GPUs -> no read-only / stale-L1 path
+                va[u] = COHERENT ? __ldcv(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8)) : __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8));
+                vb[u] = COHERENT ? __ldcv(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4)) : __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
             } else { va[u] = make_float4(0.f, 0.f, 0.f, 0.f); vb[u] = va[u]; }
         }
 #pragma unroll
@@ -282,6 +284,9 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
 #ifndef B200Q_MAX_STAGES
 #define B200Q_MAX_STAGES 4
 #endif
+#ifndef B200Q_SELF_REFILL
+#define B200Q_SELF_REFILL 0          // 1: the producer warp only pre-fills the ring (before griddepcontrol.wait); in the main loop every
+#endif                               //    consumer warp re-arms the stage it has just drained itself.  Measured 696 vs 705 tok/s: no gain -> off
 #define B200Q_PAIR_SLOTS 124         // ncw * S stage descriptors (+ the claim counter) fit the 128-int slot table
 struct ring_geom {
     int n_planes;                 // block planes staged through the ring (the per-row scale plane is read directly)
@@ -316,6 +321,11 @@ __device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t 
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
+// ---- tensor-parallel fusion (split-mode-graph): the all-reduce of a row-parallel mat-vec happens in the switch ----
+__device__ __forceinline__ void tp_red_add_f32(float * mc, float v) { asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory"); }
+__device__ __forceinline__ void tp_red_add_u32_release(uint32_t * mc, uint32_t v) { asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t tp_ld_acquire_sys(const uint32_t * p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
 __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
 
 // Warp 0 = producer (lane l streams the units of consumer warp l), warps 1..NCW = consumers.
@@ -338,7 +348,8 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     uint32_t * kv_slot = reinterpret_cast<uint32_t *>(empty0 + ncw * S);
     int * pair_id = reinterpret_cast<int *>(kv_slot + 128);       // [ncw*S] pair index streamed into each stage (-1 = end)
     int * next_pair = pair_id + B200Q_PAIR_SLOTS;                 // CTA-wide claim counter
-    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128 + 128);
+    int * pstate = reinterpret_cast<int *>(kv_slot + 128 + 128);  // [ncw][4] producer state handed to the consumers (self-refill)
+    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128 + 128 + 64);
     int8_t * sq = reinterpret_cast<int8_t *>(xbase);
     float *  sd = reinterpret_cast<float *>(xbase + (size_t)NCOLS * K);
     int *    sis = reinterpret_cast<int *>(sd + NCOLS * n32);
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     if (threadIdx.x < 32) {
         for (int i = lane; i < ncw * S; i += 32) { rb_init(&full0[i]); rb_init(&empty0[i]); }
         kv_slot[lane * 4 + 0] = B200Q_KV4_A0; kv_slot[lane * 4 + 1] = B200Q_KV4_A1; kv_slot[lane * 4 + 2] = B200Q_KV4_B0; kv_slot[lane * 4 + 3] = B200Q_KV4_B1;
-        if (lane == 0) *next_pair = c0;
+        if (lane == 0) { *next_pair = c0; next_pair[1] = 0; }    // [1]: consumer warps that have finished (tp.out)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
     }
@@ -396,14 +407,43 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
         if (++psg == nseg) { psg = 0; if (++pt == NT) pt = 0; }
     };
     // (1) weights do not depend on the previous kernel: fill the ring before waiting for it
-    if (warp == 0) { for (int s = 0; s < S; ++s) if (!pdone) produce_one(); }
+    if (warp == 0) {
+        for (int s = 0; s < S; ++s) if (!pdone) produce_one();
+#if B200Q_SELF_REFILL
+        if (lane < ncw) { int * hs = pstate + lane * 4; hs[0] = pcur; hs[1] = pt; hs[2] = psg; hs[3] = pdone ? 1 : 0; }     // hand the stream over to the consumer warp
+#endif
+    }
     pdl_trigger();                       // the next kernel of the stream/graph may become resident and fill ITS ring
     pdl_wait();                          // (2) the activations are produced by the previous kernel
     if (a.trace && blockIdx.x == 0 && threadIdx.x == 32) a.trace[1] = gtime();
-    if (warp != 0) quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis, threadIdx.x - 32, blockDim.x - 32);
+    // Tensor-parallel mode.  `seq` = number of fused reduces completed on this communicator (device counter, so the launch arguments
+    // are constant under CUDA-graph replay); it cannot change while this grid runs before its own last CTA bumps it.
+    uint32_t tps = 0;
+    if (a.tp.in || a.tp.out) tps = *reinterpret_cast<volatile uint32_t *>(a.tp.seq);
+    if (warp != 0) {
+        if (a.tp.out) {
+            // zero this rank's copy of the NEXT reduce's buffer: peers add to it only after they have seen this rank's flag
+            // increment for the current reduce, which is ordered after these stores (fence + release below)
+            float * z = a.tp.local_base + (int64_t)((tps & 1) ^ 1) * a.tp.stride;
+            const int per = ((int)a.M_total + (int)gridDim.x - 1) / (int)gridDim.x, z0 = per * (int)blockIdx.x, z1 = min((int)a.M_total, z0 + per);
+            for (int i = z0 + (int)threadIdx.x - 32; i < z1; i += (int)blockDim.x - 32) z[i] = 0.0f;
+        }
+        if (a.tp.in) {
+            // the activations are the sum over ranks of the previous row-parallel mat-vec: wait until every rank has signalled it
+            // (flag += 1 per rank per reduce through the multicast mapping), then read this rank's copy of the buffer
+            if (threadIdx.x == 32) { const uint32_t target = a.tp.world * tps; while ((int32_t)(tp_ld_acquire_sys(a.tp.local_flag) - target) < 0) __nanosleep(20); }
+            asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x - 32) : "memory");
+            quantize_x_to_smem<NCOLS, true>(a.tp.local_base + (int64_t)((tps - 1) & 1) * a.tp.stride, a.tp.stride, K, sq, sd, sis, threadIdx.x - 32, blockDim.x - 32);
+        } else {
+            quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis, threadIdx.x - 32, blockDim.x - 32);
+        }
+    }
     __syncthreads();                     // publishes barriers, kv table and activations
     if (a.trace && blockIdx.x == 0 && threadIdx.x == 32) a.trace[2] = gtime();
 
+#if B200Q_SELF_REFILL
+    if (warp == 0) return;               // the ring is primed; from here on the consumers refill their own stages
+#endif
     if (warp == 0) {
         // ---------------- producer: refill a stage as soon as its consumer has released it ----------------
         // All lanes poll their consumer's empty barrier with a NON-blocking test_wait and stay converged: a lane parked in a
@@ -432,6 +472,39 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     int t = 0, sg = 0;
     int cs = 0, crow = 0; float rs[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
     int st = 0; uint32_t parity = 0;
+#if B200Q_SELF_REFILL
+    // the stream of this warp's units continues where the producer's pre-fill stopped (all lanes keep the state, lane 0 acts)
+    int rcur = pstate[cw * 4 + 0], rt = pstate[cw * 4 + 1], rsg = pstate[cw * 4 + 2]; bool rdone = pstate[cw * 4 + 3] != 0;
+    auto refill = [&](int stg) {                                  // re-arm stage `stg`, which every lane has finished reading
+        uint64_t * fb = &fullb[stg];
+        if (rt == 0 && rsg == 0) {
+            int v = 0; if (lane == 0) v = atomicAdd(next_pair, 1);
+            v = __shfl_sync(0xffffffffu, v, 0); rcur = v >= c1 ? -1 : v;
+        }
+        if (lane == 0) pair_id[cw * S + stg] = rcur;
+        if (rcur < 0) { if (lane == 0) rb_arrive(fb); rdone = true; return; }
+        int s2, row; locate(RPU * rcur, s2, row);
+        const mmvq_seg & sgm = a.seg[MULTI ? s2 : 0];
+        const b200q_planes & P = (UPGATE && rt == 1) ? sgm.P2 : sgm.P;
+        const int g8 = min(B200Q_SEG_ITEMS, n32 - rsg * B200Q_SEG_ITEMS) >> 3;
+        const bool two = PAIR && row + 1 < (int)sgm.M;
+        if (lane == 0) {
+            unsigned char * dstb = ring + (size_t)stg * pair_stage;
+            uint32_t bytes = 0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) if (p < g.n_planes) bytes += (uint32_t)(g8 * g.b8[p]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            rb_expect(fb, two ? 2 * bytes : bytes);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) if (p < g.n_planes) {
+                const uint8_t * src = P.p[p] + ((int64_t)row * n8 + (int64_t)rsg * (B200Q_SEG_ITEMS / 8)) * g.b8[p];
+                bulk_g2s(dstb + g.seg_off[p], src, (uint32_t)(g8 * g.b8[p]), fb);
+                if (two) bulk_g2s(dstb + row_stage + g.seg_off[p], src + (int64_t)n8 * g.b8[p], (uint32_t)(g8 * g.b8[p]), fb);
+            }
+        }
+        if (++rsg == nseg) { rsg = 0; if (++rt == NT) rt = 0; }
+    };
+#endif
     for (;;) {
         rb_wait(&fullb[st], parity);
         const int pid = pair_id[cw * S + st];
@@ -474,7 +547,12 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
             for (int itl = lane; itl < items; itl += 32) do_item(itl);
         }
         __syncwarp();
+#if B200Q_SELF_REFILL
+        if (!rdone) refill(st);
+        __syncwarp();
+#else
         if (lane == 0) rb_arrive(&emptyb[st]);                  // stage may be overwritten by the producer
+#endif
         if (++st == S) { st = 0; parity ^= 1; }
         if (++sg == nseg) {
             sg = 0;
@@ -498,9 +576,28 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
                         if (a.limit > 0.0f) { v0 = fminf(v0, a.limit); u0 = fminf(fmaxf(u0, -a.limit), a.limit); v1 = fminf(v1, a.limit); u1 = fminf(fmaxf(u1, -a.limit), a.limit); }
                         v0 = act_apply(a.act, v0) * u0; v1 = act_apply(a.act, v1) * u1;
                     } else if (sgm.bias) { v0 += sgm.bias[crow]; if (two) v1 += sgm.bias[crow + 1]; }
-                    if (lane == 0) { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
+                    if (lane == 0) {
+                        if (a.tp.out) {                                           // partial result: summed over ranks inside the switch
+                            float * mc = a.tp.mc_base + (int64_t)(tps & 1) * a.tp.stride + (int64_t)sgm.row0 + crow;
+                            tp_red_add_f32(mc, v0); if (two) tp_red_add_f32(mc + 1, v1);
+                        } else { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
+                    }
                 }
                 t = 0;
+            }
+        }
+    }
+    if (a.tp.out) {
+        // completion: every consumer warp fences its multimem.reds (and its share of the zeroing), the last warp of the last CTA
+        // publishes this rank's flag increment on every GPU
+        __threadfence_system();
+        if (lane == 0) {
+            if (atomicAdd(next_pair + 1, 1) == ncw - 1) {
+                __threadfence();
+                if (atomicAdd(a.tp.cta_counter, 1u) == gridDim.x - 1) {
+                    *a.tp.cta_counter = 0; *reinterpret_cast<volatile uint32_t *>(a.tp.seq) = tps + 1; __threadfence_system();
+                    tp_red_add_u32_release(a.tp.mc_flag, 1u);
+                }
             }
         }
     }
@@ -578,7 +675,7 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     mmvq_ring_args ra; ra.a = a; ra.g = g0;
     for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
     if (a.M_total >= (int64_t)1 << 30) return -100;
-    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 512;
+    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 512 + 256;
     const size_t budget = 112 * 1024;                   // two CTAs per SM (same kernel, or this one + the next under PDL)
     const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
     int ncw = 11, S = 0;                                // consumer warps (+1 producer warp)
@@ -632,6 +729,7 @@ static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_
         else rc = ncols == 1 ? launch_mmvq_ring_t<TYPE, 1, false, false>(a, g, sm_count, pdl, cps, st) : launch_mmvq_ring_t<TYPE, 2, false, false>(a, g, sm_count, pdl, cps, st);
         if (rc != -100) return rc;
     }
+    if (a.tp.in || a.tp.out) return -7;
 #define CASE(N) case N: return upgate ? launch_mmvq_t<TYPE, N, true>(a, sm_count, pdl, st) : launch_mmvq_t<TYPE, N, false>(a, sm_count, pdl, st);
     switch (ncols) { CASE(1) CASE(2) CASE(4) CASE(8) default: return -2; }
 #undef CASE
@@ -657,7 +755,11 @@ int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
         a.seg[i].dst = d.seg[i].dst; a.seg[i].bias = d.seg[i].bias; a.seg[i].M = d.seg[i].M; a.seg[i].row0 = r0; r0 += d.seg[i].M;
     }
     a.n_seg = d.n_seg; a.M_total = r0; a.K = d.K; a.x = d.x; a.x_stride = d.x_stride ? d.x_stride : d.K; a.act = d.act; a.limit = d.limit;
+    a.tp = d.tp;
     const bool upgate = d.seg[0].W2 != nullptr;
+    if (a.tp.in || a.tp.out) {          // only the TMA-ring kernel implements the fused reduce
+        if (d.ncols != 1 || !d.ring || d.K % 256 || (a.tp.out && r0 > a.tp.stride) || (a.tp.in && d.K > a.tp.stride)) return -7;
+    }
     switch (d.type) {
 #define X(T) case T: return launch_mmvq_type<T>(a, d.ncols, upgate, d.sm_count, d.pdl != 0, d.ring != 0, st);
         B200Q_FOR_TYPES(X)

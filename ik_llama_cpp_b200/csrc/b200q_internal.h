@@ -17,10 +17,16 @@ B200Q_HD constexpr bool b200q_split16(int type) {
     return type == B200Q_TYPE_Q6_K || type == B200Q_TYPE_IQ4_K || type == B200Q_TYPE_IQ5_K;
 }
 
+// device view of the NVLS communicator of include/b200q.h (b200q_nvls_comm) + the direction flags of one launch
+struct b200q_tp_comm {
+    float * mc_base; float * local_base; int64_t stride; uint32_t * mc_flag; const uint32_t * local_flag; uint32_t world;
+    uint32_t * seq; uint32_t * cta_counter; int in; int out;
+};
 struct b200q_mmvq_seg_desc { const void * W; const void * W2; float * dst; const float * bias; int64_t M; };
 struct b200q_mmvq_desc {
     int type; int n_seg; b200q_mmvq_seg_desc seg[B200Q_MAX_SEGS];
     int64_t K; const float * x; int64_t x_stride; int ncols; int act; float limit; int sm_count; int pdl; int ring;
+    b200q_tp_comm tp;
 };
 
 int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L, int inverse, cudaStream_t st);

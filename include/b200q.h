@@ -90,6 +90,19 @@ B200Q_API int b200q_fused_up_gate_gemm_bf16(int type, const void * W_up, const v
 B200Q_API int b200q_reduce_sum_nvls(const float * in, float * out, int64_t n, void * mc_base, void * local_base, int64_t parity_stride,
                           void * mc_flag, const void * local_flag, uint32_t world_size, void * seq_counter, void * cta_counter, void * stream);
 
+/* ---- tensor-parallel decode (n = 1): the GGML_OP_REDUCE after a row-parallel mat-vec fused INTO the mat-vec kernels ----
+ * (reference: ggml_cuda_op_reduce runs as its own node after wo / ffn_down under -sm graph, ggml-cuda/reduce.cu:125-598).
+ * Same symmetric buffers as b200q_reduce_sum_nvls.  reduce_out: the kernel's epilogue adds its partial rows into every rank's copy
+ * of the buffer with multimem.red (dst is not written; m_total <= parity_stride), the last CTA raises the multicast flag.
+ * reduce_in: `x` is ignored, the kernel waits for the flags of all ranks and takes its activations (k <= parity_stride floats) from
+ * this rank's copy of the buffer filled by the preceding reduce_out launch.  W_gate != NULL: fused up/gate mode (n_tensors = 1). */
+typedef struct b200q_nvls_comm {
+    void * mc_base; void * local_base; int64_t parity_stride; void * mc_flag; const void * local_flag; uint32_t world_size;
+    void * seq_counter; void * cta_counter;
+} b200q_nvls_comm;
+B200Q_API int b200q_mul_mat_vec_tp(int type, int n_tensors, const void * const * W, const void * W_gate, float * const * dst, const int64_t * m,
+                         int64_t k, const float * x, int unary, float limit, const b200q_nvls_comm * comm, int reduce_in, int reduce_out, void * stream);
+
 /* ---- dispatcher (what GGML_OP_MUL_MAT calls): n <= 8 -> mat-vec, else GEMM ---- */
 B200Q_API int b200q_mul_mat(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
                   void * workspace, size_t workspace_bytes, void * stream);

@@ -56,6 +56,47 @@ def _worker(rank, world, port, q):
         err = float(((part.cpu().numpy() - ref) ** 2).sum() / (ref ** 2).sum())
         assert err <= 5e-4, err
         res["tp_nmse"] = err
+        if red.ok:
+            # ---- fused path: reduce inside the mat-vec kernels (multimem.red epilogue -> flag wait + read in the next prologue) ----
+            m1, k1, m2 = 512, 2048, 384                       # "wo": [m1 x k1] K-split; consumer "up/gate": [m2 x m1], replicated
+            wire1 = random_wire("IQ4_NL", m1, k1, np.random.default_rng(31))
+            wire2 = random_wire("IQ4_NL", m2, m1, np.random.default_rng(32)); wire3 = random_wire("IQ4_NL", m2, m1, np.random.default_rng(33))
+            sh1, ks1, k01 = tp.shard_cols(wire1, t, m1, k1, world, rank, granularity=256)
+            w1 = be.set_tensor(t, sh1, m1, ks1); w2 = be.set_tensor(t, wire2, m2, m1); w3 = be.set_tensor(t, wire3, m2, m1)
+            orc = Oracle()
+            y2 = torch.empty((1, m2), device="cuda"); y3 = torch.empty((1, m2), device="cuda")
+            xs = [np.random.default_rng(40 + i).standard_normal((1, k1)).astype(np.float32) for i in range(5)]
+            xg = torch.empty((1, ks1), device="cuda")
+
+            def chain():
+                be.mul_mat_vec_tp([w1], xg, None, red, reduce_out=True)                        # partial rows -> switch
+                be.mul_mat_vec_tp([w2], None, [y2], red, reduce_in=True)                       # consumer 1: plain mat-vec
+                be.mul_mat_vec_tp([w1], xg, None, red, reduce_out=True)                        # second reduce (other parity)
+                be.mul_mat_vec_tp([w2], None, [y3], red, reduce_in=True, gate=w3, unary="silu")  # consumer 2: fused up/gate
+
+            def check(x):
+                h = red.reduced_view(m1).cpu().numpy()[None, :]          # what the consumers saw
+                ref1 = orc.mul_mat_exact(t, wire1, x, m1)
+                e1 = float(((h - ref1) ** 2).sum() / (ref1 ** 2).sum())
+                assert e1 <= 5e-4, e1                                     # sum of per-rank q8_1 partials vs exact
+                r2 = orc.mul_mat_q8_1(t, wire2, h, m2, variant="b200")
+                assert np.abs(y2.cpu().numpy() - r2).max() <= 2e-5 * float(np.sqrt((r2 ** 2).mean()))
+                u = r2.astype(np.float64); gt = orc.mul_mat_q8_1(t, wire3, h, m2, variant="b200").astype(np.float64)
+                r3 = gt / (1 + np.exp(-gt)) * u
+                assert np.abs(y3.cpu().numpy() - r3).max() <= 5e-5 * float(np.sqrt((r3 ** 2).mean()))
+                return e1
+
+            for i in range(2):                                             # eager, both parities twice
+                xg.copy_(torch.from_numpy(np.ascontiguousarray(xs[i][:, k01:k01 + ks1]))); chain(); res["fused_eager_nmse"] = check(xs[i])
+            s2 = torch.cuda.Stream(); s2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s2):
+                chain()
+            torch.cuda.current_stream().wait_stream(s2); torch.cuda.synchronize()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                chain()
+            for i in range(2, 5):                                          # CUDA-graph replay (PDL edges inside the graph)
+                xg.copy_(torch.from_numpy(np.ascontiguousarray(xs[i][:, k01:k01 + ks1]))); g2.replay(); res["fused_graph_nmse"] = check(xs[i])
         q.put(res)
     finally:
         dist.destroy_process_group()
@@ -78,3 +119,5 @@ def test_nvls_allreduce_and_row_parallel_matvec_world2():
         assert p.exitcode == 0
     print(res)
     assert all(r["tp_nmse"] <= 5e-4 for r in res)
+    if all(r["nvls"] for r in res):
+        assert all(r.get("fused_graph_nmse", 1.0) <= 5e-4 for r in res)
