@@ -424,8 +424,10 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
         if (a.tp.out) {
             // zero this rank's copy of the NEXT reduce's buffer: peers add to it only after they have seen this rank's flag
             // increment for the current reduce, which is ordered after these stores (fence + release below)
+            // (seq[1 + p] = floats of parity buffer p that its last use left non-zero, see b200q_reduce.cu)
             float * z = a.tp.local_base + (int64_t)((tps & 1) ^ 1) * a.tp.stride;
-            const int per = ((int)a.M_total + (int)gridDim.x - 1) / (int)gridDim.x, z0 = per * (int)blockIdx.x, z1 = min((int)a.M_total, z0 + per);
+            const int nd = (int)reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + ((tps & 1) ^ 1)];
+            const int per = (nd + (int)gridDim.x - 1) / (int)gridDim.x, z0 = per * (int)blockIdx.x, z1 = min(nd, z0 + per);
             for (int i = z0 + (int)threadIdx.x - 32; i < z1; i += (int)blockDim.x - 32) z[i] = 0.0f;
         }
         if (a.tp.in) {
@@ -595,7 +597,9 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
             if (atomicAdd(next_pair + 1, 1) == ncw - 1) {
                 __threadfence();
                 if (atomicAdd(a.tp.cta_counter, 1u) == gridDim.x - 1) {
-                    *a.tp.cta_counter = 0; *reinterpret_cast<volatile uint32_t *>(a.tp.seq) = tps + 1; __threadfence_system();
+                    *a.tp.cta_counter = 0;
+                    reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + ((tps & 1) ^ 1)] = 0; reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + (tps & 1)] = (uint32_t)a.M_total;
+                    *reinterpret_cast<volatile uint32_t *>(a.tp.seq) = tps + 1; __threadfence_system();
                     tp_red_add_u32_release(a.tp.mc_flag, 1u);
                 }
             }

@@ -2,7 +2,7 @@
 // Replaces ggml_cuda_op_reduce (ggml/src/ggml-cuda/reduce.cu:125-598: ncclAllReduce / copy-engine ring / k_reduce_add_T).
 //
 // One kernel per all-reduce, one process per GPU, buffers in symmetric memory with an NVLS multicast mapping:
-//   (1) zero the OTHER parity buffer (it is used by the next all-reduce; peers may only start adding to it after they have
+//   (1) zero the dirty part of the OTHER parity buffer (it is used by the next all-reduce; peers may only start adding to it after they have
 //       seen this rank's flag increment below, which is ordered after the zeroing);
 //   (2) multimem.red.add.f32 of the local partial into the multicast address: the switch adds it into EVERY rank's copy;
 //   (3) last CTA: multimem.red.add.u32 on the multicast flag (release.sys) -> every rank's flag += 1;
@@ -34,6 +34,9 @@ __global__ void __launch_bounds__(512) k_allreduce_nvls(const float * __restrict
                                                          uint32_t * mc_flag, const uint32_t * local_flag, uint32_t world,
                                                          uint32_t * seq, uint32_t * cta_counter) {
     const uint32_t s = *reinterpret_cast<volatile uint32_t *>(seq);      // read before this CTA's counter increment (see below)
+    // seq[1 + p] = number of floats of parity buffer p that may be non-zero (left there by its last use): reduces of different
+    // lengths share the buffers (tg: n_embd floats, pp512: 512 x n_embd), so the zeroing covers what was actually dirtied
+    const int64_t n_dirty = (int64_t)reinterpret_cast<volatile uint32_t *>(seq)[1 + ((s & 1) ^ 1)];
     const uint32_t target = world * (s + 1);
     float * mc_buf = mc_base + (int64_t)(s & 1) * stride;
     const float * local_buf = local_base + (int64_t)(s & 1) * stride;
@@ -41,20 +44,26 @@ __global__ void __launch_bounds__(512) k_allreduce_nvls(const float * __restrict
     const int64_t n4 = n / 4;
     const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
     const int64_t i0 = (int64_t)blockIdx.x * per, i1 = min(n4, i0 + per);
-    // (1) + (2)
-    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        reinterpret_cast<float4 *>(local_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        mm_red_add_f32x4(mc_buf + 4 * i, __ldg(reinterpret_cast<const float4 *>(in) + i));
+    // (1)
+    {
+        const int64_t d4 = (n_dirty + 3) / 4, dper = (d4 + gridDim.x - 1) / gridDim.x;
+        const int64_t z0 = (int64_t)blockIdx.x * dper, z1 = min(d4, z0 + dper);
+        for (int64_t i = z0 + threadIdx.x; i < z1; i += blockDim.x) reinterpret_cast<float4 *>(local_zero)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // (2)
+    for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+        mm_red_add_f32x4(mc_buf + 4 * i, __ldg(reinterpret_cast<const float4 *>(in) + i));
     if (blockIdx.x == gridDim.x - 1)
-        for (int64_t i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) { local_zero[i] = 0.f; mm_red_add_f32(mc_buf + i, in[i]); }
+        for (int64_t i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) mm_red_add_f32(mc_buf + i, in[i]);
     __threadfence_system();
     __syncthreads();
     // (3)
     if (threadIdx.x == 0) {
         const uint32_t done = atomicAdd(cta_counter, 1u);
         if (done == gridDim.x - 1) {                 // every CTA has read `seq` (it does so before its atomicAdd)
-            *cta_counter = 0; *reinterpret_cast<volatile uint32_t *>(seq) = s + 1; __threadfence();
+            *cta_counter = 0;
+            reinterpret_cast<volatile uint32_t *>(seq)[1 + ((s & 1) ^ 1)] = 0; reinterpret_cast<volatile uint32_t *>(seq)[1 + (s & 1)] = (uint32_t)n;
+            *reinterpret_cast<volatile uint32_t *>(seq) = s + 1; __threadfence();
             mm_red_add_u32_release(mc_flag, 1u);
         }
         // (4)

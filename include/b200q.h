@@ -86,7 +86,8 @@ B200Q_API int b200q_fused_up_gate_gemm_bf16(int type, const void * W_up, const v
  * One process per GPU; the reduction buffers live in symmetric memory: `mc_base` / `mc_flag` = multicast (NVLS) addresses,
  * `local_base` / `local_flag` = this rank's own mapping of the same allocation.  Two parity buffers of `parity_stride` floats
  * alternate (base + parity*stride); the parity and the flag target come from the device counter `seq_counter` (rank-local,
- * zero-initialised), so the call has constant arguments and can be captured in a CUDA graph.  `cta_counter`: rank-local u32, zero. */
+ * zero-initialised), so the call has constant arguments and can be captured in a CUDA graph.  `seq_counter` points at FOUR u32
+ * {reduces done, dirty floats of parity buffer 0, of parity buffer 1, pad}, zero-initialised.  `cta_counter`: rank-local u32, zero. */
 B200Q_API int b200q_reduce_sum_nvls(const float * in, float * out, int64_t n, void * mc_base, void * local_base, int64_t parity_stride,
                           void * mc_flag, const void * local_flag, uint32_t world_size, void * seq_counter, void * cta_counter, void * stream);
 

@@ -29,6 +29,11 @@ def _worker(rank, world, port, q):
                     red.all_reduce(t)
                     exp = sum(float(r + 1 + it) for r in range(world)) + world * (torch.arange(n, device="cuda") % 7)
                     assert torch.equal(t, exp.float()), (n, it)
+            # reduces of different lengths share the parity buffers: long, short, short, long (stale tails must be zeroed)
+            for n in (8192, 256, 256, 8192, 512, 8192):
+                t = torch.full((n,), float(rank + 2), device="cuda")
+                red.all_reduce(t)
+                assert torch.equal(t, torch.full_like(t, float(sum(r + 2 for r in range(world))))), n
             # CUDA-graph replay: constant launch arguments, parity/target from the device counter
             x = torch.zeros(4096, device="cuda"); y = torch.empty_like(x)
             s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
@@ -80,7 +85,8 @@ def _worker(rank, world, port, q):
                 e1 = float(((h - ref1) ** 2).sum() / (ref1 ** 2).sum())
                 assert e1 <= 5e-4, e1                                     # sum of per-rank q8_1 partials vs exact
                 r2 = orc.mul_mat_q8_1(t, wire2, h, m2, variant="b200")
-                assert np.abs(y2.cpu().numpy() - r2).max() <= 2e-5 * float(np.sqrt((r2 ** 2).mean()))
+                d2 = float(np.abs(y2.cpu().numpy() - r2).max() / np.sqrt((r2 ** 2).mean()))
+                assert d2 <= 2e-5, ("consumer of the first reduce", d2)
                 u = r2.astype(np.float64); gt = orc.mul_mat_q8_1(t, wire3, h, m2, variant="b200").astype(np.float64)
                 r3 = gt / (1 + np.exp(-gt)) * u
                 assert np.abs(y3.cpu().numpy() - r3).max() <= 5e-5 * float(np.sqrt((r3 ** 2).mean()))
@@ -113,7 +119,7 @@ def test_nvls_allreduce_and_row_parallel_matvec_world2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=240) for _ in procs]
+    res = [q.get(timeout=150) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
