@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -k 5 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -p no:cacheprovider -x -k "not gemm" 2>&1 | tail -3
+timeout -k 5 400 python bench.py --steps 20 --warmup 3 --no-cpu --no-pp > gpurun_out/bench_r24.json 2> gpurun_out/bench_r24.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_r24.json')); print('tg', round(d['value'],1), 'frac', round(d['roofline']['frac'],3), 'e2e', round(d['e2e']['value'],1))"
+LAYERS=2 timeout 300 python scripts/trace_decode.py 2>&1 | tail -12
