@@ -335,7 +335,9 @@ __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarri
 // activation load and all loop bookkeeping, and give the scheduler two independent dependency chains.
 // PAIR = false: single-row units (used when there are fewer row pairs than warps in the grid: small matrices are latency-bound,
 // more and shorter units win there); the second half of every pair-stage is then simply unused.
-template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR>
+// TP: tensor-parallel instantiation (fused GGML_OP_REDUCE); a separate instantiation so that the single-GPU kernels carry none of it
+// (as runtime branches the extra code cost the plain path 4 %: 675 vs 705 tok/s)
+template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR, bool TP>
 __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const mmvq_args & a = ra.a; const ring_geom & g = ra.g;
@@ -351,7 +353,8 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     int * pair_id = reinterpret_cast<int *>(kv_slot + 128);       // [ncw*S] pair index streamed into each stage (-1 = end)
     int * next_pair = pair_id + B200Q_PAIR_SLOTS;                 // CTA-wide claim counter
     int * pstate = reinterpret_cast<int *>(kv_slot + 128 + 128);  // [ncw][4] producer state handed to the consumers (self-refill)
-    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128 + 128 + 64);
+    uint32_t * k16tab = reinterpret_cast<uint32_t *>(kv_slot + 128 + 128 + 64);   // 32 x 65536 at lane-dependent addresses (B200Q_SHR_VIA_IMAD)
+    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128 + 128 + 64 + 32);
     int8_t * sq = reinterpret_cast<int8_t *>(xbase);
     float *  sd = reinterpret_cast<float *>(xbase + (size_t)NCOLS * K);
     int *    sis = reinterpret_cast<int *>(sd + NCOLS * n32);
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
         for (int i = lane; i < ncw * S; i += 32) { rb_init(&full0[i]); rb_init(&empty0[i]); }
         kv_slot[lane * 4 + 0] = B200Q_KV4_A0; kv_slot[lane * 4 + 1] = B200Q_KV4_A1; kv_slot[lane * 4 + 2] = B200Q_KV4_B0; kv_slot[lane * 4 + 3] = B200Q_KV4_B1;
         if (lane == 0) { *next_pair = c0; next_pair[1] = 0; }    // [1]: consumer warps that have finished (tp.out)
+        k16tab[lane] = 65536u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
     }
@@ -421,9 +425,9 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
     // Tensor-parallel mode.  `seq` = number of fused reduces completed on this communicator (device counter, so the launch arguments
     // are constant under CUDA-graph replay); it cannot change while this grid runs before its own last CTA bumps it.
     uint32_t tps = 0;
-    if (a.tp.in || a.tp.out) tps = *reinterpret_cast<volatile uint32_t *>(a.tp.seq);
+    if (TP && (a.tp.in || a.tp.out)) tps = *reinterpret_cast<volatile uint32_t *>(a.tp.seq);
     if (warp != 0) {
-        if (a.tp.out) {
+        if (TP && a.tp.out) {
             // zero this rank's copy of the NEXT reduce's buffer: peers add to it only after they have seen this rank's flag
             // increment for the current reduce, which is ordered after these stores (fence + release below)
             // (seq[1 + p] = floats of parity buffer p that its last use left non-zero, see b200q_reduce.cu)
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
             const int per = (nd + (int)gridDim.x - 1) / (int)gridDim.x, z0 = per * (int)blockIdx.x, z1 = min(nd, z0 + per);
             for (int i = z0 + (int)threadIdx.x - 32; i < z1; i += (int)blockDim.x - 32) z[i] = 0.0f;
         }
-        if (a.tp.in) {
+        if (TP && a.tp.in) {
             // the activations are the sum over ranks of the previous row-parallel mat-vec: wait until every rank has signalled it
             // (flag += 1 per rank per reduce through the multicast mapping), then read this rank's copy of the buffer
             if (threadIdx.x == 32) { const uint32_t target = a.tp.world * tps; while ((int32_t)(tp_ld_acquire_sys(a.tp.local_flag) - target) < 0) __nanosleep(20); }
@@ -469,6 +473,7 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
 
     // ---------------- consumers ----------------
     b200q_kv4 T; T.a0 = kv_slot[lane * 4 + 0]; T.a1 = kv_slot[lane * 4 + 1]; T.b0 = kv_slot[lane * 4 + 2]; T.b1 = kv_slot[lane * 4 + 3];
+    T.k16 = k16tab[lane];
     const int cw = warp - 1;
     unsigned char * ring = ring0 + (size_t)cw * S * pair_stage;
     uint64_t * fullb = full0 + cw * S, * emptyb = empty0 + cw * S;
@@ -581,7 +586,7 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
                         v0 = act_apply(a.act, v0) * u0; v1 = act_apply(a.act, v1) * u1;
                     } else if (sgm.bias) { v0 += sgm.bias[crow]; if (two) v1 += sgm.bias[crow + 1]; }
                     if (lane == 0) {
-                        if (a.tp.out) {                                           // partial result: summed over ranks inside the switch
+                        if (TP && a.tp.out) {                                     // partial result: summed over ranks inside the switch
                             float * mc = a.tp.mc_base + (int64_t)(tps & 1) * a.tp.stride + (int64_t)sgm.row0 + crow;
                             tp_red_add_f32(mc, v0); if (two) tp_red_add_f32(mc + 1, v1);
                         } else { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
@@ -591,7 +596,7 @@ __global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
             }
         }
     }
-    if (a.tp.out) {
+    if (TP && a.tp.out) {
         // completion: every consumer warp fences its multimem.reds (and its share of the zeroing), the last warp of the last CTA
         // publishes this rank's flag increment on every GPU
         __threadfence_system();
@@ -676,12 +681,12 @@ static bool make_ring_geom(int type, int64_t K, ring_geom & g) {
     return np > 0 && np <= 4;
 }
 
-template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR>
+template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR, bool TP = false>
 static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
     mmvq_ring_args ra; ra.a = a; ra.g = g0;
     for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
     if (a.M_total >= (int64_t)1 << 30) return -100;
-    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 512 + 256;
+    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 512 + 256 + 128;
     const size_t budget = 112 * 1024;                   // two CTAs per SM (same kernel, or this one + the next under PDL)
     const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
     int ncw = 11, S = 0;                                // consumer warps (+1 producer warp)
@@ -700,7 +705,7 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     const size_t smem = (size_t)ncw * S * (pair_stage + 16) + xbytes + 64;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
+        if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
         configured = true;
     }
     int64_t grid = (n_pairs + ncw - 1) / ncw;
@@ -711,7 +716,7 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR>, ra);
+    return (int)cudaLaunchKernelEx(&cfg, k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR, TP>, ra);
 }
 
 template <int TYPE, int NCOLS, bool UPGATE, bool MULTI>
@@ -719,6 +724,10 @@ static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_
     // row pairs amortise the activation loads; single rows give more, shorter units when the matrix is small
     static const int force = [] { const char * e = getenv("B200Q_PAIR"); return e ? atoi(e) : -1; }();
     const bool pair = force >= 0 ? force != 0 : true;      // measured: pairs win for every Llama-3-8B shape (679 vs 628 tok/s)
+    if (a.tp.in || a.tp.out) {                             // tensor-parallel decode: n = 1, row pairs
+        if (NCOLS != 1) return -7;
+        return launch_mmvq_ring_tp<TYPE, 1, UPGATE, MULTI, true, true>(a, g0, sm_count, pdl, ctas_per_sm, st);
+    }
     return pair ? launch_mmvq_ring_tp<TYPE, NCOLS, UPGATE, MULTI, true>(a, g0, sm_count, pdl, ctas_per_sm, st)
                 : launch_mmvq_ring_tp<TYPE, NCOLS, UPGATE, MULTI, false>(a, g0, sm_count, pdl, ctas_per_sm, st);
 }

@@ -369,9 +369,21 @@ struct b200q_canon {        // 32 weights
 
 // The four table words are passed in registers (struct b200q_kv4): written as literals the compiler re-materialises
 // a constant->register move in front of every PRMT (16 extra instructions per 32 weights in the mat-vec inner loop).
-struct b200q_kv4 { uint32_t a0, a1, b0, b1; };
+struct b200q_kv4 { uint32_t a0, a1, b0, b1, k16; };      // k16 = 65536: see B200Q_SHR_VIA_IMAD
 B200Q_HD b200q_kv4 b200q_kv4_init() {
-    b200q_kv4 t; t.a0 = B200Q_KV4_A0; t.a1 = B200Q_KV4_A1; t.b0 = B200Q_KV4_B0; t.b1 = B200Q_KV4_B1; return t;
+    b200q_kv4 t; t.a0 = B200Q_KV4_A0; t.a1 = B200Q_KV4_A1; t.b0 = B200Q_KV4_B0; t.b1 = B200Q_KV4_B1; t.k16 = 65536u; return t;
+}
+// Tuning knob: PRMT, LOP3 and SHF share the ALU pipe (28 of the 58 instructions per item of the IQ4_NL mat-vec); with this knob the
+// eight `>> 16` per item become mul.hi.u32 by an opaque 65536 (IMAD.HI: FMA pipe).
+#ifndef B200Q_SHR_VIA_IMAD
+#define B200Q_SHR_VIA_IMAD 0
+#endif
+B200Q_HD uint32_t b200q_shr16(uint32_t q, uint32_t k16) {
+#if defined(__CUDA_ARCH__) && B200Q_SHR_VIA_IMAD
+    return __umulhi(q, k16);
+#else
+    (void)k16; return q >> 16;
+#endif
 }
 #if defined(__CUDACC__)
 // Same values, but laundered through shared memory at a LANE-DEPENDENT address, so that ptxas can neither fold them
@@ -384,7 +396,7 @@ __device__ __forceinline__ b200q_kv4 b200q_kv4_init_via_smem(volatile uint32_t *
     }
     __syncthreads();
     const int l = threadIdx.x & 31;
-    b200q_kv4 t; t.a0 = slot[l * 4 + 0]; t.a1 = slot[l * 4 + 1]; t.b0 = slot[l * 4 + 2]; t.b1 = slot[l * 4 + 3]; return t;
+    b200q_kv4 t; t.a0 = slot[l * 4 + 0]; t.a1 = slot[l * 4 + 1]; t.b0 = slot[l * 4 + 2]; t.b1 = slot[l * 4 + 3]; t.k16 = 65536u; return t;
 }
 #endif
 B200Q_HD void b200q_lut4(const b200q_kv4 & t, uint32_t q, int & a_lo, int & b_lo, int & a_hi, int & b_hi) {
@@ -392,8 +404,8 @@ B200Q_HD void b200q_lut4(const b200q_kv4 & t, uint32_t q, int & a_lo, int & b_lo
     const uint32_t qx = q ^ 0x88888888u;
     a_lo = (int)b200q_prmt(t.a0, t.a1, q);
     b_lo = (int)b200q_prmt(t.b0, t.b1, qx);
-    a_hi = (int)b200q_prmt(t.a0, t.a1, q >> 16);
-    b_hi = (int)b200q_prmt(t.b0, t.b1, qx >> 16);
+    a_hi = (int)b200q_prmt(t.a0, t.a1, b200q_shr16(q, t.k16));
+    b_hi = (int)b200q_prmt(t.b0, t.b1, b200q_shr16(qx, t.k16));
 }
 
 // byte i (0..15) of a 4-word register group, without dynamic register indexing
