@@ -38,7 +38,7 @@
 
 // ggml_type ids (reference ggml/include/ggml.h:391-492)
 enum b200q_type : int {
-    B200Q_TYPE_Q4_0 = 2, B200Q_TYPE_Q4_1 = 3, B200Q_TYPE_Q5_0 = 6, B200Q_TYPE_Q5_1 = 7, B200Q_TYPE_Q6_0 = 133, B200Q_TYPE_Q8_0 = 8, B200Q_TYPE_Q4_K = 12, B200Q_TYPE_Q5_K = 13, B200Q_TYPE_Q6_K = 14,
+    B200Q_TYPE_Q4_0 = 2, B200Q_TYPE_Q4_1 = 3, B200Q_TYPE_Q5_0 = 6, B200Q_TYPE_Q5_1 = 7, B200Q_TYPE_Q6_0 = 133, B200Q_TYPE_Q8_0 = 8, B200Q_TYPE_Q2_K = 10, B200Q_TYPE_Q3_K = 11, B200Q_TYPE_Q4_K = 12, B200Q_TYPE_Q5_K = 13, B200Q_TYPE_Q6_K = 14,
     B200Q_TYPE_IQ4_NL = 20, B200Q_TYPE_IQ4_XS = 23, B200Q_TYPE_IQ2_BN = 135, B200Q_TYPE_IQ4_K = 139,
     B200Q_TYPE_IQ5_K = 140, B200Q_TYPE_IQ4_KS = 144,
 };
@@ -118,6 +118,8 @@ inline int b200q_make_layout(int type, int64_t M, int64_t K, b200q_layout * L) {
         case B200Q_TYPE_Q5_0:   set(32,  22, 0, 3, 16, 4, 2, 0, -1); break;   // qs | qh | d
         case B200Q_TYPE_Q5_1:   set(32,  24, 0, 3, 16, 4, 4, 0, -1); break;   // qs | qh | {d,m}
         case B200Q_TYPE_Q6_0:   set(32,  26, 0, 3, 16, 8, 2, 0, -1); break;   // qs | qh(2 bits) | d
+        case B200Q_TYPE_Q2_K:   set(256, 84, 0, 3, 64, 16, 4, 0, -1); break;   // qs (2 bit) | scales[16] | {d,dmin}
+        case B200Q_TYPE_Q3_K:   set(256, 110, 0, 4, 64, 32, 12, 2, -1); break;  // qs (low 2 bits) | hmask | scales[12] | d
         case B200Q_TYPE_Q4_K:   set(256, 144, 0, 2, 128, 16, 0, 0, -1); break; // qs | {d,dmin,scales[12]}
         case B200Q_TYPE_Q5_K:   set(256, 176, 0, 3, 128, 32, 16, 0, -1); break; // qs | qh | {d,dmin,scales[12]}
         case B200Q_TYPE_Q6_K:   set(256, 210, 0, 4, 128, 64, 16, 2, -1); break; // ql | qh | scales[16] | d
@@ -178,6 +180,21 @@ B200Q_HD void b200q_unpack_h2(const uint32_t U[2], uint8_t h2[32]) {
     for (int u = 0; u < 2; ++u) for (int wp = 0; wp < 2; ++wp) for (int g = 0; g < 2; ++g) for (int b = 0; b < 4; ++b)
         h2[8 * (2 * u + wp) + 4 * g + b] = (U[u] >> (8 * b + 2 * (2 * wp + g))) & 3;
 }
+
+// 2-bit plane (Q2_K, Q3_K low bits): 8 bytes per item = two u32; U[u] byte b, field f (bits 2f..2f+1) = e 16u + 4f + b, so that
+// (U[u] >> 2f) & 0x03030303 is the int8x4 word of weights 16u+4f .. +3
+B200Q_HD void b200q_pack_q2(const uint8_t idx[32], uint32_t U[2]) {
+    U[0] = U[1] = 0;
+    for (int u = 0; u < 2; ++u) for (int f = 0; f < 4; ++f) for (int b = 0; b < 4; ++b) U[u] |= (uint32_t)(idx[16 * u + 4 * f + b] & 3) << (8 * b + 2 * f);
+}
+B200Q_HD void b200q_unpack_q2(const uint32_t U[2], uint8_t idx[32]) {
+    for (int u = 0; u < 2; ++u) for (int f = 0; f < 4; ++f) for (int b = 0; b < 4; ++b) idx[16 * u + 4 * f + b] = (U[u] >> (8 * b + 2 * f)) & 3;
+}
+// 1-bit plane for Q3_K: bit (8b + w) = hb(e 4w + b), w = 0..7: (H >> w) & 0x01010101 is the bit of the four weights of word w
+B200Q_HD uint32_t b200q_pack_hb8(const uint8_t hb[32]) {
+    uint32_t q = 0; for (int w = 0; w < 8; ++w) for (int b = 0; b < 4; ++b) q |= (uint32_t)(hb[4 * w + b] & 1) << (8 * b + w); return q;
+}
+B200Q_HD void b200q_unpack_hb8(uint32_t q, uint8_t hb[32]) { for (int w = 0; w < 8; ++w) for (int b = 0; b < 4; ++b) hb[4 * w + b] = (q >> (8 * b + w)) & 1; }
 
 // ---------------------------------------------------------------------------------------------
 // repack / unrepack of ONE wire block (generic over the layout; runs as one GPU thread per block,
@@ -249,6 +266,37 @@ B200Q_HD void b200q_repack_block(const b200q_layout & L, const uint8_t * wire, u
         uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * pd = b200q_plane_ptr(dst, L, 1, row, blk);
         if (!inverse) { for (int j = 0; j < 32; ++j) pq[j] = w[2 + j]; pd[0] = w[0]; pd[1] = w[1]; }
         else          { for (int j = 0; j < 32; ++j) w[2 + j] = pq[j]; w[0] = pd[0]; w[1] = pd[1]; }
+    } break;
+    case B200Q_TYPE_Q2_K: case B200Q_TYPE_Q3_K: {
+        // Q2_K {u8 scales[16]; u8 qs[64]; half d, dmin}  (ggml-common.h block_q2_K; dequantize_row_q2_K ggml-quants.c:2162-2190)
+        // Q3_K {u8 hmask[32]; u8 qs[64]; u8 scales[12]; half d}  (block_q3_K; dequantize_row_q3_K ggml-quants.c:2563-2605)
+        // both: item s = 4h + j (h = 128-half, j = 0..3): weight e <-> qs[32h + e] bits 2j..2j+1 ; Q3_K high bit = hmask[e] bit s
+        const bool q3 = L.type == B200Q_TYPE_Q3_K;
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk);
+        uint8_t * wqs = w + (q3 ? 32 : 16);
+        if (!q3) {
+            uint8_t * ps = b200q_plane_ptr(dst, L, 1, row, blk); uint8_t * pd = b200q_plane_ptr(dst, L, 2, row, blk);
+            if (!inverse) { for (int j = 0; j < 16; ++j) ps[j] = w[j]; for (int j = 0; j < 4; ++j) pd[j] = w[80 + j]; }
+            else          { for (int j = 0; j < 16; ++j) w[j] = ps[j]; for (int j = 0; j < 4; ++j) w[80 + j] = pd[j]; }
+        } else {
+            uint8_t * ps = b200q_plane_ptr(dst, L, 2, row, blk); uint8_t * pd = b200q_plane_ptr(dst, L, 3, row, blk);
+            if (!inverse) { for (int j = 0; j < 12; ++j) ps[j] = w[96 + j]; pd[0] = w[108]; pd[1] = w[109]; }
+            else          { for (int j = 0; j < 12; ++j) w[96 + j] = ps[j]; w[108] = pd[0]; w[109] = pd[1]; for (int j = 0; j < 32; ++j) w[j] = 0; }
+        }
+        if (inverse) for (int j = 0; j < 64; ++j) wqs[j] = 0;
+        uint8_t * ph = q3 ? b200q_plane_ptr(dst, L, 1, row, blk) : nullptr;
+        for (int s = 0; s < 8; ++s) {
+            const int h = s / 4, j = s % 4;
+            if (!inverse) {
+                for (int e = 0; e < 32; ++e) { idx[e] = (wqs[32 * h + e] >> (2 * j)) & 3; if (q3) hb[e] = (w[e] >> s) & 1; }
+                uint32_t U[2]; b200q_pack_q2(idx, U); memcpy(pq + 8 * s, U, 8);
+                if (q3) { uint32_t q = b200q_pack_hb8(hb); memcpy(ph + 4 * s, &q, 4); }
+            } else {
+                uint32_t U[2]; memcpy(U, pq + 8 * s, 8); b200q_unpack_q2(U, idx);
+                if (q3) { uint32_t q; memcpy(&q, ph + 4 * s, 4); b200q_unpack_hb8(q, hb); }
+                for (int e = 0; e < 32; ++e) { wqs[32 * h + e] |= (uint8_t)(idx[e] << (2 * j)); if (q3) w[e] |= (uint8_t)(hb[e] << s); }
+            }
+        }
     } break;
     case B200Q_TYPE_Q4_K: case B200Q_TYPE_Q5_K: {      // {half d,dmin; u8 scales[12]; [u8 qh[32];] u8 qs[128]}
         const bool q5 = L.type == B200Q_TYPE_Q5_K;
@@ -446,6 +494,8 @@ B200Q_DEF_TRAITS(B200Q_TYPE_Q4_1,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q5_0,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q5_1,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q6_0,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q2_K,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_Q3_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q4_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q5_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q6_K,  false, 32)
@@ -539,6 +589,16 @@ B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, typename b
         const uint8_t * p = P.p[0] + (row * n32 + it) * 32;
         LD::ld16(I.q, p); LD::ld16(I.q + 4, p + 16);
         I.m[0] = LD::ld2(P.p[1] + (row * n32 + it) * 2);
+    } else if (TYPE == B200Q_TYPE_Q2_K) {
+        LD::ld8(I.q, P.p[0] + (row * n32 + it) * 8);
+        I.m[0] = LD::ld2(P.p[1] + (row * nb + it / 8) * 16 + 2 * (it % 8));   // the two {scale, min} bytes of this item
+        I.m[1] = LD::ld4(P.p[2] + (row * nb + it / 8) * 4);                   // {d, dmin}
+    } else if (TYPE == B200Q_TYPE_Q3_K) {
+        LD::ld8(I.q, P.p[0] + (row * n32 + it) * 8);
+        I.h[0] = LD::ld4(P.p[1] + (row * n32 + it) * 4);
+        const uint8_t * ps = P.p[2] + (row * nb + it / 8) * 12;
+        I.m[0] = LD::ld4(ps); I.m[1] = LD::ld4(ps + 4); I.m[2] = LD::ld4(ps + 8);
+        I.m[3] = LD::ld2(P.p[3] + (row * nb + it / 8) * 2);
     } else if (TYPE == B200Q_TYPE_Q4_K || TYPE == B200Q_TYPE_IQ4_K) {
         LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         LD::ld16(I.m, P.p[1] + (row * nb + it / 8) * 16);
@@ -622,6 +682,24 @@ B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & 
             C.va[2 * w] = (int)lo; C.va[2 * w + 1] = (int)hi;
         }
         C.dl[0] = d * s0; C.dl[1] = d * s1; C.ml[0] = 32.0f * C.dl[0]; C.ml[1] = 32.0f * C.dl[1];
+    } else if (TYPE == B200Q_TYPE_Q2_K) {             // w = d*(sc & 0xF)*q - dmin*(sc >> 4), one {scale,min} byte per 16 weights
+        const float d = b200q_h2f((uint16_t)(I.m[1] & 0xFFFF)), dmin = b200q_h2f((uint16_t)(I.m[1] >> 16));
+        const uint32_t s0 = I.m[0] & 0xFF, s1 = (I.m[0] >> 8) & 0xFF;
+        for (int f = 0; f < 4; ++f) { C.va[f] = (int)((I.q[0] >> (2 * f)) & 0x03030303u); C.va[4 + f] = (int)((I.q[1] >> (2 * f)) & 0x03030303u); }
+        C.dl[0] = d * (float)(s0 & 0xF); C.dl[1] = d * (float)(s1 & 0xF); C.ml[0] = dmin * (float)(s0 >> 4); C.ml[1] = dmin * (float)(s1 >> 4);
+    } else if (TYPE == B200Q_TYPE_Q3_K) {             // w = d*(sc - 32)*(q3 - 4), q3 = low2 | hbit << 2; 6-bit scales as in ggml-quants.c:2580-2586
+        const float d = b200q_h2f((uint16_t)I.m[3]); const int s = (int)(it % 8);
+        int sc[2];
+        for (int t = 0; t < 2; ++t) {
+            const int is = 2 * s + t, i = is >> 2, b = is & 3;
+            const uint32_t lo4 = ((i & 1 ? I.m[1] : I.m[0]) >> (8 * b + 4 * (i >> 1))) & 0xF, hi2 = (I.m[2] >> (8 * b + 2 * i)) & 3;
+            sc[t] = (int)(lo4 | (hi2 << 4)) - 32;
+        }
+        for (int f = 0; f < 4; ++f) {
+            C.va[f]     = (int)(((I.q[0] >> (2 * f)) & 0x03030303u) | (((I.h[0] >> f) & 0x01010101u) << 2));
+            C.va[4 + f] = (int)(((I.q[1] >> (2 * f)) & 0x03030303u) | (((I.h[0] >> (4 + f)) & 0x01010101u) << 2));
+        }
+        C.dl[0] = d * (float)sc[0]; C.dl[1] = d * (float)sc[1]; C.ml[0] = 4.0f * C.dl[0]; C.ml[1] = 4.0f * C.dl[1];
     } else if (TYPE == B200Q_TYPE_IQ4_XS) {           // meta {half d; u16 scales_h; u8 scales_l[4]}
         const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const uint32_t sh = I.m[0] >> 16; const int ib = (int)(it % 8);
         const uint32_t sl = (I.m[1] >> (8 * (ib / 2) + 4 * (ib % 2))) & 0xF;   // scales_l[ib/2] nibble ib%2

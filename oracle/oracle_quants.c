@@ -177,6 +177,43 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
                 ql += 32; is += 2; u1 <<= 2; u2 <<= 2;
             }
         } break;
+        case T_Q2_K: {  // ggml-quants.c:2162-2190  {u8 scales[16]; u8 qs[64]; half d, dmin}
+            const uint8_t * sc = x; const uint8_t * q = x + 16; const float d = h2f(rd16(x + 80)), dmin = h2f(rd16(x + 82));
+            float * yy = y; int is = 0;
+            for (int n = 0; n < 256; n += 128) {
+                int shift = 0;
+                for (int j = 0; j < 4; ++j) {
+                    float dl = d * (sc[is] & 0xF), ml = dmin * (sc[is] >> 4); ++is;
+                    for (int l = 0; l < 16; ++l) *yy++ = dl * ((int8_t)((q[l] >> shift) & 3)) - ml;
+                    dl = d * (sc[is] & 0xF); ml = dmin * (sc[is] >> 4); ++is;
+                    for (int l = 0; l < 16; ++l) *yy++ = dl * ((int8_t)((q[l + 16] >> shift) & 3)) - ml;
+                    shift += 2;
+                }
+                q += 32;
+            }
+        } break;
+        case T_Q3_K: {  // ggml-quants.c:2563-2605  {u8 hmask[32]; u8 qs[64]; u8 scales[12]; half d}
+            const uint8_t * hm = x; const uint8_t * q = x + 32; const float d_all = h2f(rd16(x + 108));
+            uint32_t aux[4]; memcpy(aux, x + 96, 12);
+            const uint32_t kmask1 = 0x03030303, kmask2 = 0x0f0f0f0f; const uint32_t tmp = aux[2];
+            aux[2] = ((aux[0] >> 4) & kmask2) | (((tmp >> 4) & kmask1) << 4);
+            aux[3] = ((aux[1] >> 4) & kmask2) | (((tmp >> 6) & kmask1) << 4);
+            aux[0] = (aux[0] & kmask2) | (((tmp >> 0) & kmask1) << 4);
+            aux[1] = (aux[1] & kmask2) | (((tmp >> 2) & kmask1) << 4);
+            const int8_t * scales = (const int8_t *)aux;
+            float * yy = y; int is = 0; uint8_t m = 1;
+            for (int n = 0; n < 256; n += 128) {
+                int shift = 0;
+                for (int j = 0; j < 4; ++j) {
+                    float dl = d_all * (scales[is++] - 32);
+                    for (int l = 0; l < 16; ++l) *yy++ = dl * ((int8_t)((q[l] >> shift) & 3) - ((hm[l] & m) ? 0 : 4));
+                    dl = d_all * (scales[is++] - 32);
+                    for (int l = 0; l < 16; ++l) *yy++ = dl * ((int8_t)((q[l + 16] >> shift) & 3) - ((hm[l + 16] & m) ? 0 : 4));
+                    shift += 2; m <<= 1;
+                }
+                q += 32;
+            }
+        } break;
         case T_Q6_K: {  // ggml-quants.c:3231-3260  {u8 ql[128]; u8 qh[64]; i8 scales[16]; half d}
             const uint8_t * ql = x; const uint8_t * qh = x + 128; const int8_t * sc = (const int8_t *)(x + 192); const float d = h2f(rd16(x + 208));
             float * yy = y;
