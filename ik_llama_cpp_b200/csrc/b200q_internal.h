@@ -14,7 +14,8 @@ B200Q_HD constexpr bool b200q_mmvq_has_ml(int type) {
 }
 // types whose two 16-weight halves of an item carry different scales / offsets
 B200Q_HD constexpr bool b200q_split16(int type) {
-    return type == B200Q_TYPE_Q6_K || type == B200Q_TYPE_IQ4_K || type == B200Q_TYPE_IQ5_K || type == B200Q_TYPE_Q2_K || type == B200Q_TYPE_Q3_K;
+    return type == B200Q_TYPE_Q6_K || type == B200Q_TYPE_IQ4_K || type == B200Q_TYPE_IQ5_K || type == B200Q_TYPE_Q2_K || type == B200Q_TYPE_Q3_K ||
+           type == B200Q_TYPE_IQ2_K || type == B200Q_TYPE_IQ3_K;
 }
 
 // device view of the NVLS communicator of include/b200q.h (b200q_nvls_comm) + the direction flags of one launch

@@ -39,7 +39,7 @@
 // ggml_type ids (reference ggml/include/ggml.h:391-492)
 enum b200q_type : int {
     B200Q_TYPE_Q4_0 = 2, B200Q_TYPE_Q4_1 = 3, B200Q_TYPE_Q5_0 = 6, B200Q_TYPE_Q5_1 = 7, B200Q_TYPE_Q6_0 = 133, B200Q_TYPE_Q8_0 = 8, B200Q_TYPE_Q2_K = 10, B200Q_TYPE_Q3_K = 11, B200Q_TYPE_Q4_K = 12, B200Q_TYPE_Q5_K = 13, B200Q_TYPE_Q6_K = 14,
-    B200Q_TYPE_IQ4_NL = 20, B200Q_TYPE_IQ4_XS = 23, B200Q_TYPE_IQ2_BN = 135, B200Q_TYPE_IQ4_K = 139,
+    B200Q_TYPE_IQ4_NL = 20, B200Q_TYPE_IQ4_XS = 23, B200Q_TYPE_IQ2_BN = 135, B200Q_TYPE_IQ2_K = 137, B200Q_TYPE_IQ3_K = 138, B200Q_TYPE_IQ4_K = 139,
     B200Q_TYPE_IQ5_K = 140, B200Q_TYPE_IQ4_KS = 144,
 };
 
@@ -124,6 +124,8 @@ inline int b200q_make_layout(int type, int64_t M, int64_t K, b200q_layout * L) {
         case B200Q_TYPE_Q5_K:   set(256, 176, 0, 3, 128, 32, 16, 0, -1); break; // qs | qh | {d,dmin,scales[12]}
         case B200Q_TYPE_Q6_K:   set(256, 210, 0, 4, 128, 64, 16, 2, -1); break; // ql | qh | scales[16] | d
         case B200Q_TYPE_IQ4_XS: set(256, 136, 0, 2, 128, 8, 0, 0, -1); break;  // qs | {d,scales_h,scales_l[4]}
+        case B200Q_TYPE_IQ2_K:  set(256, 76, 0, 2, 64, 12, 0, 0, -1); break;   // qs (2-bit selectors) | {d,extra,scales[8]}
+        case B200Q_TYPE_IQ3_K:  set(256, 110, 0, 3, 64, 32, 16, 0, -1); break;  // qs (low 2 bits) | qh | {d,extra,scales_h,scales_l[8],pad 2}
         case B200Q_TYPE_IQ4_K:  set(256, 144, 0, 2, 128, 16, 0, 0, -1); break; // qs | {d,extra,scales_h[4],scales_l[8]}
         case B200Q_TYPE_IQ5_K:  set(256, 176, 0, 3, 128, 32, 16, 0, -1); break; // qs | qh | {d,extra,scales_h[4],scales_l[8]}
         case B200Q_TYPE_IQ4_KS: set(256, 136, 4, 3, 128, 8, 4, 0, 2); break;   // qs | scales[8] | row scale
@@ -189,6 +191,22 @@ B200Q_HD void b200q_pack_q2(const uint8_t idx[32], uint32_t U[2]) {
 }
 B200Q_HD void b200q_unpack_q2(const uint32_t U[2], uint8_t idx[32]) {
     for (int u = 0; u < 2; ++u) for (int f = 0; f < 4; ++f) for (int b = 0; b < 4; ++b) idx[16 * u + 4 * f + b] = (U[u] >> (8 * b + 2 * f)) & 3;
+}
+// 2-bit LUT plane (IQ2_K, IQ3_K): 8 bytes per item = two u32; weight e = 16u + 8p + n sits in bits 4n+2p..4n+2p+1 of W[u], so that
+// (W[u] >> 2p) & 0x33333333 is eight ready-made PRMT selector nibbles (weights 16u+8p .. +7 in order)
+B200Q_HD void b200q_pack_l2(const uint8_t idx[32], uint32_t W[2]) {
+    W[0] = W[1] = 0;
+    for (int u = 0; u < 2; ++u) for (int p = 0; p < 2; ++p) for (int n = 0; n < 8; ++n) W[u] |= (uint32_t)(idx[16 * u + 8 * p + n] & 3) << (4 * n + 2 * p);
+}
+B200Q_HD void b200q_unpack_l2(const uint32_t W[2], uint8_t idx[32]) {
+    for (int u = 0; u < 2; ++u) for (int p = 0; p < 2; ++p) for (int n = 0; n < 8; ++n) idx[16 * u + 8 * p + n] = (W[u] >> (4 * n + 2 * p)) & 3;
+}
+// third selector bit of IQ3_K: bit (4n + 2u + p) = hb(e 16u + 8p + n): ((H >> (2u+p)) & 0x11111111) << 2 drops it into bit 2 of each nibble
+B200Q_HD uint32_t b200q_pack_hl(const uint8_t hb[32]) {
+    uint32_t q = 0; for (int u = 0; u < 2; ++u) for (int p = 0; p < 2; ++p) for (int n = 0; n < 8; ++n) q |= (uint32_t)(hb[16 * u + 8 * p + n] & 1) << (4 * n + 2 * u + p); return q;
+}
+B200Q_HD void b200q_unpack_hl(uint32_t q, uint8_t hb[32]) {
+    for (int u = 0; u < 2; ++u) for (int p = 0; p < 2; ++p) for (int n = 0; n < 8; ++n) hb[16 * u + 8 * p + n] = (q >> (4 * n + 2 * u + p)) & 1;
 }
 // 1-bit plane for Q3_K: bit (8b + w) = hb(e 4w + b), w = 0..7: (H >> w) & 0x01010101 is the bit of the four weights of word w
 B200Q_HD uint32_t b200q_pack_hb8(const uint8_t hb[32]) {
@@ -295,6 +313,29 @@ B200Q_HD void b200q_repack_block(const b200q_layout & L, const uint8_t * wire, u
                 uint32_t U[2]; memcpy(U, pq + 8 * s, 8); b200q_unpack_q2(U, idx);
                 if (q3) { uint32_t q; memcpy(&q, ph + 4 * s, 4); b200q_unpack_hb8(q, hb); }
                 for (int e = 0; e < 32; ++e) { wqs[32 * h + e] |= (uint8_t)(idx[e] << (2 * j)); if (q3) w[e] |= (uint8_t)(hb[e] << s); }
+            }
+        }
+    } break;
+    case B200Q_TYPE_IQ2_K: case B200Q_TYPE_IQ3_K: {
+        // IQ2_K {half d; u16 extra; u8 scales[8]; u8 qs[64]}                              (ggml-common.h block_iq2_k; iqk_quantize.cpp:1356-1385)
+        // IQ3_K {half d; u16 extra; u16 scales_h; u8 scales_l[8]; u8 qs[64]; u8 qh[32]}   (block_iq3_k; iqk_quantize.cpp:2534-2565)
+        // both: item s: weight e <-> qs[32(s/4) + e] bits 2(s%4)..+1 ; IQ3_K third bit = qh[e] bit s
+        const bool q3 = L.type == B200Q_TYPE_IQ3_K; const int hdr = q3 ? 14 : 12;
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * ph = q3 ? b200q_plane_ptr(dst, L, 1, row, blk) : nullptr;
+        uint8_t * pm = b200q_plane_ptr(dst, L, q3 ? 2 : 1, row, blk);
+        uint8_t * wqs = w + hdr; uint8_t * wqh = w + hdr + 64;
+        if (!inverse) { for (int j = 0; j < hdr; ++j) pm[j] = w[j]; if (q3) { pm[14] = 0; pm[15] = 0; } }
+        else { for (int j = 0; j < hdr; ++j) w[j] = pm[j]; for (int j = 0; j < 64; ++j) wqs[j] = 0; if (q3) for (int j = 0; j < 32; ++j) wqh[j] = 0; }
+        for (int s = 0; s < 8; ++s) {
+            const int h = s / 4, j = s % 4;
+            if (!inverse) {
+                for (int e = 0; e < 32; ++e) { idx[e] = (wqs[32 * h + e] >> (2 * j)) & 3; if (q3) hb[e] = (wqh[e] >> s) & 1; }
+                uint32_t W[2]; b200q_pack_l2(idx, W); memcpy(pq + 8 * s, W, 8);
+                if (q3) { uint32_t q = b200q_pack_hl(hb); memcpy(ph + 4 * s, &q, 4); }
+            } else {
+                uint32_t W[2]; memcpy(W, pq + 8 * s, 8); b200q_unpack_l2(W, idx);
+                if (q3) { uint32_t q; memcpy(&q, ph + 4 * s, 4); b200q_unpack_hl(q, hb); }
+                for (int e = 0; e < 32; ++e) { wqs[32 * h + e] |= (uint8_t)(idx[e] << (2 * j)); if (q3) wqh[e] |= (uint8_t)(hb[e] << s); }
             }
         }
     } break;
@@ -500,6 +541,8 @@ B200Q_DEF_TRAITS(B200Q_TYPE_Q4_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q5_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_Q6_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_XS, true, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ2_K,  false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ3_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_K,  true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_KS, true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ5_K,  true, 32)
@@ -599,6 +642,14 @@ B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, typename b
         const uint8_t * ps = P.p[2] + (row * nb + it / 8) * 12;
         I.m[0] = LD::ld4(ps); I.m[1] = LD::ld4(ps + 4); I.m[2] = LD::ld4(ps + 8);
         I.m[3] = LD::ld2(P.p[3] + (row * nb + it / 8) * 2);
+    } else if (TYPE == B200Q_TYPE_IQ2_K) {
+        LD::ld8(I.q, P.p[0] + (row * n32 + it) * 8);
+        const uint8_t * pm = P.p[1] + (row * nb + it / 8) * 12;
+        I.m[0] = LD::ld4(pm); I.m[1] = LD::ld4(pm + 4); I.m[2] = LD::ld4(pm + 8);
+    } else if (TYPE == B200Q_TYPE_IQ3_K) {
+        LD::ld8(I.q, P.p[0] + (row * n32 + it) * 8);
+        I.h[0] = LD::ld4(P.p[1] + (row * n32 + it) * 4);
+        LD::ld16(I.m, P.p[2] + (row * nb + it / 8) * 16);
     } else if (TYPE == B200Q_TYPE_Q4_K || TYPE == B200Q_TYPE_IQ4_K) {
         LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         LD::ld16(I.m, P.p[1] + (row * nb + it / 8) * 16);
@@ -700,6 +751,24 @@ B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & 
             C.va[4 + f] = (int)(((I.q[1] >> (2 * f)) & 0x03030303u) | (((I.h[0] >> (4 + f)) & 0x01010101u) << 2));
         }
         C.dl[0] = d * (float)sc[0]; C.dl[1] = d * (float)sc[1]; C.ml[0] = 4.0f * C.dl[0]; C.ml[1] = 4.0f * C.dl[1];
+    } else if (TYPE == B200Q_TYPE_IQ2_K) {            // meta {half d; u16 extra; u8 scales[8]}; iq2nl_values = {-31,-13,1,17} (+5 when the extra bit is set)
+        const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const int s = (int)(it % 8);
+        const uint32_t ex = (I.m[0] >> 16) >> (2 * s), sc = b200q_byte(I.m, 4 + s);
+        for (int u = 0; u < 2; ++u) for (int p = 0; p < 2; ++p) {
+            const uint32_t sel = (I.q[u] >> (2 * p)) & 0x33333333u;
+            C.va[4 * u + 2 * p] = (int)b200q_prmt(0x1101F3E1u, 0u, sel); C.va[4 * u + 2 * p + 1] = (int)b200q_prmt(0x1101F3E1u, 0u, sel >> 16);
+        }
+        C.dl[0] = d * (float)((int)(sc & 0xF) - 8); C.dl[1] = d * (float)((int)(sc >> 4) - 8);
+        C.ml[0] = (ex & 1) ? -5.0f * C.dl[0] : 0.0f; C.ml[1] = (ex & 2) ? -5.0f * C.dl[1] : 0.0f;
+    } else if (TYPE == B200Q_TYPE_IQ3_K) {            // meta {half d; u16 extra; u16 scales_h; u8 scales_l[8]}; iq3nl_values (+4 with the extra bit)
+        const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const int s = (int)(it % 8);
+        const uint32_t ex = (I.m[0] >> 16) >> (2 * s), sh = (I.m[1] & 0xFFFF) >> (2 * s), sl = b200q_byte(I.m, 6 + s);
+        for (int u = 0; u < 2; ++u) for (int p = 0; p < 2; ++p) {
+            const uint32_t sel = ((I.q[u] >> (2 * p)) & 0x33333333u) | (((I.h[0] >> (2 * u + p)) & 0x11111111u) << 2);
+            C.va[4 * u + 2 * p] = (int)b200q_prmt(0xF6E9D8C1u, 0x2F1C0D01u, sel); C.va[4 * u + 2 * p + 1] = (int)b200q_prmt(0xF6E9D8C1u, 0x2F1C0D01u, sel >> 16);
+        }
+        C.dl[0] = d * (float)((2 * (int)(sl & 0xF) + 1) * ((sh & 1) ? -1 : 1)); C.dl[1] = d * (float)((2 * (int)(sl >> 4) + 1) * ((sh & 2) ? -1 : 1));
+        C.ml[0] = (ex & 1) ? -4.0f * C.dl[0] : 0.0f; C.ml[1] = (ex & 2) ? -4.0f * C.dl[1] : 0.0f;
     } else if (TYPE == B200Q_TYPE_IQ4_XS) {           // meta {half d; u16 scales_h; u8 scales_l[4]}
         const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const uint32_t sh = I.m[0] >> 16; const int ib = (int)(it % 8);
         const uint32_t sl = (I.m[1] >> (8 * (ib / 2) + 4 * (ib % 2))) & 0xF;   // scales_l[ib/2] nibble ib%2

@@ -26,7 +26,7 @@
 enum {
     T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ2_XXS = 16, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135,
+    T_IQ2_XXS = 16, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138,
     T_IQ4_K = 139, T_IQ5_K = 140, T_IQ4_KS = 144,
 };
 
@@ -92,6 +92,8 @@ static int geom(int type, int * qk, int * bs, int * meta) {
         case T_Q6_K:   *qk = 256; *bs = 210; return 0;
         case T_IQ4_NL: *qk = 32;  *bs = 18;  return 0;
         case T_IQ4_XS: *qk = 256; *bs = 136; return 0;
+        case T_IQ2_K:  *qk = 256; *bs = 76;  return 0;
+        case T_IQ3_K:  *qk = 256; *bs = 110; return 0;
         case T_IQ4_K:  *qk = 256; *bs = 144; return 0;
         case T_IQ5_K:  *qk = 256; *bs = 176; return 0;
         case T_IQ4_KS: *qk = 256; *bs = 136; *meta = 4; return 0;
@@ -241,6 +243,32 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
                 const float dl = d * (ls - 32);
                 for (int j = 0; j < 16; ++j) { yy[j] = dl * k_iq4nl[qs[j] & 0xf]; yy[j + 16] = dl * k_iq4nl[qs[j] >> 4]; }
                 yy += 32; qs += 16;
+            }
+        } break;
+        case T_IQ2_K: {  // iqk/iqk_quantize.cpp:1356-1385  {half d; u16 extra; u8 scales[8]; u8 qs[64]}; iq2nl_values ggml-common.h:2212
+            static const int8_t v2[8] = {-31, -13, 1, 17, -26, -8, 6, 22};
+            const float d = h2f(rd16(x)); uint16_t extra = rd16(x + 2); const uint8_t * sc = x + 4; const uint8_t * qs = x + 12;
+            float * yy = y; int shift = 0;
+            for (int ib = 0; ib < 8; ++ib) {
+                const float dl1 = d * ((sc[ib] & 0xf) - 8), dl2 = d * ((sc[ib] >> 4) - 8);
+                const int8_t * va = extra & 1 ? v2 + 4 : v2; const int8_t * vb = extra & 2 ? v2 + 4 : v2; extra >>= 2;
+                for (int j = 0; j < 16; ++j) { yy[j] = dl1 * va[(qs[j] >> shift) & 3]; yy[j + 16] = dl2 * vb[(qs[j + 16] >> shift) & 3]; }
+                yy += 32; shift += 2; if (shift == 8) { qs += 32; shift = 0; }
+            }
+        } break;
+        case T_IQ3_K: {  // iqk/iqk_quantize.cpp:2534-2565  {half d; u16 extra; u16 scales_h; u8 scales_l[8]; u8 qs[64]; u8 qh[32]}; iq3nl_values :2222
+            static const int8_t v3[16] = {-63, -40, -23, -10, 1, 13, 28, 47, -59, -36, -19, -6, 5, 17, 32, 51};
+            const float d = h2f(rd16(x)); uint16_t extra = rd16(x + 2); uint16_t sh = rd16(x + 4); const uint8_t * sl = x + 6; const uint8_t * qs = x + 14; const uint8_t * qh = x + 78;
+            float * yy = y;
+            for (int ib = 0; ib < 8; ++ib) {
+                const float dl1 = d * ((2 * (sl[ib] & 0xf) + 1) * ((sh & 1) ? -1 : 1)), dl2 = d * ((2 * (sl[ib] >> 4) + 1) * ((sh & 2) ? -1 : 1)); sh >>= 2;
+                const int8_t * va = extra & 1 ? v3 + 8 : v3; const int8_t * vb = extra & 2 ? v3 + 8 : v3; extra >>= 2;
+                const int shl = 2 * (ib % 4), shh = ib % 8;
+                for (int j = 0; j < 16; ++j) {
+                    yy[j]      = dl1 * va[((qs[j] >> shl) & 3) | (((qh[j] >> shh) & 1) << 2)];
+                    yy[j + 16] = dl2 * vb[((qs[j + 16] >> shl) & 3) | (((qh[j + 16] >> shh) & 1) << 2)];
+                }
+                yy += 32; if (shl == 6) qs += 32;
             }
         } break;
         case T_IQ4_K: {  // iqk/iqk_quantize.cpp:2822-2850  {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]; u8 qs[128]}
