@@ -342,8 +342,13 @@ def main():
     tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     bytes_tok = model.weight_bytes
+    traffic = {}
+    try:   # DRAM bytes per step measured by ncu --set full (scripts/make_traffic.py, committed under profiles/), N = 1 only
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))) if world == 1 and args.layers == N_LAYER else {}
+    except Exception:
+        pass
     ach = bytes_tok / (ms_tg * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "k_mmvq<IQ4_NL>", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+    roof = {"bound": "hbm", "kernel": "k_mmvq<IQ4_NL>", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic.get("tg", {}).get("dram_bytes_per_step"),
             "algorithmic_bytes_per_step": bytes_tok, "launches_per_step": model.launches_tg, "peak_source": peak_src,
             "note": "the step consists only of k_mmvq launches; achieved = weight bytes per token / step time (per rank)"}
     line = {"metric": "llama-bench tg128 tok/s (MUL_MAT hot path)", "value": tok_s, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -367,7 +372,7 @@ def main():
         line["pp512"] = {"metric": "llama-bench pp512 tok/s (MUL_MAT hot path)", "value": n * 1000.0 / ms_pp, "unit": "tok/s", "ms_per_step": ms_pp, "steps": pp_steps,
                          "dtype": "bf16 x bf16 -> f32 (tcgen05 kind::f16)", "e2e": {"value": n * 1000.0 / ms_pp_e2e, "unit": "tok/s", "h2d_bytes_per_step": n * N_EMBD * 4, "d2h_bytes_per_step": (N_VOCAB // world) * 4},
                          "roofline": {"bound": "tensor", "kernel": "k_gemm_q<IQ4_NL> (fused dequant + tcgen05; + k_f32_to_bf16)", "achieved": tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfs / tf_peak,
-                                      "traffic": None, "algorithmic_flops_per_step": fl, "peak_source": peak_src + " sustained"}}
+                                      "traffic": traffic.get("pp", {}).get("dram_bytes_per_step_gemm_only"), "algorithmic_flops_per_step": fl, "peak_source": peak_src + " sustained"}}
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu:
         try:

@@ -10,8 +10,8 @@ timeout -k 5 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_
 echo "bench ref rc=$?" >> gpurun_out/summary.txt
 timeout -k 5 500 ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1
 echo "ncu launches rc=$?" >> gpurun_out/summary.txt
-timeout -k 5 500 ncu --set full --clock-control none --import-source on -k regex:k_mmvq_ring -s 20 -c 4 -o gpurun_out/prof_mmvq_r1 python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu --no-pp > gpurun_out/ncu_mmvq.log 2>&1
+timeout -k 5 500 ncu --set full --clock-control none --import-source on -k regex:k_mmvq_ring -s 18 -c 9 -o gpurun_out/prof_mmvq_r1 python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu --no-pp > gpurun_out/ncu_mmvq.log 2>&1
 echo "ncu mmvq rc=$?" >> gpurun_out/summary.txt
-timeout -k 5 500 ncu --set full --clock-control none --import-source on -k regex:k_gemm_q -s 14 -c 7 -o gpurun_out/prof_gemmq_r1 python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_gemm.log 2>&1
+timeout -k 5 500 ncu --set full --clock-control none --import-source on -k regex:k_gemm_q -s 8 -c 8 -o gpurun_out/prof_gemmq_r1 python bench.py --layers 2 --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_gemm.log 2>&1
 echo "ncu gemm rc=$?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt; tail -3 gpurun_out/t_all.log; cut -c1-1200 gpurun_out/BENCH_r1_ours.json; echo; cut -c1-600 gpurun_out/BENCH_r1_reference.json
