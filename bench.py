@@ -376,7 +376,11 @@ def main():
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu:
         try:
-            cb = cpu_baseline(budget_s=10.0)
+            # the reference's spin-barrier pool collapses when oversubscribed: pick the better of two thread counts on a short sample
+            ncpu = os.cpu_count() or 8
+            trial = [(nt, cpu_baseline(n_threads=nt, budget_s=1.5)) for nt in sorted({max(1, ncpu // 2), min(ncpu, 16)})]
+            trial = [(nt, c) for nt, c in trial if c]
+            cb = cpu_baseline(n_threads=max(trial, key=lambda t: t[1]["value"])[0], budget_s=8.0) if trial else None
             if cb:
                 line["cpu_baseline"] = cb
         except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line

@@ -36,7 +36,8 @@ def launches(path, out):
 
 
 def full(path, out):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # `path`: an .ncu-rep, or the `ncu -i rep --page raw --csv` page exported on the GPU box (the reports themselves can exceed the copy-back limit)
+    raw = open(path).read() if path.endswith(".csv") else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(out, "w") as f:
