@@ -10,7 +10,7 @@ enum { B200Q_ACT_NONE = 0, B200Q_ACT_SILU = 1, B200Q_ACT_GELU = 2, B200Q_ACT_REL
 
 // types whose canonical decode has a non-zero subtracted offset (ml) -> the kernel needs the integer activation sums
 B200Q_HD constexpr bool b200q_mmvq_has_ml(int type) {
-    return !(type == B200Q_TYPE_IQ4_NL || type == B200Q_TYPE_Q8_0 || type == B200Q_TYPE_IQ4_XS);
+    return !(type == B200Q_TYPE_IQ4_NL || type == B200Q_TYPE_Q8_0 || type == B200Q_TYPE_IQ4_XS || type == B200Q_TYPE_MXFP4);
 }
 // types whose two 16-weight halves of an item carry different scales / offsets
 B200Q_HD constexpr bool b200q_split16(int type) {

@@ -39,7 +39,7 @@
 // ggml_type ids (reference ggml/include/ggml.h:391-492)
 enum b200q_type : int {
     B200Q_TYPE_Q4_0 = 2, B200Q_TYPE_Q4_1 = 3, B200Q_TYPE_Q5_0 = 6, B200Q_TYPE_Q5_1 = 7, B200Q_TYPE_Q6_0 = 133, B200Q_TYPE_Q8_0 = 8, B200Q_TYPE_Q2_K = 10, B200Q_TYPE_Q3_K = 11, B200Q_TYPE_Q4_K = 12, B200Q_TYPE_Q5_K = 13, B200Q_TYPE_Q6_K = 14,
-    B200Q_TYPE_IQ4_NL = 20, B200Q_TYPE_IQ4_XS = 23, B200Q_TYPE_IQ2_BN = 135, B200Q_TYPE_IQ2_K = 137, B200Q_TYPE_IQ3_K = 138, B200Q_TYPE_IQ4_K = 139,
+    B200Q_TYPE_IQ4_NL = 20, B200Q_TYPE_IQ4_XS = 23, B200Q_TYPE_MXFP4 = 39, B200Q_TYPE_IQ5_KS = 152, B200Q_TYPE_IQ2_BN = 135, B200Q_TYPE_IQ2_K = 137, B200Q_TYPE_IQ3_K = 138, B200Q_TYPE_IQ4_K = 139,
     B200Q_TYPE_IQ5_K = 140, B200Q_TYPE_IQ4_KS = 144,
 };
 
@@ -69,6 +69,7 @@ B200Q_HD uint32_t b200q_prmt(uint32_t a, uint32_t b, uint32_t s) {
     return r;
 #endif
 }
+B200Q_HD float b200q_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 B200Q_HD float b200q_h2f(uint16_t h) {
 #if defined(__CUDA_ARCH__)
     return __half2float(__ushort_as_half(h));
@@ -129,6 +130,8 @@ inline int b200q_make_layout(int type, int64_t M, int64_t K, b200q_layout * L) {
         case B200Q_TYPE_IQ4_K:  set(256, 144, 0, 2, 128, 16, 0, 0, -1); break; // qs | {d,extra,scales_h[4],scales_l[8]}
         case B200Q_TYPE_IQ5_K:  set(256, 176, 0, 3, 128, 32, 16, 0, -1); break; // qs | qh | {d,extra,scales_h[4],scales_l[8]}
         case B200Q_TYPE_IQ4_KS: set(256, 136, 4, 3, 128, 8, 4, 0, 2); break;   // qs | scales[8] | row scale
+        case B200Q_TYPE_IQ5_KS: set(256, 168, 4, 4, 128, 32, 8, 4, 3); break;  // qs | qh | scales[8] | row scale
+        case B200Q_TYPE_MXFP4:  set(32,  17, 0, 2, 16, 1, 0, 0, -1); break;    // qs | e (E8M0)
         case B200Q_TYPE_IQ2_BN: set(64,  16, 4, 2, 16, 4, 0, 0, 1); break;     // qs | row scale
         default: return -1;
     }
@@ -398,6 +401,32 @@ B200Q_HD void b200q_repack_block(const b200q_layout & L, const uint8_t * wire, u
             else { b200q_unpack_nib_L(pq + 16 * s, idx); for (int j = 0; j < 16; ++j) wqs[16 * s + j] = (uint8_t)(idx[j] | (idx[j + 16] << 4)); }
         }
     } break;
+    case B200Q_TYPE_MXFP4: {                           // {u8 e; u8 qs[16]}  (ggml-common.h:183-186; iqk_quantize.cpp:4224-4236)
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * pe = b200q_plane_ptr(dst, L, 1, row, blk);
+        if (!inverse) { for (int j = 0; j < 16; ++j) { idx[j] = w[1 + j] & 0xF; idx[j + 16] = w[1 + j] >> 4; } b200q_pack_nib_L(idx, pq); pe[0] = w[0]; }
+        else { b200q_unpack_nib_L(pq, idx); for (int j = 0; j < 16; ++j) w[1 + j] = (uint8_t)(idx[j] | (idx[j + 16] << 4)); w[0] = pe[0]; }
+    } break;
+    case B200Q_TYPE_IQ5_KS: {  // row = {float d; blocks {u8 scales[8]; u8 qs[128]; u8 qh[32]}}  (iqk_quantize.cpp:4798-4822): quants as IQ5_K
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * ph = b200q_plane_ptr(dst, L, 1, row, blk); uint8_t * pm = b200q_plane_ptr(dst, L, 2, row, blk);
+        if (!inverse) { for (int j = 0; j < 8; ++j) pm[j] = w[j]; } else { for (int j = 0; j < 8; ++j) w[j] = pm[j]; for (int j = 0; j < 32; ++j) w[136 + j] = 0; }
+        uint8_t * wqs = w + 8; uint8_t * wqh = w + 136;
+        for (int s = 0; s < 8; ++s) {
+            const int c = s / 2, second = s % 2;
+            if (!inverse) {
+                for (int l = 0; l < 32; ++l) { const uint8_t q = wqs[32 * c + l]; idx[l] = second ? (q >> 4) : (q & 0xF); hb[l] = (wqh[l] >> (2 * c + second)) & 1; }
+                b200q_pack_nib_L(idx, pq + 16 * s);
+                uint32_t q = 0; for (int e = 0; e < 32; ++e) q |= (uint32_t)hb[e] << e;
+                memcpy(ph + 4 * s, &q, 4);
+            } else {
+                b200q_unpack_nib_L(pq + 16 * s, idx);
+                uint32_t q; memcpy(&q, ph + 4 * s, 4);
+                for (int l = 0; l < 32; ++l) {
+                    if (second) wqs[32 * c + l] = (uint8_t)((wqs[32 * c + l] & 0x0F) | (idx[l] << 4)); else wqs[32 * c + l] = (uint8_t)((wqs[32 * c + l] & 0xF0) | idx[l]);
+                    wqh[l] |= (uint8_t)(((q >> l) & 1) << (2 * c + second));
+                }
+            }
+        }
+    } break;
     case B200Q_TYPE_IQ5_K: {   // {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]; u8 qs[128]; u8 qh[32]}
         // per 64 weights c: e 64c+j <- qs[32c+j] low (j<16), 64c+16+j <- qs[32c+16+j] low, 64c+32+j <- qs[32c+j] high, 64c+48+j <- qs[32c+16+j] high
         // high bit: qh[(c/4)*32 + jj] >> (2*(c%4) + {0: first 32, 1: second 32}), jj = position within the 32 bytes (see iqk_quantize.cpp:3136-3141)
@@ -545,6 +574,8 @@ B200Q_DEF_TRAITS(B200Q_TYPE_IQ2_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ3_K,  false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_K,  true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_KS, true, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ5_KS, true, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_MXFP4,  true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ5_K,  true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ2_BN, false, 32)
 
@@ -669,6 +700,14 @@ B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, typename b
         LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         I.m[0] = LD::ld1(P.p[1] + (row * nb + it / 8) * 8 + it % 8);
         if (ROWPLANE) { uint32_t r = LD::ld4(P.p[2] + row * 4); memcpy(&I.rs, &r, 4); }
+    } else if (TYPE == B200Q_TYPE_IQ5_KS) {
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
+        I.h[0] = LD::ld4(P.p[1] + (row * n32 + it) * 4);
+        I.m[0] = LD::ld1(P.p[2] + (row * nb + it / 8) * 8 + it % 8);
+        if (ROWPLANE) { uint32_t r = LD::ld4(P.p[3] + row * 4); memcpy(&I.rs, &r, 4); }
+    } else if (TYPE == B200Q_TYPE_MXFP4) {
+        LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
+        I.m[0] = LD::ld1(P.p[1] + (row * n32 + it));
     } else if (TYPE == B200Q_TYPE_IQ2_BN) {           // 64 weights per wire block: item = half a block (see decode)
         LD::ld16(I.q, P.p[0] + (row * nb + it / 2) * 16);
         if (ROWPLANE) { uint32_t r = LD::ld4(P.p[1] + row * 4); memcpy(&I.rs, &r, 4); }
@@ -679,7 +718,24 @@ B200Q_HD void b200q_load_item(b200q_item & I, const uint8_t * base, const b200q_
     b200q_load_item<TYPE>(I, b200q_planes_from(base, L), row, it);
 }
 // index of the per-row plane of a type (-1 if none)
-B200Q_HD constexpr int b200q_row_plane(int type) { return type == B200Q_TYPE_IQ4_KS ? 2 : (type == B200Q_TYPE_IQ2_BN ? 1 : -1); }
+B200Q_HD constexpr int b200q_row_plane(int type) { return type == B200Q_TYPE_IQ4_KS ? 2 : (type == B200Q_TYPE_IQ5_KS ? 3 : (type == B200Q_TYPE_IQ2_BN ? 1 : -1)); }
+
+// 5-bit codebook lookup of one item (IQ5_K, IQ5_KS): q = L-order nibbles, h[0] bit e = 5th bit of weight e; result = iq5nl_values + 2
+// split into the two sign-fill halves va / vb
+B200Q_HD void b200q_lut5_item(const b200q_item & I, b200q_canon & C) {
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t q = I.q[w], qx = q ^ 0x88888888u; const uint32_t hb = (I.h[0] >> (8 * w)) & 0xFF;
+            // byte masks from the 5th bits: lane j of half -> 0xFF if set
+            const uint32_t m_lo = (((hb & 0xF) * 0x00204081u) & 0x01010101u) * 0xFFu;
+            const uint32_t m_hi = (((hb >> 4) * 0x00204081u) & 0x01010101u) * 0xFFu;
+            const uint32_t a_lo0 = b200q_prmt(B200Q_KV5_T0_0, B200Q_KV5_T0_1, q), b_lo0 = b200q_prmt(B200Q_KV5_T1_0, B200Q_KV5_T1_1, qx);
+            const uint32_t a_lo1 = b200q_prmt(B200Q_KV5_T2_0, B200Q_KV5_T2_1, q), b_lo1 = b200q_prmt(B200Q_KV5_T3_0, B200Q_KV5_T3_1, qx);
+            const uint32_t a_hi0 = b200q_prmt(B200Q_KV5_T0_0, B200Q_KV5_T0_1, q >> 16), b_hi0 = b200q_prmt(B200Q_KV5_T1_0, B200Q_KV5_T1_1, qx >> 16);
+            const uint32_t a_hi1 = b200q_prmt(B200Q_KV5_T2_0, B200Q_KV5_T2_1, q >> 16), b_hi1 = b200q_prmt(B200Q_KV5_T3_0, B200Q_KV5_T3_1, qx >> 16);
+            C.va[2 * w]     = (int)((a_lo1 & m_lo) | (a_lo0 & ~m_lo)); C.vb[2 * w]     = (int)((b_lo1 & m_lo) | (b_lo0 & ~m_lo));
+            C.va[2 * w + 1] = (int)((a_hi1 & m_hi) | (a_hi0 & ~m_hi)); C.vb[2 * w + 1] = (int)((b_hi1 & m_hi) | (b_hi0 & ~m_hi));
+        }
+}
 
 template <int TYPE>
 B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & C, const b200q_kv4 & T) {
@@ -788,6 +844,18 @@ B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & 
         const float dl = I.rs * (float)((int)(s & 254) - 127);
         for (int w = 0; w < 4; ++w) b200q_lut4(T, I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
         C.dl[0] = C.dl[1] = dl; C.ml[0] = C.ml[1] = (s & 1) ? -4.0f * dl : 0.0f;
+    } else if (TYPE == B200Q_TYPE_MXFP4) {            // kvalues_mxfp4 (ggml-common.h:2250) = {0,1,2,3,4,6,8,12, 0,-1,-2,-3,-4,-6,-8,-12}, d = E8M0 / 2
+        // sign-fill tables: A' = entries 0..7 minus the fill that the B lookup adds for q < 8 (0 for entry 0, -1 otherwise), B' = entries 8..15
+        b200q_kv4 M; M.a0 = 0x04030200u; M.a1 = 0x0D090705u; M.b0 = 0xFDFEFF00u; M.b1 = 0xF4F8FAFCu; M.k16 = T.k16;
+        const uint32_t e = I.m[0] & 0xFF;
+        const float d = b200q_u2f(e >= 2 ? (e - 1) << 23 : (e == 0 ? 0x00200000u : 0x00400000u));      // ggml_e8m0_to_fp32_half, ggml-impl.h:40-45
+        for (int w = 0; w < 4; ++w) b200q_lut4(M, I.q[w], C.va[2 * w], C.vb[2 * w], C.va[2 * w + 1], C.vb[2 * w + 1]);
+        C.dl[0] = C.dl[1] = d; C.ml[0] = C.ml[1] = 0.0f;
+    } else if (TYPE == B200Q_TYPE_IQ5_KS) {           // m[0] = scale byte of this 32-block, rs = row scale
+        const uint32_t sc = I.m[0];
+        const float dl = I.rs * (float)((int)(sc & 254) - 127);
+        b200q_lut5_item(I, C);
+        C.dl[0] = C.dl[1] = dl; C.ml[0] = C.ml[1] = (sc & 1) ? 0.0f : 2.0f * dl;    // tables hold v+2; odd scale byte selects the +2 codebook
     } else if (TYPE == B200Q_TYPE_IQ5_K) {            // meta {half d; u16 extra; u8 scales_h[4]; u8 scales_l[8]}
         // item s: c = s/2 (64-chunk), second = s%2.  Weights 0..15 of the item use scale dl(2*second) and extra bit (2*second),
         // weights 16..31 use dl(2*second+1) / extra bit (2*second+1)  (iqk_quantize.cpp:3128-3141).
@@ -796,18 +864,7 @@ B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & 
         const uint32_t sh = b200q_byte(I.m, 4 + c), sl = b200q_byte(I.m, 8 + 2 * c + second);
         const int ls1 = (int)((sl & 0xF) | ((sh << (4 - 4 * second)) & 0x30)) - 32;     // second=0: sh<<4 ; second=1: sh>>0
         const int ls2 = (int)((sl >> 4)  | (second ? ((sh >> 2) & 0x30) : ((sh << 2) & 0x30))) - 32;
-        for (int w = 0; w < 4; ++w) {
-            const uint32_t q = I.q[w], qx = q ^ 0x88888888u; const uint32_t hb = (I.h[0] >> (8 * w)) & 0xFF;
-            // byte masks from the 5th bits: lane j of half -> 0xFF if set
-            const uint32_t m_lo = (((hb & 0xF) * 0x00204081u) & 0x01010101u) * 0xFFu;
-            const uint32_t m_hi = (((hb >> 4) * 0x00204081u) & 0x01010101u) * 0xFFu;
-            const uint32_t a_lo0 = b200q_prmt(B200Q_KV5_T0_0, B200Q_KV5_T0_1, q), b_lo0 = b200q_prmt(B200Q_KV5_T1_0, B200Q_KV5_T1_1, qx);
-            const uint32_t a_lo1 = b200q_prmt(B200Q_KV5_T2_0, B200Q_KV5_T2_1, q), b_lo1 = b200q_prmt(B200Q_KV5_T3_0, B200Q_KV5_T3_1, qx);
-            const uint32_t a_hi0 = b200q_prmt(B200Q_KV5_T0_0, B200Q_KV5_T0_1, q >> 16), b_hi0 = b200q_prmt(B200Q_KV5_T1_0, B200Q_KV5_T1_1, qx >> 16);
-            const uint32_t a_hi1 = b200q_prmt(B200Q_KV5_T2_0, B200Q_KV5_T2_1, q >> 16), b_hi1 = b200q_prmt(B200Q_KV5_T3_0, B200Q_KV5_T3_1, qx >> 16);
-            C.va[2 * w]     = (int)((a_lo1 & m_lo) | (a_lo0 & ~m_lo)); C.vb[2 * w]     = (int)((b_lo1 & m_lo) | (b_lo0 & ~m_lo));
-            C.va[2 * w + 1] = (int)((a_hi1 & m_hi) | (a_hi0 & ~m_hi)); C.vb[2 * w + 1] = (int)((b_hi1 & m_hi) | (b_hi0 & ~m_hi));
-        }
+        b200q_lut5_item(I, C);
         C.dl[0] = d * ls1; C.dl[1] = d * ls2;
         // tables hold v+2: subtract 2 unless the extra bit selects the "+2" variant of the table
         C.ml[0] = (extra & 1) ? 0.0f : 2.0f * C.dl[0]; C.ml[1] = (extra & 2) ? 0.0f : 2.0f * C.dl[1];

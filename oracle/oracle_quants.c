@@ -26,7 +26,7 @@
 enum {
     T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ2_XXS = 16, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138,
+    T_IQ2_XXS = 16, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152,
     T_IQ4_K = 139, T_IQ5_K = 140, T_IQ4_KS = 144,
 };
 
@@ -97,6 +97,8 @@ static int geom(int type, int * qk, int * bs, int * meta) {
         case T_IQ4_K:  *qk = 256; *bs = 144; return 0;
         case T_IQ5_K:  *qk = 256; *bs = 176; return 0;
         case T_IQ4_KS: *qk = 256; *bs = 136; *meta = 4; return 0;
+        case T_IQ5_KS: *qk = 256; *bs = 168; *meta = 4; return 0;
+        case T_MXFP4:  *qk = 32;  *bs = 17;  return 0;
         case T_IQ2_BN: *qk = 64;  *bs = 16;  *meta = 4; return 0;
         default: return -1;
     }
@@ -313,6 +315,23 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
                 for (int j = 0; j < 16; ++j) { yy[j] = dl * v[qs[j] & 0xf]; yy[j + 16] = dl * v[qs[j] >> 4]; }
                 yy += 32; qs += 16;
             }
+        } break;
+        case T_IQ5_KS: {  // iqk/iqk_quantize.cpp:4798-4822  row = {float d; blocks {u8 scales[8]; u8 qs[128]; u8 qh[32]}}
+            const uint8_t * sc = x; const uint8_t * qs = x + 8; const uint8_t * qh = x + 136; float * yy = y;
+            for (int ib64 = 0; ib64 < 4; ++ib64) {
+                const float dl1 = row_scale * ((int)(sc[2 * ib64] & 254) - 127), dl2 = row_scale * ((int)(sc[2 * ib64 + 1] & 254) - 127);
+                const int8_t * v1 = k_iq5nl + ((sc[2 * ib64] & 1) << 5); const int8_t * v2 = k_iq5nl + ((sc[2 * ib64 + 1] & 1) << 5);
+                for (int j = 0; j < 32; ++j) {
+                    yy[j]      = dl1 * v1[(qs[j] & 0xf) | (((qh[j] >> (2 * ib64)) & 1) << 4)];
+                    yy[j + 32] = dl2 * v2[(qs[j] >> 4) | (((qh[j] >> (2 * ib64 + 1)) & 1) << 4)];
+                }
+                yy += 64; qs += 32;
+            }
+        } break;
+        case T_MXFP4: {  // iqk/iqk_quantize.cpp:4224-4236  {u8 e; u8 qs[16]}; kvalues_mxfp4 ggml-common.h:2250; E8M0/2: ggml-impl.h:40-45
+            static const int8_t kv[16] = {0, 1, 2, 3, 4, 6, 8, 12, 0, -1, -2, -3, -4, -6, -8, -12};
+            const uint8_t e = x[0]; uint32_t u = e >= 2 ? (uint32_t)(e - 1) << 23 : (e == 0 ? 0x00200000u : 0x00400000u); float d; memcpy(&d, &u, 4);
+            for (int j = 0; j < 16; ++j) { y[j] = d * kv[x[1 + j] & 0xf]; y[j + 16] = d * kv[x[1 + j] >> 4]; }
         } break;
         case T_IQ2_BN: {  // iqk/iqk_quantize.cpp:418-436 + row scale written at :227-229 (SURVEY §8c pitfall 1):
                           // w = row_scale * (q - 1), q = 2-bit field (j div 16) of byte (j mod 16)

@@ -74,7 +74,7 @@ static int run_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, int64
         for (int64_t j = 0; j < n; ++j) for (int64_t i = 0; i < m; ++i) { double acc = 0; for (int64_t l = 0; l < k; ++l) acc += (double)wdeq[i * k + l] * xf[j * k + l]; ref[j * m + i] = (float)acc; }
         e_truth = nmse(y.data(), ref.data(), y.size());
     }
-    const bool cpu_known_off = (type == GGML_TYPE_IQ4_XS || type == GGML_TYPE_IQ4_K || type == GGML_TYPE_IQ4_KS || type == GGML_TYPE_IQ5_K);
+    const bool cpu_known_off = (type == GGML_TYPE_IQ4_XS || type == GGML_TYPE_IQ4_K || type == GGML_TYPE_IQ4_KS || type == GGML_TYPE_IQ5_K || type == GGML_TYPE_IQ5_KS);
     const bool ok = d.n > 0 && e_truth <= 5e-4 && (d.worst <= 5e-4 || cpu_known_off);
     printf("  %-8s %s m=%lld k=%lld n=%lld: NMSE vs CPU backend %.3g%s, vs f64(to_float) %.3g -> %s\n", ggml_type_name(type), up_gate ? "FUSED_UP_GATE" : "MUL_MAT",
            (long long)m, (long long)k, (long long)n, d.worst, cpu_known_off && d.worst > 5e-4 ? " (reference CPU kernel known to deviate)" : "", e_truth, ok ? "OK" : "FAIL");
@@ -138,7 +138,7 @@ int main(int argc, char ** argv) {
     size_t fr, tot; ggml_backend_cuda_get_device_memory(0, &fr, &tot);
     printf("backend %s on %s (%.1f GiB), devices %d\n", ggml_backend_name(be), desc, tot / 1073741824.0, ggml_backend_cuda_get_device_count());
     const ggml_type types[] = { GGML_TYPE_Q4_0, GGML_TYPE_Q4_1, GGML_TYPE_Q5_0, GGML_TYPE_Q5_1, GGML_TYPE_Q6_0, GGML_TYPE_Q8_0, GGML_TYPE_Q2_K, GGML_TYPE_Q3_K, GGML_TYPE_Q4_K, GGML_TYPE_Q5_K, GGML_TYPE_Q6_K, GGML_TYPE_IQ4_NL, GGML_TYPE_IQ4_XS, GGML_TYPE_IQ2_K, GGML_TYPE_IQ3_K,
-                                GGML_TYPE_IQ4_K, GGML_TYPE_IQ5_K, GGML_TYPE_IQ4_KS, GGML_TYPE_IQ2_BN };
+                                GGML_TYPE_IQ4_K, GGML_TYPE_IQ5_K, GGML_TYPE_IQ4_KS, GGML_TYPE_IQ5_KS, GGML_TYPE_MXFP4, GGML_TYPE_IQ2_BN };
     int fails = 0; unsigned seed = 1000;
     for (ggml_type t : types) {
         fails += run_case(be, cpu, t, 4096, 4096, 1, false, ++seed);             // BASELINE.json configs[0]: MUL_MAT 4096x4096 n_batch=1
