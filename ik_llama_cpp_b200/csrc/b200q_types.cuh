@@ -39,7 +39,7 @@
 // ggml_type ids (reference ggml/include/ggml.h:391-492)
 enum b200q_type : int {
     B200Q_TYPE_Q4_0 = 2, B200Q_TYPE_Q4_1 = 3, B200Q_TYPE_Q5_0 = 6, B200Q_TYPE_Q5_1 = 7, B200Q_TYPE_Q6_0 = 133, B200Q_TYPE_Q8_0 = 8, B200Q_TYPE_Q2_K = 10, B200Q_TYPE_Q3_K = 11, B200Q_TYPE_Q4_K = 12, B200Q_TYPE_Q5_K = 13, B200Q_TYPE_Q6_K = 14,
-    B200Q_TYPE_IQ4_NL = 20, B200Q_TYPE_IQ4_XS = 23, B200Q_TYPE_MXFP4 = 39, B200Q_TYPE_IQ5_KS = 152, B200Q_TYPE_IQ2_BN = 135, B200Q_TYPE_IQ2_K = 137, B200Q_TYPE_IQ3_K = 138, B200Q_TYPE_IQ4_K = 139,
+    B200Q_TYPE_IQ4_NL = 20, B200Q_TYPE_IQ4_XS = 23, B200Q_TYPE_MXFP4 = 39, B200Q_TYPE_IQ5_KS = 152, B200Q_TYPE_IQ2_KS = 145, B200Q_TYPE_IQ3_KS = 156, B200Q_TYPE_IQ2_BN = 135, B200Q_TYPE_IQ2_K = 137, B200Q_TYPE_IQ3_K = 138, B200Q_TYPE_IQ4_K = 139,
     B200Q_TYPE_IQ5_K = 140, B200Q_TYPE_IQ4_KS = 144,
 };
 
@@ -80,6 +80,18 @@ B200Q_HD float b200q_h2f(uint16_t h) {
     else u = s | ((e + 112) << 23) | (m << 13);
     float f; memcpy(&f, &u, 4); return f;
 #endif
+}
+
+// f32 -> f16 for values that are exactly representable in f16 (used to restore a half row scale from its f32 plane copy)
+B200Q_HD uint16_t b200q_f2h_exact(float f) {
+    uint32_t u; memcpy(&u, &f, 4);
+    const uint32_t s = (u >> 16) & 0x8000u, e = (u >> 23) & 0xFF, m = u & 0x7FFFFFu;
+    if (e == 0xFF) return (uint16_t)(s | 0x7C00u | (m ? (0x200u | (m >> 13)) : 0));      // inf / NaN (payload top bits)
+    if (e == 0) return (uint16_t)s;                                                      // +-0 (f32 subnormals cannot come from a half)
+    const int eh = (int)e - 127 + 15;
+    if (eh >= 31) return (uint16_t)(s | 0x7C00u);
+    if (eh <= 0) { if (eh < -10) return (uint16_t)s; return (uint16_t)(s | ((m | 0x800000u) >> (14 - eh))); }   // f16 subnormal
+    return (uint16_t)(s | ((uint32_t)eh << 10) | (m >> 13));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -132,6 +144,8 @@ inline int b200q_make_layout(int type, int64_t M, int64_t K, b200q_layout * L) {
         case B200Q_TYPE_IQ4_KS: set(256, 136, 4, 3, 128, 8, 4, 0, 2); break;   // qs | scales[8] | row scale
         case B200Q_TYPE_IQ5_KS: set(256, 168, 4, 4, 128, 32, 8, 4, 3); break;  // qs | qh | scales[8] | row scale
         case B200Q_TYPE_MXFP4:  set(32,  17, 0, 2, 16, 1, 0, 0, -1); break;    // qs | e (E8M0)
+        case B200Q_TYPE_IQ2_KS: set(256, 70, 2, 3, 64, 8, 4, 0, 2); break;     // qs (2-bit selectors) | {extra,scales[4],pad 2} | row scale (half on the wire, f32 in the plane)
+        case B200Q_TYPE_IQ3_KS: set(256, 102, 2, 4, 64, 32, 8, 4, 3); break;   // qs | qh | {extra,scales[4],pad 2} | row scale
         case B200Q_TYPE_IQ2_BN: set(64,  16, 4, 2, 16, 4, 0, 0, 1); break;     // qs | row scale
         default: return -1;
     }
@@ -319,6 +333,29 @@ B200Q_HD void b200q_repack_block(const b200q_layout & L, const uint8_t * wire, u
             }
         }
     } break;
+    case B200Q_TYPE_IQ2_KS: case B200Q_TYPE_IQ3_KS: {
+        // IQ2_KS row = {half d; blocks {u16 extra; u8 scales[4]; u8 qs[64]}}              (block_iq2_ks; iqk_quantize.cpp:1877-1907)
+        // IQ3_KS row = {half d; blocks {u16 extra; u8 scales[4]; u8 qs[64]; u8 qh[32]}}   (block_iq3_ks; iqk_quantize.cpp:2774-2803)
+        // quants exactly as IQ2_K / IQ3_K: item s: weight e <-> qs[32(s/4) + e] bits 2(s%4)..+1 ; third bit = qh[e] bit s
+        const bool q3 = L.type == B200Q_TYPE_IQ3_KS;
+        uint8_t * pq = b200q_plane_ptr(dst, L, 0, row, blk); uint8_t * ph = q3 ? b200q_plane_ptr(dst, L, 1, row, blk) : nullptr;
+        uint8_t * pm = b200q_plane_ptr(dst, L, q3 ? 2 : 1, row, blk);
+        uint8_t * wqs = w + 6; uint8_t * wqh = w + 70;
+        if (!inverse) { for (int j = 0; j < 6; ++j) pm[j] = w[j]; pm[6] = 0; pm[7] = 0; }
+        else { for (int j = 0; j < 6; ++j) w[j] = pm[j]; for (int j = 0; j < 64; ++j) wqs[j] = 0; if (q3) for (int j = 0; j < 32; ++j) wqh[j] = 0; }
+        for (int s = 0; s < 8; ++s) {
+            const int h = s / 4, j = s % 4;
+            if (!inverse) {
+                for (int e = 0; e < 32; ++e) { idx[e] = (wqs[32 * h + e] >> (2 * j)) & 3; if (q3) hb[e] = (wqh[e] >> s) & 1; }
+                uint32_t W[2]; b200q_pack_l2(idx, W); memcpy(pq + 8 * s, W, 8);
+                if (q3) { uint32_t q = b200q_pack_hl(hb); memcpy(ph + 4 * s, &q, 4); }
+            } else {
+                uint32_t W[2]; memcpy(W, pq + 8 * s, 8); b200q_unpack_l2(W, idx);
+                if (q3) { uint32_t q; memcpy(&q, ph + 4 * s, 4); b200q_unpack_hl(q, hb); }
+                for (int e = 0; e < 32; ++e) { wqs[32 * h + e] |= (uint8_t)(idx[e] << (2 * j)); if (q3) wqh[e] |= (uint8_t)(hb[e] << s); }
+            }
+        }
+    } break;
     case B200Q_TYPE_IQ2_K: case B200Q_TYPE_IQ3_K: {
         // IQ2_K {half d; u16 extra; u8 scales[8]; u8 qs[64]}                              (ggml-common.h block_iq2_k; iqk_quantize.cpp:1356-1385)
         // IQ3_K {half d; u16 extra; u16 scales_h; u8 scales_l[8]; u8 qs[64]; u8 qh[32]}   (block_iq3_k; iqk_quantize.cpp:2534-2565)
@@ -464,6 +501,13 @@ B200Q_HD void b200q_repack_row_meta(const b200q_layout & L, const uint8_t * wire
     int p = -1; for (int i = 0; i < L.n_planes; ++i) if (L.plane_per_row[i]) p = i;
     if (p < 0) return;
     uint8_t * pr = b200q_plane_ptr(dst, L, p, row, 0); uint8_t * w = const_cast<uint8_t *>(wire_row);
+    if (L.row_meta == 2 && L.plane_bytes[p] == 4) {
+        // half row scale on the wire (IQ2_KS, IQ3_KS: ggml.c row_meta_size = 2), kept as its exact f32 value in the plane so that the
+        // kernels read every row scale the same way; f32 -> half of a value that came from a half is exact, the round trip is bit-for-bit
+        if (!inverse) { const float f = b200q_h2f((uint16_t)(w[0] | (w[1] << 8))); memcpy(pr, &f, 4); }
+        else { float f; memcpy(&f, pr, 4); const uint16_t h = b200q_f2h_exact(f); w[0] = (uint8_t)(h & 0xFF); w[1] = (uint8_t)(h >> 8); }
+        return;
+    }
     for (int j = 0; j < L.row_meta; ++j) { if (!inverse) pr[j] = w[j]; else w[j] = pr[j]; }
 }
 
@@ -576,6 +620,8 @@ B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_K,  true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ4_KS, true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ5_KS, true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_MXFP4,  true, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ2_KS, false, 32)
+B200Q_DEF_TRAITS(B200Q_TYPE_IQ3_KS, false, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ5_K,  true, 32)
 B200Q_DEF_TRAITS(B200Q_TYPE_IQ2_BN, false, 32)
 
@@ -708,6 +754,15 @@ B200Q_HD void b200q_load_item(b200q_item & I, const b200q_planes & P, typename b
     } else if (TYPE == B200Q_TYPE_MXFP4) {
         LD::ld16(I.q, P.p[0] + (row * n32 + it0) * 16);
         I.m[0] = LD::ld1(P.p[1] + (row * n32 + it));
+    } else if (TYPE == B200Q_TYPE_IQ2_KS) {
+        LD::ld8(I.q, P.p[0] + (row * n32 + it) * 8);
+        LD::ld8(I.m, P.p[1] + (row * nb + it / 8) * 8);
+        if (ROWPLANE) { uint32_t r = LD::ld4(P.p[2] + row * 4); memcpy(&I.rs, &r, 4); }
+    } else if (TYPE == B200Q_TYPE_IQ3_KS) {
+        LD::ld8(I.q, P.p[0] + (row * n32 + it) * 8);
+        I.h[0] = LD::ld4(P.p[1] + (row * n32 + it) * 4);
+        LD::ld8(I.m, P.p[2] + (row * nb + it / 8) * 8);
+        if (ROWPLANE) { uint32_t r = LD::ld4(P.p[3] + row * 4); memcpy(&I.rs, &r, 4); }
     } else if (TYPE == B200Q_TYPE_IQ2_BN) {           // 64 weights per wire block: item = half a block (see decode)
         LD::ld16(I.q, P.p[0] + (row * nb + it / 2) * 16);
         if (ROWPLANE) { uint32_t r = LD::ld4(P.p[1] + row * 4); memcpy(&I.rs, &r, 4); }
@@ -718,7 +773,9 @@ B200Q_HD void b200q_load_item(b200q_item & I, const uint8_t * base, const b200q_
     b200q_load_item<TYPE>(I, b200q_planes_from(base, L), row, it);
 }
 // index of the per-row plane of a type (-1 if none)
-B200Q_HD constexpr int b200q_row_plane(int type) { return type == B200Q_TYPE_IQ4_KS ? 2 : (type == B200Q_TYPE_IQ5_KS ? 3 : (type == B200Q_TYPE_IQ2_BN ? 1 : -1)); }
+B200Q_HD constexpr int b200q_row_plane(int type) {
+    return type == B200Q_TYPE_IQ4_KS || type == B200Q_TYPE_IQ2_KS ? 2 : (type == B200Q_TYPE_IQ5_KS || type == B200Q_TYPE_IQ3_KS ? 3 : (type == B200Q_TYPE_IQ2_BN ? 1 : -1));
+}
 
 // 5-bit codebook lookup of one item (IQ5_K, IQ5_KS): q = L-order nibbles, h[0] bit e = 5th bit of weight e; result = iq5nl_values + 2
 // split into the two sign-fill halves va / vb
@@ -816,6 +873,26 @@ B200Q_HD void b200q_decode_item(const b200q_item & I, int64_t it, b200q_canon & 
         }
         C.dl[0] = d * (float)((int)(sc & 0xF) - 8); C.dl[1] = d * (float)((int)(sc >> 4) - 8);
         C.ml[0] = (ex & 1) ? -5.0f * C.dl[0] : 0.0f; C.ml[1] = (ex & 2) ? -5.0f * C.dl[1] : 0.0f;
+    } else if (TYPE == B200Q_TYPE_IQ2_KS || TYPE == B200Q_TYPE_IQ3_KS) {
+        // meta {u16 extra; u8 scales[4]}, one 5-bit scale per 32 weights, rs = row scale; codebooks as IQ2_K / IQ3_K
+        const int s = (int)(it % 8); const uint32_t extra = I.m[0] & 0xFFFF;
+        int ls; uint32_t sel;
+        if (TYPE == B200Q_TYPE_IQ2_KS) {              // scales[s/2] nibble s%2 | extra bit 8+s ; table bit s            (iqk_quantize.cpp:1893-1897)
+            ls = (int)(((b200q_byte(I.m, 2 + s / 2) >> (4 * (s % 2))) & 0xF) | (((extra >> (8 + s)) & 1) << 4)) - 16; sel = (extra >> s) & 1;
+        } else {                                      // scales[s%4] nibble s/4 | extra bit s ; table bit 8+s            (iqk_quantize.cpp:2784-2794)
+            ls = (int)(((b200q_byte(I.m, 2 + s % 4) >> (4 * (s / 4))) & 0xF) | (((extra >> s) & 1) << 4)) - 16; sel = (extra >> (8 + s)) & 1;
+        }
+        const float dl = I.rs * (float)ls;
+        for (int u = 0; u < 2; ++u) for (int p = 0; p < 2; ++p) {
+            if (TYPE == B200Q_TYPE_IQ2_KS) {
+                const uint32_t x = (I.q[u] >> (2 * p)) & 0x33333333u;
+                C.va[4 * u + 2 * p] = (int)b200q_prmt(0x1101F3E1u, 0u, x); C.va[4 * u + 2 * p + 1] = (int)b200q_prmt(0x1101F3E1u, 0u, x >> 16);
+            } else {
+                const uint32_t x = ((I.q[u] >> (2 * p)) & 0x33333333u) | (((I.h[0] >> (2 * u + p)) & 0x11111111u) << 2);
+                C.va[4 * u + 2 * p] = (int)b200q_prmt(0xF6E9D8C1u, 0x2F1C0D01u, x); C.va[4 * u + 2 * p + 1] = (int)b200q_prmt(0xF6E9D8C1u, 0x2F1C0D01u, x >> 16);
+            }
+        }
+        C.dl[0] = C.dl[1] = dl; C.ml[0] = C.ml[1] = sel ? (TYPE == B200Q_TYPE_IQ2_KS ? -5.0f : -4.0f) * dl : 0.0f;
     } else if (TYPE == B200Q_TYPE_IQ3_K) {            // meta {half d; u16 extra; u16 scales_h; u8 scales_l[8]}; iq3nl_values (+4 with the extra bit)
         const float d = b200q_h2f((uint16_t)(I.m[0] & 0xFFFF)); const int s = (int)(it % 8);
         const uint32_t ex = (I.m[0] >> 16) >> (2 * s), sh = (I.m[1] & 0xFFFF) >> (2 * s), sl = b200q_byte(I.m, 6 + s);

@@ -26,7 +26,7 @@
 enum {
     T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ2_XXS = 16, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152,
+    T_IQ2_XXS = 16, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152, T_IQ2_KS = 145, T_IQ3_KS = 156,
     T_IQ4_K = 139, T_IQ5_K = 140, T_IQ4_KS = 144,
 };
 
@@ -99,6 +99,8 @@ static int geom(int type, int * qk, int * bs, int * meta) {
         case T_IQ4_KS: *qk = 256; *bs = 136; *meta = 4; return 0;
         case T_IQ5_KS: *qk = 256; *bs = 168; *meta = 4; return 0;
         case T_MXFP4:  *qk = 32;  *bs = 17;  return 0;
+        case T_IQ2_KS: *qk = 256; *bs = 70;  *meta = 2; return 0;
+        case T_IQ3_KS: *qk = 256; *bs = 102; *meta = 2; return 0;
         case T_IQ2_BN: *qk = 64;  *bs = 16;  *meta = 4; return 0;
         default: return -1;
     }
@@ -123,6 +125,7 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
     const uint8_t * x = row + meta;
     float row_scale = 1.0f;
     if (meta == 4) memcpy(&row_scale, row, 4);
+    if (meta == 2) row_scale = h2f(rd16(row));           // IQ2_KS / IQ3_KS: ggml_half row scale
     for (int64_t i = 0; i < nb; ++i, x += bs, y += qk) {
         switch (type) {
         case T_Q4_0: {  // ggml-quants.c:1581-1599  {half d; u8 qs[16]}
@@ -332,6 +335,32 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
             static const int8_t kv[16] = {0, 1, 2, 3, 4, 6, 8, 12, 0, -1, -2, -3, -4, -6, -8, -12};
             const uint8_t e = x[0]; uint32_t u = e >= 2 ? (uint32_t)(e - 1) << 23 : (e == 0 ? 0x00200000u : 0x00400000u); float d; memcpy(&d, &u, 4);
             for (int j = 0; j < 16; ++j) { y[j] = d * kv[x[1 + j] & 0xf]; y[j + 16] = d * kv[x[1 + j] >> 4]; }
+        } break;
+        case T_IQ2_KS: {  // iqk/iqk_quantize.cpp:1877-1907  row = {half d; blocks {u16 extra; u8 scales[4]; u8 qs[64]}}
+            static const int8_t v2[8] = {-31, -13, 1, 17, -26, -8, 6, 22};
+            uint16_t extra = rd16(x); const uint8_t * sc = x + 2; const uint8_t * qs = x + 6; float * yy = y; int shift = 0;
+            for (int ib64 = 0; ib64 < 4; ++ib64) {
+                const float dl1 = row_scale * (((sc[ib64] & 0xf) | ((extra >> 4) & 0x10)) - 16), dl2 = row_scale * (((sc[ib64] >> 4) | ((extra >> 5) & 0x10)) - 16);
+                const int8_t * va = extra & 1 ? v2 + 4 : v2; const int8_t * vb = extra & 2 ? v2 + 4 : v2; extra >>= 2;
+                for (int j = 0; j < 32; ++j) { yy[j] = dl1 * va[(qs[j] >> (shift + 0)) & 3]; yy[j + 32] = dl2 * vb[(qs[j] >> (shift + 2)) & 3]; }
+                yy += 64; shift += 4; if (shift == 8) { qs += 32; shift = 0; }
+            }
+        } break;
+        case T_IQ3_KS: {  // iqk/iqk_quantize.cpp:2774-2803  row = {half d; blocks {u16 extra; u8 scales[4]; u8 qs[64]; u8 qh[32]}}
+            static const int8_t v3[16] = {-63, -40, -23, -10, 1, 13, 28, 47, -59, -36, -19, -6, 5, 17, 32, 51};
+            const uint16_t extra = rd16(x); const uint8_t * sc = x + 2; const uint8_t * qs = x + 6; const uint8_t * qh = x + 70; float dl[8]; float * yy = y;
+            for (int j = 0; j < 4; ++j) {
+                dl[j]     = row_scale * (((sc[j] & 0xf) | (((extra >> (j + 0)) & 1) << 4)) - 16);
+                dl[j + 4] = row_scale * (((sc[j] >> 4) | (((extra >> (j + 4)) & 1) << 4)) - 16);
+            }
+            for (int i128 = 0; i128 < 2; ++i128) {
+                for (int ib = 0; ib < 4; ++ib) {
+                    const int8_t * v = v3 + (((extra >> (8 + 4 * i128 + ib)) & 1) << 3);
+                    for (int j = 0; j < 32; ++j) yy[j] = dl[4 * i128 + ib] * v[((qs[j] >> (2 * ib)) & 3) | (((qh[j] >> (4 * i128 + ib)) & 1) << 2)];
+                    yy += 32;
+                }
+                qs += 32;
+            }
         } break;
         case T_IQ2_BN: {  // iqk/iqk_quantize.cpp:418-436 + row scale written at :227-229 (SURVEY §8c pitfall 1):
                           // w = row_scale * (q - 1), q = 2-bit field (j div 16) of byte (j mod 16)

@@ -138,7 +138,7 @@ int main(int argc, char ** argv) {
     size_t fr, tot; ggml_backend_cuda_get_device_memory(0, &fr, &tot);
     printf("backend %s on %s (%.1f GiB), devices %d\n", ggml_backend_name(be), desc, tot / 1073741824.0, ggml_backend_cuda_get_device_count());
     const ggml_type types[] = { GGML_TYPE_Q4_0, GGML_TYPE_Q4_1, GGML_TYPE_Q5_0, GGML_TYPE_Q5_1, GGML_TYPE_Q6_0, GGML_TYPE_Q8_0, GGML_TYPE_Q2_K, GGML_TYPE_Q3_K, GGML_TYPE_Q4_K, GGML_TYPE_Q5_K, GGML_TYPE_Q6_K, GGML_TYPE_IQ4_NL, GGML_TYPE_IQ4_XS, GGML_TYPE_IQ2_K, GGML_TYPE_IQ3_K,
-                                GGML_TYPE_IQ4_K, GGML_TYPE_IQ5_K, GGML_TYPE_IQ4_KS, GGML_TYPE_IQ5_KS, GGML_TYPE_MXFP4, GGML_TYPE_IQ2_BN };
+                                GGML_TYPE_IQ4_K, GGML_TYPE_IQ5_K, GGML_TYPE_IQ4_KS, GGML_TYPE_IQ5_KS, GGML_TYPE_IQ2_KS, GGML_TYPE_IQ3_KS, GGML_TYPE_MXFP4, GGML_TYPE_IQ2_BN };
     int fails = 0; unsigned seed = 1000;
     for (ggml_type t : types) {
         fails += run_case(be, cpu, t, 4096, 4096, 1, false, ++seed);             // BASELINE.json configs[0]: MUL_MAT 4096x4096 n_batch=1

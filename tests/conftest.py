@@ -9,7 +9,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-ALL_TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q6_0", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "IQ2_K", "IQ3_K", "IQ4_K", "IQ5_K", "IQ4_KS", "IQ5_KS", "MXFP4", "IQ2_BN"]
+ALL_TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q6_0", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "IQ2_K", "IQ3_K", "IQ4_K", "IQ5_K", "IQ4_KS", "IQ5_KS", "IQ2_KS", "IQ3_KS", "MXFP4", "IQ2_BN"]
 
 
 def pytest_configure(config):
@@ -54,7 +54,7 @@ def make_wire(oracle_or_ref, name, m, k, seed, reflib=None):
 # byte offsets of fp16 scale fields inside one wire block, per type: (block_bytes, [offsets of half fields], row_meta)
 _GEOM = {
     "Q4_0": (18, [0], 0), "Q4_1": (20, [0, 2], 0), "Q5_0": (22, [0], 0), "Q5_1": (24, [0, 2], 0), "Q6_0": (26, [0], 0), "Q8_0": (34, [0], 0), "IQ4_NL": (18, [0], 0), "Q4_K": (144, [0, 2], 0), "Q5_K": (176, [0, 2], 0),
-    "IQ2_K": (76, [0], 0), "IQ3_K": (110, [0], 0), "Q2_K": (84, [80, 82], 0), "Q3_K": (110, [108], 0), "Q6_K": (210, [208], 0), "IQ4_XS": (136, [0], 0), "IQ4_K": (144, [0], 0), "IQ5_K": (176, [0], 0), "IQ4_KS": (136, [], 4), "IQ5_KS": (168, [], 4), "MXFP4": (17, [], 0), "IQ2_BN": (16, [], 4),
+    "IQ2_K": (76, [0], 0), "IQ3_K": (110, [0], 0), "Q2_K": (84, [80, 82], 0), "Q3_K": (110, [108], 0), "Q6_K": (210, [208], 0), "IQ4_XS": (136, [0], 0), "IQ4_K": (144, [0], 0), "IQ5_K": (176, [0], 0), "IQ4_KS": (136, [], 4), "IQ5_KS": (168, [], 4), "IQ2_KS": (70, [], 2), "IQ3_KS": (102, [], 2), "MXFP4": (17, [], 0), "IQ2_BN": (16, [], 4),
 }
 _QK = {"Q4_0": 32, "Q4_1": 32, "Q5_0": 32, "Q5_1": 32, "Q6_0": 32, "Q8_0": 32, "IQ4_NL": 32, "MXFP4": 32, "IQ2_BN": 64}
 
@@ -73,6 +73,9 @@ def random_wire(name, m, k, rng):
     if name == "MXFP4":   # E8M0 block exponent: keep the scale in a sane range (2^-18 .. 2^-4), every other bit pattern is payload
         blocks[:, :, 0] = rng.integers(110, 125, (m, nb), dtype=np.uint8)
     rows[:, meta:] = blocks.reshape(m, nb * bs)
+    if meta == 2:       # IQ2_KS / IQ3_KS: ggml_half row scale
+        rs = (rng.uniform(0.5, 2.0, m) * 1e-3).astype(np.float16)
+        rows[:, :2] = rs.view(np.uint8).reshape(m, 2)
     if meta == 4:
         rs = (rng.uniform(0.5, 2.0, m) * 1e-3).astype(np.float32)
         rows[:, :4] = rs.view(np.uint8).reshape(m, 4)

@@ -55,7 +55,8 @@ template <int T> static void mmv(const uint8_t * planes, const b200q_layout & L,
     case B200Q_TYPE_Q5_1: F<B200Q_TYPE_Q5_1>(__VA_ARGS__); break; case B200Q_TYPE_Q6_0: F<B200Q_TYPE_Q6_0>(__VA_ARGS__); break; \
     case B200Q_TYPE_Q2_K: F<B200Q_TYPE_Q2_K>(__VA_ARGS__); break; case B200Q_TYPE_Q3_K: F<B200Q_TYPE_Q3_K>(__VA_ARGS__); break; \
     case B200Q_TYPE_IQ2_K: F<B200Q_TYPE_IQ2_K>(__VA_ARGS__); break; case B200Q_TYPE_IQ3_K: F<B200Q_TYPE_IQ3_K>(__VA_ARGS__); break; \
-    case B200Q_TYPE_MXFP4: F<B200Q_TYPE_MXFP4>(__VA_ARGS__); break; case B200Q_TYPE_IQ5_KS: F<B200Q_TYPE_IQ5_KS>(__VA_ARGS__); break; default: return -1; }
+    case B200Q_TYPE_MXFP4: F<B200Q_TYPE_MXFP4>(__VA_ARGS__); break; case B200Q_TYPE_IQ5_KS: F<B200Q_TYPE_IQ5_KS>(__VA_ARGS__); break; \
+    case B200Q_TYPE_IQ2_KS: F<B200Q_TYPE_IQ2_KS>(__VA_ARGS__); break; case B200Q_TYPE_IQ3_KS: F<B200Q_TYPE_IQ3_KS>(__VA_ARGS__); break; default: return -1; }
 
 API int emul_dequant(int type, const uint8_t * planes, long M, long K, float * out) {
     b200q_layout L; if (b200q_make_layout(type, M, K, &L)) return -1;
