@@ -15,7 +15,8 @@ import numpy as np
 
 # (block elements, block bytes, row meta bytes) — ggml type traits (ggml/src/ggml.c:640-1460)
 GEOM = {2: (32, 18, 0), 3: (32, 20, 0), 6: (32, 22, 0), 7: (32, 24, 0), 133: (32, 26, 0), 8: (32, 34, 0), 12: (256, 144, 0), 13: (256, 176, 0), 14: (256, 210, 0), 20: (32, 18, 0), 23: (256, 136, 0),
-        135: (64, 16, 4), 139: (256, 144, 0), 140: (256, 176, 0), 144: (256, 136, 4)}
+        135: (64, 16, 4), 139: (256, 144, 0), 140: (256, 176, 0), 144: (256, 136, 4),
+        10: (256, 84, 0), 11: (256, 110, 0), 137: (256, 76, 0), 138: (256, 110, 0), 39: (32, 17, 0), 152: (256, 168, 4), 145: (256, 70, 2), 156: (256, 102, 2)}
 
 
 def create_split(nr: int, granularity: int, world: int) -> list[int]:

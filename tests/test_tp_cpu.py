@@ -24,7 +24,16 @@ def test_create_split_matches_reference_rules():
     assert plan["wq_rows"] == [512] * 8 and plan["wkv_rows"] == [128] * 8 and plan["wo_cols"] == [512] * 8
 
 
-@pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K", "IQ4_KS", "IQ2_BN"])
+def test_geometry_table_covers_every_supported_type():
+    from conftest import ALL_TYPES
+    O = Oracle()
+    for name in ALL_TYPES:
+        t = GGML_TYPE[name]
+        assert t in tp.GEOM, name
+        assert tp.row_size(t, 1024) == O.row_size(t, 1024), name
+
+
+@pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K", "IQ4_KS", "IQ2_BN", "Q2_K", "IQ3_K", "MXFP4", "IQ5_KS", "IQ3_KS"])
 def test_shards_partition_the_tensor(name):
     t = GGML_TYPE[name]
     m, k, world = 12, 2048, 4
