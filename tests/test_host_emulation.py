@@ -86,3 +86,29 @@ def test_emulated_random_bit_patterns(emul, oracle, name):
     yq = oracle.mul_mat_q8_1(t, wire, x, m, variant="b200")
     rms = np.sqrt((yq.astype(np.float64) ** 2).mean())
     assert np.abs(y - yq).max() <= 2e-5 * rms
+
+
+@pytest.mark.parametrize("name", ALL_TYPES)
+def test_emulated_edge_shapes(emul, oracle, name):
+    """Edge shapes of the codecs: a single block per row, an odd block count, one row, the row-scale types with every K — the
+    bijection and the canonical decode must hold for each (the reference's quantiser is not needed: any payload is a valid block)."""
+    from conftest import _QK
+    t = GGML_TYPE[name]
+    qk = _QK.get(name, 256)
+    rng = np.random.default_rng(977 + t)
+    for m, nblk in ((1, 1), (3, 1), (2, 3), (5, 7)):
+        k = nblk * max(qk, 32)
+        if k % qk:
+            continue
+        wire = random_wire(name, m, k, rng)
+        x = rng.standard_normal((1, k)).astype(np.float32)
+        nb, back, deq, y = _emul_all(emul, oracle, t, wire, m, k, x)
+        assert np.array_equal(back, wire), (name, m, k)
+        ref = oracle.dequantize(t, wire, m, k)
+        if name in ("IQ4_KS", "IQ5_KS", "IQ2_BN"):
+            np.testing.assert_allclose(deq, ref, rtol=3e-7, atol=1e-12)
+        else:
+            assert np.array_equal(deq, ref), (name, m, k)
+        yq = oracle.mul_mat_q8_1(t, wire, x, m, variant="b200")
+        rms = max(float(np.sqrt((yq.astype(np.float64) ** 2).mean())), 1e-30)
+        assert np.abs(y - yq).max() <= 2e-5 * rms, (name, m, k)
