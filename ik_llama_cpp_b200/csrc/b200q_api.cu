@@ -230,7 +230,8 @@ int b200q_mul_mat_multi(int type, int n_tensors, const void * const * W, float *
 
 size_t b200q_fused_up_gate_workspace(int type, int64_t m, int64_t k, int64_t n) {
     if (n <= 8) return 0;
-    return (size_t)b200q_align_up(n * k * 2, 256) + (size_t)b200q_align_up(m * n * 4, 256) + (size_t)b200q_align_up(m * k * 2, 256) + 0 * (size_t)type;
+    (void)type;     // bf16 activations + f32 up result + bf16 weight scratch (types without a fused kernel)
+    return (size_t)b200q_align_up(n * k * 2, 256) + (size_t)b200q_align_up(m * n * 4, 256) + (size_t)b200q_align_up(m * k * 2, 256);
 }
 // x already bf16 [n][k]; workspace >= align(m*n*4) + align(m*k*2)
 int b200q_fused_up_gate_gemm_bf16(int type, const void * W_up, const void * W_gate, const void * x_bf16, float * dst, void * dst_bf16,

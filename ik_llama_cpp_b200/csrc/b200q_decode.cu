@@ -705,10 +705,11 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     while (ncw * S > B200Q_PAIR_SLOTS) --S;
     ra.g.n_stages = S;
     const size_t smem = (size_t)ncw * S * (pair_stage + 16) + xbytes + 64;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[B200Q_MAX_DEVICES] = {};
+    const int dev = b200q_current_device();
+    if (!configured[dev]) {
         if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
-        configured = true;
+        configured[dev] = true;
     }
     int64_t grid = (n_pairs + ncw - 1) / ncw;
     if (grid > (int64_t)sm_count * ctas_per_sm) grid = (int64_t)sm_count * ctas_per_sm;

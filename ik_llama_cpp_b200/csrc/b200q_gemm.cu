@@ -490,7 +490,7 @@ k_gemm_q(const __grid_constant__ gemmq_args a) {
 
 // dst = act(clamp(gate)) * clamp(up) elementwise (the reference's ggml_fused_mul_unary after two MMQs, ggml-cuda.cu:3588-3618);
 // gate may alias dst; optional bf16 copy for the following MUL_MAT
-__global__ void k_mul_unary(const float * __restrict__ gate, const float * __restrict__ up, float * __restrict__ dst, __nv_bfloat16 * __restrict__ dst_bf,
+__global__ void k_mul_unary(const float * gate /* may alias dst: no __restrict__ */, const float * __restrict__ up, float * dst, __nv_bfloat16 * __restrict__ dst_bf,
                             int64_t total4, int act, float lim) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 g = reinterpret_cast<const float4 *>(gate)[i]; float4 u = reinterpret_cast<const float4 *>(up)[i];
@@ -552,10 +552,11 @@ int launch_gemm_bf16(const void * A_bf16, const void * B_bf16, float * dst, int6
     CUtensorMap tmA, tmB;
     if (make_tmap_bf16(&tmA, A_bf16, M, K, BM)) return -10;
     if (make_tmap_bf16(&tmB, B_bf16, N, K, BN)) return -11;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[B200Q_MAX_DEVICES] = {};
+    const int dev = b200q_current_device();
+    if (!configured[dev]) {
         if (cudaFuncSetAttribute(k_gemm_bf16<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM) != cudaSuccess) return -12;
-        configured = true;
+        configured[dev] = true;
     }
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)k_split);
     k_gemm_bf16<BN><<<grid, 192, cfg::SMEM, st>>>(tmA, tmB, dst, (int)M, (int)N, (int)K, k_split);
@@ -595,10 +596,11 @@ int launch_gemm_q(const b200q_gemm_multi & d, int k_split, cudaStream_t st) {
     }
     if (make_tmap_bf16(&a.tmB, d.xb, d.N, d.K, NB == 0 ? 128 : 256)) return -11;
     a.n_seg = d.n_seg; a.N = (int)d.N; a.K = (int)d.K; a.k_split = k_split; a.act = d.act; a.limit = d.limit;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[B200Q_MAX_DEVICES] = {};
+    const int dev = b200q_current_device();
+    if (!configured[dev]) {
         if (cudaFuncSetAttribute(k_gemm_q<TYPE, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM) != cudaSuccess) return -12;
-        configured = true;
+        configured[dev] = true;
     }
     dim3 grid((unsigned)tiles, (unsigned)((d.N + cfg::BN - 1) / cfg::BN), (unsigned)k_split);
     k_gemm_q<TYPE, NB><<<grid, 64 + 32 * DQ_WARPS, cfg::SMEM, st>>>(a);

@@ -5,6 +5,9 @@
 #include "b200q_types.cuh"
 
 #define B200Q_MAX_SEGS 4
+// function attributes (opt-in shared memory size) are per device: remember per device whether a kernel has been configured
+#define B200Q_MAX_DEVICES 16
+static inline int b200q_current_device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= B200Q_MAX_DEVICES) d = 0; return d; }
 
 enum { B200Q_ACT_NONE = 0, B200Q_ACT_SILU = 1, B200Q_ACT_GELU = 2, B200Q_ACT_RELU = 3 };
 
