@@ -57,6 +57,12 @@ def _plug():
     from ik_llama_cpp_b200.build import PLUG_LIB
     if not os.path.exists(PLUG_LIB):
         pytest.skip("libggml_b200.so not built (needs the reference headers at build time)")
+    # the plug is a ggml plug-in: its ggml_* core symbols come from the host process.  In the tests the host's libggml is the
+    # reference CPU build of oracle/_ref (test infrastructure), loaded first with RTLD_GLOBAL
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libggml_ref_avx2.so")
+    if not os.path.exists(ref):
+        pytest.skip("oracle/_ref not built: no libggml to host the plug")
+    ctypes.CDLL(ref, mode=ctypes.RTLD_GLOBAL)
     return PLUG_LIB
 
 
