@@ -289,6 +289,9 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
 #ifndef B200Q_SELF_REFILL
 #define B200Q_SELF_REFILL 0          // 1: the producer warp only pre-fills the ring (before griddepcontrol.wait); in the main loop every
 #endif                               //    consumer warp re-arms the stage it has just drained itself.  Measured 696 vs 705 tok/s: no gain -> off
+#ifndef B200Q_RING_CONSUMERS
+#define B200Q_RING_CONSUMERS 11      // consumer warps per CTA (+1 producer): 12 warps x 2 CTAs per SM at <= 80 registers.  Round-2 knob: 15 with
+#endif                               // -maxrregcount 64 gives 32 warps per SM (more latency hiding) if the ring stages are shrunk to fit
 #define B200Q_PAIR_SLOTS 124         // ncw * S stage descriptors (+ the claim counter) fit the 128-int slot table
 struct ring_geom {
     int n_planes;                 // block planes staged through the ring (the per-row scale plane is read directly)
@@ -338,7 +341,7 @@ __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarri
 // TP: tensor-parallel instantiation (fused GGML_OP_REDUCE); a separate instantiation so that the single-GPU kernels carry none of it
 // (as runtime branches the extra code cost the plain path 4 %: 675 vs 705 tok/s)
 template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR, bool TP>
-__global__ void __launch_bounds__(384, 2) k_mmvq_ring(const mmvq_ring_args ra) {
+__global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), 2) k_mmvq_ring(const mmvq_ring_args ra) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const mmvq_args & a = ra.a; const ring_geom & g = ra.g;
     const int K = (int)a.K, n32 = K / 32, n8 = n32 / 8;
@@ -691,7 +694,7 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 512 + 256 + 128;
     const size_t budget = 112 * 1024;                   // two CTAs per SM (same kernel, or this one + the next under PDL)
     const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
-    int ncw = 11, S = 0;                                // consumer warps (+1 producer warp)
+    int ncw = B200Q_RING_CONSUMERS, S = 0;              // consumer warps (+1 producer warp)
     for (;;) {
         const size_t per_stage = (size_t)ncw * (pair_stage + 16);
         S = xbytes + 64 < budget ? (int)((budget - xbytes - 64) / per_stage) : 0;
