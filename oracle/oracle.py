@@ -77,6 +77,13 @@ class Oracle:
         L.oracle_h2f.argtypes = [c_uint16]
         L.oracle_f2h.restype = c_uint16
         L.oracle_f2h.argtypes = [c_float]
+        # codebook fixtures extracted from the running reference (tests/golden/gen_codebooks.py); kept alive for the library's lifetime
+        cb = os.path.join(os.path.dirname(HERE), "tests", "golden", "iq2xxs_codebook.npz")
+        if os.path.exists(cb):
+            z = np.load(cb)
+            self._iq2xxs = (np.ascontiguousarray(z["grid"], np.uint8), np.ascontiguousarray(z["ksigns"], np.uint8))
+            L.oracle_set_iq2xxs_codebook.argtypes = [c_void_p, c_void_p]
+            L.oracle_set_iq2xxs_codebook(_p(self._iq2xxs[0]), _p(self._iq2xxs[1]))
 
     def supported(self, t: int) -> bool:
         return bool(self.lib.oracle_type_supported(t))

@@ -75,6 +75,13 @@ static void init_tables(void) {
     tables_ready = 1;
 }
 
+// ---- IQ2_XXS codebook: NOT restated from the reference sources.  The 256 x 8 magnitude grid and the 128 sign masks are extracted by
+// running the reference's own to_float on crafted blocks (tests/golden/gen_codebooks.py -> tests/golden/iq2xxs_codebook.npz) and handed
+// in at run time.  Device kernel for this type: round 2; the oracle is ready and pinned.
+static const uint8_t * g_iq2xxs_grid = NULL;     // [256][8]
+static const uint8_t * g_iq2xxs_signs = NULL;    // [128]
+ORACLE_API void oracle_set_iq2xxs_codebook(const uint8_t * grid, const uint8_t * ksigns) { g_iq2xxs_grid = grid; g_iq2xxs_signs = ksigns; }
+
 // ---- wire geometry: {block elements, block bytes, row meta bytes} (ggml.c type_traits :640-1460) ----
 static int geom(int type, int * qk, int * bs, int * meta) {
     *meta = 0;
@@ -85,6 +92,7 @@ static int geom(int type, int * qk, int * bs, int * meta) {
         case T_Q5_1:   *qk = 32;  *bs = 24;  return 0;
         case T_Q6_0:   *qk = 32;  *bs = 26;  return 0;
         case T_Q8_0:   *qk = 32;  *bs = 34;  return 0;
+        case T_IQ2_XXS: if (!g_iq2xxs_grid) return -1; *qk = 256; *bs = 66; return 0;     // needs the codebook fixture (oracle_set_iq2xxs_codebook)
         case T_Q2_K:   *qk = 256; *bs = 84;  return 0;
         case T_Q3_K:   *qk = 256; *bs = 110; return 0;
         case T_Q4_K:   *qk = 256; *bs = 144; return 0;
@@ -182,6 +190,19 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
                 for (int l = 0; l < 32; ++l) *yy++ = d1 * ((ql[l] & 0xF) + (qh[l] & u1 ? 16 : 0)) - mm1;
                 for (int l = 0; l < 32; ++l) *yy++ = d2 * ((ql[l] >> 4) + (qh[l] & u2 ? 16 : 0)) - mm2;
                 ql += 32; is += 2; u1 <<= 2; u2 <<= 2;
+            }
+        } break;
+        case T_IQ2_XXS: {  // ggml-quants.c:3674-3698  {half d; u16 qs[32]}: per 32 weights [4 grid indices][4 x 7-bit sign index | scale << 28]
+            const float d = h2f(rd16(x)); float * yy = y;
+            for (int ib32 = 0; ib32 < 8; ++ib32) {
+                uint32_t aux32[2]; memcpy(aux32, x + 2 + 8 * ib32, 8); const uint8_t * aux8 = (const uint8_t *)aux32;
+                const float db = d * (0.5f + (aux32[1] >> 28)) * 0.25f;
+                for (int l = 0; l < 4; ++l) {
+                    const uint8_t * grid = g_iq2xxs_grid + 8 * aux8[l];
+                    const uint8_t signs = g_iq2xxs_signs[(aux32[1] >> 7 * l) & 127];
+                    for (int j = 0; j < 8; ++j) yy[j] = db * grid[j] * (signs & (1 << j) ? -1.f : 1.f);
+                    yy += 8;
+                }
             }
         } break;
         case T_Q2_K: {  // ggml-quants.c:2162-2190  {u8 scales[16]; u8 qs[64]; half d, dmin}

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import ALL_TYPES, load_golden
+from conftest import ALL_TYPES, ORACLE_ONLY_TYPES, load_golden
 from oracle.oracle import GGML_TYPE, nmse
 
 REF_CPU_DEVIATES = {"IQ4_XS", "IQ5_KS"}      # reference CPU kernels that deviate from their own to_float (SURVEY §8c pitfall 2)
@@ -92,3 +92,17 @@ def test_oracle_vs_live_reference(oracle, reflib, name):
     x = rng.uniform(-1, 1, (n, k)).astype(np.float32)
     y_ref, _ = reflib.mul_mat(t, wire, x, m, n_threads=2)
     assert nmse(y_ref, oracle.mul_mat_exact(t, wire, x, m)) <= (1e-1 if name in REF_CPU_DEVIATES else 5e-4)
+
+
+@pytest.mark.parametrize("name", ORACLE_ONLY_TYPES)
+def test_oracle_only_types_are_pinned_to_the_reference(oracle, name):
+    """Types staged for the next round: the oracle (with the codebook extracted from the running reference, tests/golden/gen_codebooks.py)
+    must already equal the reference to_float bit-for-bit on reference-quantised data, and reproduce the MMVQ / exact relation."""
+    g = load_golden(name)
+    t, m, k = int(g["ggml_type"]), int(g["m"]), int(g["k"])
+    assert oracle.supported(t) and oracle.row_size(t, k) == int(g["row_size"])
+    deq = oracle.dequantize(t, g["wire"], m, k)
+    assert np.array_equal(deq, g["dequant_ref"])
+    exact = oracle.mul_mat_exact(t, g["wire"], g["x"], m)
+    assert nmse(g["y_ref_cpu"], exact) <= 5e-4                 # the reference CPU backend agrees with the f64 dot on its own to_float
+    assert nmse(oracle.mul_mat_q8_1(t, g["wire"], g["x"], m), exact) <= 5e-4
