@@ -84,6 +84,12 @@ class Oracle:
             self._iq2xxs = (np.ascontiguousarray(z["grid"], np.uint8), np.ascontiguousarray(z["ksigns"], np.uint8))
             L.oracle_set_iq2xxs_codebook.argtypes = [c_void_p, c_void_p]
             L.oracle_set_iq2xxs_codebook(_p(self._iq2xxs[0]), _p(self._iq2xxs[1]))
+            L.oracle_set_grid.argtypes = [c_int, c_void_p]
+            self._grids = {}
+            for tid, key in ((17, "iq2xs_grid"), (18, "iq3xxs_grid")):
+                if key in z.files:
+                    self._grids[tid] = np.ascontiguousarray(z[key], np.uint8)
+                    L.oracle_set_grid(tid, _p(self._grids[tid]))
 
     def supported(self, t: int) -> bool:
         return bool(self.lib.oracle_type_supported(t))

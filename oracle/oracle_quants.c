@@ -26,7 +26,7 @@
 enum {
     T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ2_XXS = 16, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152, T_IQ2_KS = 145, T_IQ3_KS = 156,
+    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152, T_IQ2_KS = 145, T_IQ3_KS = 156,
     T_IQ4_K = 139, T_IQ5_K = 140, T_IQ4_KS = 144,
 };
 
@@ -80,7 +80,10 @@ static void init_tables(void) {
 // in at run time.  Device kernel for this type: round 2; the oracle is ready and pinned.
 static const uint8_t * g_iq2xxs_grid = NULL;     // [256][8]
 static const uint8_t * g_iq2xxs_signs = NULL;    // [128]
+static const uint8_t * g_iq2xs_grid = NULL;      // [512][8]
+static const uint8_t * g_iq3xxs_grid = NULL;     // [256][4]
 ORACLE_API void oracle_set_iq2xxs_codebook(const uint8_t * grid, const uint8_t * ksigns) { g_iq2xxs_grid = grid; g_iq2xxs_signs = ksigns; }
+ORACLE_API void oracle_set_grid(int which, const uint8_t * grid) { if (which == 17) g_iq2xs_grid = grid; else if (which == 18) g_iq3xxs_grid = grid; }
 
 // ---- wire geometry: {block elements, block bytes, row meta bytes} (ggml.c type_traits :640-1460) ----
 static int geom(int type, int * qk, int * bs, int * meta) {
@@ -93,6 +96,8 @@ static int geom(int type, int * qk, int * bs, int * meta) {
         case T_Q6_0:   *qk = 32;  *bs = 26;  return 0;
         case T_Q8_0:   *qk = 32;  *bs = 34;  return 0;
         case T_IQ2_XXS: if (!g_iq2xxs_grid) return -1; *qk = 256; *bs = 66; return 0;     // needs the codebook fixture (oracle_set_iq2xxs_codebook)
+        case T_IQ2_XS:  if (!g_iq2xs_grid || !g_iq2xxs_signs) return -1; *qk = 256; *bs = 74; return 0;
+        case T_IQ3_XXS: if (!g_iq3xxs_grid || !g_iq2xxs_signs) return -1; *qk = 256; *bs = 98; return 0;
         case T_Q2_K:   *qk = 256; *bs = 84;  return 0;
         case T_Q3_K:   *qk = 256; *bs = 110; return 0;
         case T_Q4_K:   *qk = 256; *bs = 144; return 0;
@@ -203,6 +208,32 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
                     for (int j = 0; j < 8; ++j) yy[j] = db * grid[j] * (signs & (1 << j) ? -1.f : 1.f);
                     yy += 8;
                 }
+            }
+        } break;
+        case T_IQ2_XS: {  // ggml-quants.c:3702-3725  {half d; u16 qs[32]; u8 scales[8]}
+            const float d = h2f(rd16(x)); const uint8_t * sc = x + 66; float * yy = y;
+            for (int ib32 = 0; ib32 < 8; ++ib32) {
+                const float db[2] = { d * (0.5f + (sc[ib32] & 0xf)) * 0.25f, d * (0.5f + (sc[ib32] >> 4)) * 0.25f };
+                for (int l = 0; l < 4; ++l) {
+                    const uint16_t q = rd16(x + 2 + 2 * (4 * ib32 + l));
+                    const uint8_t * grid = g_iq2xs_grid + 8 * (q & 511); const uint8_t signs = g_iq2xxs_signs[q >> 9];
+                    for (int j = 0; j < 8; ++j) yy[j] = db[l / 2] * grid[j] * (signs & (1 << j) ? -1.f : 1.f);
+                    yy += 8;
+                }
+            }
+        } break;
+        case T_IQ3_XXS: {  // ggml-quants.c:3761-3789  {half d; u8 qs[64]; u8 scales_and_signs[32]}
+            const float d = h2f(rd16(x)); const uint8_t * qs = x + 2; const uint8_t * sas = x + 66; float * yy = y;
+            for (int ib32 = 0; ib32 < 8; ++ib32) {
+                uint32_t aux32; memcpy(&aux32, sas + 4 * ib32, 4);
+                const float db = d * (0.5f + (aux32 >> 28)) * 0.5f;
+                for (int l = 0; l < 4; ++l) {
+                    const uint8_t signs = g_iq2xxs_signs[(aux32 >> 7 * l) & 127];
+                    const uint8_t * g1 = g_iq3xxs_grid + 4 * qs[2 * l + 0]; const uint8_t * g2 = g_iq3xxs_grid + 4 * qs[2 * l + 1];
+                    for (int j = 0; j < 4; ++j) { yy[j] = db * g1[j] * (signs & (1 << j) ? -1.f : 1.f); yy[j + 4] = db * g2[j] * (signs & (1 << (j + 4)) ? -1.f : 1.f); }
+                    yy += 8;
+                }
+                qs += 8;
             }
         } break;
         case T_Q2_K: {  // ggml-quants.c:2162-2190  {u8 scales[16]; u8 qs[64]; half d, dmin}

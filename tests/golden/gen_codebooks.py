@@ -39,8 +39,26 @@ def main():
     neg = (y[:, :8] < 0)
     assert np.array_equal(np.abs(y[:, :8]), np.broadcast_to(grid[0].astype(np.float32), (128, 8)))
     ksigns = (neg * (1 << np.arange(8))).sum(1).astype(np.uint8)
-    np.savez_compressed(os.path.join(HERE, "iq2xxs_codebook.npz"), grid=grid, ksigns=ksigns)
-    print("grid", grid.shape, sorted(set(grid.ravel().tolist())), "ksigns", ksigns[:8].tolist(), "...")
+    # IQ2_XS {half d; u16 qs[32]; u8 scales[8]} (ggml-quants.c:3702-3725): qs = 9-bit index into iq2xs_grid (512 x 8) | 7-bit sign index << 9;
+    # db = d * (0.5 + scale nibble) * 0.25 -> d = 8, scales = 0 gives db = 1
+    t2 = GGML_TYPE["IQ2_XS"]
+    blk = []
+    for b in range(512 // 32):
+        qs = np.arange(32 * b, 32 * b + 32, dtype=np.uint16)
+        blk.append(np.float16(8.0).tobytes() + qs.tobytes() + bytes(8))
+    y = R.to_float(t2, np.frombuffer(b"".join(blk), np.uint8), 1, 512 * 8).reshape(512, 8)
+    grid_xs = y.astype(np.uint8); assert np.array_equal(grid_xs.astype(np.float32), y)
+    # IQ3_XXS {half d; u8 qs[64]; u8 scales_and_signs[32]} (ggml-quants.c:3761-3789): qs = index into iq3xxs_grid (256 x 4);
+    # db = d * (0.5 + scale) * 0.5 -> d = 4, scale 0 gives db = 1
+    t3 = GGML_TYPE["IQ3_XXS"]
+    blk = []
+    for b in range(256 // 64):
+        blk.append(np.float16(4.0).tobytes() + np.arange(64 * b, 64 * b + 64, dtype=np.uint8).tobytes() + bytes(32))
+    y = R.to_float(t3, np.frombuffer(b"".join(blk), np.uint8), 1, 256 * 4).reshape(256, 4)
+    grid_3xxs = y.astype(np.uint8); assert np.array_equal(grid_3xxs.astype(np.float32), y)
+    np.savez_compressed(os.path.join(HERE, "iq2xxs_codebook.npz"), grid=grid, ksigns=ksigns, iq2xs_grid=grid_xs, iq3xxs_grid=grid_3xxs)
+    print("grid", grid.shape, sorted(set(grid.ravel().tolist())), "ksigns", ksigns[:8].tolist(), "...",
+          "iq2xs", grid_xs.shape, sorted(set(grid_xs.ravel().tolist())), "iq3xxs", grid_3xxs.shape, sorted(set(grid_3xxs.ravel().tolist())))
 
 
 if __name__ == "__main__":
