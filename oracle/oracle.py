@@ -86,7 +86,7 @@ class Oracle:
             L.oracle_set_iq2xxs_codebook(_p(self._iq2xxs[0]), _p(self._iq2xxs[1]))
             L.oracle_set_grid.argtypes = [c_int, c_void_p]
             self._grids = {}
-            for tid, key in ((17, "iq2xs_grid"), (18, "iq3xxs_grid")):
+            for tid, key in ((17, "iq2xs_grid"), (18, "iq3xxs_grid"), (22, "iq2s_grid"), (21, "iq3s_grid")):
                 if key in z.files:
                     self._grids[tid] = np.ascontiguousarray(z[key], np.uint8)
                     L.oracle_set_grid(tid, _p(self._grids[tid]))

@@ -26,7 +26,7 @@
 enum {
     T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152, T_IQ2_KS = 145, T_IQ3_KS = 156,
+    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ3_S = 21, T_IQ2_S = 22, T_IQ6_K = 141, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152, T_IQ2_KS = 145, T_IQ3_KS = 156,
     T_IQ4_K = 139, T_IQ5_K = 140, T_IQ4_KS = 144,
 };
 
@@ -82,8 +82,10 @@ static const uint8_t * g_iq2xxs_grid = NULL;     // [256][8]
 static const uint8_t * g_iq2xxs_signs = NULL;    // [128]
 static const uint8_t * g_iq2xs_grid = NULL;      // [512][8]
 static const uint8_t * g_iq3xxs_grid = NULL;     // [256][4]
+static const uint8_t * g_iq2s_grid = NULL;       // [1024][8]
+static const uint8_t * g_iq3s_grid = NULL;       // [512][4]
 ORACLE_API void oracle_set_iq2xxs_codebook(const uint8_t * grid, const uint8_t * ksigns) { g_iq2xxs_grid = grid; g_iq2xxs_signs = ksigns; }
-ORACLE_API void oracle_set_grid(int which, const uint8_t * grid) { if (which == 17) g_iq2xs_grid = grid; else if (which == 18) g_iq3xxs_grid = grid; }
+ORACLE_API void oracle_set_grid(int which, const uint8_t * grid) { if (which == 17) g_iq2xs_grid = grid; else if (which == 18) g_iq3xxs_grid = grid; else if (which == 22) g_iq2s_grid = grid; else if (which == 21) g_iq3s_grid = grid; }
 
 // ---- wire geometry: {block elements, block bytes, row meta bytes} (ggml.c type_traits :640-1460) ----
 static int geom(int type, int * qk, int * bs, int * meta) {
@@ -98,6 +100,9 @@ static int geom(int type, int * qk, int * bs, int * meta) {
         case T_IQ2_XXS: if (!g_iq2xxs_grid) return -1; *qk = 256; *bs = 66; return 0;     // needs the codebook fixture (oracle_set_iq2xxs_codebook)
         case T_IQ2_XS:  if (!g_iq2xs_grid || !g_iq2xxs_signs) return -1; *qk = 256; *bs = 74; return 0;
         case T_IQ3_XXS: if (!g_iq3xxs_grid || !g_iq2xxs_signs) return -1; *qk = 256; *bs = 98; return 0;
+        case T_IQ2_S:   if (!g_iq2s_grid) return -1; *qk = 256; *bs = 82; return 0;
+        case T_IQ3_S:   if (!g_iq3s_grid) return -1; *qk = 256; *bs = 110; return 0;
+        case T_IQ6_K:   *qk = 256; *bs = 212; return 0;
         case T_Q2_K:   *qk = 256; *bs = 84;  return 0;
         case T_Q3_K:   *qk = 256; *bs = 110; return 0;
         case T_Q4_K:   *qk = 256; *bs = 144; return 0;
@@ -234,6 +239,53 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
                     yy += 8;
                 }
                 qs += 8;
+            }
+        } break;
+        case T_IQ2_S: {  // ggml-quants.c:3727-3757  {half d; u8 qs[64]; u8 qh[8]; u8 scales[8]}, qs[32..63] = sign bytes
+            const float d = h2f(rd16(x)); const uint8_t * qs = x + 2; const uint8_t * signs = qs + 32; const uint8_t * qh = x + 66; const uint8_t * sc = x + 74; float * yy = y;
+            for (int ib32 = 0; ib32 < 8; ++ib32) {
+                const float db[2] = { d * (0.5f + (sc[ib32] & 0xf)) * 0.25f, d * (0.5f + (sc[ib32] >> 4)) * 0.25f };
+                for (int l = 0; l < 4; ++l) {
+                    const uint8_t * grid = g_iq2s_grid + 8 * (qs[l] | ((qh[ib32] << (8 - 2 * l)) & 0x300));
+                    for (int j = 0; j < 8; ++j) yy[j] = db[l / 2] * grid[j] * (signs[l] & (1 << j) ? -1.f : 1.f);
+                    yy += 8;
+                }
+                qs += 4; signs += 4;
+            }
+        } break;
+        case T_IQ3_S: {  // ggml-quants.c:3793-3835  {half d; u8 qs[64]; u8 qh[8]; u8 signs[32]; u8 scales[4]}
+            const float d = h2f(rd16(x)); const uint8_t * qs = x + 2; const uint8_t * qh = x + 66; const uint8_t * signs = x + 74; const uint8_t * sc = x + 106; float * yy = y;
+            for (int ib32 = 0; ib32 < 8; ib32 += 2) {
+                const float dbs[2] = { d * (1 + 2 * (sc[ib32 / 2] & 0xf)), d * (1 + 2 * (sc[ib32 / 2] >> 4)) };
+                for (int half = 0; half < 2; ++half) {
+                    for (int l = 0; l < 4; ++l) {
+                        const uint8_t * g1 = g_iq3s_grid + 4 * (qs[2 * l + 0] | ((qh[half] << (8 - 2 * l)) & 256));
+                        const uint8_t * g2 = g_iq3s_grid + 4 * (qs[2 * l + 1] | ((qh[half] << (7 - 2 * l)) & 256));
+                        for (int j = 0; j < 4; ++j) { yy[j] = dbs[half] * g1[j] * (signs[l] & (1 << j) ? -1.f : 1.f); yy[j + 4] = dbs[half] * g2[j] * (signs[l] & (1 << (j + 4)) ? -1.f : 1.f); }
+                        yy += 8;
+                    }
+                    qs += 8; signs += 4;
+                }
+                qh += 2;
+            }
+        } break;
+        case T_IQ6_K: {  // iqk/iqk_quantize.cpp:3442-3486  {half d; u16 extra; i8 scales[16]; u8 qs[128]; u8 qh[64]}: cubic codebook A + q(B + q(-C + qD)) (+1 with the extra bit)
+            const float A = -127.f, B = 6.2568f, C = 0.11218f, D = 0.0011972f, S = 1.f;
+            const float d = h2f(rd16(x)); uint16_t extra = rd16(x + 2); const int8_t * sl = (const int8_t *)(x + 4); const uint8_t * qs = x + 20; const uint8_t * qh = x + 148; float * yy = y;
+            int shift = 0;
+            for (int ib64 = 0; ib64 < 4; ++ib64) {
+                const float dl1 = d * sl[4 * ib64 + 0], dl2 = d * sl[4 * ib64 + 1], dl3 = d * sl[4 * ib64 + 2], dl4 = d * sl[4 * ib64 + 3];
+                const float m1 = extra & 1 ? S : 0, m2 = extra & 2 ? S : 0, m3 = extra & 4 ? S : 0, m4 = extra & 8 ? S : 0;
+                for (int j = 0; j < 16; ++j) {
+                    const float q1 = ((qs[j] & 0xf) | (((qh[j] >> shift) & 0x03) << 4)), q2 = ((qs[j + 16] & 0xf) | (((qh[j + 16] >> shift) & 0x03) << 4));
+                    const float q3 = ((qs[j] >> 4) | (((qh[j] >> shift) & 0x0c) << 2)), q4 = ((qs[j + 16] >> 4) | (((qh[j + 16] >> shift) & 0x0c) << 2));
+                    yy[j]      = dl1 * (A + q1 * (B + q1 * (-C + q1 * D)) + m1);
+                    yy[j + 16] = dl2 * (A + q2 * (B + q2 * (-C + q2 * D)) + m2);
+                    yy[j + 32] = dl3 * (A + q3 * (B + q3 * (-C + q3 * D)) + m3);
+                    yy[j + 48] = dl4 * (A + q4 * (B + q4 * (-C + q4 * D)) + m4);
+                }
+                yy += 64; qs += 32; extra >>= 4; shift += 4;
+                if (shift == 8) { qh += 32; shift = 0; }
             }
         } break;
         case T_Q2_K: {  // ggml-quants.c:2162-2190  {u8 scales[16]; u8 qs[64]; half d, dmin}

@@ -56,7 +56,31 @@ def main():
         blk.append(np.float16(4.0).tobytes() + np.arange(64 * b, 64 * b + 64, dtype=np.uint8).tobytes() + bytes(32))
     y = R.to_float(t3, np.frombuffer(b"".join(blk), np.uint8), 1, 256 * 4).reshape(256, 4)
     grid_3xxs = y.astype(np.uint8); assert np.array_equal(grid_3xxs.astype(np.float32), y)
-    np.savez_compressed(os.path.join(HERE, "iq2xxs_codebook.npz"), grid=grid, ksigns=ksigns, iq2xs_grid=grid_xs, iq3xxs_grid=grid_3xxs)
+    # IQ2_S {half d; u8 qs[64] (32 index bytes + 32 sign bytes); u8 qh[8]; u8 scales[8]} (ggml-quants.c:3727-3757):
+    # index_l = qs[l] | ((qh[ib32] >> 2l) & 3) << 8 into iq2s_grid (1024 x 8); d = 8, scales 0 -> db = 1
+    t2s = GGML_TYPE["IQ2_S"]
+    blk = []
+    for b in range(1024 // 32):                       # 32 grid entries per block (8 groups x 4)
+        idx = np.arange(32 * b, 32 * b + 32)
+        qs = (idx & 255).astype(np.uint8).tobytes() + bytes(32)
+        qh = bytes(int(sum(((idx[4 * g + l] >> 8) & 3) << (2 * l) for l in range(4))) for g in range(8))
+        blk.append(np.float16(8.0).tobytes() + qs + qh + bytes(8))
+    y = R.to_float(t2s, np.frombuffer(b"".join(blk), np.uint8), 1, 1024 * 8).reshape(1024, 8)
+    grid_2s = y.astype(np.uint8); assert np.array_equal(grid_2s.astype(np.float32), y)
+    # IQ3_S {half d; u8 qs[64]; u8 qh[8]; u8 signs[32]; u8 scales[4]} (ggml-quants.c:3793-3835): index = qs[i] | 9th bit from qh (bit i%8 of qh[i/8])
+    # into iq3s_grid (512 x 4); db = d * (1 + 2 * scale) -> d = 1, scales 0 gives db = 1
+    t3s = GGML_TYPE["IQ3_S"]
+    blk = []
+    for b in range(512 // 64):
+        idx = np.arange(64 * b, 64 * b + 64)
+        qs = (idx & 255).astype(np.uint8).tobytes()
+        qh = bytes(int(sum(((idx[8 * g + i] >> 8) & 1) << i for i in range(8))) for g in range(8))
+        blk.append(np.float16(1.0).tobytes() + qs + qh + bytes(32) + bytes(4))
+    y = R.to_float(t3s, np.frombuffer(b"".join(blk), np.uint8), 1, 512 * 4).reshape(512, 4)
+    grid_3s = y.astype(np.uint8); assert np.array_equal(grid_3s.astype(np.float32), y)
+    np.savez_compressed(os.path.join(HERE, "iq2xxs_codebook.npz"), grid=grid, ksigns=ksigns, iq2xs_grid=grid_xs, iq3xxs_grid=grid_3xxs,
+                        iq2s_grid=grid_2s, iq3s_grid=grid_3s)
+    print("iq2s", grid_2s.shape, sorted(set(grid_2s.ravel().tolist())), "iq3s", grid_3s.shape, sorted(set(grid_3s.ravel().tolist())))
     print("grid", grid.shape, sorted(set(grid.ravel().tolist())), "ksigns", ksigns[:8].tolist(), "...",
           "iq2xs", grid_xs.shape, sorted(set(grid_xs.ravel().tolist())), "iq3xxs", grid_3xxs.shape, sorted(set(grid_3xxs.ravel().tolist())))
 

@@ -17,7 +17,7 @@ from oracle.oracle import GGML_TYPE, RefLib  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q6_0", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "IQ2_K", "IQ3_K", "IQ4_K", "IQ5_K", "IQ4_KS", "IQ5_KS", "IQ2_KS", "IQ3_KS", "MXFP4", "IQ2_BN"]
 # types whose ORACLE is pinned already while the device kernel is still to come: fixtures for tests/test_oracle.py only
-ORACLE_ONLY = ["IQ2_XXS", "IQ2_XS", "IQ3_XXS"]
+ORACLE_ONLY = ["IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S", "IQ6_K"]
 M, K, N = 16, 512, 3
 
 

@@ -102,7 +102,10 @@ def test_oracle_only_types_are_pinned_to_the_reference(oracle, name):
     t, m, k = int(g["ggml_type"]), int(g["m"]), int(g["k"])
     assert oracle.supported(t) and oracle.row_size(t, k) == int(g["row_size"])
     deq = oracle.dequantize(t, g["wire"], m, k)
-    assert np.array_equal(deq, g["dequant_ref"])
+    if name == "IQ6_K":     # the reference to_float evaluates a float cubic (iqk_quantize.cpp:3442-3486); its build contracts it into FMAs
+        np.testing.assert_allclose(deq, g["dequant_ref"], rtol=3e-6, atol=1e-5 * float(np.abs(g["dequant_ref"]).max()))   # cancellation near the cubic's zero
+    else:
+        assert np.array_equal(deq, g["dequant_ref"])
     exact = oracle.mul_mat_exact(t, g["wire"], g["x"], m)
     assert nmse(g["y_ref_cpu"], exact) <= 5e-4                 # the reference CPU backend agrees with the f64 dot on its own to_float
     assert nmse(oracle.mul_mat_q8_1(t, g["wire"], g["x"], m), exact) <= 5e-4
