@@ -26,7 +26,7 @@
 enum {
     T_F32 = 0, T_F16 = 1, T_Q4_0 = 2, T_Q4_1 = 3, T_Q5_0 = 6, T_Q5_1 = 7, T_Q8_0 = 8,
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
-    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ3_S = 21, T_IQ2_S = 22, T_IQ6_K = 141, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152, T_IQ2_KS = 145, T_IQ3_KS = 156,
+    T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ3_S = 21, T_IQ2_S = 22, T_IQ6_K = 141, T_IQ1_BN = 134, T_IQ4_KSS = 146, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152, T_IQ2_KS = 145, T_IQ3_KS = 156,
     T_IQ4_K = 139, T_IQ5_K = 140, T_IQ4_KS = 144,
 };
 
@@ -103,6 +103,8 @@ static int geom(int type, int * qk, int * bs, int * meta) {
         case T_IQ2_S:   if (!g_iq2s_grid) return -1; *qk = 256; *bs = 82; return 0;
         case T_IQ3_S:   if (!g_iq3s_grid) return -1; *qk = 256; *bs = 110; return 0;
         case T_IQ6_K:   *qk = 256; *bs = 212; return 0;
+        case T_IQ1_BN:  *qk = 64;  *bs = 13;  *meta = 2; return 0;
+        case T_IQ4_KSS: *qk = 256; *bs = 128; *meta = 4; return 0;
         case T_Q2_K:   *qk = 256; *bs = 84;  return 0;
         case T_Q3_K:   *qk = 256; *bs = 110; return 0;
         case T_Q4_K:   *qk = 256; *bs = 144; return 0;
@@ -464,6 +466,29 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
                     yy += 32;
                 }
                 qs += 32;
+            }
+        } break;
+        case T_IQ1_BN: {  // iqk/iqk_quantize.cpp:375-396 (+ half row scale, ggml.c:1273; to_float itself ignores it, SURVEY §8c pitfall 1)
+                          // {u8 ql[12]; u8 extra}: 5 ternary digits per byte, digit j of byte b = ((v + (v >> 1)) >> 7) with v = u8(b * {81,27,9,3,1}[j]); w = row_scale * (digit - 1)
+            static const uint8_t k_mult[5] = {81, 27, 9, 3, 1};
+            const uint8_t extra = x[12]; const uint8_t * ql = x; float * yy = y;
+            for (int i16 = 0; i16 < 4; ++i16) {
+                for (int kk = 0; kk < 3; ++kk) for (int j = 0; j < 5; ++j) { const uint8_t v = (uint8_t)(ql[kk] * k_mult[j]); *yy++ = row_scale * (float)((int8_t)((v + (v >> 1)) >> 7) - 1); }
+                ql += 3;
+                const uint8_t v = (uint8_t)(extra * k_mult[i16]); *yy++ = row_scale * (float)((int8_t)((v + (v >> 1)) >> 7) - 1);
+            }
+        } break;
+        case T_IQ4_KSS: {  // iqk/iqk_quantize.cpp:5161-5187  row = {float d; blocks {u32 qs[32]}}: per 32 weights eight u16, bit 0 of each = one bit of the
+                           // scale byte, the other 15 bits hold 4 nibbles XOR-folded (v ^= v >> 1); codebook iq4k_values (+4 variant by the scale's bit 0)
+            float * yy = y;
+            for (int ib = 0; ib < 8; ++ib) {
+                uint16_t aux16[8]; int ls = 0;
+                for (int kk = 0; kk < 8; ++kk) { const uint16_t q = rd16(x + 2 * (8 * ib + kk)); aux16[kk] = q & 0xfffe; aux16[kk] ^= (aux16[kk] >> 1); ls |= (q & 1) << kk; }
+                const uint8_t * aux8 = (const uint8_t *)aux16;
+                const int8_t * v = k_iq4k + ((ls & 1) << 4);
+                const float dl = row_scale * ((ls & 254) - 127);
+                for (int j = 0; j < 16; ++j) { yy[j] = dl * v[aux8[j] & 0xf]; yy[j + 16] = dl * v[aux8[j] >> 4]; }
+                yy += 32;
             }
         } break;
         case T_IQ2_BN: {  // iqk/iqk_quantize.cpp:418-436 + row scale written at :227-229 (SURVEY §8c pitfall 1):

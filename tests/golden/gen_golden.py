@@ -17,7 +17,7 @@ from oracle.oracle import GGML_TYPE, RefLib  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q6_0", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "IQ2_K", "IQ3_K", "IQ4_K", "IQ5_K", "IQ4_KS", "IQ5_KS", "IQ2_KS", "IQ3_KS", "MXFP4", "IQ2_BN"]
 # types whose ORACLE is pinned already while the device kernel is still to come: fixtures for tests/test_oracle.py only
-ORACLE_ONLY = ["IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S", "IQ6_K"]
+ORACLE_ONLY = ["IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S", "IQ6_K", "IQ1_BN", "IQ4_KSS"]
 M, K, N = 16, 512, 3
 
 
@@ -29,7 +29,7 @@ def main():
         w = (rng.standard_normal((M, K)) * 0.02).astype(np.float32)
         w[0, :32] = 0.0                       # an all-zero block (d == 0 edge case)
         w[1, 5] = 1.5                         # an outlier
-        if name == "IQ2_BN":                  # ternary weights so the quantiser is lossless
+        if name in ("IQ2_BN", "IQ1_BN"):     # ternary weights so the quantiser is lossless
             w = (rng.integers(-1, 2, (M, K)) * 0.043).astype(np.float32)
         x = rng.uniform(-1, 1, (N, K)).astype(np.float32)
         x[0, :32] = 0.0                       # an all-zero activation block (amax == 0 edge case of quantize_q8_1)
