@@ -1,0 +1,89 @@
+"""Model of the NVLS reduce protocol of b200q_reduce.cu / the fused TP mat-vec (k_mmvq_ring, tp.in / tp.out), executed under random
+interleavings of the ranks: two parity buffers per rank, a flag word per rank that every rank's completion increments (multicast),
+a rank-local sequence counter, and the per-parity DIRTY EXTENT that tells the next user how much of a buffer must be zeroed.
+The model checks the invariants the kernels rely on: a consumer that passed its flag wait sees the complete sum, and no add can land in a
+buffer before its owner has zeroed the part that is still dirty — for reduces of MIXED lengths (tg: n_embd floats, pp: 512 x n_embd), which is
+exactly the case that the first implementation (zeroing only the current length) got wrong on the GPU."""
+import random
+
+import pytest
+
+
+class Rank:
+    def __init__(self, r, world, stride):
+        self.r, self.world = r, world
+        self.buf = [[0.0] * stride, [0.0] * stride]
+        self.flag = 0
+        self.seq = 0
+        self.dirty = [0, 0]
+        self.pc = 0            # index of the next op of this rank's program
+        self.stage = 0         # sub-step inside the op
+
+
+def run(world, lengths, seed, zero_dirty=True):
+    """lengths[i] = length of reduce i; every rank runs: producer(i) ; consumer(i) for i in order.  Returns the consumer results."""
+    rnd = random.Random(seed)
+    stride = max(lengths)
+    ranks = [Rank(r, world, stride) for r in range(world)]
+    partial = lambda r, i, j: float((r + 1) * 1000 + i * 7 + (j % 5))       # integer-valued: sums are exact in any order
+    expect = lambda i, j: sum(partial(r, i, j) for r in range(world))
+    seen = [[None] * len(lengths) for _ in range(world)]
+    # every rank's program: for each reduce i: [zero, add..., signal] then [wait, read]
+    done = 0
+    pending_adds = {r: [] for r in range(world)}       # adds issued by rank r but not yet delivered (delivered in random order, before r's signal)
+    while done < world:
+        R = rnd.choice([x for x in ranks if x.pc < 2 * len(lengths)])
+        i, kind = divmod(R.pc, 2)
+        n = lengths[i]
+        if kind == 0:                                   # ---- producer of reduce i (the row-parallel mat-vec / k_allreduce_nvls) ----
+            if R.stage == 0:
+                s = R.seq; assert s == i
+                p = s & 1
+                ext = R.dirty[p ^ 1] if zero_dirty else n          # (old protocol: zero only the current length)
+                for j in range(ext):
+                    R.buf[p ^ 1][j] = 0.0
+                pending_adds[R.r] = [(q, j) for q in range(world) for j in range(n)]
+                rnd.shuffle(pending_adds[R.r])
+                R.stage = 1
+            elif R.stage == 1:                          # deliver some of the multimem.red adds (they reach the ranks in any order)
+                for _ in range(rnd.randint(1, max(1, len(pending_adds[R.r])))):
+                    if not pending_adds[R.r]:
+                        break
+                    q, j = pending_adds[R.r].pop()
+                    ranks[q].buf[i & 1][j] += partial(R.r, i, j)
+                if not pending_adds[R.r]:
+                    R.stage = 2
+            else:                                       # last CTA: bookkeeping, then the release-flag on every rank (after all adds: fence + release)
+                p = i & 1
+                R.dirty[p ^ 1] = 0; R.dirty[p] = n; R.seq = i + 1
+                for q in ranks:
+                    q.flag += 1
+                R.stage = 0; R.pc += 1
+        else:                                           # ---- consumer of reduce i (prologue of the next mat-vec / copy-out) ----
+            if R.flag >= world * R.seq and R.seq == i + 1:
+                seen[R.r][i] = [R.buf[i & 1][j] for j in range(n)]
+                R.pc += 1
+                if R.pc == 2 * len(lengths):
+                    done += 1
+            # else: still spinning on the flag; another rank gets scheduled
+    return seen, expect
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_protocol_holds_for_mixed_lengths_under_random_interleavings(world):
+    lengths = [8, 8, 64, 64, 8, 8, 8, 64, 16, 8, 64, 8]       # tg-sized and pp-sized reduces sharing the parity buffers
+    for seed in range(40):
+        seen, expect = run(world, lengths, seed)
+        for r in range(world):
+            for i, n in enumerate(lengths):
+                assert seen[r][i] == [expect(i, j) for j in range(n)], (world, seed, r, i)
+
+
+def test_zeroing_only_the_current_length_is_wrong():
+    """The first implementation zeroed only [0, n) of the other parity buffer: a long reduce after short ones then adds into stale tails."""
+    lengths = [64, 8, 16]          # long on parity 0, short on parity 1 (zeroes only 8 floats of parity 0), medium on parity 0: [8, 16) is stale
+    bad = 0
+    for seed in range(20):
+        seen, expect = run(2, lengths, seed, zero_dirty=False)
+        bad += any(seen[r][i] != [expect(i, j) for j in range(n)] for r in range(2) for i, n in enumerate(lengths))
+    assert bad == 20
