@@ -134,6 +134,7 @@ class Model:
         f = lambda *s: t.empty(s, dtype=t.float32, device="cuda")
         self.x = f(n, N_EMBD); self.q = f(n, N_EMBD // tp); self.kk = f(n, N_KV_DIM // tp); self.v = f(n, N_KV_DIM // tp)
         self.h = f(n, N_EMBD); self.a = f(n, N_FF // tp); self.x2 = f(n, N_EMBD); self.logits = f(1, N_VOCAB // tp)
+        self.q8a = be.Q8Scratch(N_FF // tp) if n == 1 and hasattr(be, "Q8Scratch") else None
         self.u = f(n, N_FF // tp) if n > 8 else None
         self.g = f(n, N_FF // tp) if n > 8 else None
         b = lambda *s: t.empty(s, dtype=t.bfloat16, device="cuda")
@@ -168,8 +169,9 @@ class Model:
         for L in self.layers:
             be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v])
             be.mul_mat(L["wo"], self.q, out=self.h); self.allreduce(self.h)
-            be.fused_up_gate(L["up"], L["gate"], self.h, "silu", out=self.a)
-            be.mul_mat(L["down"], self.a, out=self.x2); self.allreduce(self.x2)
+            # the up/gate launch also emits its result quantised to q8_1 (once, in its epilogue) for ffn_down
+            be.fused_up_gate(L["up"], L["gate"], self.h, "silu", out=self.a, q8_out=self.q8a)
+            be.mul_mat(L["down"], self.a, out=self.x2, q8_in=self.q8a); self.allreduce(self.x2)
             x = self.x2
         be.mul_mat(self.head, x, out=self.logits)
 

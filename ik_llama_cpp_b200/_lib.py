@@ -49,6 +49,11 @@ def lib() -> ctypes.CDLL:
     L.b200q_mul_mat_vec.argtypes = [i32, vp, vp, vp, i64, i64, i32, i64, vp, vp]
     L.b200q_mul_mat_vec_multi.argtypes = [i32, i32, POINTER(vp), POINTER(vp), POINTER(i64), i64, vp, i32, i64, vp]
     L.b200q_fused_up_gate_vec.argtypes = [i32, vp, vp, vp, vp, i64, i64, i32, i64, i32, c_float, vp]
+    L.b200q_q8_scratch_bytes.restype = c_size_t
+    L.b200q_q8_scratch_bytes.argtypes = [i64]
+    L.b200q_q8_scratch_init.argtypes = [vp, i64, vp]
+    L.b200q_fused_up_gate_vec_q8.argtypes = [i32, vp, vp, vp, vp, i64, i64, i32, c_float, vp, POINTER(i32), vp]
+    L.b200q_mul_mat_vec_q8.argtypes = [i32, vp, vp, vp, vp, i64, i64, vp, vp]
     L.b200q_mul_mat_workspace.restype = c_size_t
     L.b200q_mul_mat_workspace.argtypes = [i32, i64, i64, i64]
     L.b200q_mul_mat_gemm.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp, c_size_t, vp]

@@ -23,7 +23,7 @@ from ._lib import B200QError, check
 # ggml_type ids (reference ggml/include/ggml.h:391-492) of the types the backend implements
 GGML_TYPE = {"Q4_0": 2, "Q4_1": 3, "Q5_0": 6, "Q5_1": 7, "Q6_0": 133, "Q8_0": 8, "Q2_K": 10, "Q3_K": 11, "Q4_K": 12, "Q5_K": 13, "Q6_K": 14, "IQ4_NL": 20, "IQ4_XS": 23,
              "IQ2_BN": 135, "IQ2_K": 137, "IQ3_K": 138, "IQ4_K": 139, "IQ5_K": 140, "IQ4_KS": 144, "IQ5_KS": 152, "MXFP4": 39, "IQ2_KS": 145, "IQ3_KS": 156}
-UNARY = {"none": 0, "silu": 1, "gelu": 2, "relu": 3}
+UNARY = {"none": 0, "silu": 1, "gelu": 2, "relu": 3, "swiglu_oai": 4}
 MMVQ_MAX_BATCH_SIZE = 8          # ggml-cuda/mmvq.cuh:10 — n <= 8 takes the mat-vec path
 
 
@@ -120,16 +120,31 @@ def convert_activations(x: torch.Tensor, out: torch.Tensor | None = None) -> tor
     return xb
 
 
-def mul_mat(w: QuantTensor, x: torch.Tensor, out: torch.Tensor | None = None, x_bf16: torch.Tensor | None = None) -> torch.Tensor:
+class Q8Scratch:
+    """Device scratch of the q8_1 hand-off FUSED_UP_GATE -> MUL_MAT (n = 1): b200q_q8_scratch_bytes(k), zeroed once."""
+
+    def __init__(self, k: int, device=None):
+        _require_cuda()
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.k = k
+        self.buf = torch.zeros(int(_lib.lib().b200q_q8_scratch_bytes(k)), dtype=torch.uint8, device=device)
+        self.valid = False          # set by fused_up_gate(q8_out=self): the image describes the latest result
+
+
+def mul_mat(w: QuantTensor, x: torch.Tensor, out: torch.Tensor | None = None, x_bf16: torch.Tensor | None = None,
+            q8_in: "Q8Scratch | None" = None) -> torch.Tensor:
     """GGML_OP_MUL_MAT: x f32 [N, K] -> dst f32 [N, M]  (ggml ne: src1 [K, N], dst [M, N]).
-    x_bf16: optional result of convert_activations(x) (prefill only) to skip the per-call conversion."""
+    x_bf16: optional result of convert_activations(x) (prefill only) to skip the per-call conversion.
+    q8_in: n = 1 only, x was produced by fused_up_gate(q8_out=q8_in): consume its already quantised image."""
     _require_cuda()
     assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[1] == w.k and x.stride(1) == 1
     n = x.shape[0]
     dst = out if out is not None else torch.empty((n, w.m), dtype=torch.float32, device=x.device)
     L = _lib.lib()
     with torch.cuda.device(x.device):
-        if n > MMVQ_MAX_BATCH_SIZE and x_bf16 is not None:
+        if n == 1 and q8_in is not None and q8_in.valid and q8_in.k == w.k:
+            check(L.b200q_mul_mat_vec_q8(w.ggml_type, w.ptr, x.data_ptr(), q8_in.buf.data_ptr(), dst.data_ptr(), w.m, w.k, None, _stream()), "b200q_mul_mat_vec_q8")
+        elif n > MMVQ_MAX_BATCH_SIZE and x_bf16 is not None:
             assert x_bf16.dtype == torch.bfloat16 and x_bf16.shape == x.shape and x_bf16.is_contiguous()
             need = w.m * w.k * 2 + 256
             ws = _workspace(need, x.device)
@@ -174,7 +189,8 @@ def mul_mat_multi(ws: list[QuantTensor], x: torch.Tensor, outs: list[torch.Tenso
 
 
 def fused_up_gate(up: QuantTensor, gate: QuantTensor, x: torch.Tensor, unary: str = "silu", limit: float = 0.0,
-                  out: torch.Tensor | None = None, x_bf16: torch.Tensor | None = None, out_bf16: torch.Tensor | None = None) -> torch.Tensor:
+                  out: torch.Tensor | None = None, x_bf16: torch.Tensor | None = None, out_bf16: torch.Tensor | None = None,
+                  q8_out: "Q8Scratch | None" = None) -> torch.Tensor:
     """GGML_OP_FUSED_UP_GATE: dst = unary(gate.x) * (up.x).
     n <= 8: one mat-vec launch; n > 8: two GEMMs with the mul-unary in the gate GEMM's epilogue (the reference runs two MMQs +
     ggml_fused_mul_unary, ggml-cuda.cu:3588-3618).  x_bf16 / out_bf16 (prefill only): reuse an already converted activation /
@@ -185,7 +201,14 @@ def fused_up_gate(up: QuantTensor, gate: QuantTensor, x: torch.Tensor, unary: st
     dst = out if out is not None else torch.empty((n, up.m), dtype=torch.float32, device=x.device)
     L = _lib.lib()
     with torch.cuda.device(x.device):
-        if n <= MMVQ_MAX_BATCH_SIZE:
+        if n == 1 and q8_out is not None and q8_out.k == up.m and x.is_contiguous():
+            produced = ctypes.c_int32(0)
+            check(L.b200q_fused_up_gate_vec_q8(up.ggml_type, up.ptr, gate.ptr, x.data_ptr(), dst.data_ptr(), up.m, up.k, UNARY[unary], float(limit),
+                                               q8_out.buf.data_ptr(), ctypes.byref(produced), _stream()), "b200q_fused_up_gate_vec_q8")
+            q8_out.valid = bool(produced.value)
+        elif n <= MMVQ_MAX_BATCH_SIZE:
+            if q8_out is not None:
+                q8_out.valid = False
             check(L.b200q_fused_up_gate_vec(up.ggml_type, up.ptr, gate.ptr, x.data_ptr(), dst.data_ptr(), up.m, up.k, n,
                                             x.stride(0), UNARY[unary], float(limit), _stream()), "b200q_fused_up_gate_vec")
         elif x_bf16 is not None or out_bf16 is not None:

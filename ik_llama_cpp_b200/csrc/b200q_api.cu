@@ -54,6 +54,7 @@ thread_local scratch g_x, g_y, g_ws, g_stage;
 int & opt_ring() { static int v = [] { const char * e = getenv("B200Q_RING"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_fuse_epi() { static int v = [] { const char * e = getenv("B200Q_FUSE_EPILOGUE"); return e ? atoi(e) : 0; }(); return v; }
 int & opt_fused() { static int v = [] { const char * e = getenv("B200Q_FUSED_GEMM"); return e ? atoi(e) : 1; }(); return v; }
+int & opt_q8() { static int v = [] { const char * e = getenv("B200Q_Q8_HANDOFF"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_pdl() { static int v = [] { const char * e = getenv("B200Q_PDL"); return e ? atoi(e) : 1; }(); return v; }
 }  // namespace
 
@@ -63,6 +64,7 @@ int b200q_abi_version(void) { return B200Q_ABI_VERSION; }
 const char * b200q_last_error(void) { return g_err; }
 int b200q_set_option(const char * key, int value) {
     if (key && !strcmp(key, "pdl")) { opt_pdl() = value; return B200Q_OK; }
+    if (key && !strcmp(key, "q8_handoff")) { opt_q8() = value; return B200Q_OK; }
     if (key && !strcmp(key, "ring")) { opt_ring() = value; return B200Q_OK; }
     if (key && !strcmp(key, "fused_gemm")) { opt_fused() = value; return B200Q_OK; }
     if (key && !strcmp(key, "fuse_epilogue")) { opt_fuse_epi() = value; return B200Q_OK; }
@@ -153,6 +155,49 @@ int b200q_fused_up_gate_vec(int type, const void * W_up, const void * W_gate, co
     b200q_mmvq_desc d; memset(&d, 0, sizeof d);
     d.type = type; d.n_seg = 1; d.seg[0] = {W_up, W_gate, dst, nullptr, m}; d.K = k; d.x = x; d.act = unary; d.limit = limit; d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = opt_ring();
     return mmvq_cols(d, n, x_stride, (cudaStream_t)stream, "b200q_fused_up_gate_vec");
+}
+
+/* q8 hand-off between FUSED_UP_GATE and the following MUL_MAT (ffn_down), n = 1: the up/gate launch also emits its result quantised to
+ * q8_1 (by the warp that completes each 32-row block), the next mat-vec bulk-copies that image instead of re-quantising per CTA. */
+size_t b200q_q8_scratch_bytes(int64_t k) { return k > 0 && k % 32 == 0 ? b200q_q8_image_bytes(k) : 0; }
+int b200q_q8_scratch_init(void * q8, int64_t k, void * stream) {
+    if (!q8 || k <= 0 || k % 32) return fail(B200Q_E_ARG, "b200q_q8_scratch_init: bad argument");
+    cudaError_t e = cudaMemsetAsync(q8, 0, b200q_q8_image_bytes(k), (cudaStream_t)stream);
+    return e == cudaSuccess ? B200Q_OK : cuda_fail("b200q_q8_scratch_init", e);
+}
+int b200q_fused_up_gate_vec_q8(int type, const void * W_up, const void * W_gate, const float * x, float * dst, int64_t m, int64_t k,
+                               int unary, float limit, void * q8_out, int * q8_produced, void * stream) {
+    if (q8_produced) *q8_produced = 0;
+    if (!W_up || !W_gate || !x || !dst || m <= 0) return fail(B200Q_E_ARG, "b200q_fused_up_gate_vec_q8: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_fused_up_gate_vec_q8: no CUDA device");
+    b200q_mmvq_desc d; memset(&d, 0, sizeof d);
+    d.type = type; d.n_seg = 1; d.seg[0] = {W_up, W_gate, dst, nullptr, m}; d.K = k; d.x = x; d.x_stride = k; d.ncols = 1; d.act = unary; d.limit = limit;
+    d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = opt_ring();
+    if (((uintptr_t)x & 15) || (k & 3)) return fail(B200Q_E_ARG, "b200q_fused_up_gate_vec_q8: activations must be 16-byte aligned");
+    if (q8_out && opt_q8()) {
+        d.q8_out = q8_out;
+        const int rc = b200q_launch_mmvq(d, (cudaStream_t)stream);
+        if (rc == 0) { if (q8_produced) *q8_produced = 1; return B200Q_OK; }
+        if (rc != -8) return check_launch(rc, "b200q_fused_up_gate_vec_q8");
+        d.q8_out = nullptr;              // shape not eligible for the hand-off: plain launch
+    }
+    return check_launch(b200q_launch_mmvq(d, (cudaStream_t)stream), "b200q_fused_up_gate_vec_q8");
+}
+int b200q_mul_mat_vec_q8(int type, const void * W, const float * x, const void * q8_in, float * dst, int64_t m, int64_t k,
+                         const float * bias, void * stream) {
+    if (!W || !x || !dst || m <= 0) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_q8: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_vec_q8: no CUDA device");
+    b200q_mmvq_desc d; memset(&d, 0, sizeof d);
+    d.type = type; d.n_seg = 1; d.seg[0] = {W, nullptr, dst, bias, m}; d.K = k; d.x = x; d.x_stride = k; d.ncols = 1; d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = opt_ring();
+    if (((uintptr_t)x & 15) || (k & 3)) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_q8: activations must be 16-byte aligned");
+    if (q8_in && opt_q8()) {
+        d.q8_in = q8_in;
+        const int rc = b200q_launch_mmvq(d, (cudaStream_t)stream);
+        if (rc == 0) return B200Q_OK;
+        if (rc != -8) return check_launch(rc, "b200q_mul_mat_vec_q8");
+        d.q8_in = nullptr;
+    }
+    return check_launch(b200q_launch_mmvq(d, (cudaStream_t)stream), "b200q_mul_mat_vec_q8");
 }
 
 int b200q_mul_mat_vec_tp(int type, int n_tensors, const void * const * W, const void * W_gate, float * const * dst, const int64_t * m,

@@ -79,7 +79,10 @@ struct mmvq_args {
     int          act;           // B200Q_ACT_* for the up/gate mode
     float        limit;         // clamp for swiglu variants (0 = none)
     b200q_tp_comm tp;           // tensor-parallel decode: GGML_OP_REDUCE fused into the mat-vec (tp.in / tp.out), see k_mmvq_ring
-    unsigned long long * trace; // optional phase timestamps (b200q_debug_trace): [slot][4] = entry, after griddepcontrol.wait, prologue done, last consumer done
+    unsigned long long * trace; // optional phase timestamps (b200q_debug_trace): [slot][8] = entry, after griddepcontrol.wait, prologue done, last consumer done,
+                                //   activation loads landed, quantised (before the barrier), 2^62 - first consumer done, first unit of CTA 0 / warp 1 done
+    const void * q8_in;         // activations already quantised by the producing kernel (b200q_q8 layout, n = 1): bulk-copied instead of re-quantised
+    void *       q8_out;        // fused up/gate, n = 1: also emit dst quantised to q8_1 for the following MUL_MAT (ffn_down), see q8_emit_block
 };
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
@@ -87,14 +90,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-__device__ __forceinline__ float act_apply(int act, float g) {
-    switch (act) {
-        case B200Q_ACT_SILU: return g / (1.0f + expf(-g));
-        case B200Q_ACT_GELU: { const float c = 0.79788456080286535587989211986876f, a = 0.044715f; return 0.5f * g * (1.0f + tanhf(c * g * (1.0f + a * g * g))); }
-        case B200Q_ACT_RELU: return fmaxf(g, 0.0f);
-        default: return g;
-    }
 }
 // programmatic dependent launch (no-ops unless the launch carries the PDL attribute)
 __device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -105,7 +100,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // Cooperative and vectorised: a thread owns 8 consecutive floats (two LDG.128), 4 adjacent lanes own one 32-block.
 template <int NCOLS, bool COHERENT = false>
 __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x, int64_t x_stride, int64_t K,
-                                                   int8_t * sq, float * sd, int * sis, int tid, int nthreads) {
+                                                   int8_t * sq, float * sd, int * sis, int tid, int nthreads, unsigned long long * tr = nullptr) {
     const int nch = (int)(K / 8), total = nch * NCOLS, n32 = (int)(K / 32);
     constexpr int B = 4;                                   // chunks per thread per batch: 8 independent LDG.128 in flight, so the
                                                            // activation vector costs 1 (K=4096) .. 2 (K=14336) L2 round trips, not 2 .. 6
@@ -122,6 +117,7 @@ __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x,
                 vb[u] = COHERENT ? __ldcv(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4)) : __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
             } else { va[u] = make_float4(0.f, 0.f, 0.f, 0.f); vb[u] = va[u]; }
         }
+        if (tr && base == 0 && va[0].x != 123456.789f) *tr = gtime();       // (debug trace) first batch of loads has landed
 #pragma unroll
         for (int u = 0; u < B; ++u) {
             const int c = base + u * nthreads + tid;
@@ -161,6 +157,30 @@ __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x,
             }
         }
     }
+}
+
+
+// ---- q8 hand-off between two mat-vec launches (n = 1) -------------------------------------------------------------
+// Layout of a b200q_q8 scratch for a vector of K floats (K % 64 == 0): [K int8 q][K/32 f32 d][K/32 i32 packed int16 sums]
+// = exactly the shared-memory image (sq | sd | sis) the mat-vec consumes, followed by [K/32 u32 arrival counters].
+// Producer side (fused up/gate epilogue): the warp that completes the LAST rows of a 32-block (arrival counter) quantises that
+// block from the f32 results in L2 with the arithmetic of quantize_x_to_smem; consumer side: one bulk copy instead of
+// 296 CTAs re-reading and re-quantising K floats (reference: quantize_q8_1 runs once per activation, quantize.cu:13-47).
+__device__ __forceinline__ void q8_emit_block(void * q8, int64_t K, const float * dst, int64_t M, int blk, int lane) {
+    int8_t * q8q = reinterpret_cast<int8_t *>(q8);
+    float * q8d = reinterpret_cast<float *>(q8q + K);
+    int * q8s = reinterpret_cast<int *>(q8d + K / 32);
+    const int64_t r = (int64_t)blk * 32 + lane;
+    const float v = r < M ? __ldcg(dst + r) : 0.0f;
+    float amax = fabsf(v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float d = __fdiv_rn(amax, 127.0f);
+    const float inv = d > 0.0f ? __frcp_rn(d) : 0.0f;
+    const int q = max(-127, min(127, __float2int_rn(__fmul_rn(v, inv))));
+    q8q[r] = (int8_t)q;
+    const int s_lo = __reduce_add_sync(0xffffffffu, lane < 16 ? q : 0), s_hi = __reduce_add_sync(0xffffffffu, lane < 16 ? 0 : q);
+    if (lane == 0) { q8d[blk] = __half2float(__float2half_rn(d)); q8s[blk] = (s_lo & 0xFFFF) | (s_hi << 16); }
 }
 
 template <int TYPE, int NCOLS>
@@ -261,8 +281,7 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
             float v = warp_sum(acc[c]);
             if (UPGATE) {
                 float g = warp_sum(acc2[c]);      // acc = up . x, acc2 = gate . x
-                if (a.limit > 0.0f) { g = fminf(g, a.limit); v = fminf(fmaxf(v, -a.limit), a.limit); }
-                v = act_apply(a.act, g) * v;
+                v = b200q_glu<false>(a.act, g, v, a.limit);
             } else if (sg.bias) v += sg.bias[row];
             if (lane == 0) sg.dst[(int64_t)c * sg.M + row] = v;
         }
@@ -292,6 +311,12 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
 #ifndef B200Q_RING_CONSUMERS
 #define B200Q_RING_CONSUMERS 11      // consumer warps per CTA (+1 producer): 12 warps x 2 CTAs per SM at <= 80 registers.  Round-2 knob: 15 with
 #endif                               // -maxrregcount 64 gives 32 warps per SM (more latency hiding) if the ring stages are shrunk to fit
+#ifndef B200Q_MIN_CTAS
+#define B200Q_MIN_CTAS 2             // resident CTAs per SM the ring kernel is compiled for (register cap = 65536 / (MIN_CTAS * threads))
+#endif
+#ifndef B200Q_SMEM_BUDGET
+#define B200Q_SMEM_BUDGET (112 * 1024)   // dynamic shared memory per CTA: two CTAs per SM (same kernel, or this one + the next under PDL)
+#endif
 #define B200Q_PAIR_SLOTS 124         // ncw * S stage descriptors (+ the claim counter) fit the 128-int slot table
 struct ring_geom {
     int n_planes;                 // block planes staged through the ring (the per-row scale plane is read directly)
@@ -341,7 +366,7 @@ __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarri
 // TP: tensor-parallel instantiation (fused GGML_OP_REDUCE); a separate instantiation so that the single-GPU kernels carry none of it
 // (as runtime branches the extra code cost the plain path 4 %: 675 vs 705 tok/s)
 template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR, bool TP>
-__global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), 2) k_mmvq_ring(const mmvq_ring_args ra) {
+__global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTAS) k_mmvq_ring(const mmvq_ring_args ra) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const mmvq_args & a = ra.a; const ring_geom & g = ra.g;
     const int K = (int)a.K, n32 = K / 32, n8 = n32 / 8;
@@ -354,7 +379,8 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), 2) k_mmvq_rin
     uint64_t * empty0 = full0 + ncw * S;
     uint32_t * kv_slot = reinterpret_cast<uint32_t *>(empty0 + ncw * S);
     int * pair_id = reinterpret_cast<int *>(kv_slot + 128);       // [ncw*S] pair index streamed into each stage (-1 = end)
-    int * next_pair = pair_id + B200Q_PAIR_SLOTS;                 // CTA-wide claim counter
+    int * next_pair = pair_id + B200Q_PAIR_SLOTS;                 // CTA-wide claim counter ([1]: finished consumer warps (tp.out))
+    uint64_t * xbar = reinterpret_cast<uint64_t *>(next_pair + 2); // completion of the q8_in bulk copy
     int * pstate = reinterpret_cast<int *>(kv_slot + 128 + 128);  // [ncw][4] producer state handed to the consumers (self-refill)
     uint32_t * k16tab = reinterpret_cast<uint32_t *>(kv_slot + 128 + 128 + 64);   // 32 x 65536 at lane-dependent addresses (B200Q_SHR_VIA_IMAD)
     unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128 + 128 + 64 + 32);
@@ -382,6 +408,7 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), 2) k_mmvq_rin
     if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[0] = gtime();
     if (threadIdx.x < 32) {
         for (int i = lane; i < ncw * S; i += 32) { rb_init(&full0[i]); rb_init(&empty0[i]); }
+        if (lane == 0) rb_init(xbar);
         kv_slot[lane * 4 + 0] = B200Q_KV4_A0; kv_slot[lane * 4 + 1] = B200Q_KV4_A1; kv_slot[lane * 4 + 2] = B200Q_KV4_B0; kv_slot[lane * 4 + 3] = B200Q_KV4_B1;
         if (lane == 0) { *next_pair = c0; next_pair[1] = 0; }    // [1]: consumer warps that have finished (tp.out)
         k16tab[lane] = 65536u;
@@ -445,11 +472,20 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), 2) k_mmvq_rin
             if (threadIdx.x == 32) { const uint32_t target = a.tp.world * tps; while ((int32_t)(tp_ld_acquire_sys(a.tp.local_flag) - target) < 0) __nanosleep(20); }
             asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x - 32) : "memory");
             quantize_x_to_smem<NCOLS, true>(a.tp.local_base + (int64_t)((tps - 1) & 1) * a.tp.stride, a.tp.stride, K, sq, sd, sis, threadIdx.x - 32, blockDim.x - 32);
+        } else if (NCOLS == 1 && !TP && a.q8_in) {
+            // quantised once by the producing kernel: nothing to do here, the producer warp bulk-copies the image (below)
         } else {
-            quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis, threadIdx.x - 32, blockDim.x - 32);
+            quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis, threadIdx.x - 32, blockDim.x - 32,
+                                      a.trace && blockIdx.x == 0 && threadIdx.x == 32 ? a.trace + 4 : nullptr);
         }
+        if (a.trace && blockIdx.x == 0 && threadIdx.x == 32) a.trace[5] = gtime();
+    } else if (NCOLS == 1 && !TP && a.q8_in && lane == 0) {
+        const uint32_t bytes = (uint32_t)(K + 8 * n32);
+        rb_expect(xbar, bytes);
+        bulk_g2s(sq, a.q8_in, bytes, xbar);
     }
     __syncthreads();                     // publishes barriers, kv table and activations
+    if (NCOLS == 1 && !TP && a.q8_in && warp != 0) rb_wait(xbar, 0);
     if (a.trace && blockIdx.x == 0 && threadIdx.x == 32) a.trace[2] = gtime();
 
 #if B200Q_SELF_REFILL
@@ -585,8 +621,7 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), 2) k_mmvq_rin
                         if (UPGATE) { u0 += __shfl_xor_sync(0xffffffffu, u0, o); if (PAIR) u1 += __shfl_xor_sync(0xffffffffu, u1, o); }
                     }
                     if (UPGATE) {                                                 // v = gate . x, u = up . x
-                        if (a.limit > 0.0f) { v0 = fminf(v0, a.limit); u0 = fminf(fmaxf(u0, -a.limit), a.limit); v1 = fminf(v1, a.limit); u1 = fminf(fmaxf(u1, -a.limit), a.limit); }
-                        v0 = act_apply(a.act, v0) * u0; v1 = act_apply(a.act, v1) * u1;
+                        v0 = b200q_glu<false>(a.act, v0, u0, a.limit); v1 = b200q_glu<false>(a.act, v1, u1, a.limit);
                     } else if (sgm.bias) { v0 += sgm.bias[crow]; if (two) v1 += sgm.bias[crow + 1]; }
                     if (lane == 0) {
                         if (TP && a.tp.out) {                                     // partial result: summed over ranks inside the switch
@@ -594,7 +629,22 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), 2) k_mmvq_rin
                             tp_red_add_f32(mc, v0); if (two) tp_red_add_f32(mc + 1, v1);
                         } else { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
                     }
+                    if (UPGATE && NCOLS == 1 && !TP && a.q8_out) {
+                        // arrival counter of the 32-row block these rows belong to (row pairs never straddle a block); the warp that
+                        // completes the block quantises it for the next MUL_MAT
+                        const int blk = crow >> 5, add = two ? 2 : 1, need = min(32, (int)sgm.M - 32 * blk);
+                        uint32_t * cnt = reinterpret_cast<uint32_t *>(reinterpret_cast<int8_t *>(a.q8_out) + sgm.M + 8 * (sgm.M / 32)) + blk;
+                        int old = 0;
+                        if (lane == 0) { __threadfence(); old = (int)atomicAdd(cnt, (uint32_t)add); }
+                        old = __shfl_sync(0xffffffffu, old, 0);
+                        if (old + add == need) {
+                            __threadfence();
+                            q8_emit_block(a.q8_out, sgm.M, sgm.dst, sgm.M, blk, lane);
+                            if (lane == 0) *cnt = 0;
+                        }
+                    }
                 }
+                if (a.trace && blockIdx.x == 0 && warp == 1 && lane == 0 && a.trace[7] == 0) a.trace[7] = gtime();
                 t = 0;
             }
         }
@@ -615,17 +665,21 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), 2) k_mmvq_rin
             }
         }
     }
-    if (a.trace && lane == 0) atomicMax(a.trace + 3, gtime());
+    if (a.trace && lane == 0) { const unsigned long long tt = gtime(); atomicMax(a.trace + 3, tt); atomicMax(a.trace + 6, (1ull << 62) - tt); }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
+#ifdef B200Q_BENCH_TYPES_ONLY      // tuning variants (scripts/build_variant.sh): only the benchmarked type, small and quick to build
+#define B200Q_FOR_TYPES(X) X(B200Q_TYPE_IQ4_NL)
+#else
 #define B200Q_FOR_TYPES(X) X(B200Q_TYPE_IQ4_NL) X(B200Q_TYPE_Q4_0) X(B200Q_TYPE_Q8_0) X(B200Q_TYPE_Q4_K) X(B200Q_TYPE_Q5_K) \
     X(B200Q_TYPE_Q6_K) X(B200Q_TYPE_IQ4_XS) X(B200Q_TYPE_IQ4_K) X(B200Q_TYPE_IQ4_KS) X(B200Q_TYPE_IQ5_K) X(B200Q_TYPE_IQ2_BN) \
     X(B200Q_TYPE_Q4_1) X(B200Q_TYPE_Q5_0) X(B200Q_TYPE_Q5_1) X(B200Q_TYPE_Q6_0) X(B200Q_TYPE_Q2_K) X(B200Q_TYPE_Q3_K) \
     X(B200Q_TYPE_IQ2_K) X(B200Q_TYPE_IQ3_K) X(B200Q_TYPE_MXFP4) X(B200Q_TYPE_IQ5_KS) \
     X(B200Q_TYPE_IQ2_KS) X(B200Q_TYPE_IQ3_KS)
+#endif
 
 int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L, int inverse, cudaStream_t st) {
     const int64_t total = L.M * L.nb;
@@ -692,7 +746,7 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
     if (a.M_total >= (int64_t)1 << 30) return -100;
     const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 512 + 256 + 128;
-    const size_t budget = 112 * 1024;                   // two CTAs per SM (same kernel, or this one + the next under PDL)
+    const size_t budget = B200Q_SMEM_BUDGET;
     const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
     int ncw = B200Q_RING_CONSUMERS, S = 0;              // consumer warps (+1 producer warp)
     for (;;) {
@@ -714,7 +768,9 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
         if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
         configured[dev] = true;
     }
-    int64_t grid = (n_pairs + ncw - 1) / ncw;
+    // B200Q_GRID_FULL=1 (experiment): always spread over every SM, even when a CTA then has fewer units than consumer warps
+    static const int grid_full = [] { const char * e = getenv("B200Q_GRID_FULL"); return e ? atoi(e) : 0; }();
+    int64_t grid = grid_full ? n_pairs : (n_pairs + ncw - 1) / ncw;
     if (grid > (int64_t)sm_count * ctas_per_sm) grid = (int64_t)sm_count * ctas_per_sm;
     if (grid < 1) grid = 1;
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
@@ -743,7 +799,7 @@ static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_
     ring_geom g;
     if (ring && ncols <= 2 && make_ring_geom(TYPE, a.K, g)) {
         int rc;
-        static const int cps = [] { const char * e = getenv("B200Q_CTAS_PER_SM"); return e ? atoi(e) : 2; }();
+        static const int cps = [] { const char * e = getenv("B200Q_CTAS_PER_SM"); return e ? atoi(e) : B200Q_MIN_CTAS; }();
         const bool multi = a.n_seg > 1;
         if (upgate) rc = ncols == 1 ? launch_mmvq_ring_t<TYPE, 1, true, false>(a, g, sm_count, pdl, cps, st) : launch_mmvq_ring_t<TYPE, 2, true, false>(a, g, sm_count, pdl, cps, st);
         else if (multi) rc = ncols == 1 ? launch_mmvq_ring_t<TYPE, 1, false, true>(a, g, sm_count, pdl, cps, st) : launch_mmvq_ring_t<TYPE, 2, false, true>(a, g, sm_count, pdl, cps, st);
@@ -751,6 +807,7 @@ static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_
         if (rc != -100) return rc;
     }
     if (a.tp.in || a.tp.out) return -7;
+    if (a.q8_in || a.q8_out) return -8;                    // only the ring kernel implements the q8 hand-off (callers retry without it)
 #define CASE(N) case N: return upgate ? launch_mmvq_t<TYPE, N, true>(a, sm_count, pdl, st) : launch_mmvq_t<TYPE, N, false>(a, sm_count, pdl, st);
     switch (ncols) { CASE(1) CASE(2) CASE(4) CASE(8) default: return -2; }
 #undef CASE
@@ -759,14 +816,14 @@ static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_
 // per-launch phase timestamps (debug aid for the PDL pipeline; see scripts/trace_decode.py)
 static unsigned long long * g_trace = nullptr; static int g_trace_slot = 0;
 extern "C" __attribute__((visibility("default"))) int b200q_debug_trace(int enable, unsigned long long * host_out, int max_slots) {
-    if (enable == 1) { if (!g_trace) { cudaMalloc(&g_trace, 4096 * 4 * sizeof(unsigned long long)); } cudaMemset(g_trace, 0, 4096 * 4 * sizeof(unsigned long long)); g_trace_slot = 0; return 0; }
+    if (enable == 1) { if (!g_trace) { cudaMalloc(&g_trace, 4096 * 8 * sizeof(unsigned long long)); } cudaMemset(g_trace, 0, 4096 * 8 * sizeof(unsigned long long)); g_trace_slot = 0; return 0; }
     if (enable == 2) { g_trace_slot = 0; return 0; }                               // rewind (start of a step)
-    if (enable == 0 && host_out && g_trace) { cudaMemcpy(host_out, g_trace, (size_t)max_slots * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost); return g_trace_slot; }
+    if (enable == 0 && host_out && g_trace) { cudaMemcpy(host_out, g_trace, (size_t)max_slots * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost); return g_trace_slot; }
     return -1;
 }
 int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
     mmvq_args a; memset(&a, 0, sizeof a);
-    if (g_trace && g_trace_slot < 4096) a.trace = g_trace + 4 * (g_trace_slot++);
+    if (g_trace && g_trace_slot < 4096) a.trace = g_trace + 8 * (g_trace_slot++);
     if (d.n_seg < 1 || d.n_seg > B200Q_MAX_SEGS || d.ncols < 1 || d.ncols > 8) return -2;
     int64_t r0 = 0;
     for (int i = 0; i < d.n_seg; ++i) {
@@ -778,6 +835,12 @@ int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
     a.n_seg = d.n_seg; a.M_total = r0; a.K = d.K; a.x = d.x; a.x_stride = d.x_stride ? d.x_stride : d.K; a.act = d.act; a.limit = d.limit;
     a.tp = d.tp;
     const bool upgate = d.seg[0].W2 != nullptr;
+    if (d.q8_in || d.q8_out) {          // q8 hand-off: n = 1, single tensor, ring kernel, bulk-copyable image
+        if (d.ncols != 1 || d.n_seg != 1 || !d.ring || a.tp.in || a.tp.out) return -8;
+        if (d.q8_in && (d.K % 64 || ((uintptr_t)d.q8_in & 15))) return -8;
+        if (d.q8_out && (!upgate || d.seg[0].M % 64 || ((uintptr_t)d.q8_out & 15))) return -8;
+        a.q8_in = d.q8_in; a.q8_out = d.q8_out;
+    }
     if (a.tp.in || a.tp.out) {          // only the TMA-ring kernel implements the fused reduce
         if (d.ncols != 1 || !d.ring || d.K % 256 || (a.tp.out && r0 > a.tp.stride) || (a.tp.in && d.K > a.tp.stride)) return -7;
     }

@@ -248,14 +248,6 @@ struct gemmq_args {
     gemmq_seg seg[GEMMQ_MAX_SEGS];
     int n_seg, N, K, k_split, act; float limit;
 };
-__device__ __forceinline__ float gemm_act_apply(int act, float g) {
-    switch (act) {
-        case B200Q_ACT_SILU: return __fdividef(g, 1.0f + __expf(-g));       // |rel err| ~1e-6: far below the bf16 operand noise of this path
-        case B200Q_ACT_GELU: { const float c = 0.79788456080286535587989211986876f, a = 0.044715f; return 0.5f * g * (1.0f + tanhf(c * g * (1.0f + a * g * g))); }
-        case B200Q_ACT_RELU: return fmaxf(g, 0.0f);
-        default: return g;
-    }
-}
 
 // carry-less per-byte add of two packed int8x4 (the A/B halves of the sign-fill LUT)
 __device__ __forceinline__ uint32_t vadd4_wrap(uint32_t a, uint32_t b) {
@@ -455,11 +447,7 @@ k_gemm_q(const __grid_constant__ gemmq_args a) {
                         const int n = n0 + c0 + j;
                         if (n < N) {
                             float v = __uint_as_float(rr[j]);
-                            if (mul != nullptr) {
-                                float w = uu[j];
-                                if (lim > 0.0f) { v = fminf(v, lim); w = fminf(fmaxf(w, -lim), lim); }
-                                v = gemm_act_apply(act, v) * w;
-                            }
+                            if (mul != nullptr) v = b200q_glu<true>(act, v, uu[j], lim);
                             dst[(size_t)n * M + m] = v;
                             if (dst_bf != nullptr) dst_bf[(size_t)n * M + m] = __float2bfloat16_rn(v);
                         }
@@ -494,11 +482,7 @@ __global__ void k_mul_unary(const float * gate /* may alias dst: no __restrict__
                             int64_t total4, int act, float lim) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 g = reinterpret_cast<const float4 *>(gate)[i]; float4 u = reinterpret_cast<const float4 *>(up)[i];
-        if (lim > 0.0f) {
-            g.x = fminf(g.x, lim); g.y = fminf(g.y, lim); g.z = fminf(g.z, lim); g.w = fminf(g.w, lim);
-            u.x = fminf(fmaxf(u.x, -lim), lim); u.y = fminf(fmaxf(u.y, -lim), lim); u.z = fminf(fmaxf(u.z, -lim), lim); u.w = fminf(fmaxf(u.w, -lim), lim);
-        }
-        float4 r; r.x = gemm_act_apply(act, g.x) * u.x; r.y = gemm_act_apply(act, g.y) * u.y; r.z = gemm_act_apply(act, g.z) * u.z; r.w = gemm_act_apply(act, g.w) * u.w;
+        float4 r; r.x = b200q_glu<true>(act, g.x, u.x, lim); r.y = b200q_glu<true>(act, g.y, u.y, lim); r.z = b200q_glu<true>(act, g.z, u.z, lim); r.w = b200q_glu<true>(act, g.w, u.w, lim);
         reinterpret_cast<float4 *>(dst)[i] = r;
         if (dst_bf != nullptr) {
             __nv_bfloat162 b0 = __floats2bfloat162_rn(r.x, r.y), b1 = __floats2bfloat162_rn(r.z, r.w);

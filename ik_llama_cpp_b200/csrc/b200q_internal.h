@@ -9,7 +9,32 @@
 #define B200Q_MAX_DEVICES 16
 static inline int b200q_current_device() { int d = 0; if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= B200Q_MAX_DEVICES) d = 0; return d; }
 
-enum { B200Q_ACT_NONE = 0, B200Q_ACT_SILU = 1, B200Q_ACT_GELU = 2, B200Q_ACT_RELU = 3 };
+enum { B200Q_ACT_NONE = 0, B200Q_ACT_SILU = 1, B200Q_ACT_GELU = 2, B200Q_ACT_RELU = 3, B200Q_ACT_SWIGLU_OAI = 4 };
+
+#if defined(__CUDACC__)
+// act(gate) * up of GGML_OP_FUSED_UP_GATE, with the reference's order of operations (fused_mul_mat_vec_q, mmvq-templates.cuh:240-275;
+// fused_mul_silu_f32 with limit, ggml-cuda/unary.cu:63-72; CPU: ggml.c:16939-16945):
+//   SILU:  g = silu(g); if (limit > 1e-6) { g = min(g, limit); u = clamp(u, -limit, limit); }  r = g * u      (the clamp follows the activation)
+//   GELU / RELU: limit is ignored;   SWIGLU_OAI (no bias): g = min(g, 7), u = clamp(u, -7, 7), r = g / (1 + exp(-1.702 g)) * (1 + u)
+// FAST: __expf / __fdividef (prefill epilogue: |rel err| ~1e-6, far below the bf16 operand noise of that path)
+template <bool FAST>
+__device__ __forceinline__ float b200q_glu(int act, float g, float u, float limit) {
+    switch (act) {
+        case B200Q_ACT_SILU: {
+            g = FAST ? __fdividef(g, 1.0f + __expf(-g)) : g / (1.0f + expf(-g));
+            if (limit > 1e-6f) { g = fminf(g, limit); u = fmaxf(-limit, fminf(limit, u)); }
+            return g * u;
+        }
+        case B200Q_ACT_GELU: { const float c = 0.79788456080286535587989211986876f, a = 0.044715f; return 0.5f * g * (1.0f + tanhf(c * g * (1.0f + a * g * g))) * u; }
+        case B200Q_ACT_RELU: return fmaxf(g, 0.0f) * u;
+        case B200Q_ACT_SWIGLU_OAI: {
+            g = fminf(g, 7.0f); u = fmaxf(fminf(u, 7.0f), -7.0f);
+            return (FAST ? __fdividef(g, 1.0f + __expf(-g * 1.702f)) : g / (1.0f + expf(-g * 1.702f))) * (1.0f + u);
+        }
+        default: return g * u;
+    }
+}
+#endif
 
 // types whose canonical decode has a non-zero subtracted offset (ml) -> the kernel needs the integer activation sums
 B200Q_HD constexpr bool b200q_mmvq_has_ml(int type) {
@@ -31,7 +56,11 @@ struct b200q_mmvq_desc {
     int type; int n_seg; b200q_mmvq_seg_desc seg[B200Q_MAX_SEGS];
     int64_t K; const float * x; int64_t x_stride; int ncols; int act; float limit; int sm_count; int pdl; int ring;
     b200q_tp_comm tp;
+    const void * q8_in;     // n = 1: activations already quantised by the producing launch (b200q_q8 image); x is still passed for the fallback
+    void * q8_out;          // fused up/gate, n = 1: also emit dst as a b200q_q8 image for the next MUL_MAT
 };
+// b200q_q8 image of a K-vector: [K int8][K/32 f32 d][K/32 i32 sums][K/32 u32 arrival counters] (+ 16 B slack)
+static inline size_t b200q_q8_image_bytes(int64_t k) { return (size_t)(k + 12 * (k / 32) + 16); }
 
 int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L, int inverse, cudaStream_t st);
 int b200q_launch_dequant_bf16(const void * W, const b200q_layout & L, void * out, cudaStream_t st);

@@ -35,7 +35,10 @@ extern "C" {
 #endif
 
 enum { B200Q_OK = 0, B200Q_E_TYPE = -1, B200Q_E_SHAPE = -2, B200Q_E_CUDA = -3, B200Q_E_ARG = -4, B200Q_E_NOMEM = -5 };
-enum { B200Q_UNARY_NONE = 0, B200Q_UNARY_SILU = 1, B200Q_UNARY_GELU = 2, B200Q_UNARY_RELU = 3 };
+/* unary of GGML_OP_FUSED_UP_GATE.  `limit` (op_params[1]) follows the reference: SILU only, applied AFTER the activation
+ * (g = min(silu(g), limit), u = clamp(u, +-limit)), ignored when <= 1e-6 (mmvq-templates.cuh:253-258, unary.cu:63-72).
+ * SWIGLU_OAI: alpha 1.702, limit 7, no bias (ggml-cuda.cu:3607-3611). */
+enum { B200Q_UNARY_NONE = 0, B200Q_UNARY_SILU = 1, B200Q_UNARY_GELU = 2, B200Q_UNARY_RELU = 3, B200Q_UNARY_SWIGLU_OAI = 4 };
 
 B200Q_API int          b200q_abi_version(void);
 B200Q_API const char * b200q_last_error(void);
@@ -62,6 +65,17 @@ B200Q_API int b200q_mul_mat_vec_multi(int type, int n_tensors, const void * cons
 /* dst = unary(gate.x) * (up.x)   (optionally clamped: limit > 0) */
 B200Q_API int b200q_fused_up_gate_vec(int type, const void * W_up, const void * W_gate, const float * x, float * dst,
                             int64_t m, int64_t k, int n, int64_t x_stride, int unary, float limit, void * stream);
+
+/* q8_1 hand-off FUSED_UP_GATE -> MUL_MAT(ffn_down) for n = 1 (the reference quantises each activation once, quantize_row_q8_1_cuda in
+ * ggml_cuda_op_mul_mat_vec_q, ggml-cuda.cu:2503-2604; here the producer's epilogue does it): `q8` is a device scratch of
+ * b200q_q8_scratch_bytes(m_of_up_gate) bytes, zeroed ONCE with b200q_q8_scratch_init.  *q8_produced = 1 if the launch emitted the image
+ * (eligible shape and kernel); pass q8_in = NULL to b200q_mul_mat_vec_q8 otherwise.  x / dst are always read / written as usual. */
+B200Q_API size_t b200q_q8_scratch_bytes(int64_t k);
+B200Q_API int b200q_q8_scratch_init(void * q8, int64_t k, void * stream);
+B200Q_API int b200q_fused_up_gate_vec_q8(int type, const void * W_up, const void * W_gate, const float * x, float * dst, int64_t m, int64_t k,
+                               int unary, float limit, void * q8_out, int * q8_produced, void * stream);
+B200Q_API int b200q_mul_mat_vec_q8(int type, const void * W, const float * x, const void * q8_in, float * dst, int64_t m, int64_t k,
+                         const float * bias, void * stream);
 
 /* ---- prefill: tcgen05 GEMM ---- */
 B200Q_API size_t b200q_mul_mat_workspace(int type, int64_t m, int64_t k, int64_t n);

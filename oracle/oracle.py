@@ -201,6 +201,9 @@ class RefLib:
         L.refshim_chain_run.restype = c_double
         L.refshim_chain_run.argtypes = [c_void_p]
         L.refshim_chain_free.argtypes = [c_void_p]
+        if hasattr(L, "refshim_fused_up_gate"):
+            L.refshim_fused_up_gate.argtypes = [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_float, c_int]
+            L.refshim_unary_op_id.argtypes = [c_char_p]
 
     def row_size(self, t: int, k: int) -> int:
         return int(self.lib.refshim_row_size(t, k))
@@ -249,6 +252,18 @@ class RefLib:
         sec = self.lib.refshim_mul_mat(t, _p(wire), _p(x), _p(out), m, k, n, n_threads, reps)
         assert sec >= 0, sec
         return out, sec
+
+
+    def fused_up_gate(self, t: int, w_up: np.ndarray, w_gate: np.ndarray, x: np.ndarray, m: int, unary: str = "silu", limit: float = 0.0, n_threads: int = 4):
+        """GGML_OP_FUSED_UP_GATE through the reference CPU backend (op_params[1] = limit)."""
+        x = np.ascontiguousarray(x, np.float32)
+        n, k = x.shape
+        out = np.empty((n, m), np.float32)
+        op = self.lib.refshim_unary_op_id(unary.encode())
+        assert op >= 0, unary
+        rc = self.lib.refshim_fused_up_gate(t, _p(np.ascontiguousarray(w_up, np.uint8)), _p(np.ascontiguousarray(w_gate, np.uint8)), _p(x), _p(out), m, k, n, op, float(limit), n_threads)
+        assert rc == 0, rc
+        return out
 
 
 def nmse(a: np.ndarray, b: np.ndarray) -> float:

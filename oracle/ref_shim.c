@@ -158,3 +158,40 @@ SHIM_API void refshim_chain_free(struct refshim_chain * ch) {
     ggml_free(ch->ctx);
     free(ch->a); free(ch->b); free(ch->c); free(ch);
 }
+
+// GGML_OP_FUSED_UP_GATE through the reference CPU backend: dst[n][m] = unary(gate.x) * (up.x), op_params[1] = swiglu limit
+// (ggml.c ggml_fused_up_gate; CPU compute ggml.c:16895-16990).  Pins the activation / clamp order of operations.
+SHIM_API int refshim_fused_up_gate(int type, const void * W_up, const void * W_gate, const float * x, float * dst,
+                                   int64_t m, int64_t k, int64_t n, int unary_op, float limit, int n_threads) {
+    struct ggml_init_params ip = { ggml_tensor_overhead()*16 + ggml_graph_overhead() + 4096, NULL, true };
+    struct ggml_context * ctx = ggml_init(ip);
+    if (!ctx) return -1;
+    struct ggml_tensor * up = ggml_new_tensor_2d(ctx, (enum ggml_type)type, k, m);
+    struct ggml_tensor * gate = ggml_new_tensor_2d(ctx, (enum ggml_type)type, k, m);
+    struct ggml_tensor * b = ggml_new_tensor_2d(ctx, GGML_TYPE_F32, k, n);
+    struct ggml_tensor * c = ggml_fused_up_gate(ctx, up, gate, b, (enum ggml_unary_op)unary_op);
+    memcpy((char *)c->op_params + sizeof(int32_t), &limit, sizeof(float));
+    struct ggml_cgraph * gf = ggml_new_graph(ctx);
+    ggml_build_forward_expand(gf, c);
+    ggml_backend_t cpu = ggml_backend_cpu_init();
+    if (!cpu) { ggml_free(ctx); return -2; }
+    ggml_backend_cpu_set_n_threads(cpu, n_threads);
+    ggml_backend_buffer_t buf = ggml_backend_alloc_ctx_tensors(ctx, cpu);
+    if (!buf) { ggml_backend_free(cpu); ggml_free(ctx); return -3; }
+    ggml_backend_tensor_set(up, W_up, 0, ggml_nbytes(up));
+    ggml_backend_tensor_set(gate, W_gate, 0, ggml_nbytes(gate));
+    ggml_backend_tensor_set(b, x, 0, ggml_nbytes(b));
+    int rc = ggml_backend_graph_compute(cpu, gf) == GGML_STATUS_SUCCESS ? 0 : -4;
+    if (rc == 0) ggml_backend_tensor_get(c, dst, 0, ggml_nbytes(c));
+    ggml_backend_buffer_free(buf);
+    ggml_backend_free(cpu);
+    ggml_free(ctx);
+    return rc;
+}
+SHIM_API int refshim_unary_op_id(const char * name) {
+    if (!strcmp(name, "silu")) return GGML_UNARY_OP_SILU;
+    if (!strcmp(name, "gelu")) return GGML_UNARY_OP_GELU;
+    if (!strcmp(name, "relu")) return GGML_UNARY_OP_RELU;
+    if (!strcmp(name, "swiglu_oai")) return GGML_UNARY_OP_SWIGLU_OAI;
+    return -1;
+}

@@ -1,0 +1,24 @@
+#!/usr/bin/env python
+"""Run bench.py's tg step (tok/s only) for the product library and every tuning variant under experiments/_variants,
+each in its own process (the library is chosen at import time), optionally with extra environment knobs."""
+import json, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+configs = [("product", None, {}), ("product q8off", None, {"B200Q_Q8_HANDOFF": "0"}), ("product gridfull", None, {"B200Q_GRID_FULL": "1"})]
+vd = os.path.join(ROOT, "experiments", "_variants")
+for f in sorted(os.listdir(vd)) if os.path.isdir(vd) else []:
+    if f.endswith(".so"):
+        name = f[len("libb200q_"):-3]
+        configs.append((name, os.path.join(vd, f), {}))
+        configs.append((name + " gridfull", os.path.join(vd, f), {"B200Q_GRID_FULL": "1"}))
+only = sys.argv[1:]
+for name, lib, env in configs:
+    if only and not any(o in name for o in only):
+        continue
+    e = dict(os.environ); e.update(env)
+    if lib: e["B200Q_LIB_PATH"] = lib
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-pp", "--no-cpu", "--steps", "20", "--warmup", "3"], env=e, capture_output=True, text=True)
+    try:
+        line = json.loads(r.stdout.strip().splitlines()[-1])
+        print(f"{name:28s} tg {line['value']:8.1f} tok/s  frac {line['roofline']['frac']:.3f}  e2e {line['e2e']['value']:8.1f}", flush=True)
+    except Exception:
+        print(f"{name:28s} FAILED rc={r.returncode}: {r.stderr[-400:]}", flush=True)

@@ -28,15 +28,26 @@ for _ in range(5):
     g.replay()
 torch.cuda.synchronize()
 n = model.launches_tg
-out = np.zeros((n, 4), np.uint64)
+out = np.zeros((n, 8), np.uint64)
 L.b200q_debug_trace(0, out.ctypes.data, n)
 t = out.astype(np.int64)
 t0 = t[0, 0]
 names = ["qkv", "wo", "upgate", "down"]
-print("launch  name    entry   wait_ret  prologue   done   | dur(entry->done) wait->done  gap(prev done -> wait_ret)")
+print("launch  name    entry   wait_ret  prologue   done   | dur(entry->done) wait->done  gap(prev done -> wait_ret) | wait->x_loaded  ->quantised  ->barrier | barrier->1st unit (CTA0/w1)  first warp done  last warp done (after barrier)")
+agg = {}
 for i in range(n):
     nm = names[i % 4] if i < n - 1 else "head"
-    e, w, p, d = (t[i] - t0) / 1000.0
+    e, w, p, d = (t[i, :4] - t0) / 1000.0
     gap = (t[i, 1] - t[i - 1, 3]) / 1000.0 if i else 0.0
-    print(f"{i:4d}  {nm:7s} {e:8.2f} {w:8.2f} {p:8.2f} {d:8.2f} | {d-e:8.2f} {d-w:8.2f} {gap:8.2f}")
+    xl = (t[i, 4] - t[i, 1]) / 1000.0 if t[i, 4] else float("nan")
+    qd = (t[i, 5] - t[i, 1]) / 1000.0 if t[i, 5] else float("nan")
+    fu = (t[i, 7] - t[i, 2]) / 1000.0 if t[i, 7] else float("nan")
+    fd = (((1 << 62) - t[i, 6]) - t[i, 2]) / 1000.0 if t[i, 6] else float("nan")
+    print(f"{i:4d}  {nm:7s} {e:8.2f} {w:8.2f} {p:8.2f} {d:8.2f} | {d-e:8.2f} {d-w:8.2f} {gap:8.2f} | {xl:6.2f} {qd:6.2f} {p-w:6.2f} | {fu:6.2f} {fd:6.2f} {d-p:6.2f}")
+    if i >= 4:
+        agg.setdefault(nm, []).append((d - w, gap, p - w, d - p, fd))
 print("total us", (t[n - 1, 3] - t0) / 1000.0)
+print("median per kernel (layers >= 1): wait->done, gap, prologue, main(last), main(first warp)")
+for nm, v in agg.items():
+    a = np.median(np.array(v), axis=0)
+    print(f"  {nm:7s} " + " ".join(f"{x:7.2f}" for x in a))

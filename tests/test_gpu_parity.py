@@ -39,6 +39,25 @@ def rms(a):
     return float(np.sqrt((a.astype(np.float64) ** 2).mean()))
 
 
+def glu_ref(unary, g, u, limit=0.0):
+    """act(gate) * up with the reference's order of operations (fused_mul_mat_vec_q, mmvq-templates.cuh:240-275; fused_mul_silu_f32 with
+    limit, unary.cu:63-72; CPU ggml.c:16939-16945): the clamp FOLLOWS silu and exists for silu only; swiglu_oai: alpha 1.702, limit 7."""
+    g = np.asarray(g, np.float64); u = np.asarray(u, np.float64)
+    if unary == "silu":
+        a = g / (1 + np.exp(-g))
+        if limit > 1e-6:
+            a = np.minimum(a, limit); u = np.clip(u, -limit, limit)
+        return a * u
+    if unary == "gelu":
+        return 0.5 * g * (1 + np.tanh(0.79788456080286535588 * g * (1 + 0.044715 * g * g))) * u
+    if unary == "relu":
+        return np.maximum(g, 0) * u
+    if unary == "swiglu_oai":
+        g = np.minimum(g, 7.0); u = np.clip(u, -7.0, 7.0)
+        return g / (1 + np.exp(-1.702 * g)) * (1 + u)
+    raise ValueError(unary)
+
+
 @pytest.mark.parametrize("name", ALL_TYPES)
 def test_set_get_tensor_roundtrip(be, name):
     g = load_golden(name)
@@ -141,18 +160,81 @@ def test_multi_tensor_launch_qkv(be, oracle):
 
 
 @pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K", "IQ2_BN"])
-@pytest.mark.parametrize("unary", ["silu", "gelu", "relu"])
-def test_fused_up_gate(be, oracle, name, unary):
+@pytest.mark.parametrize("unary,limit", [("silu", 0.0), ("gelu", 0.0), ("relu", 0.0), ("silu", 1.5), ("gelu", 1.5), ("swiglu_oai", 0.0)])
+@pytest.mark.parametrize("n", [1, 2, 5])
+def test_fused_up_gate(be, oracle, name, unary, limit, n):
+    """n = 1, 2: the TMA-ring kernel; n = 5: the LDG kernel.  limit: after the activation, silu only (gelu ignores it)."""
     t = GGML_TYPE[name]
     m, k = 384, 1024
     wu, wg = make_wire(oracle, name, m, k, seed=31), make_wire(oracle, name, m, k, seed=32)
-    x = np.random.default_rng(3).standard_normal((1, k)).astype(np.float32) * 4
+    x = np.random.default_rng(3).standard_normal((n, k)).astype(np.float32) * 4
     up, gate = be.set_tensor(t, wu, m, k), be.set_tensor(t, wg, m, k)
-    y = be.fused_up_gate(up, gate, torch.from_numpy(x).cuda(), unary=unary).cpu().numpy()
+    y = be.fused_up_gate(up, gate, torch.from_numpy(x).cuda(), unary=unary, limit=limit).cpu().numpy()
     u, g = oracle.mul_mat_q8_1(t, wu, x, m, variant="b200").astype(np.float64), oracle.mul_mat_q8_1(t, wg, x, m, variant="b200").astype(np.float64)
-    act = {"silu": g / (1 + np.exp(-g)), "gelu": 0.5 * g * (1 + np.tanh(0.79788456080286535588 * g * (1 + 0.044715 * g * g))), "relu": np.maximum(g, 0)}[unary]
-    ref = act * u
+    ref = glu_ref(unary, g, u, limit)
     assert np.abs(y - ref).max() <= 5e-5 * max(rms(ref), 1e-30)
+
+
+def test_fused_up_gate_limit_matches_reference_cpu_op(be, oracle, ref_or_none):
+    """The clamp semantics pinned on the reference itself: GGML_OP_FUSED_UP_GATE with op_params limit through the unmodified CPU backend."""
+    if ref_or_none is None or not hasattr(ref_or_none.lib, "refshim_fused_up_gate"):
+        pytest.skip("reference CPU build (oracle/_ref) without the FUSED_UP_GATE shim")
+    t = GGML_TYPE["Q4_0"]
+    m, k = 256, 512
+    wu, wg = make_wire(oracle, "Q4_0", m, k, seed=61), make_wire(oracle, "Q4_0", m, k, seed=62)
+    x = np.random.default_rng(9).standard_normal((1, k)).astype(np.float32) * 6
+    up, gate = be.set_tensor(t, wu, m, k), be.set_tensor(t, wg, m, k)
+    for limit in (0.0, 1.5):
+        y = be.fused_up_gate(up, gate, torch.from_numpy(x).cuda(), unary="silu", limit=limit).cpu().numpy()
+        r = ref_or_none.fused_up_gate(t, wu, wg, x, m, "silu", limit)
+        assert nmse(y, r) <= 5e-4, (limit, nmse(y, r))
+
+
+@pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K", "Q6_K"])
+def test_q8_handoff_up_gate_to_down(be, oracle, name):
+    """FUSED_UP_GATE (n = 1) emits its result quantised to q8_1 in its epilogue; the following MUL_MAT consumes that image.
+    Bit-identical to the path that re-quantises per CTA (same arithmetic on the same f32 values), and equal to the oracle."""
+    t = GGML_TYPE[name]
+    k, ff, m2 = 1024, 1536, 512
+    wu, wg, wd = make_wire(oracle, name, ff, k, seed=71), make_wire(oracle, name, ff, k, seed=72), make_wire(oracle, name, m2, ff, seed=73)
+    up, gate, down = be.set_tensor(t, wu, ff, k), be.set_tensor(t, wg, ff, k), be.set_tensor(t, wd, m2, ff)
+    x = torch.from_numpy(np.random.default_rng(4).standard_normal((1, k)).astype(np.float32) * 3).cuda()
+    q8 = be.Q8Scratch(ff)
+    for it in range(3):                                     # the arrival counters must re-arm themselves
+        a = be.fused_up_gate(up, gate, x, unary="silu", q8_out=q8)
+        assert q8.valid, "eligible shape: the hand-off must be taken"
+        y = be.mul_mat(down, a, q8_in=q8)
+        y_plain = be.mul_mat(down, a)
+        assert torch.equal(y, y_plain), f"iteration {it}"
+        x = x * 0.5 + 0.25
+    an = a.cpu().numpy()
+    yq = oracle.mul_mat_q8_1(t, wd, an, m2, variant="b200")
+    assert np.abs(y.cpu().numpy() - yq).max() <= 2e-5 * rms(yq)
+    # the image itself: q / d / sums of the oracle's quantiser
+    q_ref, d_ref = oracle.quantize_q8_1_b200(an)[:2]
+    img = q8.buf.cpu().numpy()
+    assert np.array_equal(img[:ff].view(np.int8), np.asarray(q_ref, np.int8).reshape(-1))
+    assert np.array_equal(img[ff:ff + 4 * (ff // 32)].view(np.float32), np.asarray(d_ref, np.float32).reshape(-1))
+    assert not img[ff + 8 * (ff // 32): ff + 12 * (ff // 32)].any(), "arrival counters must be back at zero"
+
+
+@pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K"])
+@pytest.mark.parametrize("n", [1, 2, 5])
+def test_mat_vec_bias(be, oracle, name, n):
+    """bias operand of the mat-vec kernels (fused trailing ADD of ggml_cuda_mul_mat_q, ggml-cuda.cu:2590-2600)."""
+    import ctypes
+    import ik_llama_cpp_b200 as pkg
+    t = GGML_TYPE[name]
+    m, k = 322, 1024
+    wire = make_wire(oracle, name, m, k, seed=81)
+    w = be.set_tensor(t, wire, m, k)
+    x = np.random.default_rng(12).standard_normal((n, k)).astype(np.float32)
+    bias = np.random.default_rng(13).standard_normal(m).astype(np.float32)
+    xg, bg = torch.from_numpy(x).cuda(), torch.from_numpy(bias).cuda()
+    y = torch.empty((n, m), dtype=torch.float32, device="cuda")
+    pkg._lib.check(pkg.lib().b200q_mul_mat_vec(t, w.ptr, xg.data_ptr(), y.data_ptr(), m, k, n, k, bg.data_ptr(), torch.cuda.current_stream().cuda_stream), "bias")
+    yq = oracle.mul_mat_q8_1(t, wire, x, m, variant="b200") + bias[None, :]
+    assert np.abs(y.cpu().numpy() - yq).max() <= 2e-5 * rms(yq)
 
 
 @pytest.mark.parametrize("name", ALL_TYPES)
@@ -216,7 +298,7 @@ def test_gemm_multi_tensor_launch_qkv(be, oracle, name, n):
 
 
 @pytest.mark.parametrize("name,m,k", [("IQ4_NL", 1000, 256), ("IQ4_NL", 384, 1024), ("Q4_K", 1000, 256), ("Q6_K", 384, 1024), ("IQ2_BN", 256, 512)])
-@pytest.mark.parametrize("unary,limit", [("silu", 0.0), ("gelu", 0.0), ("relu", 0.0), ("silu", 1.5)])
+@pytest.mark.parametrize("unary,limit", [("silu", 0.0), ("gelu", 0.0), ("relu", 0.0), ("silu", 1.5), ("swiglu_oai", 0.0)])
 @pytest.mark.parametrize("fuse", [0, 1])
 def test_fused_up_gate_gemm(be, oracle, name, m, k, unary, limit, fuse):
     """GGML_OP_FUSED_UP_GATE for n > 8.  fuse=1 with k=256 (split-K 1): unary-mul inside the gate GEMM's epilogue; everything else:
@@ -237,11 +319,7 @@ def test_fused_up_gate_gemm(be, oracle, name, m, k, unary, limit, fuse):
     finally:
         pkg.lib().b200q_set_option(b"fuse_epilogue", 0)
     u, g = be.mul_mat(up, xg, x_bf16=xb).double(), be.mul_mat(gate, xg, x_bf16=xb).double()
-    if limit > 0:
-        g = g.clamp(max=limit); u = u.clamp(-limit, limit)
-    act = {"silu": lambda v: v / (1 + torch.exp(-v)), "gelu": lambda v: 0.5 * v * (1 + torch.tanh(0.79788456080286535588 * v * (1 + 0.044715 * v * v))),
-           "relu": lambda v: v.clamp(min=0)}[unary]
-    ref = (act(g) * u)
+    ref = torch.from_numpy(glu_ref(unary, g.cpu().numpy(), u.cpu().numpy(), limit)).cuda()
     scale = float(ref.pow(2).mean().sqrt())
     assert float((y.double() - ref).abs().max()) <= 2e-5 * scale
     assert float((y2.double() - ref).abs().max()) <= 2e-5 * scale
@@ -249,10 +327,7 @@ def test_fused_up_gate_gemm(be, oracle, name, m, k, unary, limit, fuse):
     # and against exact math on a few tokens (bf16-operand noise only)
     cols = [0, 33, 69]
     ue, ge = oracle.mul_mat_exact(t, wu, x[cols], m).astype(np.float64), oracle.mul_mat_exact(t, wg, x[cols], m).astype(np.float64)
-    if limit > 0:
-        ge = np.minimum(ge, limit); ue = np.clip(ue, -limit, limit)
-    acte = {"silu": ge / (1 + np.exp(-ge)), "gelu": 0.5 * ge * (1 + np.tanh(0.79788456080286535588 * ge * (1 + 0.044715 * ge * ge))), "relu": np.maximum(ge, 0)}[unary]
-    assert nmse(y[cols].cpu().numpy(), acte * ue) <= (2e-4 if limit == 0 else 1e-3)     # the clamp saturates most outputs: sign flips of tiny values dominate
+    assert nmse(y[cols].cpu().numpy(), glu_ref(unary, ge, ue, limit)) <= (2e-4 if limit == 0 else 1e-3)
 
 
 def test_gemm_llama_shape_properties(be, oracle):
