@@ -107,7 +107,9 @@ def random_planes_iq4nl(be, torch, m, k, gen, scale):
 class Model:
     """Llama-3-8B matmul skeleton, optionally one tensor-parallel shard (rank r of tp)."""
 
-    def __init__(self, be, torch, n_layer, tp=1, rank=0, seed=1234):
+    def __init__(self, be, torch, n_layer, tp=1, rank=0, seed=1234, collective=True):
+        """collective=False: only the weights of rank `rank`'s shard (no reducer, no head): used by rank 0 to rebuild the other ranks'
+        shards for the tensor-parallel correctness gate."""
         self.be, self.torch, self.tp, self.n_layer = be, torch, tp, n_layer
         gen = torch.Generator(device="cuda")
         gen.manual_seed(seed + rank)
@@ -119,22 +121,24 @@ class Model:
                 wq=mk(N_EMBD // tp, N_EMBD, s_e), wk=mk(N_KV_DIM // tp, N_EMBD, s_e), wv=mk(N_KV_DIM // tp, N_EMBD, s_e),
                 wo=mk(N_EMBD, N_EMBD // tp, s_e * 2), up=mk(N_FF // tp, N_EMBD, s_e * 2), gate=mk(N_FF // tp, N_EMBD, s_e * 2),
                 down=mk(N_EMBD, N_FF // tp, s_f * 4)))
-        self.head = mk(N_VOCAB // tp, N_EMBD, s_e)
+        self.head = mk(N_VOCAB // tp, N_EMBD, s_e) if collective else None
         self.launches_tg = n_layer * 4 + 1
         self.reducer = None
         self.fused_tp = False
-        if tp > 1 and os.environ.get("B200Q_NCCL_REDUCE", "0") != "1":
+        self.bf16_reduce = False
+        if tp > 1 and collective and os.environ.get("B200Q_NCCL_REDUCE", "0") != "1":
             self.reducer = be.NvlsReducer(512 * N_EMBD)
             self.fused_tp = self.reducer.ok and os.environ.get("B200Q_TP_FUSED", "1") == "1"
+            self.bf16_reduce = self.reducer.ok and os.environ.get("B200Q_TP_BF16_REDUCE", "1") == "1"
             self.launches_tg += 2 * n_layer if (self.reducer.ok and not self.fused_tp) else 0
-        self.weight_bytes = sum(t.nbytes_wire for L in self.layers for t in L.values()) + self.head.nbytes_wire
+        self.weight_bytes = sum(t.nbytes_wire for L in self.layers for t in L.values()) + (self.head.nbytes_wire if self.head is not None else 0)
 
     def alloc(self, n):
         t, tp = self.torch, self.tp
         f = lambda *s: t.empty(s, dtype=t.float32, device="cuda")
         self.x = f(n, N_EMBD); self.q = f(n, N_EMBD // tp); self.kk = f(n, N_KV_DIM // tp); self.v = f(n, N_KV_DIM // tp)
         self.h = f(n, N_EMBD); self.a = f(n, N_FF // tp); self.x2 = f(n, N_EMBD); self.logits = f(1, N_VOCAB // tp)
-        self.q8a = be.Q8Scratch(N_FF // tp) if n == 1 and hasattr(be, "Q8Scratch") else None
+        self.q8a = self.be.Q8Scratch(N_FF // tp) if n == 1 else None
         self.u = f(n, N_FF // tp) if n > 8 else None
         self.g = f(n, N_FF // tp) if n > 8 else None
         b = lambda *s: t.empty(s, dtype=t.bfloat16, device="cuda")
@@ -148,7 +152,7 @@ class Model:
                 import torch.distributed as dist
                 dist.all_reduce(t)
 
-    def step_tg_fused_tp(self):
+    def step_tg_fused_tp(self, with_head=True):
         """tp > 1: the two GGML_OP_REDUCE per layer are fused into the mat-vec kernels (multimem.red from the wo / ffn_down epilogue,
         flag wait in the prologue of the next mat-vec): 4 launches per layer like the single-GPU graph, no reduce kernel."""
         be, r = self.be, self.reducer
@@ -159,12 +163,15 @@ class Model:
             be.mul_mat_vec_tp([L["up"]], None, [self.a], r, reduce_in=True, gate=L["gate"], unary="silu")
             be.mul_mat_vec_tp([L["down"]], self.a, None, r, reduce_out=True)
             first = False
-        be.mul_mat_vec_tp([self.head], None, [self.logits], r, reduce_in=True)
+        if with_head:
+            be.mul_mat_vec_tp([self.head], None, [self.logits], r, reduce_in=True)
+        else:               # (correctness gate) a consumer that only materialises the reduced vector
+            be.mul_mat_vec_tp([self.layers[0]["wq"]], None, [self.q], r, reduce_in=True)
 
-    def step_tg(self):
+    def step_tg(self, with_head=True):
         be = self.be
         if self.tp > 1 and self.fused_tp:
-            return self.step_tg_fused_tp()
+            return self.step_tg_fused_tp(with_head)
         x = self.x
         for L in self.layers:
             be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v])
@@ -173,22 +180,84 @@ class Model:
             be.fused_up_gate(L["up"], L["gate"], self.h, "silu", out=self.a, q8_out=self.q8a)
             be.mul_mat(L["down"], self.a, out=self.x2, q8_in=self.q8a); self.allreduce(self.x2)
             x = self.x2
-        be.mul_mat(self.head, x, out=self.logits)
+        if with_head:
+            be.mul_mat(self.head, x, out=self.logits)
 
-    def step_pp(self):
+    def step_pp(self, with_head=True):
         be, t = self.be, self.torch
         x = self.x
-        for L in self.layers:
-            be.convert_activations(x, self.xb)          # f32 -> bf16 once per distinct activation (shared by Q,K,V)
+        have_xb = False
+        for li, L in enumerate(self.layers):
+            if not have_xb:
+                be.convert_activations(x, self.xb)      # f32 -> bf16 once per distinct activation (shared by Q,K,V)
             be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v], x_bf16=self.xb)      # one launch
             be.convert_activations(self.q, self.qb)
-            be.mul_mat(L["wo"], self.q, out=self.h, x_bf16=self.qb); self.allreduce(self.h)
-            be.convert_activations(self.h, self.hb)
+            be.mul_mat(L["wo"], self.q, out=self.h, x_bf16=self.qb)
+            if self.bf16_reduce:
+                # GGML_OP_REDUCE with a bf16 payload (the reference casts the partial when ne[1] > 32): two-shot in the switch, the result
+                # is the bf16 activation operand of the next GEMM (no f32 -> bf16 pass)
+                self.reducer.all_reduce_bf16(self.h, out_bf16=self.hb)
+            else:
+                self.allreduce(self.h)
+                be.convert_activations(self.h, self.hb)
             # FUSED_UP_GATE (n > 8): up GEMM, gate GEMM with silu(gate)*up in its epilogue; it also emits the bf16 operand of ffn_down
             be.fused_up_gate(L["up"], L["gate"], self.h, "silu", out=self.a, x_bf16=self.hb, out_bf16=self.ab)
-            be.mul_mat(L["down"], self.a, out=self.x2, x_bf16=self.ab); self.allreduce(self.x2)
+            be.mul_mat(L["down"], self.a, out=self.x2, x_bf16=self.ab)
+            if self.bf16_reduce:
+                last = li == len(self.layers) - 1
+                self.reducer.all_reduce_bf16(self.x2, out_bf16=self.xb, out_f32=self.x2 if last else None)    # f32 copy only where a mat-vec (head) reads it
+                have_xb = True
+            else:
+                self.allreduce(self.x2)
             x = self.x2
-        be.mul_mat(self.head, x[-1:], out=self.logits)
+        if with_head:
+            be.mul_mat(self.head, x[-1:], out=self.logits)
+
+
+def tp_correctness_gate(be, torch, dist, model, rank, world, n, n_check_layers=2, tol=5e-4):
+    """N > 1 only, before anything is timed: the reduced hidden state of a 2-layer slice of THIS model, computed by the tensor-parallel
+    path (all ranks, the collectives under test), must match what rank 0 gets by rebuilding every rank's shard locally (same seeds),
+    running each shard through the single-GPU kernels and summing the row-parallel partials in f64.  NMSE > tol -> every rank exits non-zero."""
+    saved = model.layers
+    model.layers = saved[:n_check_layers]
+    model.alloc(n)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(777)
+    x0 = torch.randn(n, N_EMBD, device="cuda", generator=gen)          # identical on every rank
+    model.x.copy_(x0)
+    if n == 1:
+        model.step_tg(with_head=False)
+        torch.cuda.synchronize()
+        got = model.reducer.reduced_view(N_EMBD)[None, :].double() if model.fused_tp else model.x2.double()
+    else:
+        model.step_pp(with_head=False)
+        torch.cuda.synchronize()
+        got = model.x2.double()
+    verdict = torch.zeros(1, device="cuda")
+    err = float("nan")
+    if rank == 0:
+        shards = [model if r == 0 else Model(be, torch, n_check_layers, tp=world, rank=r, collective=False) for r in range(world)]
+        x = x0.clone()
+        for li in range(n_check_layers):
+            part = torch.zeros(n, N_EMBD, dtype=torch.float64, device="cuda")
+            for sh in shards:
+                L = sh.layers[li]
+                q = be.mul_mat(L["wq"], x)                               # (wk / wv feed attention, which is not on this path)
+                part += be.mul_mat(L["wo"], q).double()
+            h = part.float()
+            part = torch.zeros(n, N_EMBD, dtype=torch.float64, device="cuda")
+            for sh in shards:
+                L = sh.layers[li]
+                a = be.fused_up_gate(L["up"], L["gate"], h, "silu")
+                part += be.mul_mat(L["down"], a).double()
+            x = part.float()
+        ref = x.double()
+        err = float(((got - ref) ** 2).sum() / (ref ** 2).sum())
+        verdict[0] = 0.0 if err <= tol else 1.0
+        del shards
+    dist.all_reduce(verdict)
+    model.layers = saved
+    torch.cuda.empty_cache()
+    return err, float(verdict.item()) == 0.0
 
 
 def time_graph(torch, fn, steps, warmup, dist=None, pre=None, post=None):
@@ -322,7 +391,24 @@ def main():
 
     model = Model(be, torch, args.layers, tp=world, rank=rank)
     if model.fused_tp:
-        config["reduce"] = "fused into the mat-vec kernels (multimem.red from the wo/ffn_down epilogue, flag wait in the next prologue); pp512: b200q NVLS kernel"
+        config["reduce"] = "tg: fused into the mat-vec kernels (multimem.red from the wo/ffn_down epilogue, flag wait in the next prologue); pp512: " + \
+            ("two-shot bf16 NVLS kernel (multimem.ld_reduce + multimem.st)" if model.bf16_reduce else "one-shot f32 NVLS kernel")
+    # ---------------- N > 1: correctness gate on the collectives, before anything is timed ----------------
+    if world > 1:
+        gate = {}
+        ok_all = True
+        for n_chk, nm in ((1, "tg"), (512, "pp512")):
+            if nm == "pp512" and args.no_pp:
+                continue
+            err, ok = tp_correctness_gate(be, torch, dist, model, rank, world, n_chk)
+            gate[nm] = err
+            ok_all = ok_all and ok
+        config["tp_gate"] = {"nmse_vs_unsharded": gate, "tol": 5e-4, "layers_checked": 2}
+        if not ok_all:
+            if rank == 0:
+                print(f"bench.py: tensor-parallel correctness gate FAILED: NMSE of the reduced hidden state vs the unsharded result = {gate}", file=sys.stderr)
+            dist.destroy_process_group()
+            return 3
     # ---------------- tg128 ----------------
     model.alloc(1)
     x_host = torch.randn(1, N_EMBD).pin_memory()

@@ -256,6 +256,12 @@ class NvlsComm(ctypes.Structure):
                 ("world_size", ctypes.c_uint32), ("seq_counter", c_void_p), ("cta_counter", c_void_p)]
 
 
+class NvlsStage(ctypes.Structure):
+    """struct b200q_nvls_stage of include/b200q.h"""
+    _fields_ = [("mc_stage", c_void_p), ("local_stage", c_void_p), ("stage_elems", c_int64), ("mc_flag", c_void_p), ("local_flag", c_void_p),
+                ("world_size", ctypes.c_uint32), ("rank", ctypes.c_uint32), ("state", c_void_p)]
+
+
 def mul_mat_vec_tp(ws: list[QuantTensor], x: torch.Tensor | None, outs: list[torch.Tensor] | None, reducer: "NvlsReducer",
                    reduce_in: bool = False, reduce_out: bool = False, gate: QuantTensor | None = None, unary: str = "silu", limit: float = 0.0):
     """Tensor-parallel decode (n = 1) with GGML_OP_REDUCE fused into the mat-vec kernels (b200q_mul_mat_vec_tp).
@@ -293,14 +299,18 @@ class NvlsReducer:
         dev = torch.device("cuda", torch.cuda.current_device())
         self.ok = False
         try:
-            self.buf = symm.empty(2 * self.stride + 64, dtype=torch.float32, device=dev)
+            # [2 parity buffers of `stride` f32][64 f32: flag words][bf16 staging of `stride` elements (two-shot all-reduce)]
+            self.buf = symm.empty(2 * self.stride + 64 + (self.stride + 1) // 2, dtype=torch.float32, device=dev)
             self.hdl = symm.rendezvous(self.buf, self.group)
             self.mc = int(self.hdl.multicast_ptr) if self.hdl.has_multicast_support else 0
             if self.mc:
                 self.buf.zero_()
                 self.local = self.buf.data_ptr()
                 self.flag_off = 2 * self.stride * 4
-                self.state = torch.zeros(8, dtype=torch.int32, device=dev)      # [0] seq counter, [4] cta counter
+                self.state = torch.zeros(16, dtype=torch.int32, device=dev)     # [0] seq counter, [4] cta counter, [8..11] two-shot state
+                self.rank = dist.get_rank(self.group)
+                self.flag2_off = self.flag_off + 128                          # second flag word (own 128-byte line): two-shot bf16 all-reduce
+                self.stage_off = (2 * self.stride + 64) * 4
                 torch.cuda.synchronize()
                 self.hdl.barrier()
                 self.ok = True
@@ -323,6 +333,28 @@ class NvlsReducer:
         seq = int(self.state[0].item())
         par = (seq + use) & 1
         return self.buf[par * self.stride: par * self.stride + n].clone()
+
+    def stage(self):
+        """ctypes b200q_nvls_stage for b200q_reduce_sum_nvls_bf16."""
+        assert self.ok
+        if not hasattr(self, "_stage"):
+            self._stage = NvlsStage(self.mc + self.stage_off, self.local + self.stage_off, self.stride, self.mc + self.flag2_off, self.local + self.flag2_off,
+                                    self.world, self.rank, self.state.data_ptr() + 32)
+        return self._stage
+
+    def all_reduce_bf16(self, t: torch.Tensor, out_bf16: torch.Tensor | None = None, out_f32: torch.Tensor | None = None):
+        """Sum over ranks of a contiguous f32 tensor with a bf16 payload (two-shot, in the switch): the reference's reduce for ne[1] > 32.
+        out_bf16: bf16 result (activation operand of the next GEMM); out_f32: f32 result (may alias t).  At least one."""
+        assert self.ok and t.dtype == torch.float32 and t.is_contiguous() and t.numel() % 8 == 0 and t.numel() <= self.stride
+        assert out_bf16 is not None or out_f32 is not None
+        if out_bf16 is not None:
+            assert out_bf16.dtype == torch.bfloat16 and out_bf16.is_contiguous() and out_bf16.numel() == t.numel()
+        if out_f32 is not None:
+            assert out_f32.dtype == torch.float32 and out_f32.is_contiguous() and out_f32.numel() == t.numel()
+        check(_lib.lib().b200q_reduce_sum_nvls_bf16(t.data_ptr(), out_f32.data_ptr() if out_f32 is not None else None,
+                                                    out_bf16.data_ptr() if out_bf16 is not None else None, t.numel(), ctypes.byref(self.stage()), _stream()),
+              "b200q_reduce_sum_nvls_bf16")
+        return out_bf16 if out_bf16 is not None else out_f32
 
     def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
         """In-place sum over ranks of a contiguous f32 tensor."""

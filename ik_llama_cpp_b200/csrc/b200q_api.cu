@@ -11,6 +11,9 @@
 int b200q_launch_allreduce_nvls(const float * in, float * out, int64_t n, void * mc_base, void * local_base, int64_t stride,
                                 void * mc_flag, const void * local_flag, uint32_t world, void * seq, void * cta_counter, int sm_count, cudaStream_t st);
 
+int b200q_launch_allreduce_nvls_2shot(const float * in, float * out_f32, void * out_bf16, int64_t n, void * mc_stage, void * local_stage,
+                                      void * mc_flag, const void * local_flag, uint32_t world, uint32_t rank, void * state, int sm_count, cudaStream_t st);
+
 namespace {
 thread_local char g_err[512] = "";
 int fail(int code, const char * fmt, ...) {
@@ -40,15 +43,23 @@ int check_launch(int rc, const char * what) {
     return fail(B200Q_E_CUDA, "%s: launch failed (%d)", what, rc);
 }
 // per-thread scratch for the host-buffer entry points
-struct scratch { void * p = nullptr; size_t n = 0; };
-int ensure(scratch & s, size_t n) {
-    if (s.n >= n) return 0;
-    if (s.p) cudaFree(s.p);
-    s.p = nullptr; s.n = 0;
-    cudaError_t e = cudaMalloc(&s.p, n);
-    if (e != cudaSuccess) return cuda_fail("cudaMalloc(scratch)", e);
-    s.n = n; return 0;
+// (device-aware: a loader thread may serve several GPUs in turn; an allocation made on another device is never reused)
+struct scratch { void * p = nullptr; size_t n = 0; int dev = -1; };
+void release(scratch & s) {
+    if (!s.p) return;
+    int cur = 0; cudaGetDevice(&cur);
+    if (s.dev >= 0 && s.dev != cur) { cudaSetDevice(s.dev); cudaFree(s.p); cudaSetDevice(cur); } else cudaFree(s.p);
+    s.p = nullptr; s.n = 0; s.dev = -1;
 }
+int ensure(scratch & s, size_t n) {
+    int cur = 0; cudaGetDevice(&cur);
+    if (s.p && s.dev == cur && s.n >= n) return 0;
+    release(s);
+    cudaError_t e = cudaMalloc(&s.p, n);
+    if (e != cudaSuccess) { s.p = nullptr; return cuda_fail("cudaMalloc(scratch)", e); }
+    s.n = n; s.dev = cur; return 0;
+}
+constexpr size_t STAGE_KEEP = (size_t)64 << 20;      // upload staging above this size is freed right after use (model load)
 thread_local scratch g_x, g_y, g_ws, g_stage;
 // programmatic dependent launch for the decode kernels (default on; B200Q_PDL=0 or b200q_set_option("pdl",0) disables)
 int & opt_ring() { static int v = [] { const char * e = getenv("B200Q_RING"); return e ? atoi(e) : 1; }(); return v; }
@@ -96,6 +107,7 @@ int b200q_set_tensor(int type, const void * wire_host, void * planes_dev, int64_
     if ((e = cudaMemcpyAsync(g_stage.p, wire_host, nbytes, cudaMemcpyHostToDevice, st)) != cudaSuccess) return cuda_fail("set_tensor H2D", e);
     if ((rc = check_launch(b200q_launch_repack(g_stage.p, planes_dev, L, 0, st), "b200q_set_tensor"))) return rc;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail("set_tensor sync", e);
+    if (g_stage.n > STAGE_KEEP) release(g_stage);
     return B200Q_OK;
 }
 int b200q_get_tensor(int type, const void * planes_dev, void * wire_host, int64_t m, int64_t k, void * stream) {
@@ -107,6 +119,7 @@ int b200q_get_tensor(int type, const void * planes_dev, void * wire_host, int64_
     if ((rc = check_launch(b200q_launch_repack(g_stage.p, const_cast<void *>(planes_dev), L, 1, st), "b200q_get_tensor"))) return rc;
     if ((e = cudaMemcpyAsync(wire_host, g_stage.p, nbytes, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return cuda_fail("get_tensor D2H", e);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return cuda_fail("get_tensor sync", e);
+    if (g_stage.n > STAGE_KEEP) release(g_stage);
     return B200Q_OK;
 }
 
@@ -225,6 +238,15 @@ int b200q_reduce_sum_nvls(const float * in, float * out, int64_t n, void * mc_ba
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_reduce_sum_nvls: no CUDA device");
     return check_launch(b200q_launch_allreduce_nvls(in, out, n, mc_base, local_base, parity_stride, mc_flag, local_flag, world_size, seq_counter, cta_counter,
                                                     di.sm_count, (cudaStream_t)stream), "b200q_reduce_sum_nvls");
+}
+
+int b200q_reduce_sum_nvls_bf16(const float * in, float * out_f32, void * out_bf16, int64_t n, const b200q_nvls_stage * sg, void * stream) {
+    if (!in || (!out_f32 && !out_bf16) || !sg || !sg->mc_stage || !sg->local_stage || !sg->mc_flag || !sg->local_flag || !sg->state || sg->world_size < 2 || sg->rank >= sg->world_size)
+        return fail(B200Q_E_ARG, "b200q_reduce_sum_nvls_bf16: bad argument");
+    if (n > sg->stage_elems || (n & 7)) return fail(B200Q_E_SHAPE, "b200q_reduce_sum_nvls_bf16: n must be a multiple of 8 and fit the staging buffer");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_reduce_sum_nvls_bf16: no CUDA device");
+    return check_launch(b200q_launch_allreduce_nvls_2shot(in, out_f32, out_bf16, n, sg->mc_stage, sg->local_stage, sg->mc_flag, sg->local_flag, sg->world_size, sg->rank,
+                                                          sg->state, di.sm_count, (cudaStream_t)stream), "b200q_reduce_sum_nvls_bf16");
 }
 
 size_t b200q_mul_mat_workspace(int type, int64_t m, int64_t k, int64_t n) { return n <= 8 ? 0 : b200q_gemm_workspace_bytes(type, m, k, n); }

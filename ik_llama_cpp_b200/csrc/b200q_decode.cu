@@ -703,10 +703,11 @@ int b200q_launch_dequant_bf16(const void * W, const b200q_layout & L, void * out
 template <int TYPE, int NCOLS, bool UPGATE>
 static int launch_mmvq_t(const mmvq_args & a, int sm_count, bool pdl, cudaStream_t st) {
     const size_t smem = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static size_t configured[B200Q_MAX_DEVICES] = {};     // function attributes are per device
+    const int dev = b200q_current_device();
+    if (smem > 48 * 1024 && smem > configured[dev]) {
         if (cudaFuncSetAttribute(k_mmvq<TYPE, NCOLS, UPGATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
-        configured = smem;
+        configured[dev] = smem;
     }
     // one warp per row, one CTA per SM; shrink the CTA when there are fewer rows than warps
     int nwarps = 16;

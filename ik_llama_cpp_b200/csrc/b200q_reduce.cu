@@ -75,7 +75,89 @@ __global__ void __launch_bounds__(512) k_allreduce_nvls(const float * __restrict
     if (blockIdx.x == gridDim.x - 1)
         for (int64_t i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) out[i] = __ldcv(local_buf + i);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Two-shot bf16 all-reduce for the prefill-sized REDUCE (the reference casts the partial to bf16/f16 when ne[1] > 32,
+// src/llama-build-context.cpp:1198-1200, and runs reduce-scatter + all-gather, ggml-cuda/reduce.cu:306-372).  One kernel:
+//   (a) f32 partial -> bf16 into this rank's slice-addressable STAGING buffer in symmetric memory (local stores);
+//       barrier A (multicast flag): every rank's staging is complete;
+//   (b) reduce-scatter + all-gather in the switch: rank r owns slice r: multimem.ld_reduce (f32 accumulation of the world's bf16
+//       values inside the NVSwitch) and multimem.st of the sum back into EVERY rank's staging (16 bytes per instruction);
+//       barrier B: every slice has been broadcast;
+//   (c) the fully reduced bf16 vector is copied out of the local staging (bf16 for the next GEMM's activation operand and / or f32).
+// Per GPU and reduce the NVLink carries ~2 x n x 2 bytes (one-shot f32: world x n x 4 inbound); the payload of pp512 is 4 MiB.
+// state: rank-local u32[4] {reduces done, CTA counter a, CTA counter b, pad}; the flag counts 2 x world per reduce.
+// Safe with ONE staging buffer: (a) of reduce k+1 follows this rank's (c) of reduce k in stream order, and no peer touches this
+// rank's staging outside its own phase (b), which lies between the two barriers.
+// ---------------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 mm_ld_reduce_bf16x8(const void * mc) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mm_st_b128(void * mc, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    uint32_t r; asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r;      // low half = a
+}
+__device__ __forceinline__ void grid_rendezvous(uint32_t * cta_counter, uint32_t * mc_flag, const uint32_t * local_flag, uint32_t target,
+                                                uint32_t * seq_to_bump, uint32_t seq_next) {
+    __threadfence_system();                     // this thread's staging stores / multimem stores are performed system-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(cta_counter, 1u) == gridDim.x - 1) {
+            *cta_counter = 0;
+            if (seq_to_bump) *reinterpret_cast<volatile uint32_t *>(seq_to_bump) = seq_next;
+            __threadfence();
+            mm_red_add_u32_release(mc_flag, 1u);
+        }
+        while ((int32_t)(ld_acquire_sys(local_flag) - target) < 0) __nanosleep(32);
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(512) k_allreduce_nvls_2shot(const float * __restrict__ in, float * __restrict__ out_f32, uint4 * __restrict__ out_bf16, int64_t n8,
+                                                              uint4 * mc_stage, uint4 * local_stage, uint32_t * mc_flag, const uint32_t * local_flag,
+                                                              uint32_t world, uint32_t rank, uint32_t * state) {
+    const uint32_t s = *reinterpret_cast<volatile uint32_t *>(state);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    // (a)
+    for (int64_t i = tid; i < n8; i += nth) {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4 *>(in) + 2 * i + 1);
+        local_stage[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    grid_rendezvous(state + 1, mc_flag, local_flag, world * (2 * s + 1), nullptr, 0);
+    // (b)
+    {
+        const int64_t per = (n8 + world - 1) / world, b0 = per * rank, b1 = min(n8, b0 + per);
+        for (int64_t i = b0 + tid; i < b1; i += nth) mm_st_b128(mc_stage + i, mm_ld_reduce_bf16x8(mc_stage + i));
+    }
+    grid_rendezvous(state + 2, mc_flag, local_flag, world * (2 * s + 2), state, s + 1);
+    // (c)
+    for (int64_t i = tid; i < n8; i += nth) {
+        const uint4 v = __ldcv(local_stage + i);
+        if (out_bf16) out_bf16[i] = v;
+        if (out_f32) {
+            float4 a, b;
+            a.x = __uint_as_float(v.x << 16); a.y = __uint_as_float(v.x & 0xFFFF0000u); a.z = __uint_as_float(v.y << 16); a.w = __uint_as_float(v.y & 0xFFFF0000u);
+            b.x = __uint_as_float(v.z << 16); b.y = __uint_as_float(v.z & 0xFFFF0000u); b.z = __uint_as_float(v.w << 16); b.w = __uint_as_float(v.w & 0xFFFF0000u);
+            reinterpret_cast<float4 *>(out_f32)[2 * i] = a; reinterpret_cast<float4 *>(out_f32)[2 * i + 1] = b;
+        }
+    }
+}
 }  // namespace
+
+int b200q_launch_allreduce_nvls_2shot(const float * in, float * out_f32, void * out_bf16, int64_t n, void * mc_stage, void * local_stage,
+                                      void * mc_flag, const void * local_flag, uint32_t world, uint32_t rank, void * state, int sm_count, cudaStream_t st) {
+    if (n <= 0 || (n & 7) || ((uintptr_t)in & 15) || ((uintptr_t)out_f32 & 15) || ((uintptr_t)out_bf16 & 15) || ((uintptr_t)mc_stage & 15) || ((uintptr_t)local_stage & 15)) return -2;
+    int64_t grid = (n / 8 + 2047) / 2048;          // >= 4 vectors per thread
+    if (grid > sm_count) grid = sm_count;          // all CTAs must be co-resident: they spin on the flag
+    if (grid < 1) grid = 1;
+    k_allreduce_nvls_2shot<<<(unsigned)grid, 512, 0, st>>>(in, out_f32, (uint4 *)out_bf16, n / 8, (uint4 *)mc_stage, (uint4 *)local_stage,
+                                                          (uint32_t *)mc_flag, (const uint32_t *)local_flag, world, rank, (uint32_t *)state);
+    return (int)cudaGetLastError();
+}
 
 int b200q_launch_allreduce_nvls(const float * in, float * out, int64_t n, void * mc_base, void * local_base, int64_t stride,
                                 void * mc_flag, const void * local_flag, uint32_t world, void * seq, void * cta_counter, int sm_count, cudaStream_t st) {

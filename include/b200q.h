@@ -105,6 +105,18 @@ B200Q_API int b200q_fused_up_gate_gemm_bf16(int type, const void * W_up, const v
 B200Q_API int b200q_reduce_sum_nvls(const float * in, float * out, int64_t n, void * mc_base, void * local_base, int64_t parity_stride,
                           void * mc_flag, const void * local_flag, uint32_t world_size, void * seq_counter, void * cta_counter, void * stream);
 
+/* Prefill-sized REDUCE: two-shot bf16 all-reduce in ONE kernel (the reference casts the partial to bf16/f16 when ne[1] > 32,
+ * src/llama-build-context.cpp:1198-1200, and runs reduce-scatter + all-gather, ggml-cuda/reduce.cu:306-372): f32 partial -> bf16 staging in
+ * symmetric memory, barrier, multimem.ld_reduce of the rank's 1/world slice (f32 accumulation in the switch) + multimem.st of the sum to every
+ * rank, barrier, copy-out as bf16 (out_bf16: the activation operand of the next GEMM) and / or f32 (out_f32).  `state`: rank-local u32[4], zero. */
+typedef struct b200q_nvls_stage {
+    void * mc_stage; void * local_stage; int64_t stage_elems;   /* bf16 staging buffer: multicast address / this rank's mapping / capacity in elements */
+    void * mc_flag; const void * local_flag;                    /* u32 flag word in symmetric memory (multicast / local), zero-initialised */
+    uint32_t world_size; uint32_t rank;
+    void * state;
+} b200q_nvls_stage;
+B200Q_API int b200q_reduce_sum_nvls_bf16(const float * in, float * out_f32, void * out_bf16, int64_t n, const b200q_nvls_stage * stage, void * stream);
+
 /* ---- tensor-parallel decode (n = 1): the GGML_OP_REDUCE after a row-parallel mat-vec fused INTO the mat-vec kernels ----
  * (reference: ggml_cuda_op_reduce runs as its own node after wo / ffn_down under -sm graph, ggml-cuda/reduce.cu:125-598).
  * Same symmetric buffers as b200q_reduce_sum_nvls.  reduce_out: the kernel's epilogue adds its partial rows into every rank's copy

@@ -48,6 +48,36 @@ def _worker(rank, world, port, q):
                 inner = sum(float(r + it) for r in range(world))
                 assert torch.equal(y, torch.full_like(y, inner * 0.5 * world)), it
             res["graph"] = True
+        if red.ok:
+            # ---- two-shot bf16 all-reduce (prefill-sized REDUCE): small integers are exact in bf16 and in the switch's f32 accumulation ----
+            for n in (8, 4096, 4104, 512 * 4096):
+                for it in range(3):
+                    t = (torch.arange(n, device="cuda") % 5 - 2 + (rank + it) % 3).float()
+                    exp = sum((torch.arange(n, device="cuda") % 5 - 2 + (r + it) % 3) for r in range(world)).float()
+                    ob = torch.empty(n, dtype=torch.bfloat16, device="cuda"); of = torch.empty(n, device="cuda")
+                    red.all_reduce_bf16(t, out_bf16=ob, out_f32=of)
+                    assert torch.equal(of, exp) and torch.equal(ob.float(), exp), ("2shot", n, it)
+            # in place (out_f32 aliases the input), bf16-rounded random values: result == sum of the bf16-rounded partials (f32 accumulation, one rounding)
+            gen = torch.Generator(device="cuda"); gen.manual_seed(1234)
+            parts = [torch.randn(64 * 4096, device="cuda", generator=gen) for _ in range(world)]      # same on every rank
+            t = parts[rank].clone()
+            red.all_reduce_bf16(t, out_f32=t)
+            exact = sum(p.to(torch.bfloat16).double() for p in parts)
+            assert torch.equal(t, exact.float().to(torch.bfloat16).float()) or float((t.double() - exact).abs().max()) <= float(exact.abs().max()) * 2 ** -8
+            # interleaved with the one-shot f32 reduce and replayed from a CUDA graph
+            x = torch.zeros(8192, device="cuda"); y = torch.empty_like(x); yb = torch.empty(8192, dtype=torch.bfloat16, device="cuda")
+            s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                y.copy_(x); red.all_reduce_bf16(y, out_bf16=yb, out_f32=y); red.all_reduce(y)
+            torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                y.copy_(x); red.all_reduce_bf16(y, out_bf16=yb, out_f32=y); red.all_reduce(y); red.all_reduce_bf16(y, out_f32=y)
+            for it in range(4):
+                x.fill_(float((rank + it) % 2)); g.replay(); torch.cuda.synchronize()
+                inner = sum(float((r + it) % 2) for r in range(world))
+                assert torch.equal(y, torch.full_like(y, inner * world * world)), ("2shot graph", it)
+            res["two_shot"] = True
         # row-parallel (K-split) mat-vec + reduce == unsharded result
         t = GGML_TYPE["IQ4_NL"]; m, k = 256, 2048
         rng = np.random.default_rng(9)
@@ -108,18 +138,19 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_nvls_allreduce_and_row_parallel_matvec_world2():
-    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
-        pytest.skip("needs >= 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_nvls_allreduce_and_row_parallel_matvec(world):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs >= {world} GPUs")
     import torch.multiprocessing as mp
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=150) for _ in procs]
+    res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -127,3 +158,4 @@ def test_nvls_allreduce_and_row_parallel_matvec_world2():
     assert all(r["tp_nmse"] <= 5e-4 for r in res)
     if all(r["nvls"] for r in res):
         assert all(r.get("fused_graph_nmse", 1.0) <= 5e-4 for r in res)
+        assert all(r.get("two_shot") for r in res)
