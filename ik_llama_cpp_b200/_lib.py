@@ -49,11 +49,6 @@ def lib() -> ctypes.CDLL:
     L.b200q_mul_mat_vec.argtypes = [i32, vp, vp, vp, i64, i64, i32, i64, vp, vp]
     L.b200q_mul_mat_vec_multi.argtypes = [i32, i32, POINTER(vp), POINTER(vp), POINTER(i64), i64, vp, i32, i64, vp]
     L.b200q_fused_up_gate_vec.argtypes = [i32, vp, vp, vp, vp, i64, i64, i32, i64, i32, c_float, vp]
-    L.b200q_q8_scratch_bytes.restype = c_size_t
-    L.b200q_q8_scratch_bytes.argtypes = [i64]
-    L.b200q_q8_scratch_init.argtypes = [vp, i64, vp]
-    L.b200q_fused_up_gate_vec_q8.argtypes = [i32, vp, vp, vp, vp, i64, i64, i32, c_float, vp, POINTER(i32), vp]
-    L.b200q_mul_mat_vec_q8.argtypes = [i32, vp, vp, vp, vp, i64, i64, vp, vp]
     L.b200q_mul_mat_workspace.restype = c_size_t
     L.b200q_mul_mat_workspace.argtypes = [i32, i64, i64, i64]
     L.b200q_mul_mat_gemm.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp, c_size_t, vp]
@@ -70,9 +65,17 @@ def lib() -> ctypes.CDLL:
     L.b200q_fused_up_gate.argtypes = [i32, vp, vp, vp, vp, i64, i64, i64, i32, c_float, vp, c_size_t, vp]
     L.b200q_mul_mat_vec_tp.argtypes = [i32, i32, vp, vp, vp, vp, i64, vp, i32, c_float, vp, i32, i32, vp]
     L.b200q_reduce_sum_nvls.argtypes = [vp, vp, i64, vp, vp, i64, vp, vp, ctypes.c_uint32, vp, vp, vp]
-    L.b200q_reduce_sum_nvls_bf16.argtypes = [vp, vp, vp, i64, vp, vp]
     L.b200q_mul_mat.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp, c_size_t, vp]
     L.b200q_mul_mat_host.argtypes = [i32, vp, vp, vp, i64, i64, i64, vp]
+    if os.environ.get("B200Q_LIB_PATH") and not hasattr(L, "b200q_reduce_sum_nvls_bf16"):
+        _lib = L                    # an older build loaded for an A/B experiment (scripts/sweep_decode.py): only the round-1 entry points
+        return L
+    L.b200q_q8_scratch_bytes.restype = c_size_t
+    L.b200q_q8_scratch_bytes.argtypes = [i64]
+    L.b200q_q8_scratch_init.argtypes = [vp, i64, vp]
+    L.b200q_fused_up_gate_vec_q8.argtypes = [i32, vp, vp, vp, vp, i64, i64, i32, c_float, vp, POINTER(i32), vp]
+    L.b200q_mul_mat_vec_q8.argtypes = [i32, vp, vp, vp, vp, i64, i64, vp, vp]
+    L.b200q_reduce_sum_nvls_bf16.argtypes = [vp, vp, vp, i64, vp, vp]
     _lib = L
     return L
 

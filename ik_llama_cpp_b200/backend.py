@@ -127,7 +127,9 @@ class Q8Scratch:
         _require_cuda()
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.k = k
-        self.buf = torch.zeros(int(_lib.lib().b200q_q8_scratch_bytes(k)), dtype=torch.uint8, device=device)
+        L = _lib.lib()
+        self.supported = hasattr(L, "b200q_q8_scratch_bytes")          # (false only for an older library loaded through B200Q_LIB_PATH)
+        self.buf = torch.zeros(int(L.b200q_q8_scratch_bytes(k)) if self.supported else 16, dtype=torch.uint8, device=device)
         self.valid = False          # set by fused_up_gate(q8_out=self): the image describes the latest result
 
 
@@ -201,7 +203,7 @@ def fused_up_gate(up: QuantTensor, gate: QuantTensor, x: torch.Tensor, unary: st
     dst = out if out is not None else torch.empty((n, up.m), dtype=torch.float32, device=x.device)
     L = _lib.lib()
     with torch.cuda.device(x.device):
-        if n == 1 and q8_out is not None and q8_out.k == up.m and x.is_contiguous():
+        if n == 1 and q8_out is not None and q8_out.supported and q8_out.k == up.m and x.is_contiguous():
             produced = ctypes.c_int32(0)
             check(L.b200q_fused_up_gate_vec_q8(up.ggml_type, up.ptr, gate.ptr, x.data_ptr(), dst.data_ptr(), up.m, up.k, UNARY[unary], float(limit),
                                                q8_out.buf.data_ptr(), ctypes.byref(produced), _stream()), "b200q_fused_up_gate_vec_q8")

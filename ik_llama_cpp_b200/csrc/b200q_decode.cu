@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
         if (TP && a.tp.in) {
             // the activations are the sum over ranks of the previous row-parallel mat-vec: wait until every rank has signalled it
             // (flag += 1 per rank per reduce through the multicast mapping), then read this rank's copy of the buffer
-            if (threadIdx.x == 32) { const uint32_t target = a.tp.world * tps; while ((int32_t)(tp_ld_acquire_sys(a.tp.local_flag) - target) < 0) __nanosleep(20); }
+            if (threadIdx.x == 32) { const uint32_t target = a.tp.world * tps; while ((int32_t)(tp_ld_acquire_sys(a.tp.local_flag) - target) < 0) { } }
             asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x - 32) : "memory");
             quantize_x_to_smem<NCOLS, true>(a.tp.local_base + (int64_t)((tps - 1) & 1) * a.tp.stride, a.tp.stride, K, sq, sd, sis, threadIdx.x - 32, blockDim.x - 32);
         } else if (NCOLS == 1 && !TP && a.q8_in) {
@@ -652,14 +652,17 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
     if (TP && a.tp.out) {
         // completion: every consumer warp fences its multimem.reds (and its share of the zeroing), the last warp of the last CTA
         // publishes this rank's flag increment on every GPU
+        // Every warp makes its own multimem.reds (and zeroing stores) performed system-wide (fence.sys, all warps in parallel), THEN counts
+        // itself in; the thread that sees the last arrival of the last CTA therefore runs after every contribution of this rank has
+        // landed in every peer, and publishes the flag with a release (the rank-local bookkeeping stores precede it in program order).
+        // No further fences on this critical path (round 1 had a fence.gpu and a second fence.sys in front of the release).
         __threadfence_system();
         if (lane == 0) {
             if (atomicAdd(next_pair + 1, 1) == ncw - 1) {
-                __threadfence();
                 if (atomicAdd(a.tp.cta_counter, 1u) == gridDim.x - 1) {
                     *a.tp.cta_counter = 0;
                     reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + ((tps & 1) ^ 1)] = 0; reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + (tps & 1)] = (uint32_t)a.M_total;
-                    *reinterpret_cast<volatile uint32_t *>(a.tp.seq) = tps + 1; __threadfence_system();
+                    *reinterpret_cast<volatile uint32_t *>(a.tp.seq) = tps + 1;
                     tp_red_add_u32_release(a.tp.mc_flag, 1u);
                 }
             }
@@ -819,6 +822,7 @@ static unsigned long long * g_trace = nullptr; static int g_trace_slot = 0;
 extern "C" __attribute__((visibility("default"))) int b200q_debug_trace(int enable, unsigned long long * host_out, int max_slots) {
     if (enable == 1) { if (!g_trace) { cudaMalloc(&g_trace, 4096 * 8 * sizeof(unsigned long long)); } cudaMemset(g_trace, 0, 4096 * 8 * sizeof(unsigned long long)); g_trace_slot = 0; return 0; }
     if (enable == 2) { g_trace_slot = 0; return 0; }                               // rewind (start of a step)
+    if (enable == 3 && g_trace) { cudaDeviceSynchronize(); cudaMemset(g_trace, 0, 4096 * 8 * sizeof(unsigned long long)); return 0; }   // clear, keep the slot assignment
     if (enable == 0 && host_out && g_trace) { cudaMemcpy(host_out, g_trace, (size_t)max_slots * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost); return g_trace_slot; }
     return -1;
 }

@@ -24,8 +24,11 @@ L.b200q_debug_trace(2, None, 0)
 g = torch.cuda.CUDAGraph()
 with torch.cuda.graph(g):
     model.step_tg()
-for _ in range(5):
+for _ in range(int(os.environ.get("TRACE_WARMUP", "400"))):      # bring the SM clock up: the timestamps of a cold, short run are taken at idle clocks
     g.replay()
+torch.cuda.synchronize()
+L.b200q_debug_trace(3, None, 0)          # clear the accumulated min/max slots, then ONE traced replay at warm clocks
+g.replay()
 torch.cuda.synchronize()
 n = model.launches_tg
 out = np.zeros((n, 8), np.uint64)
