@@ -29,7 +29,9 @@ GGML_TYPE = {
     "Q6_0": 133, "IQ1_BN": 134, "IQ2_BN": 135, "IQ2_K": 137, "IQ3_K": 138, "IQ4_K": 139, "IQ5_K": 140,
     "IQ6_K": 141, "IQ4_KS": 144, "IQ2_KS": 145, "IQ4_KSS": 146, "IQ5_KS": 152, "IQ2_KT": 153,
     "IQ3_KT": 154, "IQ4_KT": 155, "IQ3_KS": 156, "IQ2_KL": 157, "IQ1_KT": 158,
+    "IQ1_S_R4": 219, "IQ1_M_R4": 229, "IQ2_K_R4": 337, "IQ3_K_R4": 338, "IQ4_K_R4": 339, "IQ5_K_R4": 340, "IQ4_KS_R4": 344, "IQ5_KS_R4": 352,
 }
+ROWS_INTERLEAVED = {n: 4 for n in ("IQ1_S_R4", "IQ1_M_R4", "IQ2_K_R4", "IQ3_K_R4", "IQ4_K_R4", "IQ5_K_R4", "IQ4_KS_R4", "IQ5_KS_R4")}
 TYPE_NAME = {v: k for k, v in GGML_TYPE.items()}
 
 
@@ -86,10 +88,12 @@ class Oracle:
             L.oracle_set_iq2xxs_codebook(_p(self._iq2xxs[0]), _p(self._iq2xxs[1]))
             L.oracle_set_grid.argtypes = [c_int, c_void_p]
             self._grids = {}
-            for tid, key in ((17, "iq2xs_grid"), (18, "iq3xxs_grid"), (22, "iq2s_grid"), (21, "iq3s_grid")):
+            for tid, key in ((17, "iq2xs_grid"), (18, "iq3xxs_grid"), (22, "iq2s_grid"), (21, "iq3s_grid"), (19, "iq1s_grid"), (157, "iq2kl_values")):
                 if key in z.files:
-                    self._grids[tid] = np.ascontiguousarray(z[key], np.uint8)
+                    self._grids[tid] = np.ascontiguousarray(z[key]).view(np.uint8)
                     L.oracle_set_grid(tid, _p(self._grids[tid]))
+        L.oracle_dequantize_matrix.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int64]
+        L.oracle_rows_interleaved.argtypes = [c_int]
 
     def supported(self, t: int) -> bool:
         return bool(self.lib.oracle_type_supported(t))
@@ -104,10 +108,11 @@ class Oracle:
         rs = self.row_size(t, k)
         wire = np.ascontiguousarray(wire, dtype=np.uint8).reshape(m, rs)
         out = np.empty((m, k), np.float32)
-        for i in range(m):
-            rc = self.lib.oracle_dequantize_row(t, _p(wire[i]), _p(out[i]), k)
-            assert rc == 0
+        assert self.lib.oracle_dequantize_matrix(t, _p(wire), _p(out), m, k) == 0      # (handles the 4-row groups of the _R4 repacks)
         return out
+
+    def rows_interleaved(self, t: int) -> int:
+        return int(self.lib.oracle_rows_interleaved(t))
 
     def quantize_q8_1(self, x: np.ndarray):
         x = np.ascontiguousarray(x, np.float32)
@@ -235,6 +240,12 @@ class RefLib:
         meta = self.row_meta_size(t)
         wire = np.ascontiguousarray(wire, np.uint8).reshape(m, rs)
         out = np.empty((m, k), np.float32)
+        if TYPE_NAME.get(t) in ROWS_INTERLEAVED:       # to_float of an _R4 type takes a group of 4 rows and n = 4 * k
+            assert m % 4 == 0
+            for g in range(m // 4):
+                grp = np.ascontiguousarray(wire[4 * g: 4 * g + 4]).reshape(-1)
+                assert self.lib.refshim_to_float(t, _p(grp), _p(out[4 * g: 4 * g + 4]), 4 * k) == 0
+            return out
         for i in range(m):
             skip = meta if t in self.TO_FLOAT_IGNORES_ROW_SCALE else 0
             row = np.ascontiguousarray(wire[i, skip:])

@@ -28,6 +28,9 @@ enum {
     T_Q2_K = 10, T_Q3_K = 11, T_Q4_K = 12, T_Q5_K = 13, T_Q6_K = 14,
     T_IQ2_XXS = 16, T_IQ2_XS = 17, T_IQ3_XXS = 18, T_IQ3_S = 21, T_IQ2_S = 22, T_IQ6_K = 141, T_IQ1_BN = 134, T_IQ4_KSS = 146, T_IQ4_NL = 20, T_IQ4_XS = 23, T_Q6_0 = 133, T_IQ2_BN = 135, T_IQ2_K = 137, T_IQ3_K = 138, T_MXFP4 = 39, T_IQ5_KS = 152, T_IQ2_KS = 145, T_IQ3_KS = 156,
     T_IQ4_K = 139, T_IQ5_K = 140, T_IQ4_KS = 144,
+    T_IQ1_S = 19, T_IQ1_M = 29, T_IQ2_KT = 153, T_IQ3_KT = 154, T_IQ4_KT = 155, T_IQ2_KL = 157, T_IQ1_KT = 158,
+    // row-interleaved (x4) repacks the CUDA back-end accepts (ggml-cuda.cu:4906-4913)
+    T_IQ1_S_R4 = 219, T_IQ1_M_R4 = 229, T_IQ2_K_R4 = 337, T_IQ3_K_R4 = 338, T_IQ4_K_R4 = 339, T_IQ5_K_R4 = 340, T_IQ4_KS_R4 = 344, T_IQ5_KS_R4 = 352,
 };
 
 static float h2f(uint16_t h) {                    // IEEE binary16 -> binary32 (GGML_FP16_TO_FP32)
@@ -84,8 +87,10 @@ static const uint8_t * g_iq2xs_grid = NULL;      // [512][8]
 static const uint8_t * g_iq3xxs_grid = NULL;     // [256][4]
 static const uint8_t * g_iq2s_grid = NULL;       // [1024][8]
 static const uint8_t * g_iq3s_grid = NULL;       // [512][4]
+static const int8_t * g_iq1s_grid = NULL;        // [2048][8], values in {-1, 0, 1} (IQ1_S / IQ1_M and their _R4 repacks)
+static const int8_t * g_iq2kl = NULL;            // [32][2] value pairs of IQ2_KL
 ORACLE_API void oracle_set_iq2xxs_codebook(const uint8_t * grid, const uint8_t * ksigns) { g_iq2xxs_grid = grid; g_iq2xxs_signs = ksigns; }
-ORACLE_API void oracle_set_grid(int which, const uint8_t * grid) { if (which == 17) g_iq2xs_grid = grid; else if (which == 18) g_iq3xxs_grid = grid; else if (which == 22) g_iq2s_grid = grid; else if (which == 21) g_iq3s_grid = grid; }
+ORACLE_API void oracle_set_grid(int which, const uint8_t * grid) { if (which == 17) g_iq2xs_grid = grid; else if (which == 18) g_iq3xxs_grid = grid; else if (which == 22) g_iq2s_grid = grid; else if (which == 21) g_iq3s_grid = grid; else if (which == 19) g_iq1s_grid = (const int8_t *)grid; else if (which == 157) g_iq2kl = (const int8_t *)grid; }
 
 // ---- wire geometry: {block elements, block bytes, row meta bytes} (ggml.c type_traits :640-1460) ----
 static int geom(int type, int * qk, int * bs, int * meta) {
@@ -122,6 +127,22 @@ static int geom(int type, int * qk, int * bs, int * meta) {
         case T_IQ2_KS: *qk = 256; *bs = 70;  *meta = 2; return 0;
         case T_IQ3_KS: *qk = 256; *bs = 102; *meta = 2; return 0;
         case T_IQ2_BN: *qk = 64;  *bs = 16;  *meta = 4; return 0;
+        case T_IQ1_S:  if (!g_iq1s_grid) return -1; *qk = 256; *bs = 50; return 0;
+        case T_IQ1_M:  if (!g_iq1s_grid) return -1; *qk = 256; *bs = 56; return 0;
+        case T_IQ2_KL: if (!g_iq2kl) return -1; *qk = 256; *bs = 86; *meta = 2; return 0;
+        case T_IQ1_KT: *qk = 256; *bs = 56;  *meta = 4; return 0;
+        case T_IQ2_KT: *qk = 256; *bs = 68;  *meta = 4; return 0;
+        case T_IQ3_KT: *qk = 256; *bs = 100; *meta = 4; return 0;
+        case T_IQ4_KT: *qk = 256; *bs = 128; *meta = 4; return 0;
+        // _R4: per-ROW figures (the wire interleaves 4 rows: a group of 4 rows = 4 x row bytes, the 4 row scales first)
+        case T_IQ1_S_R4: if (!g_iq1s_grid) return -1; *qk = 32; *bs = 6; *meta = 2; return 0;
+        case T_IQ1_M_R4: if (!g_iq1s_grid) return -1; *qk = 32; *bs = 7; *meta = 2; return 0;
+        case T_IQ2_K_R4: *qk = 256; *bs = 76;  return 0;
+        case T_IQ3_K_R4: *qk = 256; *bs = 110; return 0;
+        case T_IQ4_K_R4: *qk = 256; *bs = 144; return 0;
+        case T_IQ5_K_R4: *qk = 256; *bs = 176; return 0;
+        case T_IQ4_KS_R4: *qk = 256; *bs = 136; *meta = 4; return 0;
+        case T_IQ5_KS_R4: *qk = 256; *bs = 168; *meta = 4; return 0;
         default: return -1;
     }
 }
@@ -130,6 +151,21 @@ ORACLE_API int64_t oracle_row_size(int type, int64_t k) {
     return (int64_t)meta + (k / qk) * bs;
 }
 ORACLE_API int oracle_type_supported(int type) { int a, b, c; return geom(type, &a, &b, &c) == 0; }
+// rows interleaved on the wire: 1, or 4 for the _R4 repacks (then rows are addressable only in groups of 4)
+ORACLE_API int oracle_rows_interleaved(int type) {
+    switch (type) { case T_IQ1_S_R4: case T_IQ1_M_R4: case T_IQ2_K_R4: case T_IQ3_K_R4: case T_IQ4_K_R4: case T_IQ5_K_R4: case T_IQ4_KS_R4: case T_IQ5_KS_R4: return 4; default: return 1; }
+}
+// trellis generator of the IQx_KT types (QuantizerIQKT<...>::set_values, integer variant, iqk/iqk_quantize.cpp:8626-8640):
+// x <- 0xCBAC1FED * x; value = (sum of the four 6-bit fields of x) - 126
+static void kt_values(uint32_t idx, uint32_t offset, int n, float scale, int is_abs, float * out) {
+    uint32_t x = idx + offset;
+    for (int k = 0; k < n; ++k) {
+        x *= 0xCBAC1FEDu;
+        const uint32_t s = x & 0x3f3f3f3fu;
+        const float v = (float)((int)(s & 0xff) + (int)((s >> 8) & 0xff) + (int)((s >> 16) & 0xff) + (int)(s >> 24)) - 126.f;
+        out[k] = scale * (is_abs ? fabsf(v) : v);
+    }
+}
 
 // get_scale_min_k4 (ggml-quants.c:2036-2044)
 static void scale_min_k4(int j, const uint8_t * q, int * sc, int * m) {
@@ -495,9 +531,187 @@ ORACLE_API int oracle_dequantize_row(int type, const uint8_t * row, float * y, i
                           // w = row_scale * (q - 1), q = 2-bit field (j div 16) of byte (j mod 16)
             for (int j = 0; j < 64; ++j) y[j] = row_scale * (float)(((x[j % 16] >> (2 * (j / 16))) & 3) - 1);
         } break;
+        case T_IQ1_S: {  // ggml-quants.c:3836-3859  {half d; u8 qs[32]; u16 qh[8]}: 11-bit grid index, 3-bit scale, sign of the +-1/8 shift
+            const float d = h2f(rd16(x)); const uint8_t * qs = x + 2; float * yy = y;
+            for (int ib = 0; ib < 8; ++ib) {
+                const uint16_t qh = rd16(x + 34 + 2 * ib);
+                const float dl = d * (2 * ((qh >> 12) & 7) + 1), delta = qh & 0x8000 ? -0.125f : 0.125f;
+                for (int l = 0; l < 4; ++l) {
+                    const int8_t * grid = g_iq1s_grid + 8 * (qs[l] | (((qh >> 3 * l) & 7) << 8));
+                    for (int j = 0; j < 8; ++j) yy[j] = dl * (grid[j] + delta);
+                    yy += 8;
+                }
+                qs += 4;
+            }
+        } break;
+        case T_IQ1_M: {  // ggml-quants.c:3861-3911  {u8 qs[32]; u8 qh[16]; u8 scales[8]}: the half super-scale is spread over the top nibbles of the 4 u16 scale words
+            const uint8_t * qs = x; const uint8_t * qh = x + 32; uint16_t sc[4]; for (int i = 0; i < 4; ++i) sc[i] = rd16(x + 48 + 2 * i);
+            const float d = h2f((uint16_t)((sc[0] >> 12) | ((sc[1] >> 8) & 0x00f0) | ((sc[2] >> 4) & 0x0f00) | (sc[3] & 0xf000)));
+            float * yy = y;
+            for (int ib = 0; ib < 8; ++ib) {
+                const float dl[2] = { d * (2 * ((sc[ib / 2] >> (6 * (ib % 2) + 0)) & 7) + 1), d * (2 * ((sc[ib / 2] >> (6 * (ib % 2) + 3)) & 7) + 1) };
+                for (int l = 0; l < 4; ++l) {
+                    const uint8_t h = qh[l / 2] >> (4 * (l % 2));
+                    const int8_t * grid = g_iq1s_grid + 8 * (qs[l] | ((h & 7) << 8));
+                    const float delta = h & 8 ? -0.125f : 0.125f;
+                    for (int j = 0; j < 8; ++j) yy[j] = dl[l / 2] * (grid[j] + delta);
+                    yy += 8;
+                }
+                qs += 4; qh += 2;
+            }
+        } break;
+        case T_IQ2_KL: {  // iqk/iqk_quantize.cpp:2243-2275  row = {half d; blocks {u16 scales_h; u8 scales_l[4]; u8 qs[64]; u8 qh[16]}}: 5-bit index -> PAIR of values
+            const uint16_t scales_h = rd16(x); const uint8_t * sl = x + 2; const uint8_t * qs = x + 6; const uint8_t * qh = x + 70; float * yy = y;
+            for (int ib64 = 0; ib64 < 4; ++ib64) {
+                const float dl1 = row_scale * (float)((int)(((sl[(2 * ib64 + 0) % 4] >> 4 * (ib64 / 2)) & 0xf) | (((scales_h >> (4 * ib64 + 0)) & 3) << 4)) - 32);
+                const float dl2 = row_scale * (float)((int)(((sl[(2 * ib64 + 1) % 4] >> 4 * (ib64 / 2)) & 0xf) | (((scales_h >> (4 * ib64 + 2)) & 3) << 4)) - 32);
+                for (int j = 0; j < 16; ++j) {
+                    const int8_t * v1 = g_iq2kl + 2 * ((qs[j] & 0xf) | (((qh[j] >> (2 * ib64 + 0)) & 1) << 4));
+                    const int8_t * v2 = g_iq2kl + 2 * ((qs[j] >> 4) | (((qh[j] >> (2 * ib64 + 1)) & 1) << 4));
+                    yy[2 * j] = dl1 * v1[0]; yy[2 * j + 1] = dl1 * v1[1]; yy[2 * j + 32] = dl2 * v2[0]; yy[2 * j + 33] = dl2 * v2[1];
+                }
+                yy += 64; qs += 16;
+            }
+        } break;
+        case T_IQ1_KT: {  // iqk/iqk_quantize.cpp:9470-9491  row = {float d; blocks {u8 sh[8]; u8 ql[32]; u8 qh[16]}}: 13-bit trellis index per 8 weights
+            const uint8_t * sh = x; const uint8_t * ql = x + 8; const uint8_t * qh = x + 40; float * yy = y;
+            for (int ib = 0; ib < 8; ++ib) {
+                const float sl = row_scale * k_iq4k[sh[ib] & 0xf];
+                for (int ig = 0; ig < 4; ++ig) {
+                    uint32_t idx = ql[ib * 4 + ig] | ((qh[(ib % 4) * 4 + ig] << (8 - 4 * (ib / 4))) & 0xf00);
+                    idx |= ((uint32_t)sh[ib] << (8 - ig)) & 0x1000;
+                    kt_values(idx, 4096, 8, sl, 0, yy); yy += 8;
+                }
+            }
+        } break;
+        case T_IQ2_KT: case T_IQ3_KT: {  // iqk/iqk_quantize.cpp:9751-9779 / :10021-10058  row = {float d; blocks {u8 scales[4]; u16 ql[32]; [u8 qh[32]]}}:
+                                        // 16-bit trellis index per 8 weights; first 16 indices = weights 0..127, next 16 = 128..255; IQ3_KT: |value| and a sign bit plane
+            const int q3 = type == T_IQ3_KT; const uint8_t * sc = x; const uint8_t * ql = x + 4; const uint8_t * qh = x + 68;
+            for (int ib = 0; ib < 4; ++ib) {
+                const float sl = row_scale * (q3 ? (float)(sc[ib] & 0xf) : (float)k_iq4k[sc[ib] & 0xf]), shh = row_scale * (q3 ? (float)(sc[ib] >> 4) : (float)k_iq4k[sc[ib] >> 4]);
+                for (int ig = 0; ig < 4; ++ig) {
+                    const int g = 4 * ib + ig; float * yl = y + 8 * g; float * yh = yl + 128;
+                    kt_values(rd16(ql + 2 * g), 4096, 8, sl, q3, yl); kt_values(rd16(ql + 32 + 2 * g), 4096, 8, shh, q3, yh);
+                    if (q3) for (int j = 0; j < 8; ++j) { if (qh[8 * ig + j] & (1 << ib)) yl[j] = -yl[j]; if (qh[8 * ig + j] & (16 << ib)) yh[j] = -yh[j]; }
+                }
+            }
+        } break;
+        case T_IQ4_KT: {  // iqk/iqk_quantize.cpp:10286-10313  row = {float d; blocks {u32 shb[8]; u8 ql[64]; u8 qh[32]}}: 15-bit index per 4 weights,
+                          // 7-bit block scale - 64, bit 0 of shb selects the second half of the trellis (offset + 32768)
+            const uint8_t * ql = x + 32; const uint8_t * qh = x + 96; float * yy = y;
+            for (int ib = 0; ib < 8; ++ib) {
+                uint32_t shb; memcpy(&shb, x + 4 * ib, 4);
+                const uint32_t offset = shb & 1 ? 32768 + 4096 : 4096; const float sl = row_scale * (float)((int)((shb & 0xff) >> 1) - 64);
+                for (int ig = 0; ig < 8; ++ig) {
+                    const int jj = ib * 8 + ig;
+                    const uint32_t idx = ql[jj] | ((qh[jj % 32] << (8 - 4 * (jj / 32))) & 0xf00) | (((shb >> (8 + 3 * ig)) & 7) << 12);
+                    kt_values(idx, offset, 4, sl, 0, yy); yy += 4;
+                }
+            }
+        } break;
         default: return -1;
         }
     }
+    return 0;
+}
+
+// The _R4 repacks: 4 rows interleaved.  `g` points at a group of 4 rows (= 4 x row bytes, the four row scales first where the type has them),
+// y receives the 4 rows [4][k].  Each function follows the reference's dequantize_row_<type>_r4 (iqk/iqk_quantize.cpp, lines cited per case).
+static int dequant_group4(int type, const uint8_t * g, float * y, int64_t k) {
+    int qk, bs, meta; if (geom(type, &qk, &bs, &meta) || k % qk) return -1;
+    init_tables();
+    const int64_t nb = k / qk;
+    float d4[4] = {1.f, 1.f, 1.f, 1.f};
+    if (meta == 4) memcpy(d4, g, 16);
+    if (meta == 2) for (int r = 0; r < 4; ++r) d4[r] = h2f(rd16(g + 2 * r));
+    const uint8_t * x = g + 4 * meta;
+    for (int64_t ibl = 0; ibl < nb; ++ibl, x += 4 * bs) {
+        for (int r = 0; r < 4; ++r) {
+            float * yr = y + r * k + ibl * qk;
+            switch (type) {
+            case T_IQ1_S_R4: {  // :8195-8216  block {u8 qs[16]; u16 qh[4]} = 32 weights of 4 rows
+                const uint16_t qh = rd16(x + 16 + 2 * r);
+                const float shift = qh & 0x8000 ? -0.125f : 0.125f, dl = d4[r] * (2 * ((qh >> 12) & 7) + 1);
+                for (int i = 0; i < 4; ++i) { const int8_t * grid = g_iq1s_grid + 8 * (x[4 * i + r] | (((qh >> 3 * i) & 7) << 8)); for (int j = 0; j < 8; ++j) yr[8 * i + j] = dl * (grid[j] + shift); }
+            } break;
+            case T_IQ1_M_R4: {  // :8336-8362  block {u8 qs[16]; u8 qh[8]; u8 scales[4]}
+                const uint8_t * qs = x; const uint8_t * qh = x + 16; const uint8_t sc = x[24 + r];
+                const float dl[2] = { d4[r] * (sc & 0xf), d4[r] * (sc >> 4) };
+                for (int i = 0; i < 2; ++i) {
+                    const uint8_t h = qh[4 * i + r];
+                    const int8_t * g1 = g_iq1s_grid + 8 * (qs[8 * i + r] | ((h & 0x07) << 8)); const int8_t * g2 = g_iq1s_grid + 8 * (qs[8 * i + r + 4] | ((h & 0x70) << 4));
+                    const float e1 = h & 0x08 ? -0.125f : 0.125f, e2 = h & 0x80 ? -0.125f : 0.125f;
+                    for (int j = 0; j < 8; ++j) { yr[16 * i + j] = dl[i] * (g1[j] + e1); yr[16 * i + j + 8] = dl[i] * (g2[j] + e2); }
+                }
+            } break;
+            case T_IQ2_K_R4: case T_IQ3_K_R4: {  // :7586-7616 / :7460-7494
+                const int q3 = type == T_IQ3_K_R4;
+                const float d = h2f(rd16(x + 2 * r)); const uint8_t * extra = x + 8;
+                const uint8_t * scales_h = x + 16; const uint8_t * scales_l = x + (q3 ? 24 : 16); const uint8_t * ql = x + (q3 ? 56 : 48); const uint8_t * qh = x + 56 + 256;
+                static const int8_t v2[8] = {-31, -13, 1, 17, -26, -8, 6, 22};                             // iq2nl_values (ggml-common.h:2212)
+                static const int8_t v3[16] = {-63, -40, -23, -10, 1, 13, 28, 47, -59, -36, -19, -6, 5, 17, 32, 51};   // iq3nl_values (:2222)
+                for (int ib = 0; ib < 8; ++ib) {
+                    float dl[2];
+                    for (int h = 0; h < 2; ++h) {
+                        const int is = 8 * ib + r + 4 * h; const int nib = (scales_l[is % 32] >> 4 * (is / 32)) & 0xf;
+                        dl[h] = q3 ? d * (2 * nib + 1) * ((scales_h[is % 8] >> (is / 8)) & 1 ? -1 : 1) : d * (nib - 8);
+                    }
+                    const int e1 = extra[r] & (1 << ib) ? 1 : 0, e2 = extra[r + 4] & (1 << ib) ? 1 : 0;
+                    for (int i = 0; i < 4; ++i) for (int f = 0; f < 4; ++f) {
+                        const int a = (ql[4 * r + i] >> 2 * f) & 3, b = (ql[4 * r + i + 16] >> 2 * f) & 3;
+                        if (q3) {
+                            const int ha = (qh[4 * r + i] >> f) & 1, hb = (qh[4 * r + i] >> (4 + f)) & 1;
+                            yr[32 * ib + i + 4 * f] = dl[0] * v3[8 * e1 + (a | (ha << 2))]; yr[32 * ib + i + 4 * f + 16] = dl[1] * v3[8 * e2 + (b | (hb << 2))];
+                        } else { yr[32 * ib + i + 4 * f] = dl[0] * v2[4 * e1 + a]; yr[32 * ib + i + 4 * f + 16] = dl[1] * v2[4 * e2 + b]; }
+                    }
+                    ql += 32; qh += 16;
+                }
+            } break;
+            case T_IQ4_K_R4: case T_IQ5_K_R4: case T_IQ4_KS_R4: case T_IQ5_KS_R4: {  // :6700-6729 / :6838-6867 / :5879-5904 / :6946-6985
+                const int ks = type == T_IQ4_KS_R4 || type == T_IQ5_KS_R4, q5 = type == T_IQ5_K_R4 || type == T_IQ5_KS_R4;
+                const float d = ks ? d4[r] : h2f(rd16(x + 2 * r));
+                const uint8_t * extra = x + 8; const uint8_t * scales_h = x + 16; const uint8_t * scales_l = x + 32;
+                const uint8_t * qs = x + (ks ? 32 : 64); const uint8_t * qh = qs + 512;
+                for (int ib = 0; ib < 8; ++ib) {
+                    float dl[2]; int e[2];
+                    if (ks) { const uint8_t sc = x[4 * ib + r]; dl[0] = dl[1] = d * (float)((int)(sc & 254) - 127); e[0] = e[1] = sc & 1; }
+                    else for (int h = 0; h < 2; ++h) {
+                        const int is = 8 * ib + r + 4 * h;
+                        dl[h] = d * (float)((int)(((scales_l[is % 32] >> 4 * (is / 32)) & 0xf) | (((scales_h[is % 16] >> 2 * (is / 16)) & 3) << 4)) - 32);
+                        e[h] = extra[r + 4 * h] & (1 << ib) ? 1 : 0;
+                    }
+                    for (int i = 0; i < 4; ++i) {
+                        // byte c = qs[64 ib + 4 r + i + 16 c'] (c' = 0..3) holds weights {i, i+8}, {i+16, i+24}, {i+4, i+12}, {i+20, i+28} (low, high nibble)
+                        static const int pos[4][2] = {{0, 8}, {16, 24}, {4, 12}, {20, 28}};
+                        static const int bit[4][2] = {{0, 1}, {2, 3}, {4, 5}, {6, 7}};
+                        for (int c = 0; c < 4; ++c) for (int hn = 0; hn < 2; ++hn) {
+                            const uint8_t byte = qs[64 * ib + 4 * r + i + 16 * c]; int q = hn ? byte >> 4 : byte & 0xf;
+                            const int h = pos[c][hn] >= 16 ? 1 : 0;
+                            if (q5) { q |= ((qh[16 * ib + 4 * r + i] >> bit[c][hn]) & 1) << 4; yr[32 * ib + i + pos[c][hn]] = dl[h] * k_iq5nl[32 * e[h] + q]; }
+                            else yr[32 * ib + i + pos[c][hn]] = dl[h] * k_iq4k[16 * e[h] + q];
+                        }
+                    }
+                }
+            } break;
+            default: return -1;
+            }
+        }
+    }
+    return 0;
+}
+// Dequantize rows i0 .. i0+3 (a whole group) or one row, whatever the type addresses: W = tensor base, rs = per-row bytes.
+// Returns a pointer to row i inside `buf` ([4][k] floats), refilling buf when i enters a new group.
+static const float * dequant_row_i(int type, const uint8_t * W, int64_t i, int64_t k, int64_t rs, float * buf, int * rc) {
+    const int R = oracle_rows_interleaved(type);
+    if (R == 1) { *rc = oracle_dequantize_row(type, W + i * rs, buf, k); return buf; }
+    if (i % 4 == 0 || *rc == 1) *rc = dequant_group4(type, W + (i / 4) * 4 * rs, buf, k);
+    return buf + (i % 4) * k;
+}
+// whole matrix -> f32 [m][k] (m must be a multiple of the interleave)
+ORACLE_API int oracle_dequantize_matrix(int type, const uint8_t * W, float * y, int64_t m, int64_t k) {
+    const int64_t rs = oracle_row_size(type, k); if (rs < 0) return -1;
+    const int R = oracle_rows_interleaved(type); if (m % R) return -1;
+    for (int64_t i = 0; i < m; i += R) { const int rc = R == 1 ? oracle_dequantize_row(type, W + i * rs, y + i * k, k) : dequant_group4(type, W + i * rs, y + i * k, k); if (rc) return rc; }
     return 0;
 }
 
@@ -540,12 +754,13 @@ ORACLE_API int oracle_quantize_q8_1_b200(const float * x, int64_t n, int64_t k, 
 // dst[n][m] (f32) = exact f64 dot of dequant(W) rows with x columns.  W: m wire rows, x: f32 [n][k].
 ORACLE_API int oracle_mul_mat_exact(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n) {
     const int64_t rs = oracle_row_size(type, k); if (rs < 0) return -1;
-    float * w = (float *)malloc(sizeof(float) * k);
+    float * buf = (float *)malloc(sizeof(float) * 4 * k);
     for (int64_t i = 0; i < m; ++i) {
-        if (oracle_dequantize_row(type, W + i * rs, w, k)) { free(w); return -1; }
+        int rc = 0; const float * w = dequant_row_i(type, W, i, k, rs, buf, &rc);
+        if (rc) { free(buf); return -1; }
         for (int64_t j = 0; j < n; ++j) { double acc = 0; const float * xr = x + j * k; for (int64_t l = 0; l < k; ++l) acc += (double)w[l] * xr[l]; dst[j * m + i] = (float)acc; }
     }
-    free(w); return 0;
+    free(buf); return 0;
 }
 
 // dst[n][m] = the value the reference's MMVQ kernels compute up to f32 summation order (see header).
@@ -556,13 +771,14 @@ ORACLE_API int oracle_mul_mat_q8_1_b200(int type, const uint8_t * W, const float
 static int mul_mat_q8_impl(int type, const uint8_t * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n, int variant) {
     const int64_t rs = oracle_row_size(type, k); if (rs < 0 || k % 32) return -1;
     int8_t * q = (int8_t *)malloc((size_t)n * k); uint16_t * db = (uint16_t *)malloc(sizeof(uint16_t) * n * (k / 32)); uint16_t * sb = (uint16_t *)malloc(sizeof(uint16_t) * n * (k / 32));
-    float * xq = (float *)malloc(sizeof(float) * n * k); float * w = (float *)malloc(sizeof(float) * k);
+    float * xq = (float *)malloc(sizeof(float) * n * k); float * buf = (float *)malloc(sizeof(float) * 4 * k);
     if (variant) oracle_quantize_q8_1_b200(x, n, k, q, db); else oracle_quantize_q8_1(x, n, k, q, db, sb);
     for (int64_t j = 0; j < n; ++j) for (int64_t l = 0; l < k; ++l) xq[j * k + l] = h2f(db[j * (k / 32) + l / 32]) * q[j * k + l];
     int rc = 0;
     for (int64_t i = 0; i < m && !rc; ++i) {
-        rc = oracle_dequantize_row(type, W + i * rs, w, k);
+        const float * w = dequant_row_i(type, W, i, k, rs, buf, &rc);
+        if (rc) break;
         for (int64_t j = 0; j < n; ++j) { double acc = 0; const float * xr = xq + j * k; for (int64_t l = 0; l < k; ++l) acc += (double)w[l] * xr[l]; dst[j * m + i] = (float)acc; }
     }
-    free(q); free(db); free(sb); free(xq); free(w); return rc;
+    free(q); free(db); free(sb); free(xq); free(buf); return rc;
 }

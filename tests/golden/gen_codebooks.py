@@ -78,8 +78,33 @@ def main():
         blk.append(np.float16(1.0).tobytes() + qs + qh + bytes(32) + bytes(4))
     y = R.to_float(t3s, np.frombuffer(b"".join(blk), np.uint8), 1, 512 * 4).reshape(512, 4)
     grid_3s = y.astype(np.uint8); assert np.array_equal(grid_3s.astype(np.float32), y)
+    # IQ1_S {half d; u8 qs[32]; u16 qh[8]} (ggml-quants.c:3836-3859): per 32 weights 4 groups, index_l = qs[l] | ((qh >> 3l) & 7) << 8 into
+    # iq1s_grid (2048 x 8, values in {-1,0,1}); y = d * (2*((qh >> 12) & 7) + 1) * (grid + (qh & 0x8000 ? -delta : delta)); d = 1, scale 0, sign 0
+    t1s = GGML_TYPE["IQ1_S"]
+    blk = []
+    for b in range(2048 // 32):
+        idx = np.arange(32 * b, 32 * b + 32)
+        qs = (idx & 255).astype(np.uint8).tobytes()
+        qh = np.array([sum(((int(idx[4 * g + l]) >> 8) & 7) << (3 * l) for l in range(4)) for g in range(8)], np.uint16).tobytes()
+        blk.append(np.float16(1.0).tobytes() + qs + qh)
+    y = R.to_float(t1s, np.frombuffer(b"".join(blk), np.uint8), 1, 2048 * 8).reshape(2048, 8)
+    delta = float(y.ravel()[0] - np.round(y.ravel()[0]))
+    grid_1s = np.round(y - delta).astype(np.int8)
+    assert np.array_equal(grid_1s.astype(np.float32) + np.float32(delta), y) and set(grid_1s.ravel().tolist()) <= {-1, 0, 1}, delta
+    # IQ2_KL row = {half d; blocks {u16 scales_h; u8 scales_l[4]; u8 qs[64]; u8 qh[16]}} (iqk_quantize.cpp:2243-2275): 5-bit index
+    # (nibble of qs | bit of qh << 4) into iq2kl_values (32 PAIRS of int8); 6-bit scales - 32: scale 33 -> dl = d = 1
+    t2kl = GGML_TYPE["IQ2_KL"]
+    qs = bytes(((j & 15) | ((j & 15) << 4)) for j in range(16)) + bytes(48)       # ib64 = 0: low nibbles -> entries 0..15, high nibbles -> 16..31 with qh bit 1
+    qh = bytes([0b10] * 16)
+    row = np.float16(1.0).tobytes() + np.uint16(0b1010).tobytes() + bytes([0x11, 0x11, 0, 0]) + qs + qh
+    y = R.to_float(t2kl, np.frombuffer(row, np.uint8), 1, 256)[0]
+    kl = np.empty((32, 2), np.int8)
+    for j in range(16):
+        kl[j] = y[2 * j: 2 * j + 2]; kl[16 + j] = y[2 * j + 32: 2 * j + 34]
+    assert np.array_equal(kl[:16].astype(np.float32).ravel(), y[:32]) and np.array_equal(kl[16:].astype(np.float32).ravel(), y[32:64])
     np.savez_compressed(os.path.join(HERE, "iq2xxs_codebook.npz"), grid=grid, ksigns=ksigns, iq2xs_grid=grid_xs, iq3xxs_grid=grid_3xxs,
-                        iq2s_grid=grid_2s, iq3s_grid=grid_3s)
+                        iq2s_grid=grid_2s, iq3s_grid=grid_3s, iq1s_grid=grid_1s, iq1s_delta=np.float32(delta), iq2kl_values=kl)
+    print("iq1s", grid_1s.shape, "delta", delta, "iq2kl", kl.ravel().tolist())
     print("iq2s", grid_2s.shape, sorted(set(grid_2s.ravel().tolist())), "iq3s", grid_3s.shape, sorted(set(grid_3s.ravel().tolist())))
     print("grid", grid.shape, sorted(set(grid.ravel().tolist())), "ksigns", ksigns[:8].tolist(), "...",
           "iq2xs", grid_xs.shape, sorted(set(grid_xs.ravel().tolist())), "iq3xxs", grid_3xxs.shape, sorted(set(grid_3xxs.ravel().tolist())))

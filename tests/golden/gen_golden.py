@@ -17,13 +17,19 @@ from oracle.oracle import GGML_TYPE, RefLib  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q6_0", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "IQ2_K", "IQ3_K", "IQ4_K", "IQ5_K", "IQ4_KS", "IQ5_KS", "IQ2_KS", "IQ3_KS", "MXFP4", "IQ2_BN"]
 # types whose ORACLE is pinned already while the device kernel is still to come: fixtures for tests/test_oracle.py only
-ORACLE_ONLY = ["IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S", "IQ6_K", "IQ1_BN", "IQ4_KSS"]
+ORACLE_ONLY = []
+# types that are consumed verbatim on the device (wire layout, generic decode; b200q_wire.cuh): codebook / trellis / row-interleaved types
+WIRE_TYPES = ["IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S", "IQ6_K", "IQ1_BN", "IQ4_KSS", "IQ1_S", "IQ1_M", "IQ2_KL", "IQ1_KT", "IQ2_KT", "IQ3_KT", "IQ4_KT",
+              "IQ1_S_R4", "IQ1_M_R4", "IQ2_K_R4", "IQ3_K_R4", "IQ4_K_R4", "IQ5_K_R4", "IQ4_KS_R4", "IQ5_KS_R4"]
 M, K, N = 16, 512, 3
 
 
 def main():
     R = RefLib()
-    for name in TYPES + ORACLE_ONLY:
+    only = sys.argv[1:]
+    for name in TYPES + ORACLE_ONLY + WIRE_TYPES:
+        if only and name not in only:
+            continue
         t = GGML_TYPE[name]
         rng = np.random.default_rng(1234 + t)
         w = (rng.standard_normal((M, K)) * 0.02).astype(np.float32)
