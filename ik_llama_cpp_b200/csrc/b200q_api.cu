@@ -83,8 +83,8 @@ int b200q_set_option(const char * key, int value) {
 }
 int b200q_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 
-int b200q_type_supported(int type) { b200q_layout L; return b200q_make_layout(type, 1, 256, &L) == 0 ? 1 : 0; }
-int64_t b200q_wire_row_size(int type, int64_t k) { b200q_layout L; if (b200q_make_layout(type, 1, k, &L)) return -1; return b200q_wire_row_size(L); }
+int b200q_type_supported(int type) { b200q_layout L; return b200q_make_layout(type, 4, 256, &L) == 0 ? 1 : 0; }
+int64_t b200q_wire_row_size(int type, int64_t k) { b200q_layout L; if (b200q_make_layout(type, 4, k, &L)) return -1; return b200q_wire_row_size(L); }
 int64_t b200q_plane_bytes(int type, int64_t m, int64_t k) { b200q_layout L; if (b200q_make_layout(type, m, k, &L)) return -1; return L.total_bytes; }
 
 int b200q_repack(int type, const void * wire_dev, void * planes_dev, int64_t m, int64_t k, void * stream) {

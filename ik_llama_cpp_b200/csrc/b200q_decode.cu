@@ -15,6 +15,8 @@
 //   - epilogue: warp-shuffle reduce, optional bias, optional act(gate)*up fusion, one 4-byte store per row.
 #include "b200q_types.cuh"
 #include "b200q_internal.h"
+#include "b200q_decode_common.cuh"
+#include "b200q_decode_ring.cuh"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -59,647 +61,6 @@ __global__ void k_dequant_bf16(const uint8_t * __restrict__ W, b200q_layout L, _
 }
 
 // ------------------------------------------------------------------------------------------------
-// decode mat-vec
-// ------------------------------------------------------------------------------------------------
-struct mmvq_seg {               // one weight tensor of a multi-tensor launch (Q,K,V share the activation)
-    b200q_planes    P;          // resolved plane pointers
-    b200q_planes    P2;         // second tensor (gate) for the fused up/gate mode
-    float *         dst;        // [ncols][M] f32 (ggml: dst[j*M + i])
-    const float *   bias;       // optional [M]
-    int64_t         M;
-    int64_t         row0;       // first global row index of this segment
-};
-struct mmvq_args {
-    mmvq_seg     seg[B200Q_MAX_SEGS];
-    int          n_seg;
-    int64_t      M_total;
-    int64_t      K;
-    const float * x;            // [ncols][K] f32, row stride x_stride floats
-    int64_t      x_stride;
-    int          act;           // B200Q_ACT_* for the up/gate mode
-    float        limit;         // clamp for swiglu variants (0 = none)
-    b200q_tp_comm tp;           // tensor-parallel decode: GGML_OP_REDUCE fused into the mat-vec (tp.in / tp.out), see k_mmvq_ring
-    unsigned long long * trace; // optional phase timestamps (b200q_debug_trace): [slot][8] = entry, after griddepcontrol.wait, prologue done, last consumer done,
-                                //   activation loads landed, quantised (before the barrier), 2^62 - first consumer done, first unit of CTA 0 / warp 1 done
-    const void * q8_in;         // activations already quantised by the producing kernel (b200q_q8 layout, n = 1): bulk-copied instead of re-quantised
-    void *       q8_out;        // fused up/gate, n = 1: also emit dst quantised to q8_1 for the following MUL_MAT (ffn_down), see q8_emit_block
-};
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-// programmatic dependent launch (no-ops unless the launch carries the PDL attribute)
-__device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-// Quantise ncols activation columns into shared memory (q8_1 semantics of ggml-cuda/quantize.cu:13-47):
-//   d = amax/127 ; q = amax == 0 ? 0 : roundf(x/d) ; d kept as float(half(d)) ; isum = packed int16 sums of q over each 16.
-// Cooperative and vectorised: a thread owns 8 consecutive floats (two LDG.128), 4 adjacent lanes own one 32-block.
-template <int NCOLS, bool COHERENT = false>
-__device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x, int64_t x_stride, int64_t K,
-                                                   int8_t * sq, float * sd, int * sis, int tid, int nthreads, unsigned long long * tr = nullptr) {
-    const int nch = (int)(K / 8), total = nch * NCOLS, n32 = (int)(K / 32);
-    constexpr int B = 4;                                   // chunks per thread per batch: 8 independent LDG.128 in flight, so the
-                                                           // activation vector costs 1 (K=4096) .. 2 (K=14336) L2 round trips, not 2 .. 6
-    for (int base = 0; base < total; base += nthreads * B) {
-        float4 va[B], vb[B];
-#pragma unroll
-        for (int u = 0; u < B; ++u) {
-            const int c = base + u * nthreads + tid;
-            int col = 0, ch = c < total ? c : 0;
-            if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
-            if (c < total) {
-                // COHERENT: the vector was written through the NVLS multicast mapping by other GPUs -> no read-only / stale-L1 path
-                va[u] = COHERENT ? __ldcv(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8)) : __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8));
-                vb[u] = COHERENT ? __ldcv(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4)) : __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
-            } else { va[u] = make_float4(0.f, 0.f, 0.f, 0.f); vb[u] = va[u]; }
-        }
-        if (tr && base == 0 && va[0].x != 123456.789f) *tr = gtime();       // (debug trace) first batch of loads has landed
-#pragma unroll
-        for (int u = 0; u < B; ++u) {
-            const int c = base + u * nthreads + tid;
-            if (base + u * nthreads >= total) break;       // warp-uniform: the whole batch slot is past the end
-            const bool valid = c < total;
-            int col = 0, ch = valid ? c : 0;
-            if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
-            const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
-            float amax = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
-            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
-            // d = amax/127 exactly as the reference; q = rint(x * (1/d)) with a correctly rounded reciprocal: one division and one
-            // reciprocal per block instead of one division per element.  Differs from the reference's roundf(x / d) only for
-            // products within 1 ulp of a rounding tie (p ~ 1e-5 per element, 1 LSB); the oracle restates exactly this arithmetic
-            // (oracle_quantize_q8_1_b200) next to the reference's (oracle_quantize_q8_1).
-            const float d = __fdiv_rn(amax, 127.0f);
-            const float inv = d > 0.0f ? __frcp_rn(d) : 0.0f;
-            int q[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) q[j] = max(-127, min(127, __float2int_rn(__fmul_rn(v[j], inv))));
-            int2 pk;
-            pk.x = (int)__byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
-            pk.y = (int)__byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
-            int s = __dp4a(pk.x, 0x01010101, __dp4a(pk.y, 0x01010101, 0));
-            s += __shfl_xor_sync(0xffffffffu, s, 1);                       // sum over 16 weights (2 lanes)
-            const int s_hi = __shfl_down_sync(0xffffffffu, s, 2);          // the second 16 of the 32-block
-            if (valid) {
-                // natural order.  (Tried: two half planes [K/2 | K/2] so that the LDS.128 pairs of item_dot are conflict-free across the
-                // warp -> 659 vs 705 tok/s, slower; kept simple.)
-                *reinterpret_cast<int2 *>(sq + (size_t)col * K + (size_t)ch * 8) = pk;
-                if ((ch & 3) == 0) {
-                    sd[col * n32 + (ch >> 2)]  = __half2float(__float2half_rn(d));
-                    sis[col * n32 + (ch >> 2)] = (s & 0xFFFF) | (s_hi << 16);
-                }
-            }
-        }
-    }
-}
-
-
-// ---- q8 hand-off between two mat-vec launches (n = 1) -------------------------------------------------------------
-// Layout of a b200q_q8 scratch for a vector of K floats (K % 64 == 0): [K int8 q][K/32 f32 d][K/32 i32 packed int16 sums]
-// = exactly the shared-memory image (sq | sd | sis) the mat-vec consumes, followed by [K/32 u32 arrival counters].
-// Producer side (fused up/gate epilogue): the warp that completes the LAST rows of a 32-block (arrival counter) quantises that
-// block from the f32 results in L2 with the arithmetic of quantize_x_to_smem; consumer side: one bulk copy instead of
-// 296 CTAs re-reading and re-quantising K floats (reference: quantize_q8_1 runs once per activation, quantize.cu:13-47).
-__device__ __forceinline__ void q8_emit_block(void * q8, int64_t K, const float * dst, int64_t M, int blk, int lane) {
-    int8_t * q8q = reinterpret_cast<int8_t *>(q8);
-    float * q8d = reinterpret_cast<float *>(q8q + K);
-    int * q8s = reinterpret_cast<int *>(q8d + K / 32);
-    const int64_t r = (int64_t)blk * 32 + lane;
-    const float v = r < M ? __ldcg(dst + r) : 0.0f;
-    float amax = fabsf(v);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    const float d = __fdiv_rn(amax, 127.0f);
-    const float inv = d > 0.0f ? __frcp_rn(d) : 0.0f;
-    const int q = max(-127, min(127, __float2int_rn(__fmul_rn(v, inv))));
-    q8q[r] = (int8_t)q;
-    const int s_lo = __reduce_add_sync(0xffffffffu, lane < 16 ? q : 0), s_hi = __reduce_add_sync(0xffffffffu, lane < 16 ? 0 : q);
-    if (lane == 0) { q8d[blk] = __half2float(__float2half_rn(d)); q8s[blk] = (s_lo & 0xFFFF) | (s_hi << 16); }
-}
-
-template <int TYPE, int NCOLS>
-__device__ __forceinline__ void item_dot(const b200q_canon & C, const int8_t * sq, const float * sd, const int * sis,
-                                         int64_t K, int n32, int it, float acc[NCOLS]) {
-    constexpr bool HAS_B = b200q_traits<TYPE>::HAS_B;
-#pragma unroll
-    for (int c = 0; c < NCOLS; ++c) {
-        const int4 * xp = reinterpret_cast<const int4 *>(sq + (size_t)c * K + (size_t)it * 32);
-        const int4 x0 = xp[0], x1 = xp[1];
-        int s0 = 0, s1 = 0;
-        s0 = b200q_dp4a(C.va[0], x0.x, s0); s0 = b200q_dp4a(C.va[1], x0.y, s0); s0 = b200q_dp4a(C.va[2], x0.z, s0); s0 = b200q_dp4a(C.va[3], x0.w, s0);
-        s1 = b200q_dp4a(C.va[4], x1.x, s1); s1 = b200q_dp4a(C.va[5], x1.y, s1); s1 = b200q_dp4a(C.va[6], x1.z, s1); s1 = b200q_dp4a(C.va[7], x1.w, s1);
-        if (HAS_B) {
-            s0 = b200q_dp4a(C.vb[0], x0.x, s0); s0 = b200q_dp4a(C.vb[1], x0.y, s0); s0 = b200q_dp4a(C.vb[2], x0.z, s0); s0 = b200q_dp4a(C.vb[3], x0.w, s0);
-            s1 = b200q_dp4a(C.vb[4], x1.x, s1); s1 = b200q_dp4a(C.vb[5], x1.y, s1); s1 = b200q_dp4a(C.vb[6], x1.z, s1); s1 = b200q_dp4a(C.vb[7], x1.w, s1);
-        }
-        const float d8 = sd[c * n32 + it];
-        float t;
-        if (b200q_split16(TYPE)) t = C.dl[0] * (float)s0 + C.dl[1] * (float)s1;
-        else                     t = C.dl[0] * (float)(s0 + s1);
-        if (b200q_mmvq_has_ml(TYPE)) {
-            const int is = sis[c * n32 + it];
-            if (b200q_split16(TYPE)) t -= C.ml[0] * (float)(int)(short)(is & 0xFFFF) + C.ml[1] * (float)(is >> 16);
-            else                     t -= C.ml[0] * (float)((int)(short)(is & 0xFFFF) + (is >> 16));
-        }
-        acc[c] = fmaf(d8, t, acc[c]);
-    }
-}
-
-// One CTA per SM (512 threads = 16 warps, <= 64 registers): leaves half of the SM for the NEXT kernel of the graph,
-// which under programmatic dependent launch is already resident, has its first weight batch in flight and is parked
-// in griddepcontrol.wait while this one drains.
-template <int TYPE, int NCOLS, bool UPGATE>
-__global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_args a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int64_t K = a.K; const int n32 = (int)(K / 32);
-    int8_t * sq = reinterpret_cast<int8_t *>(smem_raw);
-    float *  sd = reinterpret_cast<float *>(smem_raw + (size_t)NCOLS * K);
-    int *    sis = reinterpret_cast<int *>(sd + NCOLS * n32);
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int64_t gw = (int64_t)blockIdx.x * nwarps + warp, tw = (int64_t)gridDim.x * nwarps;
-    constexpr int U = UPGATE ? 2 : 4;
-
-    auto locate = [&](int64_t grow, int & s, int64_t & row) {
-        s = 0;
-#pragma unroll
-        for (int i = 1; i < B200Q_MAX_SEGS; ++i) if (i < a.n_seg && grow >= a.seg[i].row0) s = i;
-        row = grow - a.seg[s].row0;
-    };
-
-    // (1) weights do not depend on the previous kernel: get the first batch of this warp's first row in flight now
-    b200q_item I[U], J[U];
-    int64_t grow = gw;
-    if (grow < a.M_total) {
-        int s; int64_t row; locate(grow, s, row);
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int it = lane + 32 * u;
-            if (it < n32) { b200q_load_item<TYPE>(I[u], a.seg[s].P, row, it); if (UPGATE) b200q_load_item<TYPE>(J[u], a.seg[s].P2, row, it); }
-        }
-    }
-    pdl_trigger();                       // let the next kernel of the stream/graph become resident
-    // (2) the activations are produced by the previous kernel
-    pdl_wait();
-    quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis, threadIdx.x, blockDim.x);
-    __shared__ uint32_t kv_slot[128];
-    const b200q_kv4 T = b200q_kv4_init_via_smem(kv_slot);     // includes the __syncthreads() that publishes the activations
-    for (; grow < a.M_total; grow += tw) {
-        int s; int64_t row; locate(grow, s, row);
-        const mmvq_seg & sg = a.seg[s];
-        float acc[NCOLS], acc2[NCOLS];
-#pragma unroll
-        for (int c = 0; c < NCOLS; ++c) { acc[c] = 0.0f; acc2[c] = 0.0f; }
-
-        for (int it0 = lane; it0 < n32; it0 += 32 * U) {
-            if (it0 != lane || grow != gw) {          // the very first batch is already in registers
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int it = it0 + 32 * u;
-                    if (it < n32) { b200q_load_item<TYPE>(I[u], sg.P, row, it); if (UPGATE) b200q_load_item<TYPE>(J[u], sg.P2, row, it); }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int it = it0 + 32 * u;
-                if (it < n32) {
-                    b200q_canon C;
-                    b200q_decode_item<TYPE>(I[u], it, C, T);
-                    item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc);
-                    if (UPGATE) { b200q_decode_item<TYPE>(J[u], it, C, T); item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc2); }
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < NCOLS; ++c) {
-            float v = warp_sum(acc[c]);
-            if (UPGATE) {
-                float g = warp_sum(acc2[c]);      // acc = up . x, acc2 = gate . x
-                v = b200q_glu<false>(a.act, g, v, a.limit);
-            } else if (sg.bias) v += sg.bias[row];
-            if (lane == 0) sg.dst[(int64_t)c * sg.M + row] = v;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// decode mat-vec, TMA-ring variant (the default): weights are streamed HBM -> shared memory by cp.async.bulk (1-D TMA)
-// into warp-private rings, decoupled from registers and from the data dependency on the previous kernel.
-//   * every warp owns S stages; a stage holds one SEGMENT (<= 128 items = 4096 weights) of one row of one tensor:
-//     one bulk copy per plane (rows are contiguous inside a plane), completion on a per-stage mbarrier (expect_tx);
-//   * lane 0 refills a stage as soon as the warp has consumed it, so W*S*stage bytes (~74 KB/SM) stay in flight —
-//     tools/membench.cu: 64 KB/SM of 2 KB bulk copies stream at 7.29 TB/s, LDG with 16 warps x 4 loads at 6.3 TB/s;
-//   * the first S units of every warp are issued BEFORE griddepcontrol.wait: under programmatic dependent launch the
-//     next mat-vec of the graph is already resident (one 512-thread CTA per SM leaves room for a second) and has its
-//     ring full when the previous kernel finishes; only the activation quantisation is on the dependent path.
-// ------------------------------------------------------------------------------------------------
-#ifndef B200Q_SEG_ITEMS
-#define B200Q_SEG_ITEMS 128          // items (of 32 weights) per row per ring stage; tuning knob, see experiments/README.md
-#endif
-#ifndef B200Q_MAX_STAGES
-#define B200Q_MAX_STAGES 4
-#endif
-#ifndef B200Q_SELF_REFILL
-#define B200Q_SELF_REFILL 0          // 1: the producer warp only pre-fills the ring (before griddepcontrol.wait); in the main loop every
-#endif                               //    consumer warp re-arms the stage it has just drained itself.  Measured 696 vs 705 tok/s: no gain -> off
-#ifndef B200Q_RING_CONSUMERS
-#define B200Q_RING_CONSUMERS 11      // consumer warps per CTA (+1 producer): 12 warps x 2 CTAs per SM at <= 80 registers.  Round-2 knob: 15 with
-#endif                               // -maxrregcount 64 gives 32 warps per SM (more latency hiding) if the ring stages are shrunk to fit
-#ifndef B200Q_TRACE_FINE
-#define B200Q_TRACE_FINE 0           // 1: extra phase timestamps (slots 4..7 of b200q_debug_trace); costs registers / branches, tuning builds only
-#endif
-#ifndef B200Q_PRODUCER_LAST
-#define B200Q_PRODUCER_LAST 0        // 1: the producer is the LAST warp of the CTA (the warp scheduler prefers high warp ids: B300_MICROARCH.md)
-#endif
-#ifndef B200Q_MIN_CTAS
-#define B200Q_MIN_CTAS 2             // resident CTAs per SM the ring kernel is compiled for (register cap = 65536 / (MIN_CTAS * threads))
-#endif
-#ifndef B200Q_SMEM_BUDGET
-#define B200Q_SMEM_BUDGET (112 * 1024)   // dynamic shared memory per CTA: two CTAs per SM (same kernel, or this one + the next under PDL)
-#endif
-#define B200Q_PAIR_SLOTS 124         // ncw * S stage descriptors (+ the claim counter) fit the 128-int slot table
-struct ring_geom {
-    int n_planes;                 // block planes staged through the ring (the per-row scale plane is read directly)
-    int b8[4];                    // bytes per 8 items (256 weights) of plane p
-    int seg_off[4];               // byte offset of plane p inside a stage
-    int stage_bytes;              // 16-byte aligned
-    int n_stages;                 // S
-    int row_plane;                // index of the per-row plane in b200q_planes::p, or -1
-    int merged;                   // 1: the row is ONE segment, so the two rows of a pair are adjacent inside every plane and travel as one bulk copy per
-                                  //    plane (half as many copies in flight: tools/membench.cu `r` shows the bandwidth falling with the copy count);
-                                  //    the stage is then laid out plane-major [p0 row0 | p0 row1 | p1 row0 | p1 row1 ...]
-    int row1[4];                  // byte offset of row 1 of the pair relative to row 0, per plane
-};
-struct mmvq_ring_args {
-    mmvq_args  a;
-    ring_geom  g;
-};
-
-__device__ __forceinline__ uint32_t smem_addr(const void * p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void rb_init(uint64_t * bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar))); }
-__device__ __forceinline__ void rb_expect(uint64_t * bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void rb_wait(uint64_t * bar, uint32_t parity) {
-    asm volatile("{\n\t.reg .pred p;\n\tRW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra RD_%=;\n\tbra RW_%=;\n\tRD_%=:\n\t}"
-                 ::"r"(smem_addr(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ bool rb_test(uint64_t * bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t bytes, uint64_t * bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
-}
-
-// ---- tensor-parallel fusion (split-mode-graph): the all-reduce of a row-parallel mat-vec happens in the switch ----
-__device__ __forceinline__ void tp_red_add_f32(float * mc, float v) { asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory"); }
-__device__ __forceinline__ void tp_red_add_u32_release(uint32_t * mc, uint32_t v) { asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t tp_ld_acquire_sys(const uint32_t * p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
-
-__device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
-
-// Warp 0 = producer (lane l streams the units of consumer warp l), warps 1..NCW = consumers.
-// A unit is one SEGMENT (<= 128 items) of a PAIR of adjacent output rows of one tensor: the two rows share every
-// activation load and all loop bookkeeping, and give the scheduler two independent dependency chains.
-// PAIR = false: single-row units (used when there are fewer row pairs than warps in the grid: small matrices are latency-bound,
-// more and shorter units win there); the second half of every pair-stage is then simply unused.
-// TP: tensor-parallel instantiation (fused GGML_OP_REDUCE); a separate instantiation so that the single-GPU kernels carry none of it
-// (as runtime branches the extra code cost the plain path 4 %: 675 vs 705 tok/s)
-// Q8: 0 = none, 1 = activations arrive as a b200q_q8 image (a.q8_in), 2 = fused up/gate also emits its result as one (a.q8_out)
-template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR, bool TP, int Q8 = 0>
-__global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTAS) k_mmvq_ring(const mmvq_ring_args ra) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const mmvq_args & a = ra.a; const ring_geom & g = ra.g;
-    const int K = (int)a.K, n32 = K / 32, n8 = n32 / 8;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ncw = (blockDim.x >> 5) - 1;     // consumer warps
-    const bool is_prod = B200Q_PRODUCER_LAST ? warp == ncw : warp == 0;
-    const int cw = B200Q_PRODUCER_LAST ? warp : warp - 1;                                         // consumer index (producer: out of range)
-    const int ctid = cw * 32 + lane, cthreads = ncw * 32;                                         // thread index among the consumers
-    const bool lead = cw == 0 && lane == 0;                                                       // first consumer thread (flag waits, trace)
-    const int S = g.n_stages;
-    const int row_stage = g.stage_bytes, pair_stage = 2 * row_stage;
-    // smem carve-up: [ring: ncw*S pair-stages][full barriers ncw*S][empty barriers ncw*S][kv table 128 words][x: sq | sd | sis]
-    unsigned char * ring0 = smem_raw;
-    uint64_t * full0  = reinterpret_cast<uint64_t *>(smem_raw + (size_t)ncw * S * pair_stage);
-    uint64_t * empty0 = full0 + ncw * S;
-    uint32_t * kv_slot = reinterpret_cast<uint32_t *>(empty0 + ncw * S);
-    int * pair_id = reinterpret_cast<int *>(kv_slot + 128);       // [ncw*S] pair index streamed into each stage (-1 = end)
-    int * next_pair = pair_id + B200Q_PAIR_SLOTS;                 // CTA-wide claim counter ([1]: finished consumer warps (tp.out))
-    uint64_t * xbar = reinterpret_cast<uint64_t *>(next_pair + 2); // completion of the q8_in bulk copy
-    int * pstate = reinterpret_cast<int *>(kv_slot + 128 + 128);  // [ncw][4] producer state handed to the consumers (self-refill)
-    uint32_t * k16tab = reinterpret_cast<uint32_t *>(kv_slot + 128 + 128 + 64);   // 32 x 65536 at lane-dependent addresses (B200Q_SHR_VIA_IMAD)
-    unsigned char * xbase = reinterpret_cast<unsigned char *>(kv_slot + 128 + 128 + 64 + 32);
-    int8_t * sq = reinterpret_cast<int8_t *>(xbase);
-    float *  sd = reinterpret_cast<float *>(xbase + (size_t)NCOLS * K);
-    int *    sis = reinterpret_cast<int *>(sd + NCOLS * n32);
-
-    const int nseg = (n32 + B200Q_SEG_ITEMS - 1) / B200Q_SEG_ITEMS;
-    constexpr int NT = UPGATE ? 2 : 1;                            // tensors per row (up, gate)
-    constexpr int RPU = PAIR ? 2 : 1;                             // rows per unit
-    const int n_pairs = (int)((a.M_total + RPU - 1) / RPU);       // unit p = rows RPU*p (.. +1) (segments have even row counts)
-    // static split of the pairs over CTAs (+-1 pair), dynamic claiming inside the CTA: the producer lane of a consumer
-    // warp takes the next pair from a shared counter whenever that warp's ring has room, so warps never idle on a
-    // coarse static remainder (2.2 pairs/warp for the FFN up/gate shape would otherwise mean 3 for some, 2 for others)
-    const int c0 = (int)(((int64_t)n_pairs * blockIdx.x) / gridDim.x), c1 = (int)(((int64_t)n_pairs * (blockIdx.x + 1)) / gridDim.x);
-    auto locate = [&](int grow, int & s, int & row) {
-        s = 0; row = grow;
-        if (MULTI) {
-#pragma unroll
-            for (int i = 1; i < B200Q_MAX_SEGS; ++i) if (i < a.n_seg && grow >= (int)a.seg[i].row0) s = i;
-            row = grow - (int)a.seg[s].row0;
-        }
-    };
-
-    if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) a.trace[0] = gtime();
-    if (is_prod) {
-        for (int i = lane; i < ncw * S; i += 32) { rb_init(&full0[i]); rb_init(&empty0[i]); }
-        if (Q8 == 1 && lane == 0) rb_init(xbar);
-        kv_slot[lane * 4 + 0] = B200Q_KV4_A0; kv_slot[lane * 4 + 1] = B200Q_KV4_A1; kv_slot[lane * 4 + 2] = B200Q_KV4_B0; kv_slot[lane * 4 + 3] = B200Q_KV4_B1;
-        if (lane == 0) { *next_pair = c0; next_pair[1] = 0; }    // [1]: consumer warps that have finished (tp.out)
-        k16tab[lane] = 65536u;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncwarp();
-    }
-
-    // ---------------- producer state (warp 0, lane = consumer warp index) ----------------
-    int pcur = -1, pt = 0, psg = 0, pst = 0, pu = 0; bool pdone = !(is_prod && lane < ncw);
-    auto produce_one = [&]() {                                    // issue the next unit of consumer warp `lane` into stage pst
-        uint64_t * fb = &full0[lane * S + pst];
-        if (pt == 0 && psg == 0) { pcur = atomicAdd(next_pair, 1); if (pcur >= c1) pcur = -1; }
-        pair_id[lane * S + pst] = pcur;
-        if (pcur < 0) { rb_arrive(fb); pdone = true; return; }   // sentinel: nothing left for this consumer
-        int s, row; locate(RPU * pcur, s, row);
-        const mmvq_seg & sgm = a.seg[MULTI ? s : 0];
-        const b200q_planes & P = (UPGATE && pt == 1) ? sgm.P2 : sgm.P;
-        const int g8 = min(B200Q_SEG_ITEMS, n32 - psg * B200Q_SEG_ITEMS) >> 3;
-        const bool two = PAIR && row + 1 < (int)sgm.M;
-        unsigned char * dstb = ring0 + ((size_t)lane * S + pst) * pair_stage;
-        uint32_t bytes = 0;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) if (p < g.n_planes) bytes += (uint32_t)(g8 * g.b8[p]);
-        rb_expect(fb, two ? 2 * bytes : bytes);
-#pragma unroll
-        for (int p = 0; p < 4; ++p) if (p < g.n_planes) {
-            const uint8_t * src = P.p[p] + ((int64_t)row * n8 + (int64_t)psg * (B200Q_SEG_ITEMS / 8)) * g.b8[p];
-            if (g.merged) bulk_g2s(dstb + g.seg_off[p], src, (uint32_t)((two ? 2 : 1) * g8 * g.b8[p]), fb);
-            else {
-                bulk_g2s(dstb + g.seg_off[p], src, (uint32_t)(g8 * g.b8[p]), fb);
-                if (two) bulk_g2s(dstb + g.row1[p] + g.seg_off[p], src + (int64_t)n8 * g.b8[p], (uint32_t)(g8 * g.b8[p]), fb);
-            }
-        }
-        ++pu; if (++pst == S) pst = 0;
-        if (++psg == nseg) { psg = 0; if (++pt == NT) pt = 0; }
-    };
-    // (1) weights do not depend on the previous kernel: fill the ring before waiting for it
-    if (is_prod) {
-        for (int s = 0; s < S; ++s) if (!pdone) produce_one();
-#if B200Q_SELF_REFILL
-        if (lane < ncw) { int * hs = pstate + lane * 4; hs[0] = pcur; hs[1] = pt; hs[2] = psg; hs[3] = pdone ? 1 : 0; }     // hand the stream over to the consumer warp
-#endif
-    }
-    pdl_trigger();                       // the next kernel of the stream/graph may become resident and fill ITS ring
-    pdl_wait();                          // (2) the activations are produced by the previous kernel
-    if (a.trace && blockIdx.x == 0 && lead) a.trace[1] = gtime();
-    // Tensor-parallel mode.  `seq` = number of fused reduces completed on this communicator (device counter, so the launch arguments
-    // are constant under CUDA-graph replay); it cannot change while this grid runs before its own last CTA bumps it.
-    uint32_t tps = 0;
-    if (TP && (a.tp.in || a.tp.out)) tps = *reinterpret_cast<volatile uint32_t *>(a.tp.seq);
-    if (!is_prod) {
-        if (TP && a.tp.out) {
-            // zero this rank's copy of the NEXT reduce's buffer: peers add to it only after they have seen this rank's flag
-            // increment for the current reduce, which is ordered after these stores (fence + release below)
-            // (seq[1 + p] = floats of parity buffer p that its last use left non-zero, see b200q_reduce.cu)
-            float * z = a.tp.local_base + (int64_t)((tps & 1) ^ 1) * a.tp.stride;
-            const int nd = (int)reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + ((tps & 1) ^ 1)];
-            const int per = (nd + (int)gridDim.x - 1) / (int)gridDim.x, z0 = per * (int)blockIdx.x, z1 = min(nd, z0 + per);
-            for (int i = z0 + ctid; i < z1; i += cthreads) z[i] = 0.0f;
-        }
-        if (TP && a.tp.in) {
-            // the activations are the sum over ranks of the previous row-parallel mat-vec: wait until every rank has signalled it
-            // (flag += 1 per rank per reduce through the multicast mapping), then read this rank's copy of the buffer
-            if (lead) { const uint32_t target = a.tp.world * tps; while ((int32_t)(tp_ld_acquire_sys(a.tp.local_flag) - target) < 0) { } }
-            asm volatile("bar.sync 1, %0;" ::"r"(cthreads) : "memory");
-            quantize_x_to_smem<NCOLS, true>(a.tp.local_base + (int64_t)((tps - 1) & 1) * a.tp.stride, a.tp.stride, K, sq, sd, sis, ctid, cthreads);
-        } else if (Q8 == 1) {
-            // quantised once by the producing kernel: nothing to do here, the producer warp bulk-copies the image (below)
-        } else {
-#if B200Q_TRACE_FINE
-            quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis, ctid, cthreads, a.trace && blockIdx.x == 0 && lead ? a.trace + 4 : nullptr);
-#else
-            quantize_x_to_smem<NCOLS>(a.x, a.x_stride, K, sq, sd, sis, ctid, cthreads);
-#endif
-        }
-#if B200Q_TRACE_FINE
-        if (a.trace && blockIdx.x == 0 && lead) a.trace[5] = gtime();
-#endif
-    } else if (Q8 == 1 && lane == 0) {
-        const uint32_t bytes = (uint32_t)(K + 8 * n32);
-        rb_expect(xbar, bytes);
-        bulk_g2s(sq, a.q8_in, bytes, xbar);
-    }
-    __syncthreads();                     // publishes barriers, kv table and activations
-    if (Q8 == 1 && !is_prod) rb_wait(xbar, 0);
-    if (a.trace && blockIdx.x == 0 && lead) a.trace[2] = gtime();
-
-#if B200Q_SELF_REFILL
-    if (is_prod) return;                 // the ring is primed; from here on the consumers refill their own stages
-#endif
-    if (is_prod) {
-        // ---------------- producer: refill a stage as soon as its consumer has released it ----------------
-        // All lanes poll their consumer's empty barrier with a NON-blocking test_wait and stay converged: a lane parked in a
-        // blocking try_wait would stall the refills of the other ten consumers that share this warp.
-        uint32_t epar = 1;               // first pass over the ring: the S initial units are already issued
-        int k = 0;
-        while (__any_sync(0xffffffffu, !pdone)) {
-            bool ready = false;
-            if (!pdone) ready = rb_test(&empty0[lane * S + pst], epar ^ 1);
-            if (ready) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                produce_one();
-                if (++k == S) { k = 0; epar ^= 1; }
-            }
-            if (!__any_sync(0xffffffffu, ready)) __nanosleep(64);
-        }
-        return;
-    }
-
-    // ---------------- consumers ----------------
-    b200q_kv4 T; T.a0 = kv_slot[lane * 4 + 0]; T.a1 = kv_slot[lane * 4 + 1]; T.b0 = kv_slot[lane * 4 + 2]; T.b1 = kv_slot[lane * 4 + 3];
-    T.k16 = k16tab[lane];
-    unsigned char * ring = ring0 + (size_t)cw * S * pair_stage;
-    uint64_t * fullb = full0 + cw * S, * emptyb = empty0 + cw * S;
-    float acc0[NCOLS], acc1[NCOLS], up0[NCOLS], up1[NCOLS];
-    int t = 0, sg = 0;
-    int cs = 0, crow = 0; float rs[2][2] = {{0.0f, 0.0f}, {0.0f, 0.0f}};
-    int st = 0; uint32_t parity = 0;
-#if B200Q_SELF_REFILL
-    // the stream of this warp's units continues where the producer's pre-fill stopped (all lanes keep the state, lane 0 acts)
-    int rcur = pstate[cw * 4 + 0], rt = pstate[cw * 4 + 1], rsg = pstate[cw * 4 + 2]; bool rdone = pstate[cw * 4 + 3] != 0;
-    auto refill = [&](int stg) {                                  // re-arm stage `stg`, which every lane has finished reading
-        uint64_t * fb = &fullb[stg];
-        if (rt == 0 && rsg == 0) {
-            int v = 0; if (lane == 0) v = atomicAdd(next_pair, 1);
-            v = __shfl_sync(0xffffffffu, v, 0); rcur = v >= c1 ? -1 : v;
-        }
-        if (lane == 0) pair_id[cw * S + stg] = rcur;
-        if (rcur < 0) { if (lane == 0) rb_arrive(fb); rdone = true; return; }
-        int s2, row; locate(RPU * rcur, s2, row);
-        const mmvq_seg & sgm = a.seg[MULTI ? s2 : 0];
-        const b200q_planes & P = (UPGATE && rt == 1) ? sgm.P2 : sgm.P;
-        const int g8 = min(B200Q_SEG_ITEMS, n32 - rsg * B200Q_SEG_ITEMS) >> 3;
-        const bool two = PAIR && row + 1 < (int)sgm.M;
-        if (lane == 0) {
-            unsigned char * dstb = ring + (size_t)stg * pair_stage;
-            uint32_t bytes = 0;
-#pragma unroll
-            for (int p = 0; p < 4; ++p) if (p < g.n_planes) bytes += (uint32_t)(g8 * g.b8[p]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            rb_expect(fb, two ? 2 * bytes : bytes);
-#pragma unroll
-            for (int p = 0; p < 4; ++p) if (p < g.n_planes) {
-                const uint8_t * src = P.p[p] + ((int64_t)row * n8 + (int64_t)rsg * (B200Q_SEG_ITEMS / 8)) * g.b8[p];
-                bulk_g2s(dstb + g.seg_off[p], src, (uint32_t)(g8 * g.b8[p]), fb);
-                if (two) bulk_g2s(dstb + g.row1[p] + g.seg_off[p], src + (int64_t)n8 * g.b8[p], (uint32_t)(g8 * g.b8[p]), fb);
-            }
-        }
-        if (++rsg == nseg) { rsg = 0; if (++rt == NT) rt = 0; }
-    };
-#endif
-    for (;;) {
-        rb_wait(&fullb[st], parity);
-        const int pid = pair_id[cw * S + st];
-        if (pid < 0) break;
-        if (sg == 0) {
-#pragma unroll
-            for (int c = 0; c < NCOLS; ++c) { acc0[c] = 0.0f; acc1[c] = 0.0f; }
-            if (t == 0) {
-                locate(RPU * pid, cs, crow);
-                if (b200q_row_plane(TYPE) >= 0) {              // per-row scales straight from global memory
-                    const mmvq_seg & sgm = a.seg[MULTI ? cs : 0];
-                    const int r1 = min(crow + 1, (int)sgm.M - 1);
-                    rs[0][0] = __ldg(reinterpret_cast<const float *>(sgm.P.p[b200q_row_plane(TYPE)]) + crow);
-                    rs[0][1] = __ldg(reinterpret_cast<const float *>(sgm.P.p[b200q_row_plane(TYPE)]) + r1);
-                    if (UPGATE) { rs[1][0] = __ldg(reinterpret_cast<const float *>(sgm.P2.p[b200q_row_plane(TYPE)]) + crow);
-                                  rs[1][1] = __ldg(reinterpret_cast<const float *>(sgm.P2.p[b200q_row_plane(TYPE)]) + r1); }
-                }
-            }
-        }
-        const int items = min(B200Q_SEG_ITEMS, n32 - sg * B200Q_SEG_ITEMS);
-        b200q_planes SP0, SP1;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) { SP0.p[p] = ring + (size_t)st * pair_stage + g.seg_off[p < g.n_planes ? p : 0]; SP1.p[p] = SP0.p[p] + g.row1[p < g.n_planes ? p : 0]; }
-        SP0.p[4] = SP1.p[4] = nullptr; SP0.nb = SP1.nb = 0; SP0.n32 = SP1.n32 = 0;
-        const float rsa = rs[UPGATE ? t : 0][0], rsb = rs[UPGATE ? t : 0][1];
-        auto do_item = [&](int itl) {
-            b200q_item I0, I1; b200q_canon C;
-            b200q_load_item<TYPE, b200q_ld_plain, false, int>(I0, SP0, 0, itl);
-            if (PAIR) b200q_load_item<TYPE, b200q_ld_plain, false, int>(I1, SP1, 0, itl);
-            I0.rs = rsa; I1.rs = rsb;
-            const int it = sg * B200Q_SEG_ITEMS + itl;
-            b200q_decode_item<TYPE>(I0, itl, C, T);
-            item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc0);
-            if (PAIR) { b200q_decode_item<TYPE>(I1, itl, C, T); item_dot<TYPE, NCOLS>(C, sq, sd, sis, K, n32, it, acc1); }
-        };
-        if (items == B200Q_SEG_ITEMS) {
-#pragma unroll
-            for (int i = 0; i < B200Q_SEG_ITEMS / 32; ++i) do_item(lane + 32 * i);
-        } else {
-            for (int itl = lane; itl < items; itl += 32) do_item(itl);
-        }
-        __syncwarp();
-#if B200Q_SELF_REFILL
-        if (!rdone) refill(st);
-        __syncwarp();
-#else
-        if (lane == 0) rb_arrive(&emptyb[st]);                  // stage may be overwritten by the producer
-#endif
-        if (++st == S) { st = 0; parity ^= 1; }
-        if (++sg == nseg) {
-            sg = 0;
-            const mmvq_seg & sgm = a.seg[MULTI ? cs : 0];
-            if (UPGATE && t == 0) {
-#pragma unroll
-                for (int c = 0; c < NCOLS; ++c) { up0[c] = acc0[c]; up1[c] = acc1[c]; }      // up . x (still per-lane partials)
-                t = 1;
-            } else {
-                const bool two = PAIR && crow + 1 < (int)sgm.M;
-#pragma unroll
-                for (int c = 0; c < NCOLS; ++c) {
-                    // four (two) independent butterfly chains interleave in the pipeline
-                    float v0 = acc0[c], v1 = acc1[c], u0 = UPGATE ? up0[c] : 0.0f, u1 = UPGATE ? up1[c] : 0.0f;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        v0 += __shfl_xor_sync(0xffffffffu, v0, o); if (PAIR) v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-                        if (UPGATE) { u0 += __shfl_xor_sync(0xffffffffu, u0, o); if (PAIR) u1 += __shfl_xor_sync(0xffffffffu, u1, o); }
-                    }
-                    if (UPGATE) {                                                 // v = gate . x, u = up . x
-                        v0 = b200q_glu<false>(a.act, v0, u0, a.limit); v1 = b200q_glu<false>(a.act, v1, u1, a.limit);
-                    } else if (sgm.bias) { v0 += sgm.bias[crow]; if (two) v1 += sgm.bias[crow + 1]; }
-                    if (lane == 0) {
-                        if (TP && a.tp.out) {                                     // partial result: summed over ranks inside the switch
-                            float * mc = a.tp.mc_base + (int64_t)(tps & 1) * a.tp.stride + (int64_t)sgm.row0 + crow;
-                            tp_red_add_f32(mc, v0); if (two) tp_red_add_f32(mc + 1, v1);
-                        } else { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
-                    }
-                    if (Q8 == 2) {
-                        // arrival counter of the 32-row block these rows belong to (row pairs never straddle a block); the warp that
-                        // completes the block quantises it for the next MUL_MAT
-                        const int blk = crow >> 5, add = two ? 2 : 1, need = min(32, (int)sgm.M - 32 * blk);
-                        uint32_t * cnt = reinterpret_cast<uint32_t *>(reinterpret_cast<int8_t *>(a.q8_out) + sgm.M + 8 * (sgm.M / 32)) + blk;
-                        int old = 0;
-                        if (lane == 0) { __threadfence(); old = (int)atomicAdd(cnt, (uint32_t)add); }
-                        old = __shfl_sync(0xffffffffu, old, 0);
-                        if (old + add == need) {
-                            __threadfence();
-                            q8_emit_block(a.q8_out, sgm.M, sgm.dst, sgm.M, blk, lane);
-                            if (lane == 0) *cnt = 0;
-                        }
-                    }
-                }
-#if B200Q_TRACE_FINE
-                if (a.trace && blockIdx.x == 0 && lead && a.trace[7] == 0) a.trace[7] = gtime();
-#endif
-                t = 0;
-            }
-        }
-    }
-    if (TP && a.tp.out) {
-        // completion: every consumer warp fences its multimem.reds (and its share of the zeroing), the last warp of the last CTA
-        // publishes this rank's flag increment on every GPU
-        // Every warp makes its own multimem.reds (and zeroing stores) performed system-wide (fence.sys, all warps in parallel), THEN counts
-        // itself in; the thread that sees the last arrival of the last CTA therefore runs after every contribution of this rank has
-        // landed in every peer, and publishes the flag with a release (the rank-local bookkeeping stores precede it in program order).
-        // No further fences on this critical path (round 1 had a fence.gpu and a second fence.sys in front of the release).
-        __threadfence_system();
-        if (lane == 0) {
-            if (atomicAdd(next_pair + 1, 1) == ncw - 1) {
-                if (atomicAdd(a.tp.cta_counter, 1u) == gridDim.x - 1) {
-                    *a.tp.cta_counter = 0;
-                    reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + ((tps & 1) ^ 1)] = 0; reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + (tps & 1)] = (uint32_t)a.M_total;
-                    *reinterpret_cast<volatile uint32_t *>(a.tp.seq) = tps + 1;
-                    tp_red_add_u32_release(a.tp.mc_flag, 1u);
-                }
-            }
-        }
-    }
-#if B200Q_TRACE_FINE
-    if (a.trace && lane == 0) { const unsigned long long tt = gtime(); atomicMax(a.trace + 3, tt); atomicMax(a.trace + 6, (1ull << 62) - tt); }
-#else
-    if (a.trace && lane == 0) atomicMax(a.trace + 3, gtime());
-#endif
-}
-
-// ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
 #ifdef B200Q_BENCH_TYPES_ONLY      // tuning variants (scripts/build_variant.sh): only the benchmarked type, small and quick to build
@@ -712,7 +73,16 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
     X(B200Q_TYPE_IQ2_KS) X(B200Q_TYPE_IQ3_KS)
 #endif
 
+// the per-type mat-vec launchers are instantiated in b200q_decode_i<N>.cu (parallel compilation)
+#define X(T) extern template int launch_mmvq_type<T>(const mmvq_args &, int, bool, int, bool, bool, cudaStream_t);
+B200Q_FOR_TYPES(X)
+#undef X
+
 int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L, int inverse, cudaStream_t st) {
+    if (L.wire) {       // wire-layout type: the device copy IS the GGUF payload
+        const size_t nbytes = (size_t)(L.M * b200q_wire_row_size(L));
+        return (int)(inverse ? cudaMemcpyAsync(const_cast<void *>(wire), planes, nbytes, cudaMemcpyDeviceToDevice, st) : cudaMemcpyAsync(planes, wire, nbytes, cudaMemcpyDeviceToDevice, st));
+    }
     const int64_t total = L.M * L.nb;
     const int bs = 128; const int64_t nb = (total + bs - 1) / bs;
     k_repack<<<(unsigned)(nb > 65535 * 16 ? 65535 * 16 : (nb < 1 ? 1 : nb)), bs, 0, st>>>((const uint8_t *)wire, (uint8_t *)planes, L, inverse);
@@ -720,6 +90,7 @@ int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L
 }
 
 int b200q_launch_dequant_bf16(const void * W, const b200q_layout & L, void * out, cudaStream_t st) {
+    if (L.wire) return b200q_launch_wire_dequant_bf16(L.type, W, L.M, L.K, out, st);
     const int64_t total = L.M * (L.K / 32);
     const int bs = 256; int64_t nb = (total + bs - 1) / bs; if (nb > 148 * 64) nb = 148 * 64; if (nb < 1) nb = 1;
     switch (L.type) {
@@ -729,134 +100,6 @@ int b200q_launch_dequant_bf16(const void * W, const b200q_layout & L, void * out
         default: return -1;
     }
     return (int)cudaGetLastError();
-}
-
-template <int TYPE, int NCOLS, bool UPGATE>
-static int launch_mmvq_t(const mmvq_args & a, int sm_count, bool pdl, cudaStream_t st) {
-    const size_t smem = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8;
-    static size_t configured[B200Q_MAX_DEVICES] = {};     // function attributes are per device
-    const int dev = b200q_current_device();
-    if (smem > 48 * 1024 && smem > configured[dev]) {
-        if (cudaFuncSetAttribute(k_mmvq<TYPE, NCOLS, UPGATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
-        configured[dev] = smem;
-    }
-    // one warp per row, one CTA per SM; shrink the CTA when there are fewer rows than warps
-    int nwarps = 16;
-    while (nwarps > 2 && a.M_total <= (int64_t)sm_count * (nwarps / 2)) nwarps >>= 1;
-    int64_t grid = (a.M_total + nwarps - 1) / nwarps;
-    if (grid > sm_count) grid = sm_count;
-    if (grid < 1) grid = 1;
-    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(nwarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, k_mmvq<TYPE, NCOLS, UPGATE>, a);
-}
-
-// ring geometry for a type; returns false if the planes cannot be bulk-copied (alignment) -> LDG kernel
-static bool make_ring_geom(int type, int64_t K, ring_geom & g) {
-    b200q_layout L; if (b200q_make_layout(type, 1, K, &L)) return false;
-    if (K % 256) return false;
-    const int64_t n8 = K / 256;
-    memset(&g, 0, sizeof g); g.row_plane = -1;
-    int off = 0, np = 0;
-    for (int p = 0; p < L.n_planes; ++p) {
-        if (L.plane_per_row[p]) { g.row_plane = p; continue; }
-        if (p != np) return false;                       // block planes must come first (they do for every type)
-        const int b8 = L.plane_bytes[p] * 256 / L.qk;
-        if (b8 <= 0 || (n8 * b8) % 16) return false;     // every row/segment start must be 16-byte aligned
-        g.b8[np] = b8; g.seg_off[np] = off; off += (int)b200q_align_up((B200Q_SEG_ITEMS / 8) * b8, 16); ++np;
-    }
-    g.n_planes = np; g.stage_bytes = (int)b200q_align_up(off, 128);
-    for (int p = 0; p < np; ++p) g.row1[p] = g.stage_bytes;          // row-major stage: [row 0: planes][row 1: planes]
-    // one segment per row: merge the two rows of a pair into one copy per plane (B200Q_MERGE_PAIR=0 restores the round-1 scheme)
-    static const int merge = [] { const char * e = getenv("B200Q_MERGE_PAIR"); return e ? atoi(e) : 1; }();
-    if (merge && !B200Q_SELF_REFILL && K / 32 <= B200Q_SEG_ITEMS && np > 0 && np <= 4) {
-        int o = 0;
-        for (int p = 0; p < np; ++p) { const int rb = (int)(n8 * g.b8[p]); g.seg_off[p] = o; g.row1[p] = rb; o += (int)b200q_align_up(2 * rb, 16); }
-        if (o <= 2 * g.stage_bytes) g.merged = 1;
-        else { int o2 = 0; for (int p = 0; p < np; ++p) { g.seg_off[p] = o2; o2 += (int)b200q_align_up((B200Q_SEG_ITEMS / 8) * g.b8[p], 16); g.row1[p] = g.stage_bytes; } }
-    }
-    return np > 0 && np <= 4;
-}
-
-template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR, bool TP = false, int Q8 = 0>
-static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
-    mmvq_ring_args ra; ra.a = a; ra.g = g0;
-    for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
-    if (a.M_total >= (int64_t)1 << 30) return -100;
-    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 512 + 256 + 128;
-    const size_t budget = B200Q_SMEM_BUDGET;
-    const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
-    int ncw = B200Q_RING_CONSUMERS, S = 0;              // consumer warps (+1 producer warp)
-    for (;;) {
-        const size_t per_stage = (size_t)ncw * (pair_stage + 16);
-        S = xbytes + 64 < budget ? (int)((budget - xbytes - 64) / per_stage) : 0;
-        if (S >= 2 || ncw == 3) break;
-        ncw = ncw > 7 ? 7 : 3;                           // (10 warps would still fit two stages for K = 14336 but measured slower: 13.8 vs 11.3 us)
-    }
-    if (S < 2) return -100;                              // does not fit: caller falls back to the LDG kernel
-    if (S > B200Q_MAX_STAGES) S = B200Q_MAX_STAGES;
-    const int64_t n_pairs = PAIR ? (a.M_total + 1) / 2 : a.M_total;
-    while (ncw > 3 && n_pairs <= (int64_t)sm_count * (ncw > 7 ? 7 : 3)) ncw = ncw > 7 ? 7 : 3;
-    while (ncw * S > B200Q_PAIR_SLOTS) --S;
-    ra.g.n_stages = S;
-    const size_t smem = (size_t)ncw * S * (pair_stage + 16) + xbytes + 64;
-    static bool configured[B200Q_MAX_DEVICES] = {};
-    const int dev = b200q_current_device();
-    if (!configured[dev]) {
-        if (cudaFuncSetAttribute(k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR, TP, Q8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(budget)) != cudaSuccess) return -3;
-        configured[dev] = true;
-    }
-    // B200Q_GRID_FULL=1 (experiment): always spread over every SM, even when a CTA then has fewer units than consumer warps
-    static const int grid_full = [] { const char * e = getenv("B200Q_GRID_FULL"); return e ? atoi(e) : 0; }();
-    int64_t grid = grid_full ? n_pairs : (n_pairs + ncw - 1) / ncw;
-    if (grid > (int64_t)sm_count * ctas_per_sm) grid = (int64_t)sm_count * ctas_per_sm;
-    if (grid < 1) grid = 1;
-    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((ncw + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return (int)cudaLaunchKernelEx(&cfg, k_mmvq_ring<TYPE, NCOLS, UPGATE, MULTI, PAIR, TP, Q8>, ra);
-}
-
-template <int TYPE, int NCOLS, bool UPGATE, bool MULTI>
-static int launch_mmvq_ring_t(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
-    // row pairs amortise the activation loads; single rows give more, shorter units when the matrix is small
-    static const int force = [] { const char * e = getenv("B200Q_PAIR"); return e ? atoi(e) : -1; }();
-    const bool pair = force >= 0 ? force != 0 : true;      // measured: pairs win for every Llama-3-8B shape (679 vs 628 tok/s)
-    if (a.tp.in || a.tp.out) {                             // tensor-parallel decode: n = 1, row pairs
-        if (NCOLS != 1) return -7;
-        return launch_mmvq_ring_tp<TYPE, 1, UPGATE, MULTI, true, true>(a, g0, sm_count, pdl, ctas_per_sm, st);
-    }
-    if (a.q8_in || a.q8_out) {                             // q8 hand-off: n = 1, one tensor, row pairs
-        if (NCOLS != 1 || MULTI) return -8;
-        if (a.q8_out) return UPGATE ? launch_mmvq_ring_tp<TYPE, 1, true, false, true, false, 2>(a, g0, sm_count, pdl, ctas_per_sm, st) : -8;
-        return UPGATE ? -8 : launch_mmvq_ring_tp<TYPE, 1, false, false, true, false, 1>(a, g0, sm_count, pdl, ctas_per_sm, st);
-    }
-    return pair ? launch_mmvq_ring_tp<TYPE, NCOLS, UPGATE, MULTI, true>(a, g0, sm_count, pdl, ctas_per_sm, st)
-                : launch_mmvq_ring_tp<TYPE, NCOLS, UPGATE, MULTI, false>(a, g0, sm_count, pdl, ctas_per_sm, st);
-}
-
-template <int TYPE>
-static int launch_mmvq_type(const mmvq_args & a, int ncols, bool upgate, int sm_count, bool pdl, bool ring, cudaStream_t st) {
-    ring_geom g;
-    if (ring && ncols <= 2 && make_ring_geom(TYPE, a.K, g)) {
-        int rc;
-        static const int cps = [] { const char * e = getenv("B200Q_CTAS_PER_SM"); return e ? atoi(e) : B200Q_MIN_CTAS; }();
-        const bool multi = a.n_seg > 1;
-        if (upgate) rc = ncols == 1 ? launch_mmvq_ring_t<TYPE, 1, true, false>(a, g, sm_count, pdl, cps, st) : launch_mmvq_ring_t<TYPE, 2, true, false>(a, g, sm_count, pdl, cps, st);
-        else if (multi) rc = ncols == 1 ? launch_mmvq_ring_t<TYPE, 1, false, true>(a, g, sm_count, pdl, cps, st) : launch_mmvq_ring_t<TYPE, 2, false, true>(a, g, sm_count, pdl, cps, st);
-        else rc = ncols == 1 ? launch_mmvq_ring_t<TYPE, 1, false, false>(a, g, sm_count, pdl, cps, st) : launch_mmvq_ring_t<TYPE, 2, false, false>(a, g, sm_count, pdl, cps, st);
-        if (rc != -100) return rc;
-    }
-    if (a.tp.in || a.tp.out) return -7;
-    if (a.q8_in || a.q8_out) return -8;                    // only the ring kernel implements the q8 hand-off (callers retry without it)
-#define CASE(N) case N: return upgate ? launch_mmvq_t<TYPE, N, true>(a, sm_count, pdl, st) : launch_mmvq_t<TYPE, N, false>(a, sm_count, pdl, st);
-    switch (ncols) { CASE(1) CASE(2) CASE(4) CASE(8) default: return -2; }
-#undef CASE
 }
 
 // per-launch phase timestamps (debug aid for the PDL pipeline; see scripts/trace_decode.py)
@@ -869,6 +112,7 @@ extern "C" __attribute__((visibility("default"))) int b200q_debug_trace(int enab
     return -1;
 }
 int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
+    if (b200q_is_wire_type(d.type)) return b200q_launch_wire_mmvq(d, st);
     mmvq_args a; memset(&a, 0, sizeof a);
     if (g_trace && g_trace_slot < 4096) a.trace = g_trace + 8 * (g_trace_slot++);
     if (d.n_seg < 1 || d.n_seg > B200Q_MAX_SEGS || d.ncols < 1 || d.ncols > 8) return -2;

@@ -1,0 +1,82 @@
+// b200q_decode_common.cuh — device helpers shared by the decode mat-vec kernels (b200q_decode.cu: plane-layout types, b200q_wire.cu: wire-layout types)
+#pragma once
+#include "b200q_internal.h"
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// programmatic dependent launch (no-ops unless the launch carries the PDL attribute)
+__device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Quantise ncols activation columns into shared memory (q8_1 semantics of ggml-cuda/quantize.cu:13-47):
+//   d = amax/127 ; q = amax == 0 ? 0 : roundf(x/d) ; d kept as float(half(d)) ; isum = packed int16 sums of q over each 16.
+// Cooperative and vectorised: a thread owns 8 consecutive floats (two LDG.128), 4 adjacent lanes own one 32-block.
+template <int NCOLS, bool COHERENT = false>
+__device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x, int64_t x_stride, int64_t K,
+                                                   int8_t * sq, float * sd, int * sis, int tid, int nthreads, unsigned long long * tr = nullptr) {
+    const int nch = (int)(K / 8), total = nch * NCOLS, n32 = (int)(K / 32);
+    constexpr int B = 4;                                   // chunks per thread per batch: 8 independent LDG.128 in flight, so the
+                                                           // activation vector costs 1 (K=4096) .. 2 (K=14336) L2 round trips, not 2 .. 6
+    for (int base = 0; base < total; base += nthreads * B) {
+        float4 va[B], vb[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int c = base + u * nthreads + tid;
+            int col = 0, ch = c < total ? c : 0;
+            if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
+            if (c < total) {
+                // COHERENT: the vector was written through the NVLS multicast mapping by other GPUs -> no read-only / stale-L1 path
+                va[u] = COHERENT ? __ldcv(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8)) : __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8));
+                vb[u] = COHERENT ? __ldcv(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4)) : __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
+            } else { va[u] = make_float4(0.f, 0.f, 0.f, 0.f); vb[u] = va[u]; }
+        }
+        if (tr && base == 0 && va[0].x != 123456.789f) *tr = gtime();       // (debug trace) first batch of loads has landed
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int c = base + u * nthreads + tid;
+            if (base + u * nthreads >= total) break;       // warp-uniform: the whole batch slot is past the end
+            const bool valid = c < total;
+            int col = 0, ch = valid ? c : 0;
+            if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
+            const float v[8] = {va[u].x, va[u].y, va[u].z, va[u].w, vb[u].x, vb[u].y, vb[u].z, vb[u].w};
+            float amax = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[j]));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+            amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+            // d = amax/127 exactly as the reference; q = rint(x * (1/d)) with a correctly rounded reciprocal: one division and one
+            // reciprocal per block instead of one division per element.  Differs from the reference's roundf(x / d) only for
+            // products within 1 ulp of a rounding tie (p ~ 1e-5 per element, 1 LSB); the oracle restates exactly this arithmetic
+            // (oracle_quantize_q8_1_b200) next to the reference's (oracle_quantize_q8_1).
+            const float d = __fdiv_rn(amax, 127.0f);
+            const float inv = d > 0.0f ? __frcp_rn(d) : 0.0f;
+            int q[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) q[j] = max(-127, min(127, __float2int_rn(__fmul_rn(v[j], inv))));
+            int2 pk;
+            pk.x = (int)__byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+            pk.y = (int)__byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+            int s = __dp4a(pk.x, 0x01010101, __dp4a(pk.y, 0x01010101, 0));
+            s += __shfl_xor_sync(0xffffffffu, s, 1);                       // sum over 16 weights (2 lanes)
+            const int s_hi = __shfl_down_sync(0xffffffffu, s, 2);          // the second 16 of the 32-block
+            if (valid) {
+                // natural order.  (Tried: two half planes [K/2 | K/2] so that the LDS.128 pairs of item_dot are conflict-free across the
+                // warp -> 659 vs 705 tok/s, slower; kept simple.)
+                *reinterpret_cast<int2 *>(sq + (size_t)col * K + (size_t)ch * 8) = pk;
+                if ((ch & 3) == 0) {
+                    sd[col * n32 + (ch >> 2)]  = __half2float(__float2half_rn(d));
+                    sis[col * n32 + (ch >> 2)] = (s & 0xFFFF) | (s_hi << 16);
+                }
+            }
+        }
+    }
+}
+
+

@@ -1,0 +1,3 @@
+// instantiation unit 3 of the decode mat-vec kernels (see b200q_decode_inst.inc)
+#define B200Q_INST_GROUP 3
+#include "b200q_decode_inst.inc"

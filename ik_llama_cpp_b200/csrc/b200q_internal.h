@@ -65,6 +65,9 @@ static inline size_t b200q_q8_image_bytes(int64_t k) { return (size_t)(k + 12 * 
 int b200q_launch_repack(const void * wire, void * planes, const b200q_layout & L, int inverse, cudaStream_t st);
 int b200q_launch_dequant_bf16(const void * W, const b200q_layout & L, void * out, cudaStream_t st);
 int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st);
+// wire-layout types (b200q_wire.cu)
+int b200q_launch_wire_mmvq(const b200q_mmvq_desc & d, cudaStream_t st);
+int b200q_launch_wire_dequant_bf16(int type, const void * W, int64_t M, int64_t K, void * out, cudaStream_t st);
 
 // prefill: up to 3 weight tensors of one type / K that share the bf16 activation operand xb [N][K]
 struct b200q_gemm_multi {

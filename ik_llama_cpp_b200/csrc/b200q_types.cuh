@@ -95,6 +95,50 @@ B200Q_HD uint16_t b200q_f2h_exact(float f) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// wire-layout types (decoded by b200q_wire.cuh): kept in their GGUF byte layout, no plane repack
+// ---------------------------------------------------------------------------------------------
+enum b200q_wire_type : int {
+    B200Q_TYPE_IQ2_XXS = 16, B200Q_TYPE_IQ2_XS = 17, B200Q_TYPE_IQ3_XXS = 18, B200Q_TYPE_IQ1_S = 19, B200Q_TYPE_IQ3_S = 21, B200Q_TYPE_IQ2_S = 22, B200Q_TYPE_IQ1_M = 29,
+    B200Q_TYPE_IQ1_BN = 134, B200Q_TYPE_IQ6_K = 141, B200Q_TYPE_IQ4_KSS = 146, B200Q_TYPE_IQ2_KT = 153, B200Q_TYPE_IQ3_KT = 154, B200Q_TYPE_IQ4_KT = 155,
+    B200Q_TYPE_IQ2_KL = 157, B200Q_TYPE_IQ1_KT = 158,
+    B200Q_TYPE_IQ1_S_R4 = 219, B200Q_TYPE_IQ1_M_R4 = 229, B200Q_TYPE_IQ2_K_R4 = 337, B200Q_TYPE_IQ3_K_R4 = 338, B200Q_TYPE_IQ4_K_R4 = 339, B200Q_TYPE_IQ5_K_R4 = 340,
+    B200Q_TYPE_IQ4_KS_R4 = 344, B200Q_TYPE_IQ5_KS_R4 = 352,
+};
+
+// per-ROW wire geometry: weights per block, bytes per block, bytes of row header, rows interleaved on the wire (1 or 4)
+struct b200q_wire_geom { int qk, block_bytes, row_meta, interleave; };
+B200Q_HD bool b200q_wire_geom_of(int type, b200q_wire_geom & g) {
+    switch (type) {
+        case B200Q_TYPE_IQ2_XXS: g = {256, 66, 0, 1}; return true;
+        case B200Q_TYPE_IQ2_XS:  g = {256, 74, 0, 1}; return true;
+        case B200Q_TYPE_IQ3_XXS: g = {256, 98, 0, 1}; return true;
+        case B200Q_TYPE_IQ2_S:   g = {256, 82, 0, 1}; return true;
+        case B200Q_TYPE_IQ3_S:   g = {256, 110, 0, 1}; return true;
+        case B200Q_TYPE_IQ1_S:   g = {256, 50, 0, 1}; return true;
+        case B200Q_TYPE_IQ1_M:   g = {256, 56, 0, 1}; return true;
+        case B200Q_TYPE_IQ6_K:   g = {256, 212, 0, 1}; return true;
+        case B200Q_TYPE_IQ4_KSS: g = {256, 128, 4, 1}; return true;
+        case B200Q_TYPE_IQ2_KL:  g = {256, 86, 2, 1}; return true;
+        case B200Q_TYPE_IQ1_BN:  g = {64, 13, 2, 1}; return true;
+        case B200Q_TYPE_IQ1_KT:  g = {256, 56, 4, 1}; return true;
+        case B200Q_TYPE_IQ2_KT:  g = {256, 68, 4, 1}; return true;
+        case B200Q_TYPE_IQ3_KT:  g = {256, 100, 4, 1}; return true;
+        case B200Q_TYPE_IQ4_KT:  g = {256, 128, 4, 1}; return true;
+        case B200Q_TYPE_IQ1_S_R4: g = {32, 6, 2, 4}; return true;
+        case B200Q_TYPE_IQ1_M_R4: g = {32, 7, 2, 4}; return true;
+        case B200Q_TYPE_IQ2_K_R4: g = {256, 76, 0, 4}; return true;
+        case B200Q_TYPE_IQ3_K_R4: g = {256, 110, 0, 4}; return true;
+        case B200Q_TYPE_IQ4_K_R4: g = {256, 144, 0, 4}; return true;
+        case B200Q_TYPE_IQ5_K_R4: g = {256, 176, 0, 4}; return true;
+        case B200Q_TYPE_IQ4_KS_R4: g = {256, 136, 4, 4}; return true;
+        case B200Q_TYPE_IQ5_KS_R4: g = {256, 168, 4, 4}; return true;
+        default: return false;
+    }
+}
+B200Q_HD bool b200q_is_wire_type(int type) { b200q_wire_geom g; return b200q_wire_geom_of(type, g); }
+B200Q_HD int64_t b200q_wire_type_row_size(const b200q_wire_geom & g, int64_t K) { return (int64_t)g.row_meta + (K / g.qk) * g.block_bytes; }
+
+// ---------------------------------------------------------------------------------------------
 // layout descriptor
 // ---------------------------------------------------------------------------------------------
 #define B200Q_MAX_PLANES 5
@@ -109,6 +153,7 @@ struct b200q_layout {
     int64_t  M, K, nb;                      // rows, cols, blocks per row
     int64_t  plane_off[B200Q_MAX_PLANES];
     int64_t  total_bytes;
+    int      wire;                          // 0: plane layout; 1 / 4: the tensor is stored verbatim (wire-layout type), value = rows interleaved on the wire
 };
 
 B200Q_HD int64_t b200q_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -147,7 +192,15 @@ inline int b200q_make_layout(int type, int64_t M, int64_t K, b200q_layout * L) {
         case B200Q_TYPE_IQ2_KS: set(256, 70, 2, 3, 64, 8, 4, 0, 2); break;     // qs (2-bit selectors) | {extra,scales[4],pad 2} | row scale (half on the wire, f32 in the plane)
         case B200Q_TYPE_IQ3_KS: set(256, 102, 2, 4, 64, 32, 8, 4, 3); break;   // qs | qh | {extra,scales[4],pad 2} | row scale
         case B200Q_TYPE_IQ2_BN: set(64,  16, 4, 2, 16, 4, 0, 0, 1); break;     // qs | row scale
-        default: return -1;
+        default: {
+            b200q_wire_geom g;
+            if (!b200q_wire_geom_of(type, g)) return -1;
+            if (K <= 0 || K % g.qk || K % 32 || M % g.interleave) return -2;
+            L->qk = g.qk; L->wire_block = g.block_bytes; L->row_meta = g.row_meta; L->n_planes = 1; L->plane_bytes[0] = g.block_bytes; L->wire = g.interleave;
+            L->nb = K / g.qk; L->plane_off[0] = 0;
+            L->total_bytes = b200q_align_up(M * b200q_wire_type_row_size(g, K), 256);
+            return 0;
+        }
     }
     if (K <= 0 || K % L->qk) return -2;
     L->nb = K / L->qk;

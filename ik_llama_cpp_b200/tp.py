@@ -16,7 +16,13 @@ import numpy as np
 # (block elements, block bytes, row meta bytes) — ggml type traits (ggml/src/ggml.c:640-1460)
 GEOM = {2: (32, 18, 0), 3: (32, 20, 0), 6: (32, 22, 0), 7: (32, 24, 0), 133: (32, 26, 0), 8: (32, 34, 0), 12: (256, 144, 0), 13: (256, 176, 0), 14: (256, 210, 0), 20: (32, 18, 0), 23: (256, 136, 0),
         135: (64, 16, 4), 139: (256, 144, 0), 140: (256, 176, 0), 144: (256, 136, 4),
-        10: (256, 84, 0), 11: (256, 110, 0), 137: (256, 76, 0), 138: (256, 110, 0), 39: (32, 17, 0), 152: (256, 168, 4), 145: (256, 70, 2), 156: (256, 102, 2)}
+        10: (256, 84, 0), 11: (256, 110, 0), 137: (256, 76, 0), 138: (256, 110, 0), 39: (32, 17, 0), 152: (256, 168, 4), 145: (256, 70, 2), 156: (256, 102, 2),
+        # wire-layout types (ik_llama_cpp_b200/csrc/b200q_wire.cuh)
+        16: (256, 66, 0), 17: (256, 74, 0), 18: (256, 98, 0), 22: (256, 82, 0), 21: (256, 110, 0), 19: (256, 50, 0), 29: (256, 56, 0), 141: (256, 212, 0), 146: (256, 128, 4),
+        157: (256, 86, 2), 134: (64, 13, 2), 158: (256, 56, 4), 153: (256, 68, 4), 154: (256, 100, 4), 155: (256, 128, 4),
+        219: (32, 6, 2), 229: (32, 7, 2), 337: (256, 76, 0), 338: (256, 110, 0), 339: (256, 144, 0), 340: (256, 176, 0), 344: (256, 136, 4), 352: (256, 168, 4)}
+# rows interleaved on the wire (the _R4 repacks): a wire "row group" of 4 rows = {4 row headers}{blocks of 4 rows}
+INTERLEAVE = {219: 4, 229: 4, 337: 4, 338: 4, 339: 4, 340: 4, 344: 4, 352: 4}
 
 
 def create_split(nr: int, granularity: int, world: int) -> list[int]:
@@ -38,6 +44,7 @@ def row_size(ggml_type: int, k: int) -> int:
 
 def shard_rows(wire: np.ndarray, ggml_type: int, m: int, k: int, world: int, rank: int, granularity: int = 1):
     """split_dim = 1: rows [r0, r1) of the wire tensor.  Returns (shard_bytes, m_shard)."""
+    granularity = max(granularity, INTERLEAVE.get(ggml_type, 1)) if granularity > 0 else granularity
     sizes = create_split(m, granularity, world)
     r0 = sum(sizes[:rank])
     rs = row_size(ggml_type, k)
@@ -54,10 +61,12 @@ def shard_cols(wire: np.ndarray, ggml_type: int, m: int, k: int, world: int, ran
     sizes = create_split(k, g, world)
     k0 = sum(sizes[:rank]); ks = sizes[rank]
     rs = row_size(ggml_type, k)
-    w = np.ascontiguousarray(wire, np.uint8).reshape(m, rs)
-    out = np.empty((m, meta + (ks // qk) * bs), np.uint8)
-    out[:, :meta] = w[:, :meta]
-    out[:, meta:] = w[:, meta + (k0 // qk) * bs: meta + ((k0 + ks) // qk) * bs]
+    il = INTERLEAVE.get(ggml_type, 1)                 # row groups: the K range of a group of `il` interleaved rows is contiguous on the wire
+    assert m % il == 0
+    w = np.ascontiguousarray(wire, np.uint8).reshape(m // il, il * rs)
+    out = np.empty((m // il, il * (meta + (ks // qk) * bs)), np.uint8)
+    out[:, :il * meta] = w[:, :il * meta]
+    out[:, il * meta:] = w[:, il * (meta + (k0 // qk) * bs): il * (meta + ((k0 + ks) // qk) * bs)]
     return out.reshape(-1), ks, k0
 
 

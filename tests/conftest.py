@@ -9,8 +9,13 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-ORACLE_ONLY_TYPES = ["IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S", "IQ6_K", "IQ1_BN", "IQ4_KSS"]      # oracle pinned against the reference, device kernel not built yet
-ALL_TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q6_0", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "IQ2_K", "IQ3_K", "IQ4_K", "IQ5_K", "IQ4_KS", "IQ5_KS", "IQ2_KS", "IQ3_KS", "MXFP4", "IQ2_BN"]
+ORACLE_ONLY_TYPES = []
+# plane layout (b200q_types.cuh: 16-byte low-bit plane per 32 weights, TMA-ring mat-vec, fused tcgen05 prefill for the 2-plane types)
+PLANE_TYPES = ["Q4_0", "Q4_1", "Q5_0", "Q5_1", "Q6_0", "Q8_0", "Q2_K", "Q3_K", "Q4_K", "Q5_K", "Q6_K", "IQ4_NL", "IQ4_XS", "IQ2_K", "IQ3_K", "IQ4_K", "IQ5_K", "IQ4_KS", "IQ5_KS", "IQ2_KS", "IQ3_KS", "MXFP4", "IQ2_BN"]
+# wire layout (b200q_wire.cuh: GGUF bytes verbatim, generic decode): grid-codebook, trellis and row-interleaved types
+WIRE_TYPES = ["IQ2_XXS", "IQ2_XS", "IQ3_XXS", "IQ2_S", "IQ3_S", "IQ6_K", "IQ1_BN", "IQ4_KSS", "IQ1_S", "IQ1_M", "IQ2_KL", "IQ1_KT", "IQ2_KT", "IQ3_KT", "IQ4_KT",
+              "IQ1_S_R4", "IQ1_M_R4", "IQ2_K_R4", "IQ3_K_R4", "IQ4_K_R4", "IQ5_K_R4", "IQ4_KS_R4", "IQ5_KS_R4"]
+ALL_TYPES = PLANE_TYPES + WIRE_TYPES      # every quantized type the reference's CUDA back-end accepts for MUL_MAT (ggml-cuda.cu:4862-4917)
 
 
 def pytest_configure(config):
@@ -46,8 +51,10 @@ def make_wire(oracle_or_ref, name, m, k, seed, reflib=None):
     rng = np.random.default_rng(seed)
     if reflib is not None:
         w = (rng.standard_normal((m, k)) * 0.02).astype(np.float32)
-        if name == "IQ2_BN":
+        if name in ("IQ2_BN", "IQ1_BN"):
             w = (rng.integers(-1, 2, (m, k)) * 0.043).astype(np.float32)
+        if name in _WIRE_GEOM and (m % _WIRE_GEOM[name][3] or name.endswith("_KT")):      # (the trellis quantisers take ~1 s per row: resample instead)
+            return random_wire(name, m, k, rng)
         return reflib.quantize(t, w)
     return random_wire(name, m, k, rng)
 
@@ -60,7 +67,33 @@ _GEOM = {
 _QK = {"Q4_0": 32, "Q4_1": 32, "Q5_0": 32, "Q5_1": 32, "Q6_0": 32, "Q8_0": 32, "IQ4_NL": 32, "MXFP4": 32, "IQ2_BN": 64}
 
 
+# per-ROW wire geometry of the wire-layout types: (weights per block, block bytes, row header bytes, rows interleaved)
+_WIRE_GEOM = {"IQ2_XXS": (256, 66, 0, 1), "IQ2_XS": (256, 74, 0, 1), "IQ3_XXS": (256, 98, 0, 1), "IQ2_S": (256, 82, 0, 1), "IQ3_S": (256, 110, 0, 1), "IQ1_S": (256, 50, 0, 1),
+              "IQ1_M": (256, 56, 0, 1), "IQ6_K": (256, 212, 0, 1), "IQ4_KSS": (256, 128, 4, 1), "IQ2_KL": (256, 86, 2, 1), "IQ1_BN": (64, 13, 2, 1), "IQ1_KT": (256, 56, 4, 1),
+              "IQ2_KT": (256, 68, 4, 1), "IQ3_KT": (256, 100, 4, 1), "IQ4_KT": (256, 128, 4, 1), "IQ1_S_R4": (32, 6, 2, 4), "IQ1_M_R4": (32, 7, 2, 4), "IQ2_K_R4": (256, 76, 0, 4),
+              "IQ3_K_R4": (256, 110, 0, 4), "IQ4_K_R4": (256, 144, 0, 4), "IQ5_K_R4": (256, 176, 0, 4), "IQ4_KS_R4": (256, 136, 4, 4), "IQ5_KS_R4": (256, 168, 4, 4)}
+
+
+def _resample_golden_wire(name, m, k, rng):
+    """Valid wire bytes of a wire-layout type without the reference library (GPU box): row groups assembled from randomly drawn blocks and
+    row headers of the committed golden tensor (which the reference's own quantiser produced)."""
+    qk, bs, meta, il = _WIRE_GEOM[name]
+    g = load_golden(name)
+    gm, gk = int(g["m"]), int(g["k"])
+    assert m % il == 0 and k % qk == 0
+    gw = g["wire"].reshape(gm // il, il * (meta + (gk // qk) * bs))
+    heads = gw[:, :il * meta]
+    blocks = gw[:, il * meta:].reshape(gm // il, gk // qk, il * bs)
+    ng, nb = m // il, k // qk
+    out = np.empty((ng, il * meta + nb * il * bs), np.uint8)
+    out[:, :il * meta] = heads[rng.integers(0, gm // il, ng)]
+    out[:, il * meta:] = blocks[rng.integers(0, gm // il, (ng, nb)), rng.integers(0, gk // qk, (ng, nb))].reshape(ng, nb * il * bs)
+    return out.reshape(-1)
+
+
 def random_wire(name, m, k, rng):
+    if name in _WIRE_GEOM:
+        return _resample_golden_wire(name, m, k, rng)
     bs, halfs, meta = _GEOM[name]
     qk = _QK.get(name, 256)
     nb = k // qk

@@ -2,12 +2,13 @@
 // with g++ so that the exact repack / decode bit manipulation the CUDA kernels execute can be checked
 // on a CPU-only box against the oracle.  Test infrastructure only; nothing here ships.
 #include "../../ik_llama_cpp_b200/csrc/b200q_types.cuh"
+#include "../../ik_llama_cpp_b200/csrc/b200q_wire.cuh"
 #include <vector>
 #include <cmath>
 #define API extern "C" __attribute__((visibility("default")))
 
 API long emul_layout_bytes(int type, long M, long K) { b200q_layout L; if (b200q_make_layout(type, M, K, &L)) return -1; return (long)L.total_bytes; }
-API long emul_wire_row_size(int type, long K) { b200q_layout L; if (b200q_make_layout(type, 1, K, &L)) return -1; return (long)b200q_wire_row_size(L); }
+API long emul_wire_row_size(int type, long K) { b200q_layout L; if (b200q_make_layout(type, 4, K, &L)) return -1; return (long)b200q_wire_row_size(L); }
 
 API int emul_repack(int type, const uint8_t * wire, uint8_t * planes, long M, long K, int inverse) {
     b200q_layout L; if (b200q_make_layout(type, M, K, &L)) return -1;
@@ -65,4 +66,19 @@ API int emul_dequant(int type, const uint8_t * planes, long M, long K, float * o
 API int emul_mul_mat_vec(int type, const uint8_t * planes, long M, long K, const int8_t * xq, const float * xd, const int * xis, long n, float * dst) {
     b200q_layout L; if (b200q_make_layout(type, M, K, &L)) return -1;
     DISPATCH(mmv, planes, L, xq, xd, xis, n, dst); return 0;
+}
+
+// ---- wire-layout types (b200q_wire.cuh): the product's decode32 of every 32-weight group, straight from the GGUF bytes ----
+template <int T> static void wire_deq(const uint8_t * W, long M, long K, float * out) {
+    for (long r = 0; r < M; ++r) for (long it = 0; it < K / 32; ++it) b200q_wire_decode32<T>(W, K, r, it, out + r * K + it * 32);
+}
+API int emul_wire_dequant(int type, const uint8_t * W, long M, long K, float * out) {
+    b200q_layout L; if (b200q_make_layout(type, M, K, &L) || !L.wire) return -1;
+    switch (type) {
+#define X(T) case T: wire_deq<T>(W, M, K, out); break;
+        B200Q_FOR_WIRE_TYPES(X)
+#undef X
+        default: return -1;
+    }
+    return 0;
 }

@@ -9,7 +9,7 @@ from ctypes import c_int, c_long, c_void_p
 import numpy as np
 import pytest
 
-from conftest import ALL_TYPES, ROOT, load_golden, random_wire
+from conftest import ALL_TYPES, PLANE_TYPES, WIRE_TYPES, ROOT, load_golden, random_wire
 from oracle.oracle import GGML_TYPE, _p, nmse
 
 
@@ -17,9 +17,9 @@ from oracle.oracle import GGML_TYPE, _p, nmse
 def emul():
     src = os.path.join(ROOT, "tests", "host_emul", "emul.cpp")
     so = os.path.join(ROOT, "tests", "host_emul", "libemul.so")
-    hdr = os.path.join(ROOT, "ik_llama_cpp_b200", "csrc", "b200q_types.cuh")
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    hdrs = [os.path.join(ROOT, "ik_llama_cpp_b200", "csrc", h) for h in ("b200q_types.cuh", "b200q_wire.cuh", "b200q_codebooks.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max([os.path.getmtime(src)] + [os.path.getmtime(h) for h in hdrs]):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src])
     E = ctypes.CDLL(so)
     E.emul_layout_bytes.restype = c_long
     E.emul_layout_bytes.argtypes = [c_int, c_long, c_long]
@@ -28,6 +28,7 @@ def emul():
     E.emul_repack.argtypes = [c_int, c_void_p, c_void_p, c_long, c_long, c_int]
     E.emul_dequant.argtypes = [c_int, c_void_p, c_long, c_long, c_void_p]
     E.emul_mul_mat_vec.argtypes = [c_int, c_void_p, c_long, c_long, c_void_p, c_void_p, c_void_p, c_long, c_void_p]
+    E.emul_wire_dequant.argtypes = [c_int, c_void_p, c_long, c_long, c_void_p]
     return E
 
 
@@ -49,7 +50,7 @@ def _emul_all(E, oracle, t, wire, m, k, x):
     return nb, back, deq, y
 
 
-@pytest.mark.parametrize("name", ALL_TYPES)
+@pytest.mark.parametrize("name", PLANE_TYPES)
 def test_emulated_kernel_arithmetic_on_golden(emul, oracle, name):
     g = load_golden(name)
     t, m, k = int(g["ggml_type"]), int(g["m"]), int(g["k"])
@@ -68,7 +69,7 @@ def test_emulated_kernel_arithmetic_on_golden(emul, oracle, name):
     assert nmse(y, oracle.mul_mat_exact(t, wire, x, m)) <= 5e-4
 
 
-@pytest.mark.parametrize("name", ALL_TYPES)
+@pytest.mark.parametrize("name", PLANE_TYPES)
 def test_emulated_random_bit_patterns(emul, oracle, name):
     """Every payload bit pattern is a valid block: fuzz the codecs with random bytes (catches index/LUT corner cases)."""
     t = GGML_TYPE[name]
@@ -88,7 +89,7 @@ def test_emulated_random_bit_patterns(emul, oracle, name):
     assert np.abs(y - yq).max() <= 2e-5 * rms
 
 
-@pytest.mark.parametrize("name", ALL_TYPES)
+@pytest.mark.parametrize("name", PLANE_TYPES)
 def test_emulated_edge_shapes(emul, oracle, name):
     """Edge shapes of the codecs: a single block per row, an odd block count, one row, the row-scale types with every K — the
     bijection and the canonical decode must hold for each (the reference's quantiser is not needed: any payload is a valid block)."""
@@ -112,3 +113,20 @@ def test_emulated_edge_shapes(emul, oracle, name):
         yq = oracle.mul_mat_q8_1(t, wire, x, m, variant="b200")
         rms = max(float(np.sqrt((yq.astype(np.float64) ** 2).mean())), 1e-30)
         assert np.abs(y - yq).max() <= 2e-5 * rms, (name, m, k)
+
+
+@pytest.mark.parametrize("name", WIRE_TYPES)
+def test_wire_decode32_is_bit_exact_on_golden(emul, oracle, name):
+    """Wire-layout types: the product's b200q_wire_decode32 (the function the CUDA kernels call) == the reference's own to_float output
+    (golden, generated from oracle/_ref) bit for bit, and == the oracle restatement."""
+    g = load_golden(name)
+    t, m, k = int(g["ggml_type"]), int(g["m"]), int(g["k"])
+    assert emul.emul_wire_row_size(t, k) == int(g["row_size"])
+    assert emul.emul_layout_bytes(t, m, k) >= g["wire"].size
+    deq = np.empty((m, k), np.float32)
+    assert emul.emul_wire_dequant(t, _p(np.ascontiguousarray(g["wire"])), m, k, _p(deq)) == 0
+    assert np.array_equal(deq, oracle.dequantize(t, g["wire"], m, k))          # product decode == oracle restatement, bit for bit
+    if name == "IQ6_K":     # the reference build contracts the float cubic of its to_float into FMAs (tests/test_oracle.py FMA_DEPENDENT)
+        np.testing.assert_allclose(deq, g["dequant_ref"], rtol=3e-6, atol=1e-5 * float(np.abs(g["dequant_ref"]).max()))
+    else:
+        assert np.array_equal(deq, g["dequant_ref"]), f"{name}: max |diff| {np.abs(deq - g['dequant_ref']).max()}"

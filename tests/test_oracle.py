@@ -5,7 +5,18 @@ import pytest
 from conftest import ALL_TYPES, ORACLE_ONLY_TYPES, load_golden
 from oracle.oracle import GGML_TYPE, nmse
 
-REF_CPU_DEVIATES = {"IQ4_XS", "IQ5_KS"}      # reference CPU kernels that deviate from their own to_float (SURVEY §8c pitfall 2)
+REF_CPU_DEVIATES = {"IQ4_XS", "IQ5_KS", "IQ4_KSS", "IQ2_KT"}      # reference CPU kernels that deviate from their own to_float (SURVEY §8c pitfall 2; IQ2_KT: NMSE 2.6e-3)
+# IQ6_K: the reference's to_float evaluates a float cubic (iqk_quantize.cpp:3442-3486) that its build contracts into FMAs: not bit-reproducible without them
+FMA_DEPENDENT = {"IQ6_K"}
+
+
+def _assert_dequant_equal(name, a, b):
+    if name in ("IQ4_KS", "IQ5_KS"):       # dl*(v+4) vs dl*v + 4*dl association: <= 1 ulp
+        np.testing.assert_allclose(a, b, rtol=2e-7, atol=0)
+    elif name in FMA_DEPENDENT:            # cancellation near the cubic's zero
+        np.testing.assert_allclose(a, b, rtol=3e-6, atol=1e-5 * float(np.abs(b).max()))
+    else:
+        assert np.array_equal(a, b), f"{name}: dequantize != reference to_float (bit-exact expected)"
 
 
 @pytest.mark.parametrize("name", ALL_TYPES)
@@ -14,10 +25,7 @@ def test_oracle_dequant_matches_reference_golden(oracle, name):
     t, m, k = int(g["ggml_type"]), int(g["m"]), int(g["k"])
     assert oracle.row_size(t, k) == int(g["row_size"])
     deq = oracle.dequantize(t, g["wire"], m, k)
-    if name in ("IQ4_KS", "IQ5_KS"):   # dl*(v+4) vs dl*v + 4*dl association: <= 1 ulp
-        np.testing.assert_allclose(deq, g["dequant_ref"], rtol=2e-7, atol=0)
-    else:
-        assert np.array_equal(deq, g["dequant_ref"]), f"{name}: oracle dequantize != reference to_float (bit-exact expected)"
+    _assert_dequant_equal(name, deq, g["dequant_ref"])
 
 
 @pytest.mark.parametrize("name", ALL_TYPES)
@@ -80,15 +88,12 @@ def test_oracle_vs_live_reference(oracle, reflib, name):
     rng = np.random.default_rng(99 + t)
     m, k, n = 8, 1024, 2
     w = (rng.standard_normal((m, k)) * 0.05).astype(np.float32)
-    if name == "IQ2_BN":
+    if name in ("IQ2_BN", "IQ1_BN"):
         w = (rng.integers(-1, 2, (m, k)) * 0.37).astype(np.float32)
     wire = reflib.quantize(t, w)
     assert reflib.row_size(t, k) == oracle.row_size(t, k)
     a, b = oracle.dequantize(t, wire, m, k), reflib.to_float(t, wire, m, k)
-    if name in ("IQ4_KS", "IQ5_KS"):
-        np.testing.assert_allclose(a, b, rtol=2e-7)
-    else:
-        assert np.array_equal(a, b)
+    _assert_dequant_equal(name, a, b)
     x = rng.uniform(-1, 1, (n, k)).astype(np.float32)
     y_ref, _ = reflib.mul_mat(t, wire, x, m, n_threads=2)
     assert nmse(y_ref, oracle.mul_mat_exact(t, wire, x, m)) <= (1e-1 if name in REF_CPU_DEVIATES else 5e-4)
