@@ -173,11 +173,20 @@ class Model:
         if self.tp > 1 and self.fused_tp:
             return self.step_tg_fused_tp(with_head)
         x = self.x
-        for L in self.layers:
+        pf = getattr(be, "prefetch_next", lambda *a, **k: None)       # every launch warms the first stages of the NEXT launch's weights in L2
+        nl = len(self.layers)
+        for li, L in enumerate(self.layers):
+            pf([L["wo"]])
             be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v])
+            pf([L["up"]], gate=L["gate"])
             be.mul_mat(L["wo"], self.q, out=self.h); self.allreduce(self.h)
-            # the up/gate launch also emits its result quantised to q8_1 (once, in its epilogue) for ffn_down
+            pf([L["down"]])
+            # the up/gate launch also emits its result quantised to q8_1 (once, in its tail) for ffn_down
             be.fused_up_gate(L["up"], L["gate"], self.h, "silu", out=self.a, q8_out=self.q8a)
+            if li + 1 < nl:
+                N = self.layers[li + 1]; pf([N["wq"], N["wk"], N["wv"]])
+            elif with_head:
+                pf([self.head])
             be.mul_mat(L["down"], self.a, out=self.x2, q8_in=self.q8a); self.allreduce(self.x2)
             x = self.x2
         if with_head:

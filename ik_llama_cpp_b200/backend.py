@@ -120,6 +120,16 @@ def convert_activations(x: torch.Tensor, out: torch.Tensor | None = None) -> tor
     return xb
 
 
+def prefetch_next(ws: "list[QuantTensor]", gate: "QuantTensor | None" = None) -> None:
+    """Decode chains: announce the weights of the launch AFTER the next one (b200q_decode_prefetch_next): the next mat-vec warms them in L2."""
+    L = _lib.lib()
+    if not hasattr(L, "b200q_decode_prefetch_next"):
+        return
+    nt = len(ws)
+    Wp = (c_void_p * nt)(*[w.ptr for w in ws]); Mp = (c_int64 * nt)(*[w.m for w in ws])
+    check(L.b200q_decode_prefetch_next(ws[0].ggml_type, nt, Wp, gate.ptr if gate is not None else None, Mp, ws[0].k), "b200q_decode_prefetch_next")
+
+
 class Q8Scratch:
     """Device scratch of the q8_1 hand-off FUSED_UP_GATE -> MUL_MAT (n = 1): b200q_q8_scratch_bytes(k), zeroed once."""
 

@@ -65,6 +65,7 @@ thread_local scratch g_x, g_y, g_ws, g_stage;
 int & opt_ring() { static int v = [] { const char * e = getenv("B200Q_RING"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_fuse_epi() { static int v = [] { const char * e = getenv("B200Q_FUSE_EPILOGUE"); return e ? atoi(e) : 0; }(); return v; }
 int & opt_fused() { static int v = [] { const char * e = getenv("B200Q_FUSED_GEMM"); return e ? atoi(e) : 1; }(); return v; }
+int & opt_pf() { static int v = [] { const char * e = getenv("B200Q_PREFETCH_NEXT"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_q8() { static int v = [] { const char * e = getenv("B200Q_Q8_HANDOFF"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_pdl() { static int v = [] { const char * e = getenv("B200Q_PDL"); return e ? atoi(e) : 1; }(); return v; }
 }  // namespace
@@ -75,6 +76,7 @@ int b200q_abi_version(void) { return B200Q_ABI_VERSION; }
 const char * b200q_last_error(void) { return g_err; }
 int b200q_set_option(const char * key, int value) {
     if (key && !strcmp(key, "pdl")) { opt_pdl() = value; return B200Q_OK; }
+    if (key && !strcmp(key, "prefetch_next")) { opt_pf() = value; return B200Q_OK; }
     if (key && !strcmp(key, "q8_handoff")) { opt_q8() = value; return B200Q_OK; }
     if (key && !strcmp(key, "ring")) { opt_ring() = value; return B200Q_OK; }
     if (key && !strcmp(key, "fused_gemm")) { opt_fused() = value; return B200Q_OK; }
@@ -123,7 +125,23 @@ int b200q_get_tensor(int type, const void * planes_dev, void * wire_host, int64_
     return B200Q_OK;
 }
 
+// pending "next weights" hint of this thread (b200q_decode_prefetch_next): consumed by the next decode launch
+static thread_local b200q_mmvq_desc g_next; static thread_local bool g_next_valid = false;
+static inline void attach_next(b200q_mmvq_desc & d) { d.next = nullptr; if (g_next_valid && opt_pf()) d.next = &g_next; g_next_valid = false; }
+
+int b200q_decode_prefetch_next(int type, int n_tensors, const void * const * W, const void * W_gate, const int64_t * m, int64_t k) {
+    g_next_valid = false;
+    if (n_tensors < 1 || n_tensors > B200Q_MAX_SEGS || !W || !m || (W_gate && n_tensors != 1)) return fail(B200Q_E_ARG, "b200q_decode_prefetch_next: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_decode_prefetch_next: no CUDA device");
+    memset(&g_next, 0, sizeof g_next);
+    g_next.type = type; g_next.n_seg = n_tensors; g_next.K = k; g_next.ncols = 1; g_next.sm_count = di.sm_count; g_next.ring = opt_ring();
+    for (int i = 0; i < n_tensors; ++i) g_next.seg[i] = {W[i], i == 0 ? W_gate : nullptr, nullptr, nullptr, m[i]};
+    g_next_valid = true;
+    return B200Q_OK;
+}
+
 static int mmvq_cols(b200q_mmvq_desc & d, int n, int64_t x_stride, cudaStream_t st, const char * what) {
+    attach_next(d);
     // the kernel is instantiated for 1/2/4/8 columns: cover n with the largest pieces
     int done = 0;
     const int64_t xs = x_stride ? x_stride : d.K;
@@ -139,6 +157,7 @@ static int mmvq_cols(b200q_mmvq_desc & d, int n, int64_t x_stride, cudaStream_t 
         for (int i = 0; i < d.n_seg; ++i) d.seg[i].dst = dst0[i] + (int64_t)done * d.seg[i].M;
         int rc = check_launch(b200q_launch_mmvq(d, st), what);
         if (rc) return rc;
+        d.next = nullptr;
         done += c;
     }
     return B200Q_OK;
@@ -187,6 +206,7 @@ int b200q_fused_up_gate_vec_q8(int type, const void * W_up, const void * W_gate,
     d.type = type; d.n_seg = 1; d.seg[0] = {W_up, W_gate, dst, nullptr, m}; d.K = k; d.x = x; d.x_stride = k; d.ncols = 1; d.act = unary; d.limit = limit;
     d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = opt_ring();
     if (((uintptr_t)x & 15) || (k & 3)) return fail(B200Q_E_ARG, "b200q_fused_up_gate_vec_q8: activations must be 16-byte aligned");
+    attach_next(d);
     if (q8_out && opt_q8()) {
         d.q8_out = q8_out;
         const int rc = b200q_launch_mmvq(d, (cudaStream_t)stream);
@@ -203,6 +223,7 @@ int b200q_mul_mat_vec_q8(int type, const void * W, const float * x, const void *
     b200q_mmvq_desc d; memset(&d, 0, sizeof d);
     d.type = type; d.n_seg = 1; d.seg[0] = {W, nullptr, dst, bias, m}; d.K = k; d.x = x; d.x_stride = k; d.ncols = 1; d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = opt_ring();
     if (((uintptr_t)x & 15) || (k & 3)) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_q8: activations must be 16-byte aligned");
+    attach_next(d);
     if (q8_in && opt_q8()) {
         d.q8_in = q8_in;
         const int rc = b200q_launch_mmvq(d, (cudaStream_t)stream);

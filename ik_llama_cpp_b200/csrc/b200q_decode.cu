@@ -125,6 +125,10 @@ int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
     }
     a.n_seg = d.n_seg; a.M_total = r0; a.K = d.K; a.x = d.x; a.x_stride = d.x_stride ? d.x_stride : d.K; a.act = d.act; a.limit = d.limit;
     a.tp = d.tp;
+    if (d.next) {
+        static const int cps = [] { const char * e = getenv("B200Q_CTAS_PER_SM"); return e ? atoi(e) : B200Q_MIN_CTAS; }();
+        make_next_prefetch(*d.next, d.sm_count, cps, a.pf);
+    }
     const bool upgate = d.seg[0].W2 != nullptr;
     if (d.q8_in || d.q8_out) {          // q8 hand-off: n = 1, single tensor, ring kernel, bulk-copyable image
         if (d.ncols != 1 || d.n_seg != 1 || !d.ring || a.tp.in || a.tp.out) return -8;

@@ -10,10 +10,19 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 
 // ------------------------------------------------------------------------------------------------
 // decode mat-vec
 // ------------------------------------------------------------------------------------------------
+// L2 warm-up of the NEXT mat-vec's weights.  While this kernel runs, the next one cannot stream yet: its CTAs only become resident when ours leave
+// (shared memory), and then need a full HBM round trip for their first stages (measured: 3-4 us between the last warp of a short kernel and the first
+// useful instruction of the next).  The producer warp therefore issues cp.async.bulk.prefetch.L2 for exactly the bytes the next kernel's CTAs will
+// request first; HBM works on them during OUR prologue / main loop, the next kernel's ring then fills from L2.
+//   mode 0: whole ranges ptr[q] .. +bytes[q], split evenly over this grid (small tensors: Q,K,V / wo)
+//   mode 1: plane q of a tensor whose units (rpu rows each, rowb[q] bytes per row) are split over `grid` CTAs like k_mmvq_ring does: the first
+//           per_cta units of every next-CTA chunk
+struct mmvq_pf { const uint8_t * ptr[8]; long long bytes[8]; int rowb[8]; int n; int mode; int n_units; int rpu; int grid; int per_cta; };
 struct mmvq_seg {               // one weight tensor of a multi-tensor launch (Q,K,V share the activation)
     b200q_planes    P;          // resolved plane pointers
     b200q_planes    P2;         // second tensor (gate) for the fused up/gate mode
@@ -34,6 +43,7 @@ struct mmvq_args {
     b200q_tp_comm tp;           // tensor-parallel decode: GGML_OP_REDUCE fused into the mat-vec (tp.in / tp.out), see k_mmvq_ring
     unsigned long long * trace; // optional phase timestamps (b200q_debug_trace): [slot][8] = entry, after griddepcontrol.wait, prologue done, last consumer done,
                                 //   activation loads landed, quantised (before the barrier), 2^62 - first consumer done, first unit of CTA 0 / warp 1 done
+    mmvq_pf pf;                 // weights of the NEXT decode launch to warm in L2 (b200q_decode_prefetch_next), pf.n == 0: none
     const void * q8_in;         // activations already quantised by the producing kernel (b200q_q8 layout, n = 1): bulk-copied instead of re-quantised
     void *       q8_out;        // fused up/gate, n = 1: also emit dst quantised to q8_1 for the following MUL_MAT (ffn_down), see q8_emit_block
 };
@@ -242,6 +252,26 @@ __device__ __forceinline__ uint32_t tp_ld_acquire_sys(const uint32_t * p) { uint
 
 __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
 
+__device__ __forceinline__ void bulk_prefetch_l2(const uint8_t * p, long long bytes) {
+    for (long long o = 0; o < bytes; o += 32768) {
+        const uint32_t n = (uint32_t)min(32768ll, bytes - o);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + o), "r"(n) : "memory");
+    }
+}
+__device__ __forceinline__ void issue_next_prefetch(const mmvq_pf & pf, int lane) {
+    if (lane >= pf.n) return;
+    if (pf.mode == 0) {
+        const long long per = ((pf.bytes[lane] / 16 + gridDim.x - 1) / gridDim.x) * 16, o = per * blockIdx.x;
+        if (o < pf.bytes[lane]) bulk_prefetch_l2(pf.ptr[lane] + o, min(per, pf.bytes[lane] - o));
+    } else {
+        for (int j = blockIdx.x; j < pf.grid; j += gridDim.x) {
+            const long long c0 = (long long)pf.n_units * j / pf.grid, c1 = (long long)pf.n_units * (j + 1) / pf.grid;
+            const long long cnt = min((long long)pf.per_cta, c1 - c0);
+            if (cnt > 0) bulk_prefetch_l2(pf.ptr[lane] + c0 * pf.rpu * pf.rowb[lane], cnt * pf.rpu * pf.rowb[lane]);
+        }
+    }
+}
+
 // Warp 0 = producer (lane l streams the units of consumer warp l), warps 1..NCW = consumers.
 // A stage holds 2 x B200Q_SEG_ITEMS items (8192 weights) and is filled by ONE bulk copy per plane (tools/membench.cu `r`: the achieved HBM
 // bandwidth falls with the number of bulk copies in flight per SM: 6.0 TB/s with 4 copies per stage, 6.8 with 2, 7.0 with 1):
@@ -339,6 +369,7 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
     // (1) weights do not depend on the previous kernel: fill the ring before waiting for it
     if (is_prod) {
         for (int s = 0; s < S; ++s) if (!pdone) produce_one();
+        if (a.pf.n) issue_next_prefetch(a.pf, lane);       // after our own first stages: the next kernel's first stages -> L2
     }
     pdl_trigger();                       // the next kernel of the stream/graph may become resident and fill ITS ring
     pdl_wait();                          // (2) the activations are produced by the previous kernel
@@ -599,26 +630,75 @@ static bool make_ring_geom(int type, int64_t K, ring_geom & g, bool long_rows) {
     return np > 0 && np <= 4;
 }
 
-template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR, bool TP = false, int Q8 = 0>
-static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
-    mmvq_ring_args ra; ra.a = a; ra.g = g0;
-    if (PAIR) for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
-    if (a.M_total >= (int64_t)1 << 30) return -100;
-    const size_t xbytes = (size_t)NCOLS * a.K + (size_t)NCOLS * (a.K / 32) * 8 + 512 + 512 + 256 + 128;
-    const size_t budget = B200Q_SMEM_BUDGET;
-    const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
-    int ncw = B200Q_RING_CONSUMERS, S = 0;              // consumer warps (+1 producer warp)
+// consumer warps / stages of a ring launch (shared by the launcher and by the L2 warm-up of the next launch)
+static inline size_t ring_xbytes(int ncols, int64_t K) { return (size_t)ncols * K + (size_t)ncols * (K / 32) * 8 + 512 + 512 + 256 + 128; }
+static inline bool ring_shape(int ncols, int64_t K, size_t pair_stage, int64_t n_units, int sm_count, int & ncw, int & S) {
+    const size_t xbytes = ring_xbytes(ncols, K), budget = B200Q_SMEM_BUDGET;
+    ncw = B200Q_RING_CONSUMERS; S = 0;                   // consumer warps (+1 producer warp)
     for (;;) {
         const size_t per_stage = (size_t)ncw * (pair_stage + 16);
         S = xbytes + 64 < budget ? (int)((budget - xbytes - 64) / per_stage) : 0;
         if (S >= 2 || ncw == 3) break;
         ncw = ncw > 7 ? 7 : 3;                           // (10 warps would still fit two stages for K = 14336 but measured slower: 13.8 vs 11.3 us)
     }
-    if (S < 2) return -100;                              // does not fit: caller falls back to the LDG kernel
+    if (S < 2) return false;
     if (S > B200Q_MAX_STAGES) S = B200Q_MAX_STAGES;
-    const int64_t n_pairs = PAIR ? (a.M_total + 1) / 2 : a.M_total;
-    while (ncw > 3 && n_pairs <= (int64_t)sm_count * (ncw > 7 ? 7 : 3)) ncw = ncw > 7 ? 7 : 3;
+    while (ncw > 3 && n_units <= (int64_t)sm_count * (ncw > 7 ? 7 : 3)) ncw = ncw > 7 ? 7 : 3;
     while (ncw * S > B200Q_PAIR_SLOTS) --S;
+    return true;
+}
+// what the next decode launch (descriptor nx) will request first -> mmvq_pf (see struct mmvq_pf)
+static inline void make_next_prefetch(const b200q_mmvq_desc & nx, int sm_count, int ctas_per_sm, mmvq_pf & pf) {
+    memset(&pf, 0, sizeof pf);
+    if (nx.n_seg < 1 || nx.ncols > 2 || nx.tp.in || nx.tp.out) return;
+    const bool upgate = nx.seg[0].W2 != nullptr;
+    int64_t M_total = 0; for (int i = 0; i < nx.n_seg; ++i) M_total += nx.seg[i].M;
+    if (b200q_is_wire_type(nx.type)) {                   // wire-layout tensors: whole (or the head of) each tensor
+        b200q_layout L;
+        for (int i = 0; i < nx.n_seg && pf.n < 8; ++i) for (int t = 0; t < (upgate ? 2 : 1) && pf.n < 8; ++t) {
+            if (b200q_make_layout(nx.type, nx.seg[i].M, nx.K, &L)) return;
+            pf.ptr[pf.n] = (const uint8_t *)(t ? nx.seg[i].W2 : nx.seg[i].W); pf.bytes[pf.n] = std::min<long long>(L.M * b200q_wire_row_size(L), 24ll << 20); ++pf.n;
+        }
+        pf.mode = 0; return;
+    }
+    const bool long_rows = nx.K / 32 > B200Q_SEG_ITEMS;
+    ring_geom g;
+    if (!nx.ring || !make_ring_geom(nx.type, nx.K, g, long_rows)) return;
+    const int64_t n8 = nx.K / 256;
+    const int64_t n_units = long_rows ? M_total : (M_total + 1) / 2;
+    int ncw, S; if (!ring_shape(nx.ncols, nx.K, 2 * (size_t)g.stage_bytes, n_units, sm_count, ncw, S)) return;
+    long long total = 0;
+    for (int i = 0; i < nx.n_seg; ++i) for (int p = 0; p < g.n_planes; ++p) total += (long long)nx.seg[i].M * n8 * g.b8[p] * (upgate ? 2 : 1);
+    if (nx.n_seg > 1 || total <= (24ll << 20)) {         // small: everything, split evenly over our CTAs
+        for (int i = 0; i < nx.n_seg; ++i) for (int t = 0; t < (upgate ? 2 : 1); ++t) {
+            b200q_layout L; if (b200q_make_layout(nx.type, nx.seg[i].M, nx.K, &L)) return;
+            const b200q_planes P = b200q_planes_from((const uint8_t *)(t ? nx.seg[i].W2 : nx.seg[i].W), L);
+            for (int p = 0; p < g.n_planes && pf.n < 8; ++p) { pf.ptr[pf.n] = P.p[p]; pf.bytes[pf.n] = (long long)nx.seg[i].M * n8 * g.b8[p]; ++pf.n; }
+        }
+        pf.mode = 0; return;
+    }
+    // one (or up + gate) large tensor: the first stages of every CTA of the next grid
+    const int nseg = long_rows ? (int)((nx.K / 32 + 2 * B200Q_SEG_ITEMS - 1) / (2 * B200Q_SEG_ITEMS)) : 1, nt = upgate ? 2 : 1;
+    int64_t grid = (n_units + ncw - 1) / ncw; if (grid > (int64_t)sm_count * ctas_per_sm) grid = (int64_t)sm_count * ctas_per_sm;
+    for (int t = 0; t < nt; ++t) {
+        b200q_layout L; if (b200q_make_layout(nx.type, nx.seg[0].M, nx.K, &L)) return;
+        const b200q_planes P = b200q_planes_from((const uint8_t *)(t ? nx.seg[0].W2 : nx.seg[0].W), L);
+        for (int p = 0; p < g.n_planes && pf.n < 8; ++p) { pf.ptr[pf.n] = P.p[p]; pf.rowb[pf.n] = (int)(n8 * g.b8[p]); ++pf.n; }
+    }
+    pf.mode = 1; pf.n_units = (int)n_units; pf.rpu = long_rows ? 1 : 2; pf.grid = (int)grid;
+    pf.per_cta = (ncw * S + nseg * nt - 1) / (nseg * nt);
+}
+template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR, bool TP = false, int Q8 = 0>
+static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm_count, bool pdl, int ctas_per_sm, cudaStream_t st) {
+    mmvq_ring_args ra; ra.a = a; ra.g = g0;
+    if (PAIR) for (int i = 0; i < a.n_seg; ++i) if ((a.seg[i].M & 1) && i + 1 < a.n_seg) return -100;     // row pairs must not straddle tensors
+    if (a.M_total >= (int64_t)1 << 30) return -100;
+    const size_t xbytes = ring_xbytes(NCOLS, a.K);
+    const size_t budget = B200Q_SMEM_BUDGET;
+    const size_t pair_stage = 2 * (size_t)ra.g.stage_bytes;
+    const int64_t n_pairs = PAIR ? (a.M_total + 1) / 2 : a.M_total;
+    int ncw, S;
+    if (!ring_shape(NCOLS, a.K, pair_stage, n_pairs, sm_count, ncw, S)) return -100;     // does not fit: caller falls back to the LDG kernel
     ra.g.n_stages = S;
     const size_t smem = (size_t)ncw * S * (pair_stage + 16) + xbytes + 64;
     static bool configured[B200Q_MAX_DEVICES] = {};

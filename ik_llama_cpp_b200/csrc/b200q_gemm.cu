@@ -492,8 +492,33 @@ __global__ void k_mul_unary(const float * gate /* may alias dst: no __restrict__
     }
 }
 
-// f32 [N][K] (row stride xs) -> bf16 [N][K]
-__global__ void k_f32_to_bf16(const float * __restrict__ x, int64_t xs, __nv_bfloat16 * __restrict__ out, int64_t K, int64_t N) {
+// f32 [N][K] (row stride xs) -> bf16 [N][K].  HBM-bound glue between the GEMMs (12 MB per 512 x 4096 activation): a thread converts 8 consecutive
+// values (two LDG.128 -> one STG.128) and keeps U such groups in flight; round 1's one-float4-per-thread version ran at ~1 TB/s (11.8 us per call,
+// profiles/r1_pp_breakdown.txt) and cost 10 % of the prefill layer.
+__global__ void __launch_bounds__(256) k_f32_to_bf16(const float * __restrict__ x, int64_t xs, __nv_bfloat16 * __restrict__ out, int64_t K, int64_t N) {
+    constexpr int U = 4;
+    const int64_t k8 = K / 8, total8 = N * k8, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total8; i0 += U * stride) {
+        float4 a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < total8) { const int64_t n = i / k8, c = i % k8; const float4 * p = reinterpret_cast<const float4 *>(x + n * xs + 8 * c); a[u] = __ldg(p); b[u] = __ldg(p + 1); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < total8) {
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(a[u].x, a[u].y), p1 = __floats2bfloat162_rn(a[u].z, a[u].w), p2 = __floats2bfloat162_rn(b[u].x, b[u].y), p3 = __floats2bfloat162_rn(b[u].z, b[u].w);
+                uint4 o; o.x = *reinterpret_cast<uint32_t *>(&p0); o.y = *reinterpret_cast<uint32_t *>(&p1); o.z = *reinterpret_cast<uint32_t *>(&p2); o.w = *reinterpret_cast<uint32_t *>(&p3);
+                const int64_t n = i / k8, c = i % k8;
+                *reinterpret_cast<uint4 *>(out + n * K + 8 * c) = o;
+            }
+        }
+    }
+}
+// K % 8 != 0 (K % 4 == 0): the simple version
+__global__ void k_f32_to_bf16_k4(const float * __restrict__ x, int64_t xs, __nv_bfloat16 * __restrict__ out, int64_t K, int64_t N) {
     const int64_t total4 = N * (K / 4);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t n = i / (K / 4), k4 = i % (K / 4);
@@ -639,8 +664,14 @@ size_t b200q_gemm_workspace_bytes(int type, int64_t M, int64_t K, int64_t N) {
 // f32 [N][K] -> bf16 [N][K] (shared by the mat-muls that consume the same activation)
 int b200q_launch_f32_to_bf16(const float * x, int64_t x_stride, void * out, int64_t K, int64_t N, cudaStream_t st) {
     if (K % 4) return -2;
-    const int64_t total4 = N * (K / 4); int64_t nb = (total4 + 255) / 256; if (nb > 148 * 32) nb = 148 * 32; if (nb < 1) nb = 1;
-    k_f32_to_bf16<<<(unsigned)nb, 256, 0, st>>>(x, x_stride ? x_stride : K, (__nv_bfloat16 *)out, K, N);
+    const int64_t xs = x_stride ? x_stride : K;
+    if (K % 8 == 0 && xs % 4 == 0 && !((uintptr_t)x & 15) && !((uintptr_t)out & 15)) {
+        const int64_t total8 = N * (K / 8); int64_t nb = (total8 + 256 * 4 - 1) / (256 * 4); if (nb > 148 * 8) nb = 148 * 8; if (nb < 1) nb = 1;
+        k_f32_to_bf16<<<(unsigned)nb, 256, 0, st>>>(x, xs, (__nv_bfloat16 *)out, K, N);
+    } else {
+        const int64_t total4 = N * (K / 4); int64_t nb = (total4 + 255) / 256; if (nb > 148 * 32) nb = 148 * 32; if (nb < 1) nb = 1;
+        k_f32_to_bf16_k4<<<(unsigned)nb, 256, 0, st>>>(x, xs, (__nv_bfloat16 *)out, K, N);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -58,6 +58,7 @@ struct b200q_mmvq_desc {
     b200q_tp_comm tp;
     const void * q8_in;     // n = 1: activations already quantised by the producing launch (b200q_q8 image); x is still passed for the fallback
     void * q8_out;          // fused up/gate, n = 1: also emit dst as a b200q_q8 image for the next MUL_MAT
+    const b200q_mmvq_desc * next;   // optional: the decode launch that will follow this one; its first weight stages are warmed in L2 (b200q_decode_prefetch_next)
 };
 // b200q_q8 image of a K-vector: [K int8][K/32 f32 d][K/32 i32 sums][K/32 u32 arrival counters] (+ 16 B slack)
 static inline size_t b200q_q8_image_bytes(int64_t k) { return (size_t)(k + 12 * (k / 32) + 16); }

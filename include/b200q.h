@@ -77,6 +77,11 @@ B200Q_API int b200q_fused_up_gate_vec_q8(int type, const void * W_up, const void
 B200Q_API int b200q_mul_mat_vec_q8(int type, const void * W, const float * x, const void * q8_in, float * dst, int64_t m, int64_t k,
                          const float * bias, void * stream);
 
+/* Decode chains: tell the NEXT decode launch of this thread which weights the launch AFTER it will stream, so that it can warm their first
+ * stages in L2 (cp.async.bulk.prefetch.L2) while it runs; a kernel cannot prefetch into shared memory before the previous one has left the SM.
+ * The hint is consumed (cleared) by the next b200q_mul_mat_vec* / b200q_fused_up_gate_vec* call.  W_gate != NULL: fused up/gate (n_tensors = 1). */
+B200Q_API int b200q_decode_prefetch_next(int type, int n_tensors, const void * const * W, const void * W_gate, const int64_t * m, int64_t k);
+
 /* ---- prefill: tcgen05 GEMM ---- */
 B200Q_API size_t b200q_mul_mat_workspace(int type, int64_t m, int64_t k, int64_t n);
 B200Q_API int b200q_mul_mat_gemm(int type, const void * W, const float * x, float * dst, int64_t m, int64_t k, int64_t n,

@@ -3,7 +3,7 @@
 each in its own process (the library is chosen at import time), optionally with extra environment knobs."""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-configs = [("product", None, {}), ("product q8off", None, {"B200Q_Q8_HANDOFF": "0"}), ("product gridfull", None, {"B200Q_GRID_FULL": "1"})]
+configs = [("product", None, {}), ("product pfoff", None, {"B200Q_PREFETCH_NEXT": "0"}), ("product q8off", None, {"B200Q_Q8_HANDOFF": "0"})]
 vd = os.path.join(ROOT, "experiments", "_variants")
 for f in sorted(os.listdir(vd)) if os.path.isdir(vd) else []:
     if f.endswith(".so"):

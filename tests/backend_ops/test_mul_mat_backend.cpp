@@ -10,6 +10,7 @@
 #include "ggml-alloc.h"
 #include "ggml-backend.h"
 #include "ggml-cuda.h"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -28,8 +29,29 @@ static bool cmp_cb(int, ggml_tensor * t1, ggml_tensor * t2, void * ud) {
     const double e = nmse(a.data(), b.data(), a.size()); if (e > d->worst) d->worst = e; d->n++;
     return true;
 }
+static bool is_r4(ggml_type t) {
+    switch (t) { case GGML_TYPE_IQ1_S_R4: case GGML_TYPE_IQ1_M_R4: case GGML_TYPE_IQ2_K_R4: case GGML_TYPE_IQ3_K_R4: case GGML_TYPE_IQ4_K_R4: case GGML_TYPE_IQ5_K_R4:
+                 case GGML_TYPE_IQ4_KS_R4: case GGML_TYPE_IQ5_KS_R4: return true; default: return false; }
+}
+// reference to_float of a whole [m x k] wire tensor (ternary types: the row scale is applied by hand, SURVEY §8c pitfall 1; _R4: groups of 4 rows)
+static void dequant_rows(ggml_type type, const uint8_t * wq, int64_t m, int64_t k, float * out) {
+    ggml_type_traits_t tt = ggml_internal_get_type_traits(type);
+    const size_t rs = ggml_row_size(type, k);
+    if (is_r4(type)) { for (int64_t i = 0; i < m; i += 4) tt.to_float(wq + i * rs, out + i * k, 4 * k); return; }
+    for (int64_t i = 0; i < m; ++i) {
+        const uint8_t * row = wq + i * rs;
+        if (type == GGML_TYPE_IQ2_BN) { float sc; memcpy(&sc, row, 4); tt.to_float(row + 4, out + i * k, k); for (int64_t l = 0; l < k; ++l) out[i * k + l] *= sc; }
+        else if (type == GGML_TYPE_IQ1_BN) { ggml_fp16_t h; memcpy(&h, row, 2); const float sc = ggml_fp16_to_fp32(h); tt.to_float(row + 2, out + i * k, k); for (int64_t l = 0; l < k; ++l) out[i * k + l] *= sc; }
+        else tt.to_float(row, out + i * k, k);
+    }
+}
+static void make_weights(ggml_type type, std::vector<float> & wf, std::mt19937 & rng);
 static void fill_uniform(std::vector<float> & v, std::mt19937 & rng) { std::uniform_real_distribution<float> u(-1.f, 1.f); for (auto & x : v) x = u(rng); }
 
+static void make_weights(ggml_type type, std::vector<float> & wf, std::mt19937 & rng) {
+    fill_uniform(wf, rng);
+    if (type == GGML_TYPE_IQ2_BN || type == GGML_TYPE_IQ1_BN) for (auto & x : wf) x = 0.37f * (float)((int)std::floor((x + 1.f) * 1.5f) - 1);   // ternary so the quantiser is lossless
+}
 static int run_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, int64_t m, int64_t k, int64_t n, bool up_gate, unsigned seed) {
     ggml_init_params ip = { ggml_tensor_overhead() * 16 + ggml_graph_overhead(), nullptr, true };
     ggml_context * ctx = ggml_init(ip);
@@ -45,8 +67,7 @@ static int run_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, int64
     std::vector<uint8_t> wq(ggml_row_size(type, k) * m);
     for (ggml_tensor * w : {a, g}) {
         if (!w) continue;
-        fill_uniform(wf, rng);
-        if (type == GGML_TYPE_IQ2_BN) for (auto & x : wf) x = 0.37f * (float)((int)std::floor((x + 1.f) * 1.5f) - 1);   // ternary so the quantiser is lossless
+        make_weights(type, wf, rng);
         ggml_quantize_chunk(type, wf.data(), wq.data(), 0, m, k, ggml_quantize_requires_imatrix(type) ? ones.data() : nullptr, nullptr);
         ggml_backend_tensor_set(w, wq.data(), 0, wq.size());
         std::vector<uint8_t> back(wq.size());
@@ -63,18 +84,13 @@ static int run_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, int64
     if (!up_gate) {
         std::vector<float> y(m * n), wdeq(m * k);
         ggml_backend_tensor_get(out, y.data(), 0, y.size() * sizeof(float));
-        ggml_type_traits_t tt = ggml_internal_get_type_traits(type);
-        const size_t rs = ggml_row_size(type, k);
-        for (int64_t i = 0; i < m; ++i) {
-            const uint8_t * row = wq.data() + i * rs;
-            if (type == GGML_TYPE_IQ2_BN) { float sc; memcpy(&sc, row, 4); tt.to_float(row + 4, wdeq.data() + i * k, k); for (int64_t l = 0; l < k; ++l) wdeq[i * k + l] *= sc; }
-            else tt.to_float(row, wdeq.data() + i * k, k);
-        }
+        dequant_rows(type, wq.data(), m, k, wdeq.data());
         std::vector<float> ref(m * n);
         for (int64_t j = 0; j < n; ++j) for (int64_t i = 0; i < m; ++i) { double acc = 0; for (int64_t l = 0; l < k; ++l) acc += (double)wdeq[i * k + l] * xf[j * k + l]; ref[j * m + i] = (float)acc; }
         e_truth = nmse(y.data(), ref.data(), y.size());
     }
-    const bool cpu_known_off = (type == GGML_TYPE_IQ4_XS || type == GGML_TYPE_IQ4_K || type == GGML_TYPE_IQ4_KS || type == GGML_TYPE_IQ5_K || type == GGML_TYPE_IQ5_KS);
+    const bool cpu_known_off = (type == GGML_TYPE_IQ4_XS || type == GGML_TYPE_IQ4_K || type == GGML_TYPE_IQ4_KS || type == GGML_TYPE_IQ5_K || type == GGML_TYPE_IQ5_KS ||
+                                type == GGML_TYPE_IQ4_KSS || type == GGML_TYPE_IQ2_KT || type == GGML_TYPE_IQ3_KT || type == GGML_TYPE_IQ1_KT || type == GGML_TYPE_IQ4_KT);
     const bool ok = d.n > 0 && e_truth <= 5e-4 && (d.worst <= 5e-4 || cpu_known_off);
     printf("  %-8s %s m=%lld k=%lld n=%lld: NMSE vs CPU backend %.3g%s, vs f64(to_float) %.3g -> %s\n", ggml_type_name(type), up_gate ? "FUSED_UP_GATE" : "MUL_MAT",
            (long long)m, (long long)k, (long long)n, d.worst, cpu_known_off && d.worst > 5e-4 ? " (reference CPU kernel known to deviate)" : "", e_truth, ok ? "OK" : "FAIL");
@@ -97,20 +113,14 @@ static int run_qkv_case(ggml_backend_t be, ggml_type type, int64_t k, int64_t n,
     std::mt19937 rng(seed);
     std::vector<float> xf(n * k), ones(k, 1.0f);
     std::vector<std::vector<float>> wdeq(3);
-    ggml_type_traits_t tt = ggml_internal_get_type_traits(type);
     const size_t rs = ggml_row_size(type, k);
     for (int i = 0; i < 3; ++i) {
-        std::vector<float> wf(ms[i] * k); fill_uniform(wf, rng);
-        if (type == GGML_TYPE_IQ2_BN) for (auto & x : wf) x = 0.37f * (float)((int)std::floor((x + 1.f) * 1.5f) - 1);
+        std::vector<float> wf(ms[i] * k); make_weights(type, wf, rng);
         std::vector<uint8_t> wq(rs * ms[i]);
         ggml_quantize_chunk(type, wf.data(), wq.data(), 0, ms[i], k, ggml_quantize_requires_imatrix(type) ? ones.data() : nullptr, nullptr);
         ggml_backend_tensor_set(w[i], wq.data(), 0, wq.size());
         wdeq[i].resize(ms[i] * k);
-        for (int64_t r = 0; r < ms[i]; ++r) {
-            const uint8_t * row = wq.data() + r * rs;
-            if (type == GGML_TYPE_IQ2_BN) { float sc; memcpy(&sc, row, 4); tt.to_float(row + 4, wdeq[i].data() + r * k, k); for (int64_t l = 0; l < k; ++l) wdeq[i][r * k + l] *= sc; }
-            else tt.to_float(row, wdeq[i].data() + r * k, k);
-        }
+        dequant_rows(type, wq.data(), ms[i], k, wdeq[i].data());
     }
     fill_uniform(xf, rng);
     ggml_backend_tensor_set(b, xf.data(), 0, xf.size() * sizeof(float));
@@ -124,6 +134,99 @@ static int run_qkv_case(ggml_backend_t be, ggml_type type, int64_t k, int64_t n,
     }
     const bool ok = worst <= 5e-4;
     printf("  %-8s 3x MUL_MAT sharing src1 (fused launch) k=%lld n=%lld: worst NMSE vs f64(to_float) %.3g -> %s\n", ggml_type_name(type), (long long)k, (long long)n, worst, ok ? "OK" : "FAIL");
+    ggml_backend_buffer_free(buf); ggml_free(ctx);
+    return ok ? 0 : 1;
+}
+
+// FFN-shaped graph in ONE graph_compute: y = W_down . FUSED_UP_GATE(W_up, W_gate, x) [+ bias], n tokens.  Exercises the backend's q8_1 hand-off (n = 1:
+// the up/gate kernel quantises its result for ffn_down), the bias-ADD fusion, and plain chaining for n > 1; every node is compared with the reference CPU
+// backend (ggml_backend_compare_graph_backend) — including the intermediate FUSED_UP_GATE result, which must still be written.
+static int run_ffn_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, int64_t k, int64_t ff, int64_t n, bool bias, unsigned seed) {
+    ggml_init_params ip = { ggml_tensor_overhead() * 24 + ggml_graph_overhead(), nullptr, true };
+    ggml_context * ctx = ggml_init(ip);
+    ggml_tensor * up = ggml_new_tensor_2d(ctx, type, k, ff), * gate = ggml_new_tensor_2d(ctx, type, k, ff), * down = ggml_new_tensor_2d(ctx, type, ff, k);
+    ggml_tensor * x = ggml_new_tensor_2d(ctx, GGML_TYPE_F32, k, n);
+    ggml_tensor * bv = bias ? ggml_new_tensor_1d(ctx, GGML_TYPE_F32, k) : nullptr;
+    ggml_tensor * a = ggml_fused_up_gate(ctx, up, gate, x, GGML_UNARY_OP_SILU);
+    ggml_tensor * y = ggml_mul_mat(ctx, down, a);
+    if (bias) y = ggml_add(ctx, y, bv);
+    ggml_cgraph * gf = ggml_new_graph(ctx); ggml_build_forward_expand(gf, y);
+    ggml_backend_buffer_t buf = ggml_backend_alloc_ctx_tensors(ctx, be);
+    if (!buf) { printf("  alloc failed\n"); return 1; }
+    std::mt19937 rng(seed);
+    std::vector<float> ones(std::max(k, ff), 1.0f);
+    for (ggml_tensor * w : {up, gate, down}) {
+        std::vector<float> wf(ggml_nelements(w)); make_weights(type, wf, rng);
+        for (auto & v : wf) v *= 0.05f;
+        std::vector<uint8_t> wq(ggml_nbytes(w));
+        ggml_quantize_chunk(type, wf.data(), wq.data(), 0, w->ne[1], w->ne[0], ggml_quantize_requires_imatrix(type) ? ones.data() : nullptr, nullptr);
+        ggml_backend_tensor_set(w, wq.data(), 0, wq.size());
+    }
+    std::vector<float> xf(n * k); fill_uniform(xf, rng); ggml_backend_tensor_set(x, xf.data(), 0, xf.size() * sizeof(float));
+    if (bias) { std::vector<float> bf(k); fill_uniform(bf, rng); ggml_backend_tensor_set(bv, bf.data(), 0, bf.size() * sizeof(float)); }
+    bool supported = true;
+    for (int i = 0; i < gf->n_nodes; ++i) if (gf->nodes[i]->op != GGML_OP_ADD && !ggml_backend_supports_op(be, gf->nodes[i])) supported = false;
+    if (!supported) { printf("  %-8s FFN graph: a node is not supported\n", ggml_type_name(type)); return 1; }
+    cb_data d;
+    // (ggml_backend_compare_graph_backend computes node by node: to exercise the look-ahead fusions run the whole graph first and compare the final result)
+    if (ggml_backend_graph_compute(be, gf) != GGML_STATUS_SUCCESS) { printf("  graph_compute failed\n"); return 1; }
+    std::vector<float> y_fused(ggml_nelements(y)), a_fused(ggml_nelements(a));
+    ggml_backend_tensor_get(y, y_fused.data(), 0, ggml_nbytes(y)); ggml_backend_tensor_get(a, a_fused.data(), 0, ggml_nbytes(a));
+    ggml_backend_compare_graph_backend(be, cpu, gf, cmp_cb, &d);        // node-by-node on both backends (CPU result = the reference)
+    std::vector<float> y_node(ggml_nelements(y)), a_node(ggml_nelements(a));
+    ggml_backend_tensor_get(y, y_node.data(), 0, ggml_nbytes(y)); ggml_backend_tensor_get(a, a_node.data(), 0, ggml_nbytes(a));
+    const double e_y = nmse(y_fused.data(), y_node.data(), y_fused.size()), e_a = nmse(a_fused.data(), a_node.data(), a_fused.size());
+    const bool ok = d.n > 0 && d.worst <= 5e-4 && e_y <= 1e-6 && e_a <= 1e-9;
+    printf("  %-8s FFN graph (FUSED_UP_GATE -> MUL_MAT%s) k=%lld ff=%lld n=%lld: node-by-node vs CPU backend %.3g, fused whole-graph vs node-by-node: y %.3g, up_gate %.3g -> %s\n",
+           ggml_type_name(type), bias ? " -> ADD bias" : "", (long long)k, (long long)ff, (long long)n, d.worst, e_y, e_a, ok ? "OK" : "FAIL");
+    ggml_backend_buffer_free(buf); ggml_free(ctx);
+    return ok ? 0 : 1;
+}
+
+// batched MUL_MAT: src1 [K, N, B] with src0 broadcast over B, and src0 [K, M, B] with one matrix per batch entry
+static int run_batched_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, bool per_batch_weights, unsigned seed) {
+    const int64_t m = 256, k = 512, n = 3, nb = 4;
+    ggml_init_params ip = { ggml_tensor_overhead() * 16 + ggml_graph_overhead(), nullptr, true };
+    ggml_context * ctx = ggml_init(ip);
+    ggml_tensor * w = per_batch_weights ? ggml_new_tensor_3d(ctx, type, k, m, nb) : ggml_new_tensor_2d(ctx, type, k, m);
+    ggml_tensor * x = ggml_new_tensor_3d(ctx, GGML_TYPE_F32, k, n, nb);
+    ggml_tensor * y = ggml_mul_mat(ctx, w, x);
+    ggml_cgraph * gf = ggml_new_graph(ctx); ggml_build_forward_expand(gf, y);
+    ggml_backend_buffer_t buf = ggml_backend_alloc_ctx_tensors(ctx, be);
+    if (!buf) { printf("  alloc failed\n"); return 1; }
+    std::mt19937 rng(seed);
+    std::vector<float> wf(ggml_nelements(w)), xf(ggml_nelements(x)); make_weights(type, wf, rng); fill_uniform(xf, rng);
+    std::vector<uint8_t> wq(ggml_nbytes(w));
+    ggml_quantize_chunk(type, wf.data(), wq.data(), 0, ggml_nrows(w), k, nullptr, nullptr);
+    ggml_backend_tensor_set(w, wq.data(), 0, wq.size());
+    std::vector<uint8_t> back(wq.size()); ggml_backend_tensor_get(w, back.data(), 0, back.size());
+    if (memcmp(back.data(), wq.data(), wq.size()) != 0) { printf("  3-D set/get round trip FAILED\n"); return 1; }
+    ggml_backend_tensor_set(x, xf.data(), 0, xf.size() * sizeof(float));
+    if (!ggml_backend_supports_op(be, y)) { printf("  batched MUL_MAT not supported\n"); return 1; }
+    cb_data d; ggml_backend_compare_graph_backend(be, cpu, gf, cmp_cb, &d);
+    const bool ok = d.n > 0 && d.worst <= 5e-4;
+    printf("  %-8s batched MUL_MAT (%s) m=%lld k=%lld n=%lld batch=%lld: NMSE vs CPU backend %.3g -> %s\n", ggml_type_name(type), per_batch_weights ? "one matrix per batch entry" : "src0 broadcast",
+           (long long)m, (long long)k, (long long)n, (long long)nb, d.worst, ok ? "OK" : "FAIL");
+    ggml_backend_buffer_free(buf); ggml_free(ctx);
+    return ok ? 0 : 1;
+}
+
+// async tensor access + events of the backend interface
+static int run_async_case(ggml_backend_t be) {
+    ggml_init_params ip = { ggml_tensor_overhead() * 4, nullptr, true };
+    ggml_context * ctx = ggml_init(ip);
+    ggml_tensor * t = ggml_new_tensor_1d(ctx, GGML_TYPE_F32, 1 << 16);
+    ggml_backend_buffer_t buf = ggml_backend_alloc_ctx_tensors(ctx, be);
+    std::vector<float> a(1 << 16), b(1 << 16, 0.f); for (size_t i = 0; i < a.size(); ++i) a[i] = (float)i * 0.5f;
+    ggml_backend_tensor_set_async(be, t, a.data(), 0, ggml_nbytes(t));
+    ggml_backend_event_t ev = ggml_backend_event_new(be);
+    bool ok = ev != nullptr;
+    if (ev) { ggml_backend_event_record(ev); ggml_backend_event_wait(be, ev); }
+    ggml_backend_tensor_get_async(be, t, b.data(), 0, ggml_nbytes(t));
+    if (ev) { ggml_backend_event_record(ev); ggml_backend_event_synchronize(ev); ggml_backend_event_free(ev); }
+    ggml_backend_synchronize(be);
+    ok = ok && memcmp(a.data(), b.data(), ggml_nbytes(t)) == 0;
+    printf("  async set/get + events: %s\n", ok ? "OK" : "FAIL");
     ggml_backend_buffer_free(buf); ggml_free(ctx);
     return ok ? 0 : 1;
 }
@@ -147,6 +250,22 @@ int main(int argc, char ** argv) {
         fails += run_case(be, cpu, t, 768, 2048, 1, true, ++seed);
         fails += run_case(be, cpu, t, 768, 1024, 64, true, ++seed);               // FUSED_UP_GATE, n > 8: GEMMs + unary-mul epilogue
         for (int64_t n : {1, 64}) fails += run_qkv_case(be, t, 1024, n, ++seed);
+    }
+    // wire-layout types (b200q_wire.cuh): grid codebooks, IQ6_K, IQ4_KSS, IQ2_KL, IQ1_BN, trellis (KT: the reference quantiser is slow -> few rows), _R4 repacks
+    const ggml_type wire_types[] = { GGML_TYPE_IQ2_XXS, GGML_TYPE_IQ2_XS, GGML_TYPE_IQ2_S, GGML_TYPE_IQ3_XXS, GGML_TYPE_IQ3_S, GGML_TYPE_IQ1_S, GGML_TYPE_IQ1_M, GGML_TYPE_IQ6_K, GGML_TYPE_IQ4_KSS,
+                                     GGML_TYPE_IQ2_KL, GGML_TYPE_IQ1_BN, GGML_TYPE_IQ1_KT, GGML_TYPE_IQ2_KT, GGML_TYPE_IQ3_KT, GGML_TYPE_IQ4_KT, GGML_TYPE_IQ1_S_R4, GGML_TYPE_IQ1_M_R4,
+                                     GGML_TYPE_IQ2_K_R4, GGML_TYPE_IQ3_K_R4, GGML_TYPE_IQ4_K_R4, GGML_TYPE_IQ5_K_R4, GGML_TYPE_IQ4_KS_R4, GGML_TYPE_IQ5_KS_R4 };
+    for (ggml_type t : wire_types) {
+        const bool kt = t == GGML_TYPE_IQ1_KT || t == GGML_TYPE_IQ2_KT || t == GGML_TYPE_IQ3_KT || t == GGML_TYPE_IQ4_KT;
+        const int64_t m = kt ? 32 : 256;
+        for (int64_t n : {1, 8, 32}) { fails += run_case(be, cpu, t, m, 1024, n, false, ++seed); if (quick) break; }
+        if (!quick && !kt) fails += run_case(be, cpu, t, 256, 1024, 1, true, ++seed);
+    }
+    if (!quick) {
+        for (ggml_type t : {GGML_TYPE_IQ4_NL, GGML_TYPE_Q4_K, GGML_TYPE_Q6_K}) for (int64_t n : {1, 2, 16}) for (bool bias : {false, true}) fails += run_ffn_case(be, cpu, t, 1024, 2048, n, bias, ++seed);
+        fails += run_ffn_case(be, cpu, GGML_TYPE_IQ4_NL, 4096, 14336, 1, false, ++seed);       // Llama-3-8B FFN shape: long-row ring + q8 hand-off
+        for (ggml_type t : {GGML_TYPE_IQ4_NL, GGML_TYPE_Q4_K}) for (bool pb : {false, true}) fails += run_batched_case(be, cpu, t, pb, ++seed);
+        fails += run_async_case(be);
     }
     if (!quick) {   // bitnet shapes: K = 3200 is not a multiple of 256
         for (int64_t n : {1, 4, 32}) fails += run_case(be, cpu, GGML_TYPE_IQ2_BN, 640, 3200, n, false, ++seed);

@@ -22,6 +22,9 @@ class _BE:
 
     calls = []
 
+    def prefetch_next(self, ws, gate=None):
+        assert all(hasattr(w, "m") for w in ws)
+
     def mul_mat(self, w, x, out=None, x_bf16=None, q8_in=None):
         assert x.shape[1] == w.k and (out is None or out.shape[1] == w.m)
         self.calls.append("mul_mat"); return out
