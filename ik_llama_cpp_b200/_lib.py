@@ -76,6 +76,9 @@ def lib() -> ctypes.CDLL:
     L.b200q_fused_up_gate_vec_q8.argtypes = [i32, vp, vp, vp, vp, i64, i64, i32, c_float, vp, POINTER(i32), vp]
     L.b200q_mul_mat_vec_q8.argtypes = [i32, vp, vp, vp, vp, i64, i64, vp, vp]
     L.b200q_reduce_sum_nvls_bf16.argtypes = [vp, vp, vp, i64, vp, vp]
+    if hasattr(L, "b200q_mul_mat_id_vec"):
+        L.b200q_mul_mat_id_vec.argtypes = [i32, vp, vp, i32, vp, vp, vp, i64, i64, i32, i32, i32, i32, c_float, vp]
+        L.b200q_add_rows.argtypes = [vp, vp, vp, i64, i64, i64, vp]
     if hasattr(L, "b200q_decode_prefetch_next"):
         L.b200q_decode_prefetch_next.argtypes = [i32, i32, vp, vp, vp, i64]
     _lib = L

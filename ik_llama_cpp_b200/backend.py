@@ -242,6 +242,49 @@ def fused_up_gate(up: QuantTensor, gate: QuantTensor, x: torch.Tensor, unary: st
     return dst
 
 
+@dataclass
+class ExpertTensor:
+    """src0 of GGML_OP_MUL_MAT_ID: n_expert matrices [m x k] of one type (ggml ne = [K, M, n_expert]), each in the device layout."""
+    ggml_type: int
+    n_expert: int
+    m: int
+    k: int
+    planes: torch.Tensor       # uint8 [n_expert * plane_bytes(type, m, k)]
+
+    @property
+    def ptr(self) -> int:
+        return self.planes.data_ptr()
+
+
+def set_expert_tensor(ggml_type: int, wire, n_expert: int, m: int, k: int, device=None) -> ExpertTensor:
+    """Upload a 3-D expert tensor: every [m x k] matrix is re-laid-out on its own (what the backend plug's set_tensor does for ne[2] > 1)."""
+    _require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    pb, rs = plane_bytes(ggml_type, m, k), row_size(ggml_type, k)
+    host = np.ascontiguousarray(np.frombuffer(wire, dtype=np.uint8) if not isinstance(wire, np.ndarray) else wire.view(np.uint8).ravel())
+    assert host.size == n_expert * m * rs
+    planes = torch.zeros(n_expert * pb, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        for e in range(n_expert):
+            check(_lib.lib().b200q_set_tensor(ggml_type, host[e * m * rs:].ctypes.data, planes.data_ptr() + e * pb, m, k, _stream()), "b200q_set_tensor")
+    return ExpertTensor(ggml_type, n_expert, m, k, planes)
+
+
+def mul_mat_id(w: ExpertTensor, x: torch.Tensor, ids: torch.Tensor, gate: "ExpertTensor | None" = None, unary: str = "silu", limit: float = 0.0) -> torch.Tensor:
+    """GGML_OP_MUL_MAT_ID (gate is None) / GGML_OP_MOE_FUSED_UP_GATE for small batches: x f32 [n_tokens, nb1, K], ids int32 [n_tokens, n_used]
+    -> dst f32 [n_tokens, n_used, M] with dst[t, e] = W[ids[t, e]] . x[t, e % nb1]  (gate: unary(gate[id] . x) * (W[id] . x))."""
+    _require_cuda()
+    assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.is_contiguous() and x.shape[2] == w.k
+    assert ids.is_cuda and ids.dtype == torch.int32 and ids.dim() == 2 and ids.is_contiguous() and ids.shape[0] == x.shape[0]
+    n_tokens, nb1, n_used = x.shape[0], x.shape[1], ids.shape[1]
+    assert n_used % nb1 == 0
+    dst = torch.empty((n_tokens, n_used, w.m), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().b200q_mul_mat_id_vec(w.ggml_type, w.ptr, gate.ptr if gate is not None else None, w.n_expert, ids.data_ptr(), x.data_ptr(), dst.data_ptr(),
+                                              w.m, w.k, n_used, nb1, n_tokens, UNARY[unary], float(limit), _stream()), "b200q_mul_mat_id_vec")
+    return dst
+
+
 def dequantize_bf16(w: QuantTensor) -> torch.Tensor:
     _require_cuda()
     out = torch.empty((w.m, w.k), dtype=torch.bfloat16, device=w.planes.device)

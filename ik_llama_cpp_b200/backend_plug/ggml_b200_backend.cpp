@@ -246,6 +246,20 @@ GGML_CALL static bool b200_backend_supports_op(ggml_backend_t, const ggml_tensor
     switch (op->op) {
         case GGML_OP_NONE: case GGML_OP_RESHAPE: case GGML_OP_VIEW: case GGML_OP_PERMUTE: case GGML_OP_TRANSPOSE: return true;
         case GGML_OP_MUL_MAT: return b200_can_mul_mat(op->src[0], op->src[1], op);
+        case GGML_OP_ADD:       // the bias of a mat-mul result ([M] broadcast over the columns) or a same-shape f32 add, on our buffers
+            return op->type == GGML_TYPE_F32 && op->src[0] && op->src[1] && op->src[0]->type == GGML_TYPE_F32 && op->src[1]->type == GGML_TYPE_F32 &&
+                   ggml_is_contiguous(op) && ggml_is_contiguous(op->src[0]) && ggml_is_contiguous(op->src[1]) && ggml_are_same_shape(op, op->src[0]) &&
+                   op->src[1]->ne[0] == op->ne[0] && (ggml_nelements(op->src[1]) == op->ne[0] || ggml_are_same_shape(op, op->src[1]));
+        case GGML_OP_MUL_MAT_ID: case GGML_OP_MOE_FUSED_UP_GATE: {
+            // MoE, small batches (decode): expert ids resolved on the device; larger batches are declined (the grouped prefill GEMM is the next step)
+            const bool ug = op->op == GGML_OP_MOE_FUSED_UP_GATE;
+            const ggml_tensor * w = op->src[0]; const ggml_tensor * g = ug ? op->src[1] : nullptr; const ggml_tensor * x = op->src[ug ? 2 : 1]; const ggml_tensor * ids = op->src[ug ? 3 : 2];
+            if (!w || !x || !ids || (ug && (!g || g->type != w->type || !ggml_are_same_shape(g, w) || op->src[4] || op->src[5] || b200_unary(b200_op_param_i32(op, 0)) < 0))) return false;
+            if (!b200_weight_ok(w) || (g && !b200_weight_ok(g)) || x->type != GGML_TYPE_F32 || !ggml_is_contiguous(x) || ids->type != GGML_TYPE_I32 || !ggml_is_contiguous(ids)) return false;
+            if (op->type != GGML_TYPE_F32 || !ggml_is_contiguous(op) || w->ne[0] != x->ne[0] || x->ne[3] != 1 || ids->ne[1] != x->ne[2] || ids->ne[0] % x->ne[1]) return false;
+            const int64_t ncx = x->ne[1] * x->ne[2];
+            return x->ne[2] <= 8 && ncx * (w->ne[0] + w->ne[0] / 4) <= 200 * 1024;
+        }
         case GGML_OP_FUSED_UP_GATE:
             return op->src[0] && op->src[1] && !op->src[3] && !op->src[4] && op->src[0]->type == op->src[1]->type && op->src[2] && op->src[2]->ne[2] * op->src[2]->ne[3] == 1 &&
                    op->src[0]->ne[2] == 1 && op->src[1]->ne[2] == 1 && b200_can_mul_mat(op->src[0], op->src[2], op) &&
@@ -314,6 +328,18 @@ GGML_CALL static enum ggml_status b200_backend_graph_compute(ggml_backend_t b, g
                         B200Q_CHECK(b200q_mul_mat(w->type, W[j], (const float *)x->data, D[j], M[j], k, n, ws, need, c->stream));
                     }
                 }
+            } break;
+            case GGML_OP_ADD: {
+                const ggml_tensor * a0 = node->src[0]; const ggml_tensor * a1 = node->src[1];
+                const int64_t m = node->ne[0], n = ggml_nelements(node) / m, nb = ggml_nelements(a1) / m;
+                B200Q_CHECK(b200q_add_rows((const float *)a0->data, (const float *)a1->data, (float *)node->data, m, n, nb, c->stream));
+            } break;
+            case GGML_OP_MUL_MAT_ID: case GGML_OP_MOE_FUSED_UP_GATE: {
+                const bool ug = node->op == GGML_OP_MOE_FUSED_UP_GATE;
+                const ggml_tensor * w = node->src[0]; const ggml_tensor * g = ug ? node->src[1] : nullptr; const ggml_tensor * x = node->src[ug ? 2 : 1]; const ggml_tensor * ids = node->src[ug ? 3 : 2];
+                float limit = 0.0f; if (ug) memcpy(&limit, (const char *)node->op_params + sizeof(int32_t), sizeof(float));
+                B200Q_CHECK(b200q_mul_mat_id_vec(w->type, w->data, g ? g->data : nullptr, (int)w->ne[2], (const int32_t *)ids->data, (const float *)x->data, (float *)node->data,
+                                                 w->ne[1], w->ne[0], (int)ids->ne[0], (int)x->ne[1], (int)x->ne[2], ug ? b200_unary(b200_op_param_i32(node, 0)) : 0, limit, c->stream));
             } break;
             case GGML_OP_FUSED_UP_GATE: {
                 const ggml_tensor * up = node->src[0]; const ggml_tensor * gate = node->src[1]; const ggml_tensor * x = node->src[2];

@@ -65,7 +65,8 @@ thread_local scratch g_x, g_y, g_ws, g_stage;
 int & opt_ring() { static int v = [] { const char * e = getenv("B200Q_RING"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_fuse_epi() { static int v = [] { const char * e = getenv("B200Q_FUSE_EPILOGUE"); return e ? atoi(e) : 0; }(); return v; }
 int & opt_fused() { static int v = [] { const char * e = getenv("B200Q_FUSED_GEMM"); return e ? atoi(e) : 1; }(); return v; }
-int & opt_pf() { static int v = [] { const char * e = getenv("B200Q_PREFETCH_NEXT"); return e ? atoi(e) : 1; }(); return v; }
+// L2 warm-up of the next launch's weights: measured 753 vs 771 tok/s (slower: the prefetch competes with the running kernel's own stream) -> opt-in
+int & opt_pf() { static int v = [] { const char * e = getenv("B200Q_PREFETCH_NEXT"); return e ? atoi(e) : 0; }(); return v; }
 int & opt_q8() { static int v = [] { const char * e = getenv("B200Q_Q8_HANDOFF"); return e ? atoi(e) : 1; }(); return v; }
 int & opt_pdl() { static int v = [] { const char * e = getenv("B200Q_PDL"); return e ? atoi(e) : 1; }(); return v; }
 }  // namespace
@@ -357,7 +358,21 @@ int b200q_fused_up_gate(int type, const void * W_up, const void * W_gate, const 
     if (n <= 8) return b200q_fused_up_gate_vec(type, W_up, W_gate, x, dst, m, k, (int)n, k, unary, limit, stream);
     if (!x || !workspace || workspace_bytes < b200q_fused_up_gate_workspace(type, m, k, n)) return fail(B200Q_E_ARG, "b200q_fused_up_gate: bad argument / workspace too small");
     if ((m * n) % 4) return fail(B200Q_E_SHAPE, "b200q_fused_up_gate: m*n must be a multiple of 4");
-    int rc = b200q_convert_f32_bf16(x, k, workspace, k, n, stream); if (rc) return rc;
+    int rc;
+    {   // ternary weights: both GEMMs on the int8 tensor pipe (one activation quantisation, one launch over the up and gate row tiles), then the unary-mul tail
+        static const int use_i8 = [] { const char * e = getenv("B200Q_BN_INT8"); return e ? atoi(e) : 1; }();
+        dev_info & di = device_info();
+        const size_t up_bytes = (size_t)b200q_align_up(m * n * 4, 256);
+        if (type == B200Q_TYPE_IQ2_BN && use_i8 && opt_fused() && di.ok && workspace_bytes >= up_bytes + b200q_gemm_i8_workspace_bytes(k, n)) {
+            float * up_res = (float *)workspace;
+            b200q_gemm_multi d; memset(&d, 0, sizeof d);
+            d.type = type; d.n_seg = 2; d.W[0] = W_up; d.dst[0] = up_res; d.M[0] = m; d.W[1] = W_gate; d.dst[1] = dst; d.M[1] = m; d.K = k; d.N = n;
+            rc = b200q_launch_gemm_bn_i8(d, x, k, (char *)workspace + up_bytes, workspace_bytes - up_bytes, (cudaStream_t)stream);
+            if (rc == 0) return check_launch(b200q_launch_mul_unary(dst, up_res, dst, nullptr, m * n, unary, limit, (cudaStream_t)stream), "b200q_fused_up_gate(unary)");
+            if (rc != -100) return check_launch(rc, "b200q_fused_up_gate(int8)");
+        }
+    }
+    rc = b200q_convert_f32_bf16(x, k, workspace, k, n, stream); if (rc) return rc;
     const size_t off = (size_t)b200q_align_up(n * k * 2, 256);
     return b200q_fused_up_gate_gemm_bf16(type, W_up, W_gate, workspace, dst, nullptr, m, k, n, unary, limit, (char *)workspace + off, workspace_bytes - off, stream);
 }
@@ -365,6 +380,22 @@ int b200q_mul_mat(int type, const void * W, const float * x, float * dst, int64_
                   void * workspace, size_t workspace_bytes, void * stream) {
     if (n <= 8) return b200q_mul_mat_vec(type, W, x, dst, m, k, (int)n, k, nullptr, stream);
     return b200q_mul_mat_gemm(type, W, x, dst, m, k, n, workspace, workspace_bytes, stream);
+}
+/* GGML_OP_ADD of a mat-mul result with its bias (bias [m] broadcast over the n columns, nb = 1) or with a same-shape tensor (nb = n): the node as
+ * its own launch, for graphs that compute it separately; inside a graph the mat-vec fuses it (bias operand of b200q_mul_mat_vec). */
+int b200q_add_rows(const float * a, const float * b, float * dst, int64_t m, int64_t n, int64_t nb, void * stream) {
+    if (!a || !b || !dst) return fail(B200Q_E_ARG, "b200q_add_rows: bad argument");
+    return check_launch(b200q_launch_add_rows(a, b, dst, m, n, nb, (cudaStream_t)stream), "b200q_add_rows");
+}
+int b200q_mul_mat_id_vec(int type, const void * W, const void * W_gate, int n_expert, const int32_t * ids, const float * x, float * dst,
+                         int64_t m, int64_t k, int n_used, int nb1, int n_tokens, int unary, float limit, void * stream) {
+    if (!W || !ids || !x || !dst || m <= 0 || n_expert < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_id_vec: bad argument");
+    dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_id_vec: no CUDA device");
+    if (((uintptr_t)x & 15) || (k & 3)) return fail(B200Q_E_ARG, "b200q_mul_mat_id_vec: activations must be 16-byte aligned");
+    b200q_mmvq_id_desc d; memset(&d, 0, sizeof d);
+    d.type = type; d.W = W; d.W2 = W_gate; d.ids = ids; d.x = x; d.dst = dst; d.M = m; d.K = k; d.n_expert = n_expert; d.n_used = n_used; d.nb1 = nb1; d.n_tokens = n_tokens;
+    d.act = unary; d.limit = limit; d.sm_count = di.sm_count; d.pdl = opt_pdl();
+    return check_launch(b200q_launch_mmvq_id(d, (cudaStream_t)stream), "b200q_mul_mat_id_vec");
 }
 int b200q_mul_mat_host(int type, const void * W, const float * x_host, float * dst_host, int64_t m, int64_t k, int64_t n, void * stream) {
     cudaStream_t st = (cudaStream_t)stream; cudaError_t e; int rc;

@@ -74,7 +74,8 @@ __global__ void k_dequant_bf16(const uint8_t * __restrict__ W, b200q_layout L, _
 #endif
 
 // the per-type mat-vec launchers are instantiated in b200q_decode_i<N>.cu (parallel compilation)
-#define X(T) extern template int launch_mmvq_type<T>(const mmvq_args &, int, bool, int, bool, bool, cudaStream_t);
+#define X(T) extern template int launch_mmvq_type<T>(const mmvq_args &, int, bool, int, bool, bool, cudaStream_t); \
+             extern template int launch_mmvq_id_type<T>(const mmvq_id_args &, bool, int, bool, cudaStream_t);
 B200Q_FOR_TYPES(X)
 #undef X
 
@@ -141,6 +142,23 @@ int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
     }
     switch (d.type) {
 #define X(T) case T: return launch_mmvq_type<T>(a, d.ncols, upgate, d.sm_count, d.pdl != 0, d.ring != 0, st);
+        B200Q_FOR_TYPES(X)
+#undef X
+        default: return -1;
+    }
+}
+
+// MoE decode (GGML_OP_MUL_MAT_ID / MOE_FUSED_UP_GATE, small batches): see k_mmvq_id / k_wire_mmvq_id
+int b200q_launch_mmvq_id(const b200q_mmvq_id_desc & d, cudaStream_t st) {
+    if (d.n_tokens < 1 || d.n_used < 1 || d.nb1 < 1 || d.n_used % d.nb1 || d.n_expert < 1 || !d.W || !d.ids || !d.x || !d.dst) return -2;
+    if (b200q_is_wire_type(d.type)) return b200q_launch_wire_mmvq_id(d, st);
+    b200q_layout L; const int rc = b200q_make_layout(d.type, d.M, d.K, &L); if (rc) return rc;
+    mmvq_id_args a; memset(&a, 0, sizeof a);
+    a.P = b200q_planes_from((const uint8_t *)d.W, L); if (d.W2) a.P2 = b200q_planes_from((const uint8_t *)d.W2, L);
+    a.estride = L.total_bytes; a.ids = d.ids; a.n_expert = d.n_expert; a.n_slots = d.n_tokens * d.n_used; a.n_used = d.n_used; a.nb1 = d.nb1; a.ncx = d.n_tokens * d.nb1;
+    a.M = d.M; a.K = d.K; a.x = d.x; a.dst = d.dst; a.act = d.act; a.limit = d.limit;
+    switch (d.type) {
+#define X(T) case T: return launch_mmvq_id_type<T>(a, d.W2 != nullptr, d.sm_count, d.pdl != 0, st);
         B200Q_FOR_TYPES(X)
 #undef X
         default: return -1;

@@ -175,6 +175,89 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// MoE decode: GGML_OP_MUL_MAT_ID / GGML_OP_MOE_FUSED_UP_GATE for small batches (reference: mul_mat_vec_q with `ids`, blockIdx.y = expert slot,
+// mmvq-templates.cuh:293-302; ggml_cuda_mul_mat_id / ggml_cuda_moe_up_gate_unary, ggml-cuda.cu:2836-3540).  Slot s = (token t, used expert e):
+//     dst[s][:] = W[ids[s]] . x[col(s)][:]          (W2 != nullptr: unary(W2[ids[s]] . x) * (W[ids[s]] . x))
+// One launch over all slots: the expert index is read on the DEVICE (no host round trip), every distinct activation column is quantised once
+// per CTA, a warp owns one (slot, row) at a time.  LDG kernel (same inner loop as k_mmvq).
+// ------------------------------------------------------------------------------------------------
+struct mmvq_id_args {
+    b200q_planes P, P2;             // planes of expert 0 of W (and of the gate tensor)
+    int64_t estride;                // bytes between consecutive experts (same in every plane)
+    const int32_t * ids;            // [n_slots] expert per slot
+    int n_expert, n_slots, n_used, nb1, ncx;   // slots = n_tokens * n_used; x columns = n_tokens * nb1, column of slot s = (s / n_used) * nb1 + (s % n_used) % nb1
+    int64_t M, K; const float * x; float * dst; int act; float limit;
+};
+template <int TYPE, bool UPGATE>
+__global__ void __launch_bounds__(512, 1) k_mmvq_id(const mmvq_id_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int64_t K = a.K; const int n32 = (int)(K / 32);
+    int8_t * sq = reinterpret_cast<int8_t *>(smem_raw);
+    float *  sd = reinterpret_cast<float *>(smem_raw + (size_t)a.ncx * K);
+    int *    sis = reinterpret_cast<int *>(sd + a.ncx * n32);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    pdl_trigger();
+    pdl_wait();
+    for (int c = 0; c < a.ncx; ++c) quantize_x_to_smem<1>(a.x + (int64_t)c * K, K, K, sq + (size_t)c * K, sd + c * n32, sis + c * n32, threadIdx.x, blockDim.x);
+    __shared__ uint32_t kv_slot[128];
+    const b200q_kv4 T = b200q_kv4_init_via_smem(kv_slot);     // includes the __syncthreads() that publishes the activations
+    constexpr int U = UPGATE ? 2 : 4;
+    const int64_t total = (int64_t)a.n_slots * a.M;
+    for (int64_t g = (int64_t)blockIdx.x * nwarps + warp; g < total; g += (int64_t)gridDim.x * nwarps) {
+        const int s = (int)(g / a.M); const int64_t row = g - (int64_t)s * a.M;
+        int e = __ldg(a.ids + s); e = e < 0 ? 0 : (e >= a.n_expert ? a.n_expert - 1 : e);          // (a corrupt id must not read outside the tensor)
+        const int col = (s / a.n_used) * a.nb1 + (s % a.n_used) % a.nb1;
+        b200q_planes P = a.P, P2 = a.P2;
+#pragma unroll
+        for (int p = 0; p < B200Q_MAX_PLANES; ++p) { P.p[p] += (int64_t)e * a.estride; P2.p[p] += (int64_t)e * a.estride; }
+        float acc[1] = {0.0f}, acc2[1] = {0.0f};
+        for (int it0 = lane; it0 < n32; it0 += 32 * U) {
+            b200q_item I[U], J[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int it = it0 + 32 * u;
+                if (it < n32) { b200q_load_item<TYPE>(I[u], P, row, it); if (UPGATE) b200q_load_item<TYPE>(J[u], P2, row, it); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int it = it0 + 32 * u;
+                if (it < n32) {
+                    b200q_canon C;
+                    b200q_decode_item<TYPE>(I[u], it, C, T);
+                    item_dot<TYPE, 1>(C, sq + (size_t)col * K, sd + col * n32, sis + col * n32, K, n32, it, acc);
+                    if (UPGATE) { b200q_decode_item<TYPE>(J[u], it, C, T); item_dot<TYPE, 1>(C, sq + (size_t)col * K, sd + col * n32, sis + col * n32, K, n32, it, acc2); }
+                }
+            }
+        }
+        float v = warp_sum(acc[0]);
+        if (UPGATE) { const float gt = warp_sum(acc2[0]); v = b200q_glu<false>(a.act, gt, v, a.limit); }
+        if (lane == 0) a.dst[(int64_t)s * a.M + row] = v;
+    }
+}
+template <int TYPE>
+int launch_mmvq_id_type(const mmvq_id_args & a, bool upgate, int sm_count, bool pdl, cudaStream_t st) {
+    const size_t smem = (size_t)a.ncx * a.K + (size_t)a.ncx * (a.K / 32) * 8;
+    if (smem > 200 * 1024) return -2;
+    static size_t configured[2][B200Q_MAX_DEVICES] = {};
+    const int dev = b200q_current_device();
+    if (smem > 48 * 1024 && smem > configured[upgate][dev]) {
+        const cudaError_t e = upgate ? cudaFuncSetAttribute(k_mmvq_id<TYPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                     : cudaFuncSetAttribute(k_mmvq_id<TYPE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -3;
+        configured[upgate][dev] = smem;
+    }
+    const int nwarps = 16;
+    int64_t grid = ((int64_t)a.n_slots * a.M + nwarps - 1) / nwarps; if (grid > sm_count) grid = sm_count; if (grid < 1) grid = 1;
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(nwarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return upgate ? (int)cudaLaunchKernelEx(&cfg, k_mmvq_id<TYPE, true>, a) : (int)cudaLaunchKernelEx(&cfg, k_mmvq_id<TYPE, false>, a);
+}
+
 // ------------------------------------------------------------------------------------------------
 // decode mat-vec, TMA-ring variant (the default): weights are streamed HBM -> shared memory by cp.async.bulk (1-D TMA)
 // into warp-private rings, decoupled from registers and from the data dependency on the previous kernel.
@@ -200,6 +283,12 @@ __global__ void __launch_bounds__(512, (NCOLS == 1 ? 2 : 1)) k_mmvq(const mmvq_a
 #endif
 #ifndef B200Q_PRODUCER_LAST
 #define B200Q_PRODUCER_LAST 0        // 1: the producer is the LAST warp of the CTA (the warp scheduler prefers high warp ids: B300_MICROARCH.md)
+#endif
+#ifndef B200Q_EXP_PREFILL_AFTER_WAIT
+#define B200Q_EXP_PREFILL_AFTER_WAIT 0
+#endif
+#ifndef B200Q_EXP_LATE_TRIGGER
+#define B200Q_EXP_LATE_TRIGGER 0
 #endif
 #ifndef B200Q_MIN_CTAS
 #define B200Q_MIN_CTAS 2             // resident CTAs per SM the ring kernel is compiled for (register cap = 65536 / (MIN_CTAS * threads))
@@ -367,12 +456,20 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
         if (++psg == nseg) { psg = 0; if (++pt == NT) pt = 0; }
     };
     // (1) weights do not depend on the previous kernel: fill the ring before waiting for it
+#if B200Q_EXP_PREFILL_AFTER_WAIT          // experiment: no memory traffic of this grid before the previous one has completed
+    pdl_trigger();
+    pdl_wait();
+    if (is_prod) { for (int s = 0; s < S; ++s) if (!pdone) produce_one(); }
+#else
     if (is_prod) {
         for (int s = 0; s < S; ++s) if (!pdone) produce_one();
         if (a.pf.n) issue_next_prefetch(a.pf, lane);       // after our own first stages: the next kernel's first stages -> L2
     }
+#if !B200Q_EXP_LATE_TRIGGER
     pdl_trigger();                       // the next kernel of the stream/graph may become resident and fill ITS ring
+#endif
     pdl_wait();                          // (2) the activations are produced by the previous kernel
+#endif
     if (a.trace && blockIdx.x == 0 && lead) a.trace[1] = gtime();
     // Tensor-parallel mode.  `seq` = number of fused reduces completed on this communicator (device counter, so the launch arguments
     // are constant under CUDA-graph replay); it cannot change while this grid runs before its own last CTA bumps it.
@@ -431,6 +528,9 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
             }
             if (!__any_sync(0xffffffffu, ready)) __nanosleep(64);
         }
+#if B200Q_EXP_LATE_TRIGGER
+        pdl_trigger();                   // experiment: the next grid is launched only when this CTA has issued its last weight copy
+#endif
         return;
     }
 
@@ -639,7 +739,7 @@ static inline bool ring_shape(int ncols, int64_t K, size_t pair_stage, int64_t n
         const size_t per_stage = (size_t)ncw * (pair_stage + 16);
         S = xbytes + 64 < budget ? (int)((budget - xbytes - 64) / per_stage) : 0;
         if (S >= 2 || ncw == 3) break;
-        ncw = ncw > 7 ? 7 : 3;                           // (10 warps would still fit two stages for K = 14336 but measured slower: 13.8 vs 11.3 us)
+        ncw = ncw > 19 ? 19 : ncw > 15 ? 15 : ncw > 11 ? 11 : ncw > 7 ? 7 : 3;      // (10 warps would still fit two stages for K = 14336 but measured slower: 13.8 vs 11.3 us)
     }
     if (S < 2) return false;
     if (S > B200Q_MAX_STAGES) S = B200Q_MAX_STAGES;

@@ -476,6 +476,210 @@ k_gemm_q(const __grid_constant__ gemmq_args a) {
     if (warp == 1) tmem_dealloc(tmem_base, cfg::TMEM_COLS);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Ternary prefill on the INT8 tensor pipe: IQ2_BN (bitnet b1.58) weights x per-token int8 activations -> s32 in TMEM.
+// (BASELINE config 4 / north_star "IQ*_BN ternary (int8 tcgen05)".  The reference has no integer tensor-core path for this type: its prefill is
+//  dequantize_block_iq2_bn + cublasGemmEx in f16 with f16 accumulation, ggml-cuda.cu:1723-1894)
+//   A: the 2-bit fields q in {0,1,2} of the wire blocks are expanded to UNSIGNED int8 in the K-major SWIZZLE_128B A stage (128 rows x 128 k
+//      = 128 bytes per row: one shift + mask per 4 weights, no table, no scale); w = rs * (q - 1) is applied in the epilogue:
+//      dst[n][m] = rs[m] * ts[n] * (acc[m][n] - S[n]),  acc = sum_k q[m][k] * xq[n][k]  (tcgen05.mma kind::i8, u8 x s8 -> s32, exact),
+//      S[n] = sum_k xq[n][k] and ts[n] = amax_n / 127 come from the activation quantiser (k_quantize_rows_i8).
+//   B: int8 activations [N][K], TMA (SWIZZLE_128B, 128 k = 128 bytes per row), one per-TOKEN scale: the whole K reduction is integer.
+//   Zero-filled TMA tails make any K % 64 == 0 work (bitnet: K = 3200, 8640): q = 0 and xq = 0 beyond K contribute nothing, S[n] covers real k only.
+// Same warp roles / pipelines as k_gemm_q; MMA K = 32 per instruction, 4 instructions per 128-byte k-block; 2 x 256 TMEM columns for 512 tokens.
+// Accuracy: activations rounded to 8 bits per token (NMSE ~1e-4 for Gaussian activations; the reference's own q8_1 decode path: ~2e-5, its f16-accumulate
+// prefill: ~1e-6 + f16 overflow risk); weights exact.  Tolerance in tests/test_gpu_parity.py: NMSE <= 5e-4 (the reference's test bar).
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N) {        // D = s32 (2 << 4), A = u8 (0 << 7), B = s8 (1 << 10), K-major both
+    return (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+constexpr int BNI_BK = 128;                      // k (= bytes) per A / B stage row
+constexpr int BNI_RAW_K = 512;                   // weights per row per raw stage: 128 bytes of 2-bit fields = 4 k-blocks
+template <int NB> struct gemmbn_cfg {
+    static constexpr int BN = NB == 0 ? 128 : 256 * NB;
+    static constexpr int A_STAGES = 3, B_STAGES = 2, RAW_STAGES = 2;
+    static constexpr int A_BYTES = BM * BNI_BK, B_BYTES = BN * BNI_BK, RAW_BYTES = BM * 128;
+    static constexpr int TMEM_COLS = BN;
+    static constexpr size_t SMEM = 1024 + (size_t)A_STAGES * A_BYTES + (size_t)B_STAGES * B_BYTES + (size_t)RAW_STAGES * RAW_BYTES + 256;
+};
+struct gemmbn_seg { float * dst; const float * rs; int M; int tile0; };
+struct gemmbn_args {
+    CUtensorMap tmP0[GEMMQ_MAX_SEGS], tmB;
+    gemmbn_seg seg[GEMMQ_MAX_SEGS];
+    const float * ts; const int * sx;            // per-token scale and integer sum of the quantised activations
+    int n_seg, N, K;
+};
+template <int NB>
+__global__ void __launch_bounds__(64 + 32 * DQ_WARPS, 1)
+k_gemm_bn_i8(const __grid_constant__ gemmbn_args a) {
+    using cfg = gemmbn_cfg<NB>;
+    int sg = 0;
+#pragma unroll
+    for (int s = 1; s < GEMMQ_MAX_SEGS; ++s) if (s < a.n_seg && (int)blockIdx.x >= a.seg[s].tile0) sg = s;
+    const CUtensorMap * tmP0 = &a.tmP0[sg], * tmB = &a.tmB;
+    float * __restrict__ dst = a.seg[sg].dst; const float * __restrict__ rs = a.seg[sg].rs;
+    const int M = a.seg[sg].M, N = a.N, K = a.K;
+    constexpr int BN = cfg::BN, MMA_N = NB == 0 ? 128 : 256, N_ACC = NB == 0 ? 1 : NB;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char * smem = reinterpret_cast<unsigned char *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char * sA = smem;
+    unsigned char * sB = sA + (size_t)cfg::A_STAGES * cfg::A_BYTES;
+    unsigned char * sR = sB + (size_t)cfg::B_STAGES * cfg::B_BYTES;
+    uint64_t * bars = reinterpret_cast<uint64_t *>(sR + (size_t)cfg::RAW_STAGES * cfg::RAW_BYTES);
+    uint64_t * a_full = bars, * a_empty = a_full + cfg::A_STAGES, * b_full = a_empty + cfg::A_STAGES, * b_empty = b_full + cfg::B_STAGES;
+    uint64_t * raw_full = b_empty + cfg::B_STAGES, * raw_empty = raw_full + cfg::RAW_STAGES, * tmem_full = raw_empty + cfg::RAW_STAGES;
+    uint32_t * tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = ((int)blockIdx.x - a.seg[sg].tile0) * BM, n0 = blockIdx.y * BN;
+    const int nr = (K + BNI_RAW_K - 1) / BNI_RAW_K;             // raw blocks of 512 weights
+    const int nk = (K + BNI_BK - 1) / BNI_BK;                   // 128-wide MMA k-blocks
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < cfg::A_STAGES; ++s) { mbar_init(&a_full[s], DQ_WARPS); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < cfg::B_STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < cfg::RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], DQ_WARPS); }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(tmP0); tma_prefetch_desc(tmB);
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int ib = 0;
+            for (int r = 0; r < nr; ++r) {
+                const int rsi = r % cfg::RAW_STAGES; const uint32_t rph = (r / cfg::RAW_STAGES) & 1;
+                mbar_wait(&raw_empty[rsi], rph ^ 1);
+                mbar_expect_tx(&raw_full[rsi], cfg::RAW_BYTES);
+                tma_load_2d(sR + (size_t)rsi * cfg::RAW_BYTES, tmP0, &raw_full[rsi], r * 128, m0);       // 128 bytes of 2-bit fields per row
+                for (int q = 0; q < BNI_RAW_K / BNI_BK && ib < nk; ++q, ++ib) {
+                    const int s = ib % cfg::B_STAGES; const uint32_t ph = (ib / cfg::B_STAGES) & 1;
+                    mbar_wait(&b_empty[s], ph ^ 1);
+                    mbar_expect_tx(&b_full[s], cfg::B_BYTES);
+#pragma unroll
+                    for (int j = 0; j < N_ACC; ++j)
+                        tma_load_2d(sB + (size_t)s * cfg::B_BYTES + (size_t)j * MMA_N * BNI_BK, tmB, &b_full[s], ib * BNI_BK, n0 + j * MMA_N);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_i8(BM, MMA_N);
+            for (int i = 0; i < nk; ++i) {
+                const int sa = i % cfg::A_STAGES; const uint32_t pa = (i / cfg::A_STAGES) & 1;
+                const int sb = i % cfg::B_STAGES; const uint32_t pb = (i / cfg::B_STAGES) & 1;
+                mbar_wait(&a_full[sa], pa);
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
+                const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(sA + (size_t)sa * cfg::A_BYTES));
+#pragma unroll
+                for (int j = 0; j < N_ACC; ++j) {
+                    const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(sB + (size_t)sb * cfg::B_BYTES + (size_t)j * MMA_N * BNI_BK));
+#pragma unroll
+                    for (int k = 0; k < BNI_BK / 32; ++k)        // K = 32 int8 = 32 bytes per instruction: +2 in 16-byte units of the start address
+                        umma_i8_ss(tmem_base + (uint32_t)(j * MMA_N), a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&a_empty[sa]);
+                umma_commit(&b_empty[sb]);
+            }
+            umma_commit(tmem_full);
+        }
+    } else {
+        // ---------------- expand warps (then epilogue): thread = (row, wire block of the k-block) ----------------
+        const int dq = warp - 2, q4 = warp & 3, half = dq >> 2, row = 32 * q4 + lane;
+        int ia = 0;
+        for (int r = 0; r < nr; ++r) {
+            const int rsi = r % cfg::RAW_STAGES; const uint32_t rph = (r / cfg::RAW_STAGES) & 1;
+            mbar_wait(&raw_full[rsi], rph);
+            const unsigned char * raw = sR + (size_t)rsi * cfg::RAW_BYTES + (size_t)row * 128;
+            for (int q = 0; q < BNI_RAW_K / BNI_BK && ia < nk; ++q, ++ia) {
+                const int sa = ia % cfg::A_STAGES; const uint32_t pa = (ia / cfg::A_STAGES) & 1;
+                // wire block (64 weights, 16 bytes) number 2q + half of this raw row; SWIZZLE_128B: 16-byte chunk c sits at c ^ (row & 7)
+                const uint4 wv = *reinterpret_cast<const uint4 *>(raw + (((2 * q + half) ^ (row & 7)) << 4));
+                const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+                mbar_wait(&a_empty[sa], pa ^ 1);
+                unsigned char * arow = sA + (size_t)sa * cfg::A_BYTES + (size_t)(row >> 3) * 1024 + (size_t)(row & 7) * 128;
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {                    // field f of byte j = weight 16 f + j of the block: one 16-byte chunk of 16 consecutive k
+                    const int chunk = (4 * half + f) ^ (row & 7);
+                    *reinterpret_cast<uint4 *>(arow + chunk * 16) = make_uint4((w[0] >> (2 * f)) & 0x03030303u, (w[1] >> (2 * f)) & 0x03030303u,
+                                                                               (w[2] >> (2 * f)) & 0x03030303u, (w[3] >> (2 * f)) & 0x03030303u);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[sa]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[rsi]);
+        }
+        // ---------------- epilogue: dst = rs[m] * ts[n] * (acc - S[n]) ----------------
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int m = m0 + row;
+        constexpr int COLS_PER = BN / 2;
+        const int c_begin = half * COLS_PER, c_end = min((half + 1) * COLS_PER, N - n0);
+        const bool mrow = m < M;
+        const float rsm = mrow ? __ldg(rs + m) : 0.0f;
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            uint32_t rr[32];
+            tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)c0, rr);
+            tmem_ld_wait();
+            if (mrow) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < N) dst[(size_t)n * M + m] = rsm * __ldg(a.ts + n) * (float)((int)rr[j] - __ldg(a.sx + n));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, cfg::TMEM_COLS);
+}
+
+// f32 [N][K] (row stride xs) -> int8 [N][K] with ONE scale per token: q = rint(x * 127 / amax_n); ts[n] = amax_n / 127; sx[n] = sum_k q
+__global__ void __launch_bounds__(256) k_quantize_rows_i8(const float * __restrict__ x, int64_t xs, int8_t * __restrict__ q, float * __restrict__ ts, int * __restrict__ sx, int64_t K) {
+    const int64_t n = blockIdx.x; const float * xr = x + n * xs; int8_t * qr = q + n * K;
+    __shared__ float s_amax[8]; __shared__ int s_sum[8];
+    float amax = 0.0f;
+    for (int64_t k = threadIdx.x * 4; k < K; k += blockDim.x * 4) { const float4 v = *reinterpret_cast<const float4 *>(xr + k); amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)))); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) s_amax[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = s_amax[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) amax = fmaxf(amax, s_amax[i]);
+    const float d = __fdiv_rn(amax, 127.0f), inv = d > 0.0f ? __frcp_rn(d) : 0.0f;
+    int sum = 0;
+    for (int64_t k = threadIdx.x * 4; k < K; k += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(xr + k);
+        const int a = max(-127, min(127, __float2int_rn(v.x * inv))), b = max(-127, min(127, __float2int_rn(v.y * inv)));
+        const int c = max(-127, min(127, __float2int_rn(v.z * inv))), e = max(-127, min(127, __float2int_rn(v.w * inv)));
+        sum += a + b + c + e;
+        *reinterpret_cast<uint32_t *>(qr + k) = (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(e & 0xff) << 24);
+    }
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 8; ++i) t += s_sum[i]; sx[n] = t; ts[n] = d; }
+}
+
 // dst = act(clamp(gate)) * clamp(up) elementwise (the reference's ggml_fused_mul_unary after two MMQs, ggml-cuda.cu:3588-3618);
 // gate may alias dst; optional bf16 copy for the following MUL_MAT
 __global__ void k_mul_unary(const float * gate /* may alias dst: no __restrict__ */, const float * __restrict__ up, float * dst, __nv_bfloat16 * __restrict__ dst_bf,
@@ -616,6 +820,34 @@ int launch_gemm_q(const b200q_gemm_multi & d, int k_split, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+
+// int8 activation tensor map: [rows][K bytes], box 128 bytes x box_rows, 128B swizzle, zero fill beyond K
+static int make_tmap_i8(CUtensorMap * tm, const void * ptr, int64_t rows, int64_t K, int box_rows) { return make_tmap_u8(tm, ptr, rows, K, 128, box_rows, true); }
+
+template <int NB>
+static int launch_gemm_bn_i8(const b200q_gemm_multi & d, const int8_t * xq, const float * ts, const int * sx, cudaStream_t st) {
+    using cfg = gemmbn_cfg<NB>;
+    gemmbn_args a; memset(&a, 0, sizeof a);
+    int tiles = 0;
+    for (int i = 0; i < d.n_seg; ++i) {
+        b200q_layout L; if (b200q_make_layout(B200Q_TYPE_IQ2_BN, d.M[i], d.K, &L)) return -1;
+        if (make_tmap_u8(&a.tmP0[i], (const char *)d.W[i] + L.plane_off[0], d.M[i], d.K / 4, 128, BM, true)) return -10;
+        a.seg[i].dst = d.dst[i]; a.seg[i].rs = reinterpret_cast<const float *>((const char *)d.W[i] + L.plane_off[1]); a.seg[i].M = (int)d.M[i]; a.seg[i].tile0 = tiles;
+        tiles += (int)((d.M[i] + BM - 1) / BM);
+    }
+    if (make_tmap_i8(&a.tmB, xq, d.N, d.K, NB == 0 ? 128 : 256)) return -11;
+    a.ts = ts; a.sx = sx; a.n_seg = d.n_seg; a.N = (int)d.N; a.K = (int)d.K;
+    static bool configured[B200Q_MAX_DEVICES] = {};
+    const int dev = b200q_current_device();
+    if (!configured[dev]) {
+        if (cudaFuncSetAttribute(k_gemm_bn_i8<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg::SMEM) != cudaSuccess) return -12;
+        configured[dev] = true;
+    }
+    dim3 grid((unsigned)tiles, (unsigned)((d.N + cfg::BN - 1) / cfg::BN), 1);
+    k_gemm_bn_i8<NB><<<grid, 64 + 32 * DQ_WARPS, cfg::SMEM, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
 // split-K factor of the fused kernel: minimise waves x (raw blocks per CTA + fixed cost), the fixed cost (pipeline fill,
 // TMEM round trip, epilogue) being worth ~4 raw blocks; split-K pays memset + f32 atomics
 int gemmq_choose_split(int64_t tiles, int64_t nr, int sm_count, bool allow_split) {
@@ -634,6 +866,33 @@ int gemmq_choose_split(int64_t tiles, int64_t nr, int sm_count, bool allow_split
 }
 
 }  // namespace
+
+
+// IQ2_BN prefill on the int8 tensor pipe.  X f32 [N][K] is quantised per token into `ws` (int8 [N][K] | ts[N] | sx[N]); up to 3 tensors share it.
+// Requires K % 64 == 0 (16-byte TMA strides); returns -100 when the shape is not eligible (callers use the bf16 path).
+size_t b200q_gemm_i8_workspace_bytes(int64_t K, int64_t N) { return (size_t)b200q_align_up(N * K, 256) + (size_t)b200q_align_up(N * 8, 256); }
+int b200q_launch_gemm_bn_i8(const b200q_gemm_multi & d, const float * x, int64_t x_stride, void * ws, size_t ws_bytes, cudaStream_t st) {
+    if (d.type != B200Q_TYPE_IQ2_BN || d.K % 64 || d.N < 1 || d.n_seg < 1 || d.n_seg > GEMMQ_MAX_SEGS) return -100;
+    const int64_t xs = x_stride ? x_stride : d.K;
+    if (((uintptr_t)x & 15) || (xs & 3) || ws_bytes < b200q_gemm_i8_workspace_bytes(d.K, d.N)) return -100;
+    int8_t * xq = (int8_t *)ws; float * ts = (float *)((char *)ws + b200q_align_up(d.N * d.K, 256)); int * sx = (int *)(ts + d.N);
+    k_quantize_rows_i8<<<(unsigned)d.N, 256, 0, st>>>(x, xs, xq, ts, sx, d.K);
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) return (int)e;
+    const int nb = d.N > 256 ? 2 : (d.N > 128 ? 1 : 0);
+    return nb == 2 ? launch_gemm_bn_i8<2>(d, xq, ts, sx, st) : nb == 1 ? launch_gemm_bn_i8<1>(d, xq, ts, sx, st) : launch_gemm_bn_i8<0>(d, xq, ts, sx, st);
+}
+
+// dst[j][i] = a[j][i] + b[j % nb][i]  (GGML_OP_ADD of a mat-mul result with a bias row / a same-shape tensor, when it is NOT fused into the mat-vec)
+__global__ void k_add_rows(const float * __restrict__ a, const float * __restrict__ b, float * __restrict__ dst, int64_t m, int64_t n, int64_t nb) {
+    const int64_t total = m * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) dst[i] = a[i] + b[((i / m) % nb) * m + i % m];
+}
+int b200q_launch_add_rows(const float * a, const float * b, float * dst, int64_t m, int64_t n, int64_t nb, cudaStream_t st) {
+    if (m < 1 || n < 1 || nb < 1) return -2;
+    int64_t g = (m * n + 255) / 256; if (g > 148 * 16) g = 148 * 16;
+    k_add_rows<<<(unsigned)g, 256, 0, st>>>(a, b, dst, m, n, nb);
+    return (int)cudaGetLastError();
+}
 
 // elementwise tail of GGML_OP_FUSED_UP_GATE for n > 8 when it cannot ride in the gate GEMM's epilogue
 int b200q_launch_mul_unary(const float * gate, const float * up, float * dst, void * dst_bf16, int64_t total, int act, float limit, cudaStream_t st) {
@@ -730,6 +989,13 @@ int b200q_launch_gemm_bf16x(int type, const void * W, const void * xb, float * d
 int b200q_launch_gemm(int type, const void * W, const float * x, int64_t x_stride, float * dst, int64_t M, int64_t K, int64_t N,
                       void * ws, size_t ws_bytes, int sm_count, int fused, cudaStream_t st) {
     if (ws_bytes < b200q_gemm_workspace_bytes(type, M, K, N)) return -5;
+    static const int use_i8 = [] { const char * e = getenv("B200Q_BN_INT8"); return e ? atoi(e) : 1; }();
+    if (type == B200Q_TYPE_IQ2_BN && use_i8 && fused) {          // ternary weights: int8 tensor pipe (kind::i8), exact integer accumulation
+        b200q_gemm_multi d; memset(&d, 0, sizeof d);
+        d.type = type; d.n_seg = 1; d.W[0] = W; d.dst[0] = dst; d.M[0] = M; d.K = K; d.N = N;
+        const int rc = b200q_launch_gemm_bn_i8(d, x, x_stride, ws, ws_bytes, st);
+        if (rc != -100) return rc;
+    }
     void * xb = ws;
     void * wb = (char *)ws + b200q_align_up(N * K * 2, 256);
     int rc = b200q_launch_f32_to_bf16(x, x_stride, xb, K, N, st); if (rc) return rc;

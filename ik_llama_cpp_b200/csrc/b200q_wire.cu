@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+int b200q_wire_check(int type, int64_t M, int64_t K);
+
 namespace {
 
 template <int TYPE>
@@ -122,7 +124,86 @@ int launch_wire_mmvq_type(const wire_mmvq_args & a, int ncols, bool upgate, int 
 #undef CASE
 }
 
+// MoE decode for wire-layout experts (DeepSeek-style IQ2_XXS / IQ1_S expert tensors): same contract as k_mmvq_id (b200q_decode_ring.cuh)
+struct wire_id_args {
+    const uint8_t * W; const uint8_t * W2; int64_t estride; const int32_t * ids; int n_expert, n_slots, n_used, nb1, ncx;
+    int64_t M, K; const float * x; float * dst; int act; float limit;
+};
+template <int TYPE, bool UPGATE>
+__global__ void __launch_bounds__(256) k_wire_mmvq_id(const wire_id_args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int64_t K = a.K; const int n32 = (int)(K / 32);
+    int8_t * sq = reinterpret_cast<int8_t *>(smem_raw);
+    float *  sd = reinterpret_cast<float *>(smem_raw + (size_t)a.ncx * K);
+    int *    sis = reinterpret_cast<int *>(sd + a.ncx * n32);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    pdl_trigger();
+    pdl_wait();
+    for (int c = 0; c < a.ncx; ++c) quantize_x_to_smem<1>(a.x + (int64_t)c * K, K, K, sq + (size_t)c * K, sd + c * n32, sis + c * n32, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int64_t total = (int64_t)a.n_slots * a.M;
+    for (int64_t g = (int64_t)blockIdx.x * nwarps + warp; g < total; g += (int64_t)gridDim.x * nwarps) {
+        const int s = (int)(g / a.M); const int64_t row = g - (int64_t)s * a.M;
+        int e = __ldg(a.ids + s); e = e < 0 ? 0 : (e >= a.n_expert ? a.n_expert - 1 : e);
+        const int col = (s / a.n_used) * a.nb1 + (s % a.n_used) % a.nb1;
+        const int8_t * xq = sq + (size_t)col * K; const float * xd = sd + col * n32;
+        float acc = 0.0f, acc2 = 0.0f;
+        for (int it = lane; it < n32; it += 32) {
+            float w[32]; float t = 0.0f;
+            b200q_wire_decode32<TYPE>(a.W + (int64_t)e * a.estride, K, row, it, w);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t = fmaf(w[j], (float)xq[(size_t)it * 32 + j], t);
+            acc = fmaf(xd[it], t, acc);
+            if (UPGATE) {
+                b200q_wire_decode32<TYPE>(a.W2 + (int64_t)e * a.estride, K, row, it, w); t = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) t = fmaf(w[j], (float)xq[(size_t)it * 32 + j], t);
+                acc2 = fmaf(xd[it], t, acc2);
+            }
+        }
+        float v = warp_sum(acc);
+        if (UPGATE) { const float gt = warp_sum(acc2); v = b200q_glu<false>(a.act, gt, v, a.limit); }
+        if (lane == 0) a.dst[(int64_t)s * a.M + row] = v;
+    }
+}
+template <int TYPE>
+int launch_wire_mmvq_id_t(const wire_id_args & a, bool upgate, int sm_count, bool pdl, cudaStream_t st) {
+    const size_t smem = (size_t)a.ncx * a.K + (size_t)a.ncx * (a.K / 32) * 8;
+    if (smem > 200 * 1024) return -2;
+    static size_t configured[2][B200Q_MAX_DEVICES] = {};
+    const int dev = b200q_current_device();
+    if (smem > 48 * 1024 && smem > configured[upgate][dev]) {
+        const cudaError_t e = upgate ? cudaFuncSetAttribute(k_wire_mmvq_id<TYPE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                     : cudaFuncSetAttribute(k_wire_mmvq_id<TYPE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return -3;
+        configured[upgate][dev] = smem;
+    }
+    const int nwarps = 8;
+    int64_t grid = ((int64_t)a.n_slots * a.M + nwarps - 1) / nwarps; const int64_t cap = (int64_t)sm_count * (smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 4);
+    if (grid > cap) grid = cap; if (grid < 1) grid = 1;
+    cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(nwarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return upgate ? (int)cudaLaunchKernelEx(&cfg, k_wire_mmvq_id<TYPE, true>, a) : (int)cudaLaunchKernelEx(&cfg, k_wire_mmvq_id<TYPE, false>, a);
+}
+
 }  // namespace
+
+int b200q_launch_wire_mmvq_id(const b200q_mmvq_id_desc & d, cudaStream_t st) {
+    const int rc = b200q_wire_check(d.type, d.M, d.K); if (rc) return rc;
+    b200q_layout L; if (b200q_make_layout(d.type, d.M, d.K, &L)) return -1;
+    wire_id_args a; memset(&a, 0, sizeof a);
+    a.W = (const uint8_t *)d.W; a.W2 = (const uint8_t *)d.W2; a.estride = L.total_bytes; a.ids = d.ids; a.n_expert = d.n_expert; a.n_slots = d.n_tokens * d.n_used;
+    a.n_used = d.n_used; a.nb1 = d.nb1; a.ncx = d.n_tokens * d.nb1; a.M = d.M; a.K = d.K; a.x = d.x; a.dst = d.dst; a.act = d.act; a.limit = d.limit;
+    switch (d.type) {
+#define X(T) case T: return launch_wire_mmvq_id_t<T>(a, d.W2 != nullptr, d.sm_count, d.pdl != 0, st);
+        B200Q_FOR_WIRE_TYPES(X)
+#undef X
+        default: return -1;
+    }
+}
 
 // wire "layout": the tensor is stored verbatim; M must be a multiple of the row interleave
 int b200q_wire_check(int type, int64_t M, int64_t K) {

@@ -145,6 +145,16 @@ B200Q_API int b200q_mul_mat_multi(int type, int n_tensors, const void * const * 
 B200Q_API size_t b200q_fused_up_gate_workspace(int type, int64_t m, int64_t k, int64_t n);
 B200Q_API int b200q_fused_up_gate(int type, const void * W_up, const void * W_gate, const float * x, float * dst, int64_t m, int64_t k, int64_t n,
                         int unary, float limit, void * workspace, size_t workspace_bytes, void * stream);
+/* GGML_OP_ADD of a mat-mul result with its bias row(s): dst[j][i] = a[j][i] + b[j % nb][i] (i < m, j < n) */
+B200Q_API int b200q_add_rows(const float * a, const float * b, float * dst, int64_t m, int64_t n, int64_t nb, void * stream);
+/* ---- MoE decode: GGML_OP_MUL_MAT_ID / GGML_OP_MOE_FUSED_UP_GATE for small batches (ggml_cuda_mul_mat_id / ggml_cuda_moe_up_gate_unary,
+ * ggml-cuda.cu:2836-3540; mul_mat_vec_q with ids, mmvq-templates.cuh:293-302).  W: n_expert matrices [m x k] of `type`, each in the device layout,
+ * b200q_plane_bytes(type, m, k) apart; ids: DEVICE int32 [n_tokens][n_used]; x f32 [n_tokens][nb1][k] (nb1 = 1: the column is shared by the slots of
+ * a token, nb1 = n_used: one column per slot); dst f32 [n_tokens][n_used][m]:  dst[t][e] = W[ids[t][e]] . x[t][e % nb1]
+ * (W_gate != NULL: unary(W_gate[id] . x) * (W[id] . x)).  One launch, expert ids resolved on the device.  n_tokens * nb1 activation columns must fit
+ * shared memory (<= 200 KB of q8_1); larger batches go through the grouped prefill path. */
+B200Q_API int b200q_mul_mat_id_vec(int type, const void * W, const void * W_gate, int n_expert, const int32_t * ids, const float * x, float * dst,
+                         int64_t m, int64_t k, int n_used, int nb1, int n_tokens, int unary, float limit, void * stream);
 /* same through HOST activations/results: H2D(x) -> mul_mat -> D2H(dst), synchronous (end-to-end entry point) */
 B200Q_API int b200q_mul_mat_host(int type, const void * W_planes_dev, const float * x_host, float * dst_host,
                        int64_t m, int64_t k, int64_t n, void * stream);

@@ -165,7 +165,7 @@ static int run_ffn_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, i
     std::vector<float> xf(n * k); fill_uniform(xf, rng); ggml_backend_tensor_set(x, xf.data(), 0, xf.size() * sizeof(float));
     if (bias) { std::vector<float> bf(k); fill_uniform(bf, rng); ggml_backend_tensor_set(bv, bf.data(), 0, bf.size() * sizeof(float)); }
     bool supported = true;
-    for (int i = 0; i < gf->n_nodes; ++i) if (gf->nodes[i]->op != GGML_OP_ADD && !ggml_backend_supports_op(be, gf->nodes[i])) supported = false;
+    for (int i = 0; i < gf->n_nodes; ++i) if (!ggml_backend_supports_op(be, gf->nodes[i])) supported = false;
     if (!supported) { printf("  %-8s FFN graph: a node is not supported\n", ggml_type_name(type)); return 1; }
     cb_data d;
     // (ggml_backend_compare_graph_backend computes node by node: to exercise the look-ahead fusions run the whole graph first and compare the final result)
@@ -207,6 +207,39 @@ static int run_batched_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type typ
     const bool ok = d.n > 0 && d.worst <= 5e-4;
     printf("  %-8s batched MUL_MAT (%s) m=%lld k=%lld n=%lld batch=%lld: NMSE vs CPU backend %.3g -> %s\n", ggml_type_name(type), per_batch_weights ? "one matrix per batch entry" : "src0 broadcast",
            (long long)m, (long long)k, (long long)n, (long long)nb, d.worst, ok ? "OK" : "FAIL");
+    ggml_backend_buffer_free(buf); ggml_free(ctx);
+    return ok ? 0 : 1;
+}
+
+// MoE decode: MUL_MAT_ID / MOE_FUSED_UP_GATE with n_tokens <= 8 (expert ids live in device memory; one launch)
+static int run_moe_case(ggml_backend_t be, ggml_backend_t cpu, ggml_type type, int64_t n_tokens, bool shared_col, bool up_gate, unsigned seed) {
+    const int64_t m = 256, k = 1024, n_expert = 8, n_used = 2;
+    ggml_init_params ip = { ggml_tensor_overhead() * 16 + ggml_graph_overhead(), nullptr, true };
+    ggml_context * ctx = ggml_init(ip);
+    ggml_tensor * w = ggml_new_tensor_3d(ctx, type, k, m, n_expert), * g = up_gate ? ggml_new_tensor_3d(ctx, type, k, m, n_expert) : nullptr;
+    ggml_tensor * x = ggml_new_tensor_3d(ctx, GGML_TYPE_F32, k, shared_col ? 1 : n_used, n_tokens);
+    ggml_tensor * ids = ggml_new_tensor_2d(ctx, GGML_TYPE_I32, n_used, n_tokens);
+    ggml_tensor * y = up_gate ? ggml_moe_up_gate(ctx, w, g, x, ids, GGML_UNARY_OP_SILU) : ggml_mul_mat_id(ctx, w, x, ids);
+    ggml_cgraph * gf = ggml_new_graph(ctx); ggml_build_forward_expand(gf, y);
+    ggml_backend_buffer_t buf = ggml_backend_alloc_ctx_tensors(ctx, be);
+    if (!buf) { printf("  alloc failed\n"); return 1; }
+    std::mt19937 rng(seed);
+    for (ggml_tensor * t : {w, g}) {
+        if (!t) continue;
+        std::vector<float> wf(ggml_nelements(t)); make_weights(type, wf, rng);
+        std::vector<uint8_t> wq(ggml_nbytes(t));
+        ggml_quantize_chunk(type, wf.data(), wq.data(), 0, ggml_nrows(t), k, nullptr, nullptr);
+        ggml_backend_tensor_set(t, wq.data(), 0, wq.size());
+    }
+    std::vector<float> xf(ggml_nelements(x)); fill_uniform(xf, rng); ggml_backend_tensor_set(x, xf.data(), 0, xf.size() * sizeof(float));
+    std::vector<int32_t> idv(n_used * n_tokens);
+    for (int64_t t = 0; t < n_tokens; ++t) { idv[t * n_used] = (int32_t)(rng() % n_expert); idv[t * n_used + 1] = (int32_t)((idv[t * n_used] + 1 + rng() % (n_expert - 1)) % n_expert); }
+    ggml_backend_tensor_set(ids, idv.data(), 0, idv.size() * sizeof(int32_t));
+    if (!ggml_backend_supports_op(be, y)) { printf("  %-8s %s not supported\n", ggml_type_name(type), ggml_op_name(y->op)); return 1; }
+    cb_data d; ggml_backend_compare_graph_backend(be, cpu, gf, cmp_cb, &d);
+    const bool ok = d.n > 0 && d.worst <= 5e-4;
+    printf("  %-8s %-18s experts=%lld used=%lld tokens=%lld %s: NMSE vs CPU backend %.3g -> %s\n", ggml_type_name(type), ggml_op_name(y->op), (long long)n_expert, (long long)n_used,
+           (long long)n_tokens, shared_col ? "(shared column)" : "(column per slot)", d.worst, ok ? "OK" : "FAIL");
     ggml_backend_buffer_free(buf); ggml_free(ctx);
     return ok ? 0 : 1;
 }
@@ -265,6 +298,11 @@ int main(int argc, char ** argv) {
         for (ggml_type t : {GGML_TYPE_IQ4_NL, GGML_TYPE_Q4_K, GGML_TYPE_Q6_K}) for (int64_t n : {1, 2, 16}) for (bool bias : {false, true}) fails += run_ffn_case(be, cpu, t, 1024, 2048, n, bias, ++seed);
         fails += run_ffn_case(be, cpu, GGML_TYPE_IQ4_NL, 4096, 14336, 1, false, ++seed);       // Llama-3-8B FFN shape: long-row ring + q8 hand-off
         for (ggml_type t : {GGML_TYPE_IQ4_NL, GGML_TYPE_Q4_K}) for (bool pb : {false, true}) fails += run_batched_case(be, cpu, t, pb, ++seed);
+        for (ggml_type t : {GGML_TYPE_IQ4_NL, GGML_TYPE_Q4_K, GGML_TYPE_IQ3_S, GGML_TYPE_IQ4_K_R4}) {
+            fails += run_moe_case(be, cpu, t, 1, true, true, ++seed);      // decode: up+gate experts on the token's column ...
+            fails += run_moe_case(be, cpu, t, 1, false, false, ++seed);    // ... then the down experts, one column per slot
+            fails += run_moe_case(be, cpu, t, 4, true, false, ++seed);
+        }
         fails += run_async_case(be);
     }
     if (!quick) {   // bitnet shapes: K = 3200 is not a multiple of 256
