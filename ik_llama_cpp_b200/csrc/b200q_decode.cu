@@ -105,7 +105,13 @@ int b200q_launch_dequant_bf16(const void * W, const b200q_layout & L, void * out
 
 // per-launch phase timestamps (debug aid for the PDL pipeline; see scripts/trace_decode.py)
 static unsigned long long * g_trace = nullptr; static int g_trace_slot = 0;
+static unsigned long long * g_trace_cta = nullptr;      // [512 launches][512 CTAs][4]
 extern "C" __attribute__((visibility("default"))) int b200q_debug_trace(int enable, unsigned long long * host_out, int max_slots) {
+    if (enable == 4 && host_out && g_trace_cta) {           // per-CTA timeline of launch slot `max_slots`
+        cudaMemcpy(host_out, g_trace_cta + (size_t)max_slots * 2048, 2048 * sizeof(unsigned long long), cudaMemcpyDeviceToHost); return 0;
+    }
+    if ((enable == 1 || enable == 3) && !g_trace_cta) cudaMalloc(&g_trace_cta, (size_t)512 * 2048 * sizeof(unsigned long long));
+    if ((enable == 1 || enable == 3) && g_trace_cta) cudaMemset(g_trace_cta, 0, (size_t)512 * 2048 * sizeof(unsigned long long));
     if (enable == 1) { if (!g_trace) { cudaMalloc(&g_trace, 4096 * 8 * sizeof(unsigned long long)); } cudaMemset(g_trace, 0, 4096 * 8 * sizeof(unsigned long long)); g_trace_slot = 0; return 0; }
     if (enable == 2) { g_trace_slot = 0; return 0; }                               // rewind (start of a step)
     if (enable == 3 && g_trace) { cudaDeviceSynchronize(); cudaMemset(g_trace, 0, 4096 * 8 * sizeof(unsigned long long)); return 0; }   // clear, keep the slot assignment
@@ -115,7 +121,7 @@ extern "C" __attribute__((visibility("default"))) int b200q_debug_trace(int enab
 int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
     if (b200q_is_wire_type(d.type)) return b200q_launch_wire_mmvq(d, st);
     mmvq_args a; memset(&a, 0, sizeof a);
-    if (g_trace && g_trace_slot < 4096) a.trace = g_trace + 8 * (g_trace_slot++);
+    if (g_trace && g_trace_slot < 4096) { if (g_trace_cta && g_trace_slot < 512) a.trace_cta = g_trace_cta + (size_t)g_trace_slot * 2048; a.trace = g_trace + 8 * (g_trace_slot++); }
     if (d.n_seg < 1 || d.n_seg > B200Q_MAX_SEGS || d.ncols < 1 || d.ncols > 8) return -2;
     int64_t r0 = 0;
     for (int i = 0; i < d.n_seg; ++i) {

@@ -40,6 +40,7 @@ struct mmvq_args {
     int64_t      x_stride;
     int          act;           // B200Q_ACT_* for the up/gate mode
     float        limit;         // clamp for swiglu variants (0 = none)
+    unsigned long long * trace_cta;   // tuning builds (B200Q_TRACE_FINE): per-CTA timeline, 4 words per CTA
     b200q_tp_comm tp;           // tensor-parallel decode: GGML_OP_REDUCE fused into the mat-vec (tp.in / tp.out), see k_mmvq_ring
     unsigned long long * trace; // optional phase timestamps (b200q_debug_trace): [slot][8] = entry, after griddepcontrol.wait, prologue done, last consumer done,
                                 //   activation loads landed, quantised (before the barrier), 2^62 - first consumer done, first unit of CTA 0 / warp 1 done
@@ -669,7 +670,13 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
         }
     }
 #if B200Q_TRACE_FINE
-    if (a.trace && lane == 0) { const unsigned long long tt = gtime(); atomicMax(a.trace + 3, tt); atomicMax(a.trace + 6, (1ull << 62) - tt); }
+    if (a.trace && lane == 0) {
+        const unsigned long long tt = gtime(); atomicMax(a.trace + 3, tt); atomicMax(a.trace + 6, (1ull << 62) - tt);
+        if (a.trace_cta && blockIdx.x < 512) {                       // per-CTA timeline: [end of last warp, SM id, units of the CTA, end of first warp]
+            unsigned long long * tc = a.trace_cta + 4 * blockIdx.x; unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            atomicMax(tc, tt); tc[1] = smid; tc[2] = (unsigned long long)(c1 - c0); atomicMax(tc + 3, (1ull << 62) - tt);
+        }
+    }
 #else
     if (a.trace && lane == 0) atomicMax(a.trace + 3, gtime());
 #endif

@@ -17,3 +17,4 @@ run f32reduce B200Q_TP_BF16_REDUCE=0
 run unfused B200Q_TP_FUSED=0
 timeout 600 python bench.py --gpus 1 --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_tp2_bench_n1.json 2>/dev/null; python -c "
 import json; l=json.loads(open('gpurun_out/r2_tp2_bench_n1.json').read().strip().splitlines()[-1]); print('n1 tg', round(l['value'],1), 'pp512', round(l['pp512']['value']))"
+env LAYERS=3 B200Q_LIB_PATH=experiments/_variants/libb200q_trace.so timeout 300 python scripts/trace_cta.py > gpurun_out/r2_tp2_trace_cta.txt 2>&1; grep -v "per SM" gpurun_out/r2_tp2_trace_cta.txt | tail -12
