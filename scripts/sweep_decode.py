@@ -11,9 +11,13 @@ for f in sorted(os.listdir(vd)) if os.path.isdir(vd) else []:
         configs.append((name, os.path.join(vd, f), {}))
         if name not in ("r1", "trace"):
             configs.append((name + " q8off", os.path.join(vd, f), {"B200Q_Q8_HANDOFF": "0"}))
-only = sys.argv[1:]
+# extra product configurations from the command line: name:ENV=val,ENV2=val
+for arg in [a for a in sys.argv[1:] if ":" in a]:
+    nm, kv = arg.split(":", 1)
+    configs.append((nm, None, dict(x.split("=", 1) for x in kv.split(","))))
+only = [a.split(":", 1)[0] for a in sys.argv[1:]]
 for name, lib, env in configs:
-    if only and not any(o in name for o in only):
+    if only and not any(o == name or (":" not in o and o in name) for o in only):
         continue
     e = dict(os.environ); e.update(env)
     if lib: e["B200Q_LIB_PATH"] = lib

@@ -63,7 +63,12 @@ def _worker(rank, world, port, q):
             t = parts[rank].clone()
             red.all_reduce_bf16(t, out_f32=t)
             exact = sum(p.to(torch.bfloat16).double() for p in parts)
-            assert torch.equal(t, exact.float().to(torch.bfloat16).float()) or float((t.double() - exact).abs().max()) <= float(exact.abs().max()) * 2 ** -8
+            # one rounding of the exact sum to bf16; the switch's rounding mode is not specified (RN gives <= 2^-9 relative, truncation <= 2^-8)
+            rn = exact.float().to(torch.bfloat16).float()
+            res["two_shot_rn_fraction"] = float((t == rn).float().mean())
+            worst = float(((t.double() - exact).abs() / (exact.abs() + 1e-30)).max())
+            res["two_shot_worst_rel"] = worst
+            assert bool(((t.double() - exact).abs() <= exact.abs() * 2.0 ** -7 + 1e-30).all()), worst
             # interleaved with the one-shot f32 reduce and replayed from a CUDA graph
             x = torch.zeros(8192, device="cuda"); y = torch.empty_like(x); yb = torch.empty(8192, dtype=torch.bfloat16, device="cuda")
             s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
@@ -134,6 +139,10 @@ def _worker(rank, world, port, q):
             for i in range(2, 5):                                          # CUDA-graph replay (PDL edges inside the graph)
                 xg.copy_(torch.from_numpy(np.ascontiguousarray(xs[i][:, k01:k01 + ks1]))); g2.replay(); res["fused_graph_nmse"] = check(xs[i])
         q.put(res)
+    except BaseException as e:                      # report instead of leaving the parent to time out on the queue
+        import traceback
+        q.put({"rank": rank, "error": repr(e), "trace": traceback.format_exc()})
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -150,7 +159,14 @@ def test_nvls_allreduce_and_row_parallel_matvec(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in procs]
+    res = []
+    for _ in procs:
+        res.append(q.get(timeout=300))
+        if "error" in res[-1]:                      # a failed rank leaves its peers inside a collective: stop them
+            for p in procs:
+                p.join(timeout=20)
+                if p.is_alive(): p.kill()
+            pytest.fail(f"rank {res[-1]['rank']}: {res[-1]['error']}\n{res[-1]['trace']}")
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
