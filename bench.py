@@ -113,14 +113,16 @@ class Model:
         self.be, self.torch, self.tp, self.n_layer = be, torch, tp, n_layer
         gen = torch.Generator(device="cuda")
         gen.manual_seed(seed + rank)
+        # unit-gain weights (IQ4_NL codebook rms ~ 70).  There is no norm between the layers of this MUL_MAT-only skeleton and silu(g)*u makes the
+        # magnitude map quadratic, so the values contract towards 0 over the layers instead of overflowing the fp16 scale of q8_1
         s_e, s_f = 1.0 / (70.0 * N_EMBD ** 0.5), 1.0 / (70.0 * N_FF ** 0.5)
         mk = lambda m, k, s: random_planes_iq4nl(be, torch, m, k, gen, s)
         self.layers = []
         for _ in range(n_layer):
             self.layers.append(dict(
                 wq=mk(N_EMBD // tp, N_EMBD, s_e), wk=mk(N_KV_DIM // tp, N_EMBD, s_e), wv=mk(N_KV_DIM // tp, N_EMBD, s_e),
-                wo=mk(N_EMBD, N_EMBD // tp, s_e * 2), up=mk(N_FF // tp, N_EMBD, s_e * 2), gate=mk(N_FF // tp, N_EMBD, s_e * 2),
-                down=mk(N_EMBD, N_FF // tp, s_f * 4)))
+                wo=mk(N_EMBD, N_EMBD // tp, s_e), up=mk(N_FF // tp, N_EMBD, s_e), gate=mk(N_FF // tp, N_EMBD, s_e),
+                down=mk(N_EMBD, N_FF // tp, s_f)))
         self.head = mk(N_VOCAB // tp, N_EMBD, s_e) if collective else None
         self.launches_tg = n_layer * 4 + 1
         self.reducer = None

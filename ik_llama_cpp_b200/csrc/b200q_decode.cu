@@ -131,13 +131,13 @@ static uint32_t * dyn_counter_for(cudaStream_t st) {
     std::lock_guard<std::mutex> lk(mu);
     table & t = T[b200q_current_device()];
     for (int i = 0; i < t.n; ++i) if (t.s[i] == st) return t.base + 32 * i;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
-    if (!t.base) {
+    if (!t.base) {              // the pool itself must not be created inside a capture (cudaMalloc / cudaMemset are not capturable)
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
         if (cudaMalloc(&t.base, SLOTS * 128) != cudaSuccess) { cudaGetLastError(); t.base = nullptr; return nullptr; }
         cudaMemset(t.base, 0, SLOTS * 128);
     }
-    if (t.n == SLOTS) return nullptr;
+    if (t.n == SLOTS) return nullptr;         // (registering a new stream is host-side bookkeeping only: fine during capture)
     t.s[t.n] = st;
     return t.base + 32 * (t.n++);
 }

@@ -146,6 +146,31 @@ def test_mat_vec_llama_shapes(be, oracle, ref_or_none, name):
         assert np.abs(y - yq).max() <= 2e-5 * rms(yq)
 
 
+@pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K", "Q6_K"])
+def test_mat_vec_cross_cta_claiming_shapes(be, oracle, name):
+    """Shapes with many more units than the ring holds: the units beyond the statically split share are claimed from the device-wide pool
+    (k_mmvq_ring, `dyn`).  Every row must still be computed exactly once: three launches in a row (the counter re-arms itself), all equal to the oracle."""
+    t = GGML_TYPE[name]
+    x_rng = np.random.default_rng(21)
+    for (m, k, glu) in ((14336, 4096, True), (32064, 4096, False), (4096, 14336, False)):
+        wire = make_wire(oracle, name, m, k, seed=5)
+        w = be.set_tensor(t, wire, m, k)
+        if glu:
+            wire2 = make_wire(oracle, name, m, k, seed=6); w2 = be.set_tensor(t, wire2, m, k)
+        for it in range(3):
+            x = x_rng.standard_normal((1, k)).astype(np.float32)
+            xg = torch.from_numpy(x).cuda()
+            if glu:
+                y = be.fused_up_gate(w, w2, xg, unary="silu").cpu().numpy()
+                u, g = oracle.mul_mat_q8_1(t, wire, x, m, variant="b200").astype(np.float64), oracle.mul_mat_q8_1(t, wire2, x, m, variant="b200").astype(np.float64)
+                ref = glu_ref("silu", g, u)
+                assert np.abs(y - ref).max() <= 5e-5 * rms(ref), (m, k, it)
+            else:
+                y = be.mul_mat(w, xg).cpu().numpy()
+                yq = oracle.mul_mat_q8_1(t, wire, x, m, variant="b200")
+                assert np.abs(y - yq).max() <= 2e-5 * rms(yq), (m, k, it)
+
+
 def test_multi_tensor_launch_qkv(be, oracle):
     t = GGML_TYPE["IQ4_NL"]
     k = 1024
