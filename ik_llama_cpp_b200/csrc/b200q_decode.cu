@@ -15,7 +15,6 @@
 //   - epilogue: warp-shuffle reduce, optional bias, optional act(gate)*up fusion, one 4-byte store per row.
 #include "b200q_types.cuh"
 #include "b200q_internal.h"
-#include <mutex>
 #include "b200q_decode_common.cuh"
 #include "b200q_decode_ring.cuh"
 #include <cuda_fp16.h>
@@ -119,32 +118,9 @@ extern "C" __attribute__((visibility("default"))) int b200q_debug_trace(int enab
     if (enable == 0 && host_out && g_trace) { cudaMemcpy(host_out, g_trace, (size_t)max_slots * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost); return g_trace_slot; }
     return -1;
 }
-// Counters of the cross-CTA work claiming of k_mmvq_ring, one pair per (device, stream): launches of one stream never overlap after their
-// griddepcontrol.wait, and the kernel that used a counter re-arms it before it completes.  Allocated outside stream capture only (a capture that
-// meets an unknown stream runs with the static split).
-static uint32_t * dyn_counter_for(cudaStream_t st) {
-    static const int off = [] { const char * e = getenv("B200Q_DYN"); return e && atoi(e) == 0; }();
-    if (off) return nullptr;
-    constexpr int SLOTS = 64;
-    struct table { uint32_t * base = nullptr; cudaStream_t s[SLOTS]; int n = 0; };
-    static table T[B200Q_MAX_DEVICES]; static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    table & t = T[b200q_current_device()];
-    for (int i = 0; i < t.n; ++i) if (t.s[i] == st) return t.base + 32 * i;
-    if (!t.base) {              // the pool itself must not be created inside a capture (cudaMalloc / cudaMemset are not capturable)
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) { cudaGetLastError(); return nullptr; }
-        if (cudaMalloc(&t.base, SLOTS * 128) != cudaSuccess) { cudaGetLastError(); t.base = nullptr; return nullptr; }
-        cudaMemset(t.base, 0, SLOTS * 128);
-    }
-    if (t.n == SLOTS) return nullptr;         // (registering a new stream is host-side bookkeeping only: fine during capture)
-    t.s[t.n] = st;
-    return t.base + 32 * (t.n++);
-}
 int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
     if (b200q_is_wire_type(d.type)) return b200q_launch_wire_mmvq(d, st);
     mmvq_args a; memset(&a, 0, sizeof a);
-    if (d.ring && !d.tp.in && !d.tp.out) a.dyn = dyn_counter_for(st);
     if (g_trace && g_trace_slot < 4096) { if (g_trace_cta && g_trace_slot < 512) a.trace_cta = g_trace_cta + (size_t)g_trace_slot * 2048; a.trace = g_trace + 8 * (g_trace_slot++); }
     if (d.n_seg < 1 || d.n_seg > B200Q_MAX_SEGS || d.ncols < 1 || d.ncols > 8) return -2;
     int64_t r0 = 0;

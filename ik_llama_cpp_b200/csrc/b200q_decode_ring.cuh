@@ -40,8 +40,6 @@ struct mmvq_args {
     int64_t      x_stride;
     int          act;           // B200Q_ACT_* for the up/gate mode
     float        limit;         // clamp for swiglu variants (0 = none)
-    uint32_t * dyn;             // cross-CTA work claiming: [0] units claimed from the dynamic pool, [1] CTAs that have finished claiming (nullptr: static split only)
-    int dyn_static, dyn_chunk;  // units [0, dyn_static) are split statically over the CTAs, the rest is claimed dyn_chunk units at a time
     unsigned long long * trace_cta;   // tuning builds (B200Q_TRACE_FINE): per-CTA timeline, 4 words per CTA
     b200q_tp_comm tp;           // tensor-parallel decode: GGML_OP_REDUCE fused into the mat-vec (tp.in / tp.out), see k_mmvq_ring
     unsigned long long * trace; // optional phase timestamps (b200q_debug_trace): [slot][8] = entry, after griddepcontrol.wait, prologue done, last consumer done,
@@ -408,11 +406,7 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
     // static split of the pairs over CTAs (+-1 pair), dynamic claiming inside the CTA: the producer lane of a consumer
     // warp takes the next pair from a shared counter whenever that warp's ring has room, so warps never idle on a
     // coarse static remainder (2.2 pairs/warp for the FFN up/gate shape would otherwise mean 3 for some, 2 for others)
-    // Across CTAs: the first n_static units are split statically (they include everything that is issued before griddepcontrol.wait), the remaining
-    // ones are claimed from a device-wide pool in chunks, so SMs that the memory system serves faster (profiles/r2_cta_timeline.md: +-15 % per SM,
-    // and up to 35 vs 50 us between the two CTAs that share an SM) take more units instead of idling at the end.
-    const int n_static = a.dyn ? a.dyn_static : n_pairs;
-    const int c0 = (int)(((int64_t)n_static * blockIdx.x) / gridDim.x), c1 = (int)(((int64_t)n_static * (blockIdx.x + 1)) / gridDim.x);
+    const int c0 = (int)(((int64_t)n_pairs * blockIdx.x) / gridDim.x), c1 = (int)(((int64_t)n_pairs * (blockIdx.x + 1)) / gridDim.x);
     auto locate = [&](int grow, int & s, int & row) {
         s = 0; row = grow;
         if (MULTI) {
@@ -434,11 +428,10 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
     }
 
     // ---------------- producer state (warp 0, lane = consumer warp index) ----------------
-    int pcur = -1, pt = 0, psg = 0, pst = 0, pround = 0; bool pdone = !(is_prod && lane < ncw);
-    auto claim_local = [&]() { const int v = atomicAdd(next_pair, 1); return v < c1 ? v : -1; };
-    auto produce_one = [&](int claimed) {                         // issue the next stage of consumer warp `lane` (stage pst); claimed: the unit, if a new one starts
+    int pcur = -1, pt = 0, psg = 0, pst = 0, pu = 0; bool pdone = !(is_prod && lane < ncw);
+    auto produce_one = [&]() {                                    // issue the next unit of consumer warp `lane` into stage pst
         uint64_t * fb = &full0[lane * S + pst];
-        if (pt == 0 && psg == 0) pcur = claimed;
+        if (pt == 0 && psg == 0) { pcur = atomicAdd(next_pair, 1); if (pcur >= c1) pcur = -1; }
         pair_id[lane * S + pst] = pcur;
         if (pcur < 0) { rb_arrive(fb); pdone = true; return; }   // sentinel: nothing left for this consumer
         int s, row; locate(RPU * pcur, s, row);
@@ -460,25 +453,17 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
                 if (two) bulk_g2s(dstb + g.row1[p] + g.seg_off[p], src + (int64_t)n8 * g.b8[p], (uint32_t)(g8 * g.b8[p]), fb);
             }
         }
-        if (++pst == S) { pst = 0; ++pround; }
+        ++pu; if (++pst == S) pst = 0;
         if (++psg == nseg) { psg = 0; if (++pt == NT) pt = 0; }
-    };
-    // before griddepcontrol.wait only statically assigned units are issued; with a dynamic pool a warp that got none stays alive (it claims later)
-    auto prefill = [&]() {
-        for (int s = 0; s < S; ++s) if (!pdone) {
-            int c = -1;
-            if (pt == 0 && psg == 0) { c = claim_local(); if (c < 0 && a.dyn) break; }
-            produce_one(c);
-        }
     };
     // (1) weights do not depend on the previous kernel: fill the ring before waiting for it
 #if B200Q_EXP_PREFILL_AFTER_WAIT          // experiment: no memory traffic of this grid before the previous one has completed
     pdl_trigger();
     pdl_wait();
-    if (is_prod) prefill();
+    if (is_prod) { for (int s = 0; s < S; ++s) if (!pdone) produce_one(); }
 #else
     if (is_prod) {
-        prefill();
+        for (int s = 0; s < S; ++s) if (!pdone) produce_one();
         if (a.pf.n) issue_next_prefetch(a.pf, lane);       // after our own first stages: the next kernel's first stages -> L2
     }
 #if !B200Q_EXP_LATE_TRIGGER
@@ -532,47 +517,17 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
         // ---------------- producer: refill a stage as soon as its consumer has released it ----------------
         // All lanes poll their consumer's empty barrier with a NON-blocking test_wait and stay converged: a lane parked in a
         // blocking try_wait would stall the refills of the other ten consumers that share this warp.
-        // (use number pround of stage pst: the first one needs no release, use n waits for the (n-1)-th completion of the empty barrier)
-        // dynamic pool (warp-uniform state): [dnext, dend) = the chunk being handed out; the NEXT chunk is claimed one step ahead (lane 0's dpf),
-        // so the L2 round trip of the atomic is never on the refill path
-        int dnext = 0, dend = 0, dpf = 0; bool dgone = a.dyn == nullptr;
-        const int n_dyn = n_pairs - n_static, G = a.dyn_chunk;
-        if (!dgone && lane == 0) dpf = (int)atomicAdd(a.dyn, (uint32_t)G);          // (after griddepcontrol.wait: the previous user of the counter has reset it)
+        uint32_t epar = 1;               // first pass over the ring: the S initial units are already issued
+        int k = 0;
         while (__any_sync(0xffffffffu, !pdone)) {
             bool ready = false;
-            if (!pdone) ready = pround == 0 || rb_test(&empty0[lane * S + pst], (uint32_t)(pround - 1) & 1u);
-            const bool need = ready && pt == 0 && psg == 0;
-            int c = -1;
-            if (need) c = claim_local();
-            const bool want = need && c < 0;
-            const unsigned m = __ballot_sync(0xffffffffu, want && !dgone);
-            if (m) {
-                const int cnt = __popc(m), rank = __popc(m & ((1u << lane) - 1u));
-                int avail = dend - dnext;
-                if (want && rank < avail) c = dnext + rank;
-                if (cnt <= avail) dnext += cnt;
-                else {                                                               // current chunk used up: swap in the chunk claimed ahead
-                    const int v = __shfl_sync(0xffffffffu, dpf, 0);
-                    if (v >= n_dyn) { dgone = true; dnext = dend = 0; }
-                    else {
-                        dnext = n_static + v; dend = min(n_static + v + G, n_pairs);
-                        if (lane == 0) dpf = (int)atomicAdd(a.dyn, (uint32_t)G);
-                        const int r2 = rank - avail, take = min(cnt - avail, dend - dnext);
-                        if (want && r2 >= 0 && r2 < take) c = dnext + r2;
-                        dnext += take;
-                    }
-                }
-            }
-            // a lane that wanted a unit and got none retries in the next round while the pool lasts; once it is gone, c = -1 is the end sentinel
-            if (ready && !(want && c < 0 && !dgone)) {
+            if (!pdone) ready = rb_test(&empty0[lane * S + pst], epar ^ 1);
+            if (ready) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                produce_one(c);
+                produce_one();
+                if (++k == S) { k = 0; epar ^= 1; }
             }
             if (!__any_sync(0xffffffffu, ready)) __nanosleep(64);
-        }
-        if (a.dyn && lane == 0) {
-            // this CTA's last claim has returned (dpf is consumed here); the CTA that sees every other one finished re-arms the counter for the next launch
-            if (dpf >= 0 && atomicAdd(a.dyn + 1, 1u) == gridDim.x - 1) { __threadfence(); a.dyn[0] = 0; a.dyn[1] = 0; }
         }
 #if B200Q_EXP_LATE_TRIGGER
         pdl_trigger();                   // experiment: the next grid is launched only when this CTA has issued its last weight copy
@@ -864,21 +819,6 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     int64_t grid = grid_full ? n_pairs : (n_pairs + ncw - 1) / ncw;
     if (grid > (int64_t)sm_count * ctas_per_sm) grid = (int64_t)sm_count * ctas_per_sm;
     if (grid < 1) grid = 1;
-    // cross-CTA dynamic claiming: keep what is issued before griddepcontrol.wait (and at least B200Q_DYN_STATIC of the work) static
-    ra.a.dyn_static = (int)n_pairs; ra.a.dyn_chunk = 0;
-    if (ra.a.dyn && Q8 != 2) {
-        static const float frac = [] { const char * e = getenv("B200Q_DYN_STATIC"); return e ? (float)atof(e) : 0.6f; }();
-        const int seg_i = PAIR ? B200Q_SEG_ITEMS : 2 * B200Q_SEG_ITEMS;
-        const int stages_per_unit = (UPGATE ? 2 : 1) * (int)((a.K / 32 + seg_i - 1) / seg_i);
-        const int64_t prefill_units = grid * ncw * (int64_t)((S + stages_per_unit - 1) / stages_per_unit);
-        int64_t ns = (int64_t)(frac * (float)n_pairs); if (ns < prefill_units) ns = prefill_units;
-        const int64_t nd = n_pairs - ns;
-        if (frac < 1.0f && nd >= grid) {
-            ra.a.dyn_static = (int)ns;
-            int64_t G = (nd + grid * 12 - 1) / (grid * 12); if (G < 1) G = 1; if (G > 8) G = 8;
-            ra.a.dyn_chunk = (int)G;
-        } else ra.a.dyn = nullptr;
-    } else ra.a.dyn = nullptr;
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((ncw + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];

@@ -11,8 +11,12 @@ from ik_llama_cpp_b200 import backend as be, _lib
 L = _lib.lib()
 L.b200q_debug_trace.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
 nl = int(os.environ.get("LAYERS", "8"))
-torch.cuda.set_device(0)
-model = bench.Model(be, torch, nl)
+world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+if world > 1:                      # tensor-parallel timeline (torchrun): every rank traces, rank 0 prints
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+model = bench.Model(be, torch, nl, tp=world, rank=rank)
 model.alloc(1)
 model.x.normal_()
 L.b200q_debug_trace(1, None, 0)
@@ -30,7 +34,9 @@ torch.cuda.synchronize()
 L.b200q_debug_trace(3, None, 0)          # clear the accumulated min/max slots, then ONE traced replay at warm clocks
 g.replay()
 torch.cuda.synchronize()
-n = model.launches_tg
+n = model.launches_tg if (world == 1 or model.fused_tp) else 4 * nl + 1     # (unfused TP: the reduce kernels are not traced)
+if rank != 0:
+    dist.barrier(); dist.destroy_process_group(); sys.exit(0)
 out = np.zeros((n, 8), np.uint64)
 L.b200q_debug_trace(0, out.ctypes.data, n)
 t = out.astype(np.int64)
@@ -54,3 +60,5 @@ print("median per kernel (layers >= 1): wait->done, gap, prologue, main(last), m
 for nm, v in agg.items():
     a = np.median(np.array(v), axis=0)
     print(f"  {nm:7s} " + " ".join(f"{x:7.2f}" for x in a))
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()

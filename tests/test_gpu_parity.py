@@ -147,9 +147,9 @@ def test_mat_vec_llama_shapes(be, oracle, ref_or_none, name):
 
 
 @pytest.mark.parametrize("name", ["IQ4_NL", "Q4_K", "Q6_K"])
-def test_mat_vec_cross_cta_claiming_shapes(be, oracle, name):
-    """Shapes with many more units than the ring holds: the units beyond the statically split share are claimed from the device-wide pool
-    (k_mmvq_ring, `dyn`).  Every row must still be computed exactly once: three launches in a row (the counter re-arms itself), all equal to the oracle."""
+def test_mat_vec_full_size_ffn_and_head_shapes(be, oracle, name):
+    """Full-size shapes (FFN up/gate 14336 x 4096, a quarter of the output head, ffn_down with its 14336-long rows): every CTA works through many
+    units per warp (in-CTA claiming, ring wrap-around, long-row segments); three launches in a row, all equal to the oracle."""
     t = GGML_TYPE[name]
     x_rng = np.random.default_rng(21)
     for (m, k, glu) in ((14336, 4096, True), (32064, 4096, False), (4096, 14336, False)):
