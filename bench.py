@@ -100,6 +100,8 @@ def random_planes_iq4nl(be, torch, m, k, gen, scale):
     nb = m * (k // 32)
     blocks = torch.randint(0, 256, (nb, 18), dtype=torch.uint8, device="cuda", generator=gen)
     d = (torch.rand(nb, device="cuda", generator=gen) * 0.6 + 0.7) * scale
+    # random sign per block: the IQ4_NL codebook has a non-zero mean (-5.9), with all-positive d every matrix would amplify the mean of its input
+    d = d * (torch.randint(0, 2, (nb,), device="cuda", generator=gen).float() * 2 - 1)
     blocks[:, 0:2] = d.to(torch.float16).view(torch.uint8).view(nb, 2)
     return be.set_tensor(IQ4_NL, blocks.view(-1), m, k)
 
@@ -402,7 +404,7 @@ def main():
 
     model = Model(be, torch, args.layers, tp=world, rank=rank)
     if model.fused_tp:
-        config["reduce"] = "tg: fused into the mat-vec kernels (multimem.red from the wo/ffn_down epilogue, flag wait in the next prologue); pp512: " + \
+        config["reduce"] = "tg: fused into the mat-vec kernels (wo/ffn_down epilogue broadcasts tagged partial rows with multimem.st, the next mat-vec's prologue sums them); pp512: " + \
             ("two-shot bf16 NVLS kernel (multimem.ld_reduce + multimem.st)" if model.bf16_reduce else "one-shot f32 NVLS kernel")
     # ---------------- N > 1: correctness gate on the collectives, before anything is timed ----------------
     if world > 1:

@@ -307,8 +307,8 @@ def mul_mat_host(w: QuantTensor, x_host: np.ndarray) -> np.ndarray:
 
 class NvlsComm(ctypes.Structure):
     """struct b200q_nvls_comm of include/b200q.h"""
-    _fields_ = [("mc_base", c_void_p), ("local_base", c_void_p), ("parity_stride", c_int64), ("mc_flag", c_void_p), ("local_flag", c_void_p),
-                ("world_size", ctypes.c_uint32), ("seq_counter", c_void_p), ("cta_counter", c_void_p)]
+    _fields_ = [("ll_mc", c_void_p), ("ll_local", c_void_p), ("ll_reduced", c_void_p), ("ll_stride", c_int64),
+                ("world_size", ctypes.c_uint32), ("rank", ctypes.c_uint32), ("ll_state", c_void_p)]
 
 
 class NvlsStage(ctypes.Structure):
@@ -344,6 +344,8 @@ class NvlsReducer:
     our kernel: multimem.red into the switch, flag, acquire-spin, copy-out.  Falls back to NCCL all_reduce when the
     platform has no multicast support."""
 
+    LL_STRIDE = 16384        # longest vector of a fused decode reduce (entries)
+
     def __init__(self, max_elems: int, group=None):
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
@@ -355,7 +357,10 @@ class NvlsReducer:
         self.ok = False
         try:
             # [2 parity buffers of `stride` f32][64 f32: flag words][bf16 staging of `stride` elements (two-shot all-reduce)]
-            self.buf = symm.empty(2 * self.stride + 64 + (self.stride + 1) // 2, dtype=torch.float32, device=dev)
+            # [tagged slots of the fused decode reduce: 2 parities x world x LL_STRIDE entries of {f32, u32}]
+            self.ll_stride = self.LL_STRIDE
+            base_floats = (2 * self.stride + 64 + (self.stride + 1) // 2 + 3) // 4 * 4
+            self.buf = symm.empty(base_floats + 2 * self.world * self.ll_stride * 2, dtype=torch.float32, device=dev)
             self.hdl = symm.rendezvous(self.buf, self.group)
             self.mc = int(self.hdl.multicast_ptr) if self.hdl.has_multicast_support else 0
             if self.mc:
@@ -366,6 +371,8 @@ class NvlsReducer:
                 self.rank = dist.get_rank(self.group)
                 self.flag2_off = self.flag_off + 128                          # second flag word (own 128-byte line): two-shot bf16 all-reduce
                 self.stage_off = (2 * self.stride + 64) * 4
+                self.ll_off = base_floats * 4
+                self.ll_reduced = torch.zeros(2 * self.ll_stride * 2, dtype=torch.float32, device=dev)    # rank-local: published sums {f32, tag}
                 torch.cuda.synchronize()
                 self.hdl.barrier()
                 self.ok = True
@@ -378,16 +385,18 @@ class NvlsReducer:
         """ctypes b200q_nvls_comm for the fused tensor-parallel mat-vec (b200q_mul_mat_vec_tp)."""
         assert self.ok
         if not hasattr(self, "_comm"):
-            self._comm = NvlsComm(self.mc, self.local, self.stride, self.mc + self.flag_off, self.local + self.flag_off, self.world,
-                                  self.state.data_ptr(), self.state.data_ptr() + 16)
+            self._comm = NvlsComm(self.mc + self.ll_off, self.local + self.ll_off, self.ll_reduced.data_ptr(), self.ll_stride, self.world, self.rank,
+                                  self.state.data_ptr() + 48)
         return self._comm
 
-    def reduced_view(self, n: int, use: int = -1) -> torch.Tensor:
-        """This rank's copy of the buffer written by the latest (use = -1) fused reduce: debugging / tests only (synchronises)."""
+    def reduced_view(self, n: int) -> torch.Tensor:
+        """The summed vector of the latest fused reduce as the consumer launch published it: debugging / tests only (synchronises)."""
         torch.cuda.synchronize()
-        seq = int(self.state[0].item())
-        par = (seq + use) & 1
-        return self.buf[par * self.stride: par * self.stride + n].clone()
+        seq = int(self.state[12].item())
+        par = (seq - 1) & 1
+        ent = self.ll_reduced.view(2, self.ll_stride, 2)[par, :n]
+        assert bool((ent[:, 1].view(torch.int32) == seq).all()), "the consumer of the latest reduce has not published every entry"
+        return ent[:, 0].clone()
 
     def stage(self):
         """ctypes b200q_nvls_stage for b200q_reduce_sum_nvls_bf16."""

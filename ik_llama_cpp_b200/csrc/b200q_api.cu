@@ -238,7 +238,8 @@ int b200q_mul_mat_vec_q8(int type, const void * W, const float * x, const void *
 int b200q_mul_mat_vec_tp(int type, int n_tensors, const void * const * W, const void * W_gate, float * const * dst, const int64_t * m,
                          int64_t k, const float * x, int unary, float limit, const b200q_nvls_comm * comm, int reduce_in, int reduce_out, void * stream) {
     if (n_tensors < 1 || n_tensors > B200Q_MAX_SEGS || !W || !m || (W_gate && n_tensors != 1)) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_tp: bad argument");
-    if ((reduce_in || reduce_out) && (!comm || !comm->mc_base || !comm->local_base || !comm->mc_flag || !comm->local_flag || !comm->seq_counter || !comm->cta_counter || comm->world_size < 2))
+    if ((reduce_in || reduce_out) && (!comm || !comm->ll_mc || !comm->ll_local || !comm->ll_reduced || !comm->ll_state || comm->ll_stride < 1 || comm->world_size < 2 || comm->rank >= comm->world_size
+                                      || ((uintptr_t)comm->ll_mc & 15) || ((uintptr_t)comm->ll_local & 15) || ((uintptr_t)comm->ll_reduced & 15) || (comm->ll_stride & 1)))
         return fail(B200Q_E_ARG, "b200q_mul_mat_vec_tp: incomplete communicator");
     if (!reduce_in && !x) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_tp: x is NULL");
     if (!reduce_out && !dst) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_tp: dst is NULL");
@@ -247,9 +248,8 @@ int b200q_mul_mat_vec_tp(int type, int n_tensors, const void * const * W, const 
     d.type = type; d.n_seg = n_tensors; d.K = k; d.x = x; d.x_stride = k; d.ncols = 1; d.act = unary; d.limit = limit; d.sm_count = di.sm_count; d.pdl = opt_pdl(); d.ring = 1;
     for (int i = 0; i < n_tensors; ++i) d.seg[i] = {W[i], i == 0 ? W_gate : nullptr, dst ? dst[i] : nullptr, nullptr, m[i]};
     if (comm) {
-        d.tp.mc_base = (float *)comm->mc_base; d.tp.local_base = (float *)comm->local_base; d.tp.stride = comm->parity_stride;
-        d.tp.mc_flag = (uint32_t *)comm->mc_flag; d.tp.local_flag = (const uint32_t *)comm->local_flag; d.tp.world = comm->world_size;
-        d.tp.seq = (uint32_t *)comm->seq_counter; d.tp.cta_counter = (uint32_t *)comm->cta_counter; d.tp.in = reduce_in != 0; d.tp.out = reduce_out != 0;
+        d.tp.ll_mc = (float2 *)comm->ll_mc; d.tp.ll_local = (const float2 *)comm->ll_local; d.tp.ll_red = (float2 *)comm->ll_reduced; d.tp.ll_stride = comm->ll_stride;
+        d.tp.world = comm->world_size; d.tp.rank = comm->rank; d.tp.seq = (uint32_t *)comm->ll_state; d.tp.in = reduce_in != 0; d.tp.out = reduce_out != 0;
     }
     return check_launch(b200q_launch_mmvq(d, (cudaStream_t)stream), "b200q_mul_mat_vec_tp");
 }

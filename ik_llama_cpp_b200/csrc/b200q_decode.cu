@@ -144,7 +144,7 @@ int b200q_launch_mmvq(const b200q_mmvq_desc & d, cudaStream_t st) {
         a.q8_in = d.q8_in; a.q8_out = d.q8_out;
     }
     if (a.tp.in || a.tp.out) {          // only the TMA-ring kernel implements the fused reduce
-        if (d.ncols != 1 || !d.ring || d.K % 256 || (a.tp.out && r0 > a.tp.stride) || (a.tp.in && d.K > a.tp.stride)) return -7;
+        if (d.ncols != 1 || !d.ring || d.K % 256 || (a.tp.out && r0 > a.tp.ll_stride) || (a.tp.in && d.K > a.tp.ll_stride)) return -7;
     }
     switch (d.type) {
 #define X(T) case T: return launch_mmvq_type<T>(a, d.ncols, upgate, d.sm_count, d.pdl != 0, d.ring != 0, st);

@@ -15,12 +15,33 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ void pdl_wait()    { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- tagged-slot exchange (fused tensor-parallel decode reduce) ----
+// An entry {value, id} is written with ONE 8-byte store (locally, or by a peer GPU through the NVLS multicast mapping), so a reader that sees the id
+// of the reduce it waits for also sees the value: no fences, no separate flag, no acknowledgement round trip.
+__device__ __forceinline__ float2 ll_load(const float2 * p) {
+    float2 v; asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory"); return v;
+}
+// element e of reduce `id`: the sum over ranks in rank order (every rank and every CTA gets the same bits), waiting for the peers' entries
+__device__ __forceinline__ float ll_sum_slots(const float2 * slots, int64_t stride, uint32_t world, int e, uint32_t id) {
+    float acc = 0.0f;
+    for (uint32_t r = 0; r < world; ++r) {
+        float2 v = ll_load(slots + (int64_t)r * stride + e);
+        while (__float_as_uint(v.y) != id) { __nanosleep(20); v = ll_load(slots + (int64_t)r * stride + e); }
+        acc += v.x;
+    }
+    return acc;
+}
+struct ll_source { const float2 * red; const float2 * slots; int64_t stride; uint32_t world, id; };
+
 // Quantise ncols activation columns into shared memory (q8_1 semantics of ggml-cuda/quantize.cu:13-47):
 //   d = amax/127 ; q = amax == 0 ? 0 : roundf(x/d) ; d kept as float(half(d)) ; isum = packed int16 sums of q over each 16.
 // Cooperative and vectorised: a thread owns 8 consecutive floats (two LDG.128), 4 adjacent lanes own one 32-block.
-template <int NCOLS, bool COHERENT = false>
+// LL = true (NCOLS = 1): the column is the result of a fused tensor-parallel reduce: entries of ll->red (summed by the CTA that owns the slice, see
+// k_mmvq_ring); an entry whose tag is still old is summed here from the per-rank slots instead, so no CTA ever waits for a sibling CTA.
+template <int NCOLS, bool LL = false>
 __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x, int64_t x_stride, int64_t K,
-                                                   int8_t * sq, float * sd, int * sis, int tid, int nthreads, unsigned long long * tr = nullptr) {
+                                                   int8_t * sq, float * sd, int * sis, int tid, int nthreads, unsigned long long * tr = nullptr,
+                                                   const ll_source * ll = nullptr) {
     const int nch = (int)(K / 8), total = nch * NCOLS, n32 = (int)(K / 32);
     constexpr int B = 4;                                   // chunks per thread per batch: 8 independent LDG.128 in flight, so the
                                                            // activation vector costs 1 (K=4096) .. 2 (K=14336) L2 round trips, not 2 .. 6
@@ -31,10 +52,22 @@ __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x,
             const int c = base + u * nthreads + tid;
             int col = 0, ch = c < total ? c : 0;
             if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
-            if (c < total) {
-                // COHERENT: the vector was written through the NVLS multicast mapping by other GPUs -> no read-only / stale-L1 path
-                va[u] = COHERENT ? __ldcv(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8)) : __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8));
-                vb[u] = COHERENT ? __ldcv(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4)) : __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
+            if (c < total && LL) {
+                float t[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {               // 8 entries = 64 bytes
+                    const float4 * pw = reinterpret_cast<const float4 *>(ll->red + (int64_t)ch * 8) + j;
+                    float4 w = __ldcv(pw);
+                    // the sibling CTA that owns this slice publishes it within a microsecond or two of the peers' rows arriving: wait a little before
+                    // paying world x the loads (bounded, so progress never depends on a CTA that is not resident)
+                    for (int spin = 0; spin < 6 && (__float_as_uint(w.y) != ll->id || __float_as_uint(w.w) != ll->id); ++spin) { __nanosleep(100); w = __ldcv(pw); }
+                    t[2 * j]     = __float_as_uint(w.y) == ll->id ? w.x : ll_sum_slots(ll->slots, ll->stride, ll->world, ch * 8 + 2 * j, ll->id);
+                    t[2 * j + 1] = __float_as_uint(w.w) == ll->id ? w.z : ll_sum_slots(ll->slots, ll->stride, ll->world, ch * 8 + 2 * j + 1, ll->id);
+                }
+                va[u] = make_float4(t[0], t[1], t[2], t[3]); vb[u] = make_float4(t[4], t[5], t[6], t[7]);
+            } else if (c < total) {
+                va[u] = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8));
+                vb[u] = __ldg(reinterpret_cast<const float4 *>(x + col * x_stride + (int64_t)ch * 8 + 4));
             } else { va[u] = make_float4(0.f, 0.f, 0.f, 0.f); vb[u] = va[u]; }
         }
         if (tr && base == 0 && va[0].x != 123456.789f) *tr = gtime();       // (debug trace) first batch of loads has landed

@@ -335,10 +335,14 @@ __device__ __forceinline__ void bulk_g2s(void * dst, const void * src, uint32_t 
                  ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
-// ---- tensor-parallel fusion (split-mode-graph): the all-reduce of a row-parallel mat-vec happens in the switch ----
-__device__ __forceinline__ void tp_red_add_f32(float * mc, float v) { asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory"); }
-__device__ __forceinline__ void tp_red_add_u32_release(uint32_t * mc, uint32_t v) { asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(mc), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t tp_ld_acquire_sys(const uint32_t * p) { uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+// ---- tensor-parallel fusion (split-mode-graph): the partial rows of a row-parallel mat-vec are broadcast to every rank by the switch ----
+// one multimem.st = one NVLink write that the NVSwitch replicates into every rank's copy of the slot; {value, tag} travel together (8 bytes)
+__device__ __forceinline__ void tp_bcast1(float2 * mc, float v, uint32_t id) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(mc), "f"(v), "f"(__uint_as_float(id)) : "memory");
+}
+__device__ __forceinline__ void tp_bcast2(float2 * mc, float v0, float v1, uint32_t id) {       // two adjacent rows: 16 bytes, 16-byte aligned
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v0), "f"(__uint_as_float(id)), "f"(v1), "f"(__uint_as_float(id)) : "memory");
+}
 
 __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
 
@@ -472,26 +476,25 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
     pdl_wait();                          // (2) the activations are produced by the previous kernel
 #endif
     if (a.trace && blockIdx.x == 0 && lead) a.trace[1] = gtime();
-    // Tensor-parallel mode.  `seq` = number of fused reduces completed on this communicator (device counter, so the launch arguments
-    // are constant under CUDA-graph replay); it cannot change while this grid runs before its own last CTA bumps it.
+    // Tensor-parallel mode.  seq[0] = fused reduces this rank has issued (device counter, so the launch arguments are constant under CUDA-graph
+    // replay); it cannot change while this grid runs before its own last CTA bumps it.  A reduce_out launch issues reduce number tps + 1 into
+    // parity tps & 1; a reduce_in launch consumes reduce number tps (parity (tps - 1) & 1).  Entries carry the number as their tag, so nothing is
+    // ever zeroed and stale data of the reduce two steps back (same parity) can never be mistaken for the current one.
     uint32_t tps = 0;
     if (TP && (a.tp.in || a.tp.out)) tps = *reinterpret_cast<volatile uint32_t *>(a.tp.seq);
     if (!is_prod) {
-        if (TP && a.tp.out) {
-            // zero this rank's copy of the NEXT reduce's buffer: peers add to it only after they have seen this rank's flag
-            // increment for the current reduce, which is ordered after these stores (fence + release below)
-            // (seq[1 + p] = floats of parity buffer p that its last use left non-zero, see b200q_reduce.cu)
-            float * z = a.tp.local_base + (int64_t)((tps & 1) ^ 1) * a.tp.stride;
-            const int nd = (int)reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + ((tps & 1) ^ 1)];
-            const int per = (nd + (int)gridDim.x - 1) / (int)gridDim.x, z0 = per * (int)blockIdx.x, z1 = min(nd, z0 + per);
-            for (int i = z0 + ctid; i < z1; i += cthreads) z[i] = 0.0f;
-        }
         if (TP && a.tp.in) {
-            // the activations are the sum over ranks of the previous row-parallel mat-vec: wait until every rank has signalled it
-            // (flag += 1 per rank per reduce through the multicast mapping), then read this rank's copy of the buffer
-            if (lead) { const uint32_t target = a.tp.world * tps; while ((int32_t)(tp_ld_acquire_sys(a.tp.local_flag) - target) < 0) { } }
-            asm volatile("bar.sync 1, %0;" ::"r"(cthreads) : "memory");
-            quantize_x_to_smem<NCOLS, true>(a.tp.local_base + (int64_t)((tps - 1) & 1) * a.tp.stride, a.tp.stride, K, sq, sd, sis, ctid, cthreads);
+            const int64_t par = (tps - 1) & 1;
+            ll_source src; src.slots = a.tp.ll_local + par * a.tp.world * a.tp.ll_stride; src.red = a.tp.ll_red + par * a.tp.ll_stride;
+            src.stride = a.tp.ll_stride; src.world = a.tp.world; src.id = tps;
+            // (1) this CTA sums its slice of the vector over the ranks (waiting for the peers' rows to arrive) and publishes it for its siblings,
+            // (2) every CTA quantises the whole vector from the published sums (falling back to the slots for entries that are not there yet)
+            const int e0 = (int)(((int64_t)K * blockIdx.x) / gridDim.x), e1 = (int)(((int64_t)K * (blockIdx.x + 1)) / gridDim.x);
+            for (int e = e0 + ctid; e < e1; e += cthreads) {
+                const float sum = ll_sum_slots(src.slots, src.stride, src.world, e, src.id);
+                asm volatile("st.volatile.global.v2.f32 [%0], {%1,%2};" ::"l"(a.tp.ll_red + par * a.tp.ll_stride + e), "f"(sum), "f"(__uint_as_float(src.id)) : "memory");
+            }
+            quantize_x_to_smem<NCOLS, true>(nullptr, 0, K, sq, sd, sis, ctid, cthreads, nullptr, &src);
         } else if (Q8 == 1) {
             // quantised once by the producing kernel: nothing to do here, the producer warp bulk-copies the image (below)
         } else {
@@ -615,9 +618,10 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
                         v0 = b200q_glu<false>(a.act, v0, u0, a.limit); if (PAIR) v1 = b200q_glu<false>(a.act, v1, u1, a.limit);
                     } else if (sgm.bias) { v0 += sgm.bias[crow]; if (two) v1 += sgm.bias[crow + 1]; }
                     if (lane == 0) {
-                        if (TP && a.tp.out) {                                     // partial result: summed over ranks inside the switch
-                            float * mc = a.tp.mc_base + (int64_t)(tps & 1) * a.tp.stride + (int64_t)sgm.row0 + crow;
-                            tp_red_add_f32(mc, v0); if (two) tp_red_add_f32(mc + 1, v1);
+                        if (TP && a.tp.out) {                                     // partial rows: broadcast to slot [parity][this rank] of every rank
+                            float2 * mc = a.tp.ll_mc + ((int64_t)(tps & 1) * a.tp.world + a.tp.rank) * a.tp.ll_stride + (int64_t)sgm.row0 + crow;
+                            if (two && !(((int64_t)sgm.row0 + crow) & 1)) tp_bcast2(mc, v0, v1, tps + 1);
+                            else { tp_bcast1(mc, v0, tps + 1); if (two) tp_bcast1(mc + 1, v1, tps + 1); }
                         } else { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
                     }
                 }
@@ -651,20 +655,13 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
         }
     }
     if (TP && a.tp.out) {
-        // completion: every consumer warp fences its multimem.reds (and its share of the zeroing), the last warp of the last CTA
-        // publishes this rank's flag increment on every GPU
-        // Every warp makes its own multimem.reds (and zeroing stores) performed system-wide (fence.sys, all warps in parallel), THEN counts
-        // itself in; the thread that sees the last arrival of the last CTA therefore runs after every contribution of this rank has
-        // landed in every peer, and publishes the flag with a release (the rank-local bookkeeping stores precede it in program order).
-        // No further fences on this critical path (round 1 had a fence.gpu and a second fence.sys in front of the release).
-        __threadfence_system();
+        // bookkeeping only (the data needs no completion signal: every entry carries its tag): the last warp of the last CTA advances the
+        // rank-local count of issued reduces, which the next launch of this stream reads after its griddepcontrol.wait
         if (lane == 0) {
             if (atomicAdd(next_pair + 1, 1) == ncw - 1) {
-                if (atomicAdd(a.tp.cta_counter, 1u) == gridDim.x - 1) {
-                    *a.tp.cta_counter = 0;
-                    reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + ((tps & 1) ^ 1)] = 0; reinterpret_cast<volatile uint32_t *>(a.tp.seq)[1 + (tps & 1)] = (uint32_t)a.M_total;
+                if (atomicAdd(a.tp.seq + 1, 1u) == gridDim.x - 1) {
+                    a.tp.seq[1] = 0;
                     *reinterpret_cast<volatile uint32_t *>(a.tp.seq) = tps + 1;
-                    tp_red_add_u32_release(a.tp.mc_flag, 1u);
                 }
             }
         }

@@ -48,8 +48,13 @@ B200Q_HD constexpr bool b200q_split16(int type) {
 
 // device view of the NVLS communicator of include/b200q.h (b200q_nvls_comm) + the direction flags of one launch
 struct b200q_tp_comm {
-    float * mc_base; float * local_base; int64_t stride; uint32_t * mc_flag; const uint32_t * local_flag; uint32_t world;
-    uint32_t * seq; uint32_t * cta_counter; int in; int out;
+    // tagged-slot exchange of the fused decode reduce (k_mmvq_ring<..., TP>): entry = {f32 value, u32 id of the reduce}, one 8-byte store
+    float2 * ll_mc;              // multicast address of slots[2 parities][world][ll_stride]
+    const float2 * ll_local;     // this rank's mapping of the same
+    float2 * ll_red;             // rank-local [2 parities][ll_stride]: the summed vector, same tagging (filled cooperatively by the consumer's CTAs)
+    int64_t ll_stride; uint32_t world, rank;
+    uint32_t * seq;              // rank-local: [0] reduces issued by this rank, [1] CTA arrival counter
+    int in; int out;
 };
 struct b200q_mmvq_seg_desc { const void * W; const void * W2; float * dst; const float * bias; int64_t M; };
 struct b200q_mmvq_desc {

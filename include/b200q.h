@@ -124,13 +124,17 @@ B200Q_API int b200q_reduce_sum_nvls_bf16(const float * in, float * out_f32, void
 
 /* ---- tensor-parallel decode (n = 1): the GGML_OP_REDUCE after a row-parallel mat-vec fused INTO the mat-vec kernels ----
  * (reference: ggml_cuda_op_reduce runs as its own node after wo / ffn_down under -sm graph, ggml-cuda/reduce.cu:125-598).
- * Same symmetric buffers as b200q_reduce_sum_nvls.  reduce_out: the kernel's epilogue adds its partial rows into every rank's copy
- * of the buffer with multimem.red (dst is not written; m_total <= parity_stride), the last CTA raises the multicast flag.
- * reduce_in: `x` is ignored, the kernel waits for the flags of all ranks and takes its activations (k <= parity_stride floats) from
- * this rank's copy of the buffer filled by the preceding reduce_out launch.  W_gate != NULL: fused up/gate mode (n_tensors = 1). */
+ * Tagged-slot exchange, no flag, no fence, no acknowledgement round trip: an entry is {f32 value, u32 number of the reduce}, written with one
+ * 8-byte store.  reduce_out: the kernel's epilogue broadcasts each finished partial row to slot [parity][this rank][row] of EVERY rank with
+ * multimem.st through the NVLS multicast mapping (dst is not written; m_total <= ll_stride).  reduce_in: `x` is ignored; the CTAs of the consumer
+ * sum the per-rank slots in rank order (bit-identical on every rank), each its own slice, publish the sums in ll_reduced with the same tagging and
+ * quantise their activations from there (k <= ll_stride).  W_gate != NULL: fused up/gate mode (n_tensors = 1).
+ * CONTRACT: on one communicator every reduce_out launch must be followed, on every rank, by at least one reduce_in launch before the next
+ * reduce_out (the two parities are reused every second reduce); all ranks issue the same sequence.
+ *   ll_mc / ll_local: multicast / local address of the symmetric slot array, 2 * world_size * ll_stride entries of 8 bytes, zero-initialised;
+ *   ll_reduced: rank-local, 2 * ll_stride entries, zero-initialised; ll_state: rank-local u32[2], zero-initialised; all 16-byte aligned. */
 typedef struct b200q_nvls_comm {
-    void * mc_base; void * local_base; int64_t parity_stride; void * mc_flag; const void * local_flag; uint32_t world_size;
-    void * seq_counter; void * cta_counter;
+    void * ll_mc; const void * ll_local; void * ll_reduced; int64_t ll_stride; uint32_t world_size; uint32_t rank; void * ll_state;
 } b200q_nvls_comm;
 B200Q_API int b200q_mul_mat_vec_tp(int type, int n_tensors, const void * const * W, const void * W_gate, float * const * dst, const int64_t * m,
                          int64_t k, const float * x, int unary, float limit, const b200q_nvls_comm * comm, int reduce_in, int reduce_out, void * stream);

@@ -54,6 +54,8 @@ def build_ref(variant: str = "avx2", jobs: int = 8) -> str | None:
     args = ["make", "-f", os.path.join(HERE, "Makefile.ref"), f"-j{jobs}", f"VARIANT={variant}"]
     if variant == "native":
         args.append("ARCHFLAGS=-march=native")
+    if variant == "avx512":       # the reference's AVX-512 / VNNI kernels with a PORTABLE flag set (Ice Lake server and later, Zen 4): safe on the GPU pool's hosts
+        args.append("ARCHFLAGS=-march=icelake-server -mtune=generic")
     subprocess.check_call(args, stdout=subprocess.DEVNULL)
     return so
 
@@ -170,8 +172,9 @@ class RefLib:
     @staticmethod
     def find(prefer_native: bool = True) -> str | None:
         cands = []
-        if prefer_native and {"avx512f", "avx512vnni", "avx512bw", "avx512vl"} <= _cpu_flags():
-            cands.append(os.path.join(REFDIR, "libggml_ref_native.so"))
+        # (/proc/cpuinfo spells it avx512_vnni; round 1 looked for "avx512vnni" and therefore always fell back to the AVX2 build)
+        if prefer_native and {"avx512f", "avx512bw", "avx512vl", "avx512dq", "avx512_vnni", "avx512vbmi", "avx512_vbmi2", "avx512_bitalg", "avx512_vpopcntdq"} <= _cpu_flags():
+            cands.append(os.path.join(REFDIR, "libggml_ref_avx512.so"))
         cands.append(os.path.join(REFDIR, "libggml_ref_avx2.so"))
         for c in cands:
             if os.path.exists(c):

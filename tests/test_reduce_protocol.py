@@ -87,3 +87,57 @@ def test_zeroing_only_the_current_length_is_wrong():
         seen, expect = run(2, lengths, seed, zero_dirty=False)
         bad += any(seen[r][i] != [expect(i, j) for j in range(n)] for r in range(2) for i, n in enumerate(lengths))
     assert bad == 20
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# Tagged-slot exchange of the fused decode reduce (round 2: k_mmvq_ring<..., TP>, include/b200q.h b200q_nvls_comm): every entry is
+# {value, number of the reduce}, written with one store; deliveries to the peers are NOT ordered and take arbitrarily long.
+# ------------------------------------------------------------------------------------------------------------------------------------
+def run_tagged(world, n_reduces, length, seed, parities=2):
+    """Every rank runs produce(1); consume(1); produce(2); consume(2) ...; a produce only ISSUES the stores (one per element and destination),
+    the network delivers them later in random order.  Returns (results, deadlock)."""
+    rnd = random.Random(seed)
+    slots = [[[[(0.0, 0)] * length for _ in range(world)] for _ in range(parities)] for _ in range(world)]     # [dst][parity][src][e]
+    in_flight = []                                   # (dst, parity, src, e, value, tag)
+    val = lambda r, i, e: float((r + 1) * 100 + i * 3 + e % 7)
+    pc = [0] * world                                 # 2 * (i - 1) = about to produce i, 2 * (i - 1) + 1 = consuming i
+    got = [[None] * (n_reduces + 1) for _ in range(world)]
+    while any(p < 2 * n_reduces for p in pc):
+        choices = [("rank", r) for r in range(world) if pc[r] < 2 * n_reduces] + ([("net", None)] if in_flight else [])
+        kind, r = choices[rnd.randrange(len(choices))]
+        if kind == "net":
+            dst, par, src, e, v, tag = in_flight.pop(rnd.randrange(len(in_flight)))
+            slots[dst][par][src][e] = (v, tag)
+            continue
+        i = pc[r] // 2 + 1
+        if pc[r] % 2 == 0:                           # reduce_out launch: issue, do not wait
+            for e in range(length):
+                for dst in range(world):
+                    in_flight.append((dst, (i - 1) % parities, r, e, val(r, i, e), i))
+            pc[r] += 1
+        else:                                        # reduce_in launch: completes once every slot carries tag i
+            def complete(q):
+                j = pc[q] // 2 + 1
+                return all(slots[q][(j - 1) % parities][src][e][1] == j for src in range(world) for e in range(length))
+            if complete(r):
+                mine = slots[r][(i - 1) % parities]
+                got[r][i] = [sum(mine[src][e][0] for src in range(world)) for e in range(length)]
+                pc[r] += 1
+            elif not in_flight and all(pc[q] >= 2 * n_reduces or (pc[q] % 2 == 1 and not complete(q)) for q in range(world)):
+                return got, True                     # nothing in flight, every rank is waiting for a tag that will never come
+    return got, False
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_tagged_slot_exchange_two_parities(world):
+    for seed in range(40):
+        got, dead = run_tagged(world, n_reduces=7, length=5, seed=seed)
+        assert not dead
+        for r in range(world):
+            for i in range(1, 8):
+                assert got[r][i] == [sum(float((q + 1) * 100 + i * 3 + e % 7) for q in range(world)) for e in range(5)], (seed, r, i)
+
+
+def test_tagged_slot_exchange_needs_two_parities():
+    """With a single buffer a fast rank's reduce i+1 overwrites entries a slow rank has not consumed yet: that rank then waits for tag i forever."""
+    assert any(run_tagged(2, n_reduces=6, length=4, seed=s, parities=1)[1] for s in range(40))
