@@ -106,10 +106,31 @@ def random_planes_iq4nl(be, torch, m, k, gen, scale):
     return be.set_tensor(IQ4_NL, blocks.view(-1), m, k)
 
 
+# wire geometry of the types of the default `llama-quantize ... IQ4_NL` mix (SURVEY.md §8 a-note): (ggml type id, block bytes, weights per block,
+# byte offsets of ggml_half scale fields that get a sane value, of ggml_half min fields that get a small one)
+MIX_TYPES = {"IQ4_NL": (20, 18, 32, [0], []), "Q5_K": (13, 176, 256, [0], [2]), "Q6_K": (14, 210, 256, [208], []), "IQ5_K": (140, 176, 256, [0], [])}
+
+
+def random_planes(be, torch, name, m, k, gen, scale):
+    """Random valid wire blocks of a mix type made on the GPU (every payload bit pattern is a valid encoding), re-laid-out by the product."""
+    if name == "IQ4_NL":
+        return random_planes_iq4nl(be, torch, m, k, gen, scale)
+    t, bs, qk, d_off, m_off = MIX_TYPES[name]
+    nb = m * (k // qk)
+    blocks = torch.randint(0, 256, (nb, bs), dtype=torch.uint8, device="cuda", generator=gen)
+    # sub-block scales of these types are ~6-bit integers: scale the super-block d down accordingly
+    d = (torch.rand(nb, device="cuda", generator=gen) * 0.6 + 0.7) * scale / 32.0
+    for o in d_off:
+        blocks[:, o:o + 2] = d.to(torch.float16).view(torch.uint8).view(nb, 2)
+    for o in m_off:
+        blocks[:, o:o + 2] = (d * 0.01).to(torch.float16).view(torch.uint8).view(nb, 2)
+    return be.set_tensor(t, blocks.view(-1), m, k)
+
+
 class Model:
     """Llama-3-8B matmul skeleton, optionally one tensor-parallel shard (rank r of tp)."""
 
-    def __init__(self, be, torch, n_layer, tp=1, rank=0, seed=1234, collective=True):
+    def __init__(self, be, torch, n_layer, tp=1, rank=0, seed=1234, collective=True, mix="pure"):
         """collective=False: only the weights of rank `rank`'s shard (no reducer, no head): used by rank 0 to rebuild the other ranks'
         shards for the tensor-parallel correctness gate."""
         self.be, self.torch, self.tp, self.n_layer = be, torch, tp, n_layer
@@ -118,15 +139,19 @@ class Model:
         # unit-gain weights (IQ4_NL codebook rms ~ 70).  There is no norm between the layers of this MUL_MAT-only skeleton and silu(g)*u makes the
         # magnitude map quadratic, so the values contract towards 0 over the layers instead of overflowing the fp16 scale of q8_1
         s_e, s_f = 1.0 / (70.0 * N_EMBD ** 0.5), 1.0 / (70.0 * N_FF ** 0.5)
-        mk = lambda m, k, s: random_planes_iq4nl(be, torch, m, k, gen, s)
+        # mix = "default": what `llama-quantize model IQ4_NL` produces WITHOUT --pure on this GQA model (src/llama-quantize.cpp:617-621, 739-745, 385-388):
+        # attn_v -> IQ5_K, ffn_down of the first n_layer/8 layers -> Q5_K, output.weight -> Q6_K, everything else IQ4_NL
+        self.mix = mix
+        mk = lambda m, k, s, name="IQ4_NL": random_planes(be, torch, name, m, k, gen, s)
+        dflt = mix == "default"
         self.layers = []
-        for _ in range(n_layer):
+        for li in range(n_layer):
             self.layers.append(dict(
-                wq=mk(N_EMBD // tp, N_EMBD, s_e), wk=mk(N_KV_DIM // tp, N_EMBD, s_e), wv=mk(N_KV_DIM // tp, N_EMBD, s_e),
+                wq=mk(N_EMBD // tp, N_EMBD, s_e), wk=mk(N_KV_DIM // tp, N_EMBD, s_e), wv=mk(N_KV_DIM // tp, N_EMBD, s_e, "IQ5_K" if dflt else "IQ4_NL"),
                 wo=mk(N_EMBD, N_EMBD // tp, s_e), up=mk(N_FF // tp, N_EMBD, s_e), gate=mk(N_FF // tp, N_EMBD, s_e),
-                down=mk(N_EMBD, N_FF // tp, s_f)))
-        self.head = mk(N_VOCAB // tp, N_EMBD, s_e) if collective else None
-        self.launches_tg = n_layer * 4 + 1
+                down=mk(N_EMBD, N_FF // tp, s_f, "Q5_K" if dflt and li < N_LAYER // 8 else "IQ4_NL")))
+        self.head = mk(N_VOCAB // tp, N_EMBD, s_e, "Q6_K" if dflt else "IQ4_NL") if collective else None
+        self.launches_tg = n_layer * (5 if dflt else 4) + 1      # (attn_v has its own type in the default mix: it cannot ride in the Q,K launch)
         self.reducer = None
         self.fused_tp = False
         self.bf16_reduce = False
@@ -181,7 +206,10 @@ class Model:
         nl = len(self.layers)
         for li, L in enumerate(self.layers):
             pf([L["wo"]])
-            be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v])
+            if L["wv"].ggml_type == L["wq"].ggml_type:
+                be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v])
+            else:
+                be.mul_mat_multi([L["wq"], L["wk"]], x, [self.q, self.kk]); be.mul_mat(L["wv"], x, out=self.v)
             pf([L["up"]], gate=L["gate"])
             be.mul_mat(L["wo"], self.q, out=self.h); self.allreduce(self.h)
             pf([L["down"]])
@@ -203,7 +231,10 @@ class Model:
         for li, L in enumerate(self.layers):
             if not have_xb:
                 be.convert_activations(x, self.xb)      # f32 -> bf16 once per distinct activation (shared by Q,K,V)
-            be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v], x_bf16=self.xb)      # one launch
+            if L["wv"].ggml_type == L["wq"].ggml_type:
+                be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], x, [self.q, self.kk, self.v], x_bf16=self.xb)      # one launch
+            else:
+                be.mul_mat_multi([L["wq"], L["wk"]], x, [self.q, self.kk], x_bf16=self.xb); be.mul_mat(L["wv"], x, out=self.v, x_bf16=self.xb)
             be.convert_activations(self.q, self.qb)
             be.mul_mat(L["wo"], self.q, out=self.h, x_bf16=self.qb)
             if self.bf16_reduce:
@@ -357,6 +388,7 @@ def main():
     ap.add_argument("--layers", type=int, default=N_LAYER, help="debug only: a run with fewer layers is not a bench value")
     ap.add_argument("--no-pp", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-mix", action="store_true", help="skip the default-quantisation-mix line (N = 1)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -440,17 +472,22 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    tf_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    # the pp512 timed region is ~0.1 s at full SM clock: that is the BURST regime of MEASURED_PEAKS (its sustained figure was taken after 4 s at
+    # a 1410 MHz median); report against the burst peak and give the sustained fraction next to it
+    tf_peak = float(peaks.get("bf16_tflops", 1722.0))
+    tf_peak_sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     bytes_tok = model.weight_bytes
-    traffic = {}
+    traffic, traffic_src = {}, None
     try:   # DRAM bytes per step measured by ncu --set full (scripts/make_traffic.py, committed under profiles/), N = 1 only
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))) if world == 1 and args.layers == N_LAYER else {}
+        tf = [f for f in ("r2_traffic.json", "r1_traffic.json") if os.path.exists(os.path.join(ROOT, "profiles", f))]
+        traffic = json.load(open(os.path.join(ROOT, "profiles", tf[0]))) if tf and world == 1 and args.layers == N_LAYER else {}
+        traffic_src = f"static: profiles/{tf[0]} (ncu --set full capture of the same kernels, not measured in this run)" if traffic else None
     except Exception:
         pass
     ach = bytes_tok / (ms_tg * 1e-3) / 1e9
     roof = {"bound": "hbm", "kernel": "k_mmvq<IQ4_NL>", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic.get("tg", {}).get("dram_bytes_per_step"),
-            "algorithmic_bytes_per_step": bytes_tok, "launches_per_step": model.launches_tg, "peak_source": peak_src,
+            "traffic_source": traffic_src, "algorithmic_bytes_per_step": bytes_tok, "launches_per_step": model.launches_tg, "peak_source": peak_src,
             "note": "the step consists only of k_mmvq launches; achieved = weight bytes per token / step time (per rank)"}
     line = {"metric": "llama-bench tg128 tok/s (MUL_MAT hot path)", "value": tok_s, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_tg, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -473,7 +510,27 @@ def main():
         line["pp512"] = {"metric": "llama-bench pp512 tok/s (MUL_MAT hot path)", "value": n * 1000.0 / ms_pp, "unit": "tok/s", "ms_per_step": ms_pp, "steps": pp_steps,
                          "dtype": "bf16 x bf16 -> f32 (tcgen05 kind::f16)", "e2e": {"value": n * 1000.0 / ms_pp_e2e, "unit": "tok/s", "h2d_bytes_per_step": n * N_EMBD * 4, "d2h_bytes_per_step": (N_VOCAB // world) * 4},
                          "roofline": {"bound": "tensor", "kernel": "k_gemm_q<IQ4_NL> (fused dequant + tcgen05; + k_f32_to_bf16)", "achieved": tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfs / tf_peak,
-                                      "traffic": traffic.get("pp", {}).get("dram_bytes_per_step_gemm_only"), "algorithmic_flops_per_step": fl, "peak_source": peak_src + " sustained"}}
+                                      "traffic": traffic.get("pp", {}).get("dram_bytes_per_step_gemm_only"), "traffic_source": traffic_src, "algorithmic_flops_per_step": fl,
+                                      "peak_source": peak_src + " burst (timed region << 1 s at max SM clock)", "frac_of_sustained_peak": tfs / tf_peak_sustained}}
+    # ---------------- the default quantisation mix next to --pure (N = 1): IQ5_K attn_v, Q5_K ffn_down x4, Q6_K output ----------------
+    if world == 1 and not args.no_mix and args.layers == N_LAYER:
+        del model
+        torch.cuda.empty_cache()
+        mm = Model(be, torch, args.layers, mix="default")
+        mm.alloc(1); mm.x.copy_(x_host)
+        ms_m = time_graph(torch, mm.step_tg, args.steps, args.warmup)
+        ach_m = mm.weight_bytes / (ms_m * 1e-3) / 1e9
+        mix = {"workload": "same model, default `llama-quantize ... IQ4_NL` mix (no --pure): attn_v IQ5_K, ffn_down of layers 0-3 Q5_K, output.weight Q6_K",
+               "tg": {"value": 1000.0 / ms_m, "unit": "tok/s", "ms_per_step": ms_m, "launches_per_step": mm.launches_tg,
+                      "roofline": {"bound": "hbm", "achieved": ach_m, "peak": hbm_peak, "unit": "GB/s", "frac": ach_m / hbm_peak, "algorithmic_bytes_per_step": mm.weight_bytes}}}
+        if not args.no_pp:
+            mm.alloc(512); mm.x.copy_(xh)
+            ms_mp = time_graph(torch, mm.step_pp, pp_steps, args.warmup)
+            tfm = model_flops_pp(512, args.layers) / (ms_mp * 1e-3) / 1e12
+            mix["pp512"] = {"value": 512 * 1000.0 / ms_mp, "unit": "tok/s", "ms_per_step": ms_mp,
+                            "roofline": {"bound": "tensor", "achieved": tfm, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfm / tf_peak}}
+        line["default_mix"] = mix
+        del mm
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu:
         try:

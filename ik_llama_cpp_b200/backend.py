@@ -390,13 +390,18 @@ class NvlsReducer:
         return self._comm
 
     def reduced_view(self, n: int) -> torch.Tensor:
-        """The summed vector of the latest fused reduce as the consumer launch published it: debugging / tests only (synchronises)."""
+        """The summed vector of the latest fused reduce, rebuilt from this rank's copy of the tagged slots exactly as the consumer kernels do
+        (f32, rank order): debugging / tests only (synchronises)."""
         torch.cuda.synchronize()
         seq = int(self.state[12].item())
         par = (seq - 1) & 1
-        ent = self.ll_reduced.view(2, self.ll_stride, 2)[par, :n]
-        assert bool((ent[:, 1].view(torch.int32) == seq).all()), "the consumer of the latest reduce has not published every entry"
-        return ent[:, 0].clone()
+        o = self.ll_off // 4
+        ent = self.buf[o: o + 2 * self.world * self.ll_stride * 2].view(2, self.world, self.ll_stride, 2)[par, :, :n]
+        assert bool((ent[:, :, 1].contiguous().view(torch.int32) == seq).all()), "not every rank's rows of the latest reduce have arrived"
+        acc = ent[0, :, 0].clone()
+        for r in range(1, self.world):
+            acc = acc + ent[r, :, 0]
+        return acc
 
     def stage(self):
         """ctypes b200q_nvls_stage for b200q_reduce_sum_nvls_bf16."""

@@ -21,13 +21,22 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 __device__ __forceinline__ float2 ll_load(const float2 * p) {
     float2 v; asm volatile("ld.volatile.global.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory"); return v;
 }
-// element e of reduce `id`: the sum over ranks in rank order (every rank and every CTA gets the same bits), waiting for the peers' entries
-__device__ __forceinline__ float ll_sum_slots(const float2 * slots, int64_t stride, uint32_t world, int e, uint32_t id) {
+// element e of reduce `id`: the sum over ranks in rank order (every rank and every CTA gets the same bits), waiting for the peers' entries.
+// All ranks' entries are requested at once (one L2 round trip when the data is already there), then only the missing ones are polled again.
+static __device__ __noinline__ float ll_sum_slots(const float2 * slots, int64_t stride, uint32_t world, int e, uint32_t id) {
+    float2 v[8];
+#pragma unroll
+    for (uint32_t r = 0; r < 8; ++r) if (r < world) v[r] = ll_load(slots + (int64_t)r * stride + e);
     float acc = 0.0f;
-    for (uint32_t r = 0; r < world; ++r) {
-        float2 v = ll_load(slots + (int64_t)r * stride + e);
-        while (__float_as_uint(v.y) != id) { __nanosleep(20); v = ll_load(slots + (int64_t)r * stride + e); }
-        acc += v.x;
+#pragma unroll
+    for (uint32_t r = 0; r < 8; ++r) if (r < world) {
+        while (__float_as_uint(v[r].y) != id) v[r] = ll_load(slots + (int64_t)r * stride + e);
+        acc += v[r].x;
+    }
+    for (uint32_t r = 8; r < world; ++r) {                       // (worlds beyond 8: one at a time)
+        float2 w = ll_load(slots + (int64_t)r * stride + e);
+        while (__float_as_uint(w.y) != id) w = ll_load(slots + (int64_t)r * stride + e);
+        acc += w.x;
     }
     return acc;
 }
@@ -54,15 +63,32 @@ __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x,
             if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
             if (c < total && LL) {
                 float t[8];
+                if (ll->world == 2) {
+                    // two ranks: summing the two slots directly costs the same loads as reading a published sum and saves the publish -> poll hop
+                    float4 w0[4], w1[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {               // 8 entries = 64 bytes
-                    const float4 * pw = reinterpret_cast<const float4 *>(ll->red + (int64_t)ch * 8) + j;
-                    float4 w = __ldcv(pw);
-                    // the sibling CTA that owns this slice publishes it within a microsecond or two of the peers' rows arriving: wait a little before
-                    // paying world x the loads (bounded, so progress never depends on a CTA that is not resident)
-                    for (int spin = 0; spin < 6 && (__float_as_uint(w.y) != ll->id || __float_as_uint(w.w) != ll->id); ++spin) { __nanosleep(100); w = __ldcv(pw); }
-                    t[2 * j]     = __float_as_uint(w.y) == ll->id ? w.x : ll_sum_slots(ll->slots, ll->stride, ll->world, ch * 8 + 2 * j, ll->id);
-                    t[2 * j + 1] = __float_as_uint(w.w) == ll->id ? w.z : ll_sum_slots(ll->slots, ll->stride, ll->world, ch * 8 + 2 * j + 1, ll->id);
+                    for (int j = 0; j < 4; ++j) {
+                        w0[j] = __ldcv(reinterpret_cast<const float4 *>(ll->slots + (int64_t)ch * 8) + j);
+                        w1[j] = __ldcv(reinterpret_cast<const float4 *>(ll->slots + ll->stride + (int64_t)ch * 8) + j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const bool a_ok = __float_as_uint(w0[j].y) == ll->id && __float_as_uint(w1[j].y) == ll->id;
+                        const bool b_ok = __float_as_uint(w0[j].w) == ll->id && __float_as_uint(w1[j].w) == ll->id;
+                        t[2 * j]     = a_ok ? w0[j].x + w1[j].x : ll_sum_slots(ll->slots, ll->stride, 2, ch * 8 + 2 * j, ll->id);
+                        t[2 * j + 1] = b_ok ? w0[j].z + w1[j].z : ll_sum_slots(ll->slots, ll->stride, 2, ch * 8 + 2 * j + 1, ll->id);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {               // 8 entries = 64 bytes
+                        const float4 * pw = reinterpret_cast<const float4 *>(ll->red + (int64_t)ch * 8) + j;
+                        float4 w = __ldcv(pw);
+                        // the sibling CTA that owns this slice publishes it within a microsecond or two of the peers' rows arriving: poll a few times
+                        // before paying world x the loads (bounded, so progress never depends on a CTA that is not resident)
+                        for (int spin = 0; spin < 8 && (__float_as_uint(w.y) != ll->id || __float_as_uint(w.w) != ll->id); ++spin) w = __ldcv(pw);
+                        t[2 * j]     = __float_as_uint(w.y) == ll->id ? w.x : ll_sum_slots(ll->slots, ll->stride, ll->world, ch * 8 + 2 * j, ll->id);
+                        t[2 * j + 1] = __float_as_uint(w.w) == ll->id ? w.z : ll_sum_slots(ll->slots, ll->stride, ll->world, ch * 8 + 2 * j + 1, ll->id);
+                    }
                 }
                 va[u] = make_float4(t[0], t[1], t[2], t[3]); vb[u] = make_float4(t[4], t[5], t[6], t[7]);
             } else if (c < total) {

@@ -380,7 +380,7 @@ template <int TYPE, int NCOLS, bool UPGATE, bool MULTI, bool PAIR, bool TP, int 
 __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTAS) k_mmvq_ring(const mmvq_ring_args ra) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const mmvq_args & a = ra.a; const ring_geom & g = ra.g;
-    const int K = (int)a.K, n32 = K / 32, n8 = n32 / 8;
+    const int K = (int)a.K, n32 = K / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, ncw = (blockDim.x >> 5) - 1;     // consumer warps
     const bool is_prod = B200Q_PRODUCER_LAST ? warp == ncw : warp == 0;
     const int cw = B200Q_PRODUCER_LAST ? warp : warp - 1;                                         // consumer index (producer: out of range)
@@ -441,20 +441,22 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
         int s, row; locate(RPU * pcur, s, row);
         const mmvq_seg & sgm = a.seg[MULTI ? s : 0];
         const b200q_planes & P = (UPGATE && pt == 1) ? sgm.P2 : sgm.P;
-        const int g8 = min(SEGI, n32 - psg * SEGI) >> 3;
+        const int gi = min(SEGI, n32 - psg * SEGI);               // items of this segment; bytes of plane p = gi * b8[p] / 8 (exact: make_ring_geom)
         const bool two = PAIR && row + 1 < (int)sgm.M;
         unsigned char * dstb = ring0 + ((size_t)lane * S + pst) * pair_stage;
         uint32_t bytes = 0;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) if (p < g.n_planes) bytes += (uint32_t)(g8 * g.b8[p]);
+        for (int p = 0; p < 4; ++p) if (p < g.n_planes) bytes += (uint32_t)((gi * g.b8[p]) >> 3);
         rb_expect(fb, two ? 2 * bytes : bytes);
 #pragma unroll
         for (int p = 0; p < 4; ++p) if (p < g.n_planes) {
-            const uint8_t * src = P.p[p] + ((int64_t)row * n8 + (int64_t)psg * (SEGI / 8)) * g.b8[p];
-            if (!PAIR || g.merged) bulk_g2s(dstb + g.seg_off[p], src, (uint32_t)((two ? 2 : 1) * g8 * g.b8[p]), fb);
+            const int64_t rowb = ((int64_t)n32 * g.b8[p]) >> 3;
+            const uint32_t sb = (uint32_t)((gi * g.b8[p]) >> 3);
+            const uint8_t * src = P.p[p] + (int64_t)row * rowb + (int64_t)psg * (SEGI / 8) * g.b8[p];
+            if (!PAIR || g.merged) bulk_g2s(dstb + g.seg_off[p], src, (two ? 2 : 1) * sb, fb);
             else {
-                bulk_g2s(dstb + g.seg_off[p], src, (uint32_t)(g8 * g.b8[p]), fb);
-                if (two) bulk_g2s(dstb + g.row1[p] + g.seg_off[p], src + (int64_t)n8 * g.b8[p], (uint32_t)(g8 * g.b8[p]), fb);
+                bulk_g2s(dstb + g.seg_off[p], src, sb, fb);
+                if (two) bulk_g2s(dstb + g.row1[p] + g.seg_off[p], src + rowb, sb, fb);
             }
         }
         ++pu; if (++pst == S) pst = 0;
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
             // (1) this CTA sums its slice of the vector over the ranks (waiting for the peers' rows to arrive) and publishes it for its siblings,
             // (2) every CTA quantises the whole vector from the published sums (falling back to the slots for entries that are not there yet)
             const int e0 = (int)(((int64_t)K * blockIdx.x) / gridDim.x), e1 = (int)(((int64_t)K * (blockIdx.x + 1)) / gridDim.x);
-            for (int e = e0 + ctid; e < e1; e += cthreads) {
+            if (a.tp.world > 2) for (int e = e0 + ctid; e < e1; e += cthreads) {
                 const float sum = ll_sum_slots(src.slots, src.stride, src.world, e, src.id);
                 asm volatile("st.volatile.global.v2.f32 [%0], {%1,%2};" ::"l"(a.tp.ll_red + par * a.tp.ll_stride + e), "f"(sum), "f"(__uint_as_float(src.id)) : "memory");
             }
@@ -706,15 +708,17 @@ static int launch_mmvq_t(const mmvq_args & a, int sm_count, bool pdl, cudaStream
 // long_rows: K > 4096: a stage holds up to 2 x B200Q_SEG_ITEMS items of ONE row (plane-major), else a pair of single-segment rows
 static bool make_ring_geom(int type, int64_t K, ring_geom & g, bool long_rows) {
     b200q_layout L; if (b200q_make_layout(type, 1, K, &L)) return false;
-    if (K % 256) return false;
-    const int64_t n8 = K / 256;
+    if (K % 32) return false;
+    // K % 256 != 0 (32- / 64-weight block types only: bitnet's IQ2_BN rows of 3200 / 8640): fine as long as every plane row is a whole number of
+    // bytes and stays 16-byte aligned (checked per plane below)
+    const int64_t n32 = K / 32;
     memset(&g, 0, sizeof g); g.row_plane = -1;
     int off = 0, np = 0;
     for (int p = 0; p < L.n_planes; ++p) {
         if (L.plane_per_row[p]) { g.row_plane = p; continue; }
         if (p != np) return false;                       // block planes must come first (they do for every type)
         const int b8 = L.plane_bytes[p] * 256 / L.qk;
-        if (b8 <= 0 || (n8 * b8) % 16) return false;     // every row/segment start must be 16-byte aligned
+        if (b8 <= 0 || (n32 * b8) % 128) return false;   // every row/segment start must be 16-byte aligned: row bytes = n32 * b8 / 8
         g.b8[np] = b8; g.seg_off[np] = off; off += (int)b200q_align_up((B200Q_SEG_ITEMS / 8) * b8, 16); ++np;
     }
     g.n_planes = np; g.stage_bytes = (int)b200q_align_up(off, 128);
@@ -727,7 +731,7 @@ static bool make_ring_geom(int type, int64_t K, ring_geom & g, bool long_rows) {
         g.merged = 1;
     } else if (merge && K / 32 <= B200Q_SEG_ITEMS && np > 0 && np <= 4) {
         int o = 0;
-        for (int p = 0; p < np; ++p) { const int rb = (int)(n8 * g.b8[p]); g.seg_off[p] = o; g.row1[p] = rb; o += (int)b200q_align_up(2 * rb, 16); }
+        for (int p = 0; p < np; ++p) { const int rb = (int)((n32 * g.b8[p]) >> 3); g.seg_off[p] = o; g.row1[p] = rb; o += (int)b200q_align_up(2 * rb, 16); }
         if (o <= 2 * g.stage_bytes) g.merged = 1;
         else { int o2 = 0; for (int p = 0; p < np; ++p) { g.seg_off[p] = o2; o2 += (int)b200q_align_up((B200Q_SEG_ITEMS / 8) * g.b8[p], 16); g.row1[p] = g.stage_bytes; } }
     }
@@ -768,6 +772,7 @@ static inline void make_next_prefetch(const b200q_mmvq_desc & nx, int sm_count, 
     const bool long_rows = nx.K / 32 > B200Q_SEG_ITEMS;
     ring_geom g;
     if (!nx.ring || !make_ring_geom(nx.type, nx.K, g, long_rows)) return;
+    if (nx.K % 256) return;
     const int64_t n8 = nx.K / 256;
     const int64_t n_units = long_rows ? M_total : (M_total + 1) / 2;
     int ncw, S; if (!ring_shape(nx.ncols, nx.K, 2 * (size_t)g.stage_bytes, n_units, sm_count, ncw, S)) return;

@@ -21,7 +21,7 @@ for name, lib, env in configs:
         continue
     e = dict(os.environ); e.update(env)
     if lib: e["B200Q_LIB_PATH"] = lib
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-pp", "--no-cpu", "--steps", "20", "--warmup", "3"], env=e, capture_output=True, text=True)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-pp", "--no-cpu", "--no-mix", "--steps", "20", "--warmup", "3"], env=e, capture_output=True, text=True)
     try:
         line = json.loads(r.stdout.strip().splitlines()[-1])
         print(f"{name:28s} tg {line['value']:8.1f} tok/s  frac {line['roofline']['frac']:.3f}  e2e {line['e2e']['value']:8.1f}", flush=True)

@@ -11,8 +11,8 @@ import bench
 
 
 class _T:
-    def __init__(self, m, k):
-        self.m, self.k, self.nbytes_wire = m, k, m * k * 18 // 32
+    def __init__(self, m, k, ggml_type=20):
+        self.m, self.k, self.nbytes_wire, self.ggml_type = m, k, m * k * 18 // 32, ggml_type
 
 
 class _BE:
@@ -43,7 +43,7 @@ class _BE:
 
 
 def test_model_skeleton_walks_tg_and_pp(monkeypatch):
-    monkeypatch.setattr(bench, "random_planes_iq4nl", lambda be, torch_, m, k, gen, scale: _T(m, k))
+    monkeypatch.setattr(bench, "random_planes", lambda be, torch_, name, m, k, gen, scale: _T(m, k))
     gen = types.SimpleNamespace(manual_seed=lambda s: None)
     tt = types.SimpleNamespace(Generator=lambda device=None: gen, empty=lambda s, dtype=None, device=None: torch.empty(s, dtype=dtype),
                                float32=torch.float32, bfloat16=torch.bfloat16)
@@ -56,3 +56,11 @@ def test_model_skeleton_walks_tg_and_pp(monkeypatch):
     m.alloc(512); m.step_pp()
     assert be.calls.count("cvt") == 6 and be.calls.count("mul_mat") == 5
     assert bench.model_bytes_per_token(32) == 4221370368
+    # the default quantisation mix: attn_v has its own type, so it gets its own launch
+    monkeypatch.setattr(bench, "random_planes", lambda be, torch_, name, m, k, gen, scale: _T(m, k, bench.MIX_TYPES[name][0]))
+    be.calls.clear()
+    mm = bench.Model(be, tt, 2, mix="default")
+    mm.alloc(1); mm.step_tg()
+    assert be.calls.count("multi") == 2 and be.calls.count("mul_mat") == 7 and mm.launches_tg == 11
+    assert mm.head.ggml_type == 14 and mm.layers[0]["down"].ggml_type == 13 and mm.layers[1]["wv"].ggml_type == 140
+    mm.alloc(512); mm.step_pp()
