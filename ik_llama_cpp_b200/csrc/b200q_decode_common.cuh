@@ -62,33 +62,29 @@ __device__ __forceinline__ void quantize_x_to_smem(const float * __restrict__ x,
             int col = 0, ch = c < total ? c : 0;
             if (NCOLS > 1) { col = ch / nch; ch -= col * nch; }
             if (c < total && LL) {
+                // All loads of a batch are issued together and the WHOLE batch is re-requested until every tag matches: one L2 round trip after the
+                // data has arrived, however long the wait was (a per-entry wait would serialise eight round trips behind it).
                 float t[8];
-                if (ll->world == 2) {
-                    // two ranks: summing the two slots directly costs the same loads as reading a published sum and saves the publish -> poll hop
+                const float4 * p0 = reinterpret_cast<const float4 *>((ll->world == 2 ? ll->slots : ll->red) + (int64_t)ch * 8);
+                const float4 * p1 = reinterpret_cast<const float4 *>(ll->slots + ll->stride + (int64_t)ch * 8);
+                bool ok = false;
+                for (int spin = 0; spin < 64 && !ok; ++spin) {          // bounded: progress must not depend on a sibling CTA that is not resident
                     float4 w0[4], w1[4];
+                    ok = true;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { w0[j] = __ldcv(p0 + j); if (ll->world == 2) w1[j] = __ldcv(p1 + j); }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        w0[j] = __ldcv(reinterpret_cast<const float4 *>(ll->slots + (int64_t)ch * 8) + j);
-                        w1[j] = __ldcv(reinterpret_cast<const float4 *>(ll->slots + ll->stride + (int64_t)ch * 8) + j);
+                        ok = ok && __float_as_uint(w0[j].y) == ll->id && __float_as_uint(w0[j].w) == ll->id;
+                        if (ll->world == 2) {                           // two ranks: sum the two slots directly (no publish -> poll hop)
+                            ok = ok && __float_as_uint(w1[j].y) == ll->id && __float_as_uint(w1[j].w) == ll->id;
+                            t[2 * j] = w0[j].x + w1[j].x; t[2 * j + 1] = w0[j].z + w1[j].z;
+                        } else { t[2 * j] = w0[j].x; t[2 * j + 1] = w0[j].z; }
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const bool a_ok = __float_as_uint(w0[j].y) == ll->id && __float_as_uint(w1[j].y) == ll->id;
-                        const bool b_ok = __float_as_uint(w0[j].w) == ll->id && __float_as_uint(w1[j].w) == ll->id;
-                        t[2 * j]     = a_ok ? w0[j].x + w1[j].x : ll_sum_slots(ll->slots, ll->stride, 2, ch * 8 + 2 * j, ll->id);
-                        t[2 * j + 1] = b_ok ? w0[j].z + w1[j].z : ll_sum_slots(ll->slots, ll->stride, 2, ch * 8 + 2 * j + 1, ll->id);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {               // 8 entries = 64 bytes
-                        const float4 * pw = reinterpret_cast<const float4 *>(ll->red + (int64_t)ch * 8) + j;
-                        float4 w = __ldcv(pw);
-                        // the sibling CTA that owns this slice publishes it within a microsecond or two of the peers' rows arriving: poll a few times
-                        // before paying world x the loads (bounded, so progress never depends on a CTA that is not resident)
-                        for (int spin = 0; spin < 8 && (__float_as_uint(w.y) != ll->id || __float_as_uint(w.w) != ll->id); ++spin) w = __ldcv(pw);
-                        t[2 * j]     = __float_as_uint(w.y) == ll->id ? w.x : ll_sum_slots(ll->slots, ll->stride, ll->world, ch * 8 + 2 * j, ll->id);
-                        t[2 * j + 1] = __float_as_uint(w.w) == ll->id ? w.z : ll_sum_slots(ll->slots, ll->stride, ll->world, ch * 8 + 2 * j + 1, ll->id);
-                    }
+                }
+                if (!ok) {
+#pragma unroll 1
+                    for (int j = 0; j < 8; ++j) t[j] = ll_sum_slots(ll->slots, ll->stride, ll->world, ch * 8 + j, ll->id);
                 }
                 va[u] = make_float4(t[0], t[1], t[2], t[3]); vb[u] = make_float4(t[4], t[5], t[6], t[7]);
             } else if (c < total) {

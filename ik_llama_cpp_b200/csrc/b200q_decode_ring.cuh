@@ -495,6 +495,9 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
             if (a.tp.world > 2) for (int e = e0 + ctid; e < e1; e += cthreads) {
                 const float sum = ll_sum_slots(src.slots, src.stride, src.world, e, src.id);
                 asm volatile("st.volatile.global.v2.f32 [%0], {%1,%2};" ::"l"(a.tp.ll_red + par * a.tp.ll_stride + e), "f"(sum), "f"(__uint_as_float(src.id)) : "memory");
+#if B200Q_TRACE_FINE
+                if (a.trace && blockIdx.x == 0 && e == e0) a.trace[4] = gtime();      // every rank's entry for this CTA's first element has arrived
+#endif
             }
             quantize_x_to_smem<NCOLS, true>(nullptr, 0, K, sq, sd, sis, ctid, cthreads, nullptr, &src);
         } else if (Q8 == 1) {

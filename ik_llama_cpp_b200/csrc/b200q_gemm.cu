@@ -226,14 +226,23 @@ k_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 constexpr int RAW_K = 256;                       // weights per row per raw stage (= 8 items, 4 MMA k-blocks)
 constexpr int DQ_WARPS = 8;                      // dequant / epilogue warps (warps 2..9)
 
+// bytes per 256 weights of the planes after the 128-byte low-bit plane (every one a multiple of 16: the inner box of a TMA map)
+template <int TYPE> struct gemmq_planes { static constexpr int P1 = 16, P2 = 0; };                    // IQ4_NL / Q4_0 (8 halfs), Q4_K, IQ4_K
+template <> struct gemmq_planes<B200Q_TYPE_Q4_1>  { static constexpr int P1 = 32, P2 = 0; };          // {d,m} per item
+template <> struct gemmq_planes<B200Q_TYPE_Q5_0>  { static constexpr int P1 = 32, P2 = 16; };         // qh | d
+template <> struct gemmq_planes<B200Q_TYPE_Q5_1>  { static constexpr int P1 = 32, P2 = 32; };         // qh | {d,m}
+template <> struct gemmq_planes<B200Q_TYPE_Q5_K>  { static constexpr int P1 = 32, P2 = 16; };         // qh | {d,dmin,scales}
+template <> struct gemmq_planes<B200Q_TYPE_IQ5_K> { static constexpr int P1 = 32, P2 = 16; };         // qh | {d,extra,scales}
 // NB = number of 256-column accumulators (BN = 256*NB), or BN = 128 when NB == 0
-template <int NB> struct gemmq_cfg {
+template <int TYPE, int NB> struct gemmq_cfg {
     static constexpr int BN = NB == 0 ? 128 : 256 * NB;
     static constexpr int A_STAGES = 3, B_STAGES = NB == 2 ? 2 : 3, RAW_STAGES = 2;
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
-    static constexpr int RAW_P0 = BM * 128, RAW_P1 = BM * 16, RAW_BYTES = RAW_P0 + RAW_P1;     // low-bit plane | meta plane
+    static constexpr int P1 = gemmq_planes<TYPE>::P1, P2 = gemmq_planes<TYPE>::P2;
+    static constexpr int RAW_P0 = BM * 128, RAW_P1 = BM * P1, RAW_P2 = BM * P2, RAW_BYTES = RAW_P0 + RAW_P1 + RAW_P2;     // low-bit plane | high bits / meta | meta
     static constexpr int TMEM_COLS = BN;
     static constexpr size_t SMEM = 1024 + (size_t)A_STAGES * A_BYTES + (size_t)B_STAGES * B_BYTES + (size_t)RAW_STAGES * RAW_BYTES + 256;
+    static_assert(SMEM <= 227 * 1024, "k_gemm_q: shared memory");
 };
 
 // Up to GEMMQ_MAX_SEGS weight tensors that share the activation tile (Q,K,V: the reference's look-ahead fusion,
@@ -244,7 +253,7 @@ template <int NB> struct gemmq_cfg {
 constexpr int GEMMQ_MAX_SEGS = 3;
 struct gemmq_seg { float * dst; const float * mul; __nv_bfloat16 * dst_bf; int M; int tile0; };
 struct gemmq_args {
-    CUtensorMap tmP0[GEMMQ_MAX_SEGS], tmP1[GEMMQ_MAX_SEGS], tmB;
+    CUtensorMap tmP0[GEMMQ_MAX_SEGS], tmP1[GEMMQ_MAX_SEGS], tmP2[GEMMQ_MAX_SEGS], tmB;
     gemmq_seg seg[GEMMQ_MAX_SEGS];
     int n_seg, N, K, k_split, act; float limit;
 };
@@ -274,11 +283,11 @@ template <int J> __device__ __forceinline__ float biased_byte_to_float(uint32_t 
 template <int TYPE, int NB>
 __global__ void __launch_bounds__(64 + 32 * DQ_WARPS, 1)
 k_gemm_q(const __grid_constant__ gemmq_args a) {
-    using cfg = gemmq_cfg<NB>;
+    using cfg = gemmq_cfg<TYPE, NB>;
     int sg = 0;
 #pragma unroll
     for (int s = 1; s < GEMMQ_MAX_SEGS; ++s) if (s < a.n_seg && (int)blockIdx.x >= a.seg[s].tile0) sg = s;
-    const CUtensorMap * tmP0 = &a.tmP0[sg], * tmP1 = &a.tmP1[sg], * tmB = &a.tmB;
+    const CUtensorMap * tmP0 = &a.tmP0[sg], * tmP1 = &a.tmP1[sg], * tmP2 = &a.tmP2[sg], * tmB = &a.tmB;
     float * __restrict__ dst = a.seg[sg].dst; const float * __restrict__ mul = a.seg[sg].mul; __nv_bfloat16 * __restrict__ dst_bf = a.seg[sg].dst_bf;
     const int M = a.seg[sg].M, N = a.N, K = a.K, k_split = a.k_split;
     constexpr int BN = cfg::BN;
@@ -311,7 +320,7 @@ k_gemm_q(const __grid_constant__ gemmq_args a) {
         for (int s = 0; s < cfg::RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], DQ_WARPS); }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
-        tma_prefetch_desc(tmP0); tma_prefetch_desc(tmP1); tma_prefetch_desc(tmB);
+        tma_prefetch_desc(tmP0); tma_prefetch_desc(tmP1); if (cfg::P2) tma_prefetch_desc(tmP2); tma_prefetch_desc(tmB);
     }
     if (warp == 1) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
     tc_fence_before();
@@ -328,7 +337,8 @@ k_gemm_q(const __grid_constant__ gemmq_args a) {
                 unsigned char * raw = sR + (size_t)rs * cfg::RAW_BYTES;
                 mbar_expect_tx(&raw_full[rs], cfg::RAW_BYTES);
                 tma_load_2d(raw, tmP0, &raw_full[rs], (rb0 + r) * 128, m0);                // bytes along the row
-                tma_load_2d(raw + cfg::RAW_P0, tmP1, &raw_full[rs], (rb0 + r) * 16, m0);
+                tma_load_2d(raw + cfg::RAW_P0, tmP1, &raw_full[rs], (rb0 + r) * cfg::P1, m0);
+                if (cfg::P2) tma_load_2d(raw + cfg::RAW_P0 + cfg::RAW_P1, tmP2, &raw_full[rs], (rb0 + r) * cfg::P2, m0);
                 for (int q = 0; q < RAW_K / BK && ib < nk; ++q, ++ib) {
                     const int s = ib % cfg::B_STAGES; const uint32_t ph = (ib / cfg::B_STAGES) & 1;
                     mbar_wait(&b_empty[s], ph ^ 1);
@@ -373,7 +383,7 @@ k_gemm_q(const __grid_constant__ gemmq_args a) {
             const int rs = r % cfg::RAW_STAGES; const uint32_t rph = (r / cfg::RAW_STAGES) & 1;
             mbar_wait(&raw_full[rs], rph);
             const unsigned char * raw = sR + (size_t)rs * cfg::RAW_BYTES;
-            b200q_planes SP; SP.p[0] = raw; SP.p[1] = raw + cfg::RAW_P0; SP.p[2] = SP.p[3] = SP.p[4] = nullptr; SP.n32 = 8; SP.nb = 1;
+            b200q_planes SP; SP.p[0] = raw; SP.p[1] = raw + cfg::RAW_P0; SP.p[2] = raw + cfg::RAW_P0 + cfg::RAW_P1; SP.p[3] = SP.p[4] = nullptr; SP.n32 = 8; SP.nb = 1;
             for (int q = 0; q < RAW_K / BK && ia < nk; ++q, ++ia) {
                 const int sa = ia % cfg::A_STAGES; const uint32_t pa = (ia / cfg::A_STAGES) & 1;
                 // decode before waiting for the A slot: the raw data is already there
@@ -789,21 +799,25 @@ int make_tmap_u8(CUtensorMap * tm, const void * ptr, int64_t rows, int64_t row_b
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 
-// types whose planes are {16 B / item low bits, 16 B / 256 weights of scales+meta}: IQ4_NL/Q4_0 (8 halfs), Q4_K, IQ4_K
+// types whose plane 0 is 16 B / item of low bits and whose other planes are 16 or 32 B per 256 weights (gemmq_planes): the weight slab is decoded
+// inside the GEMM.  (Q6_K / Q6_0 / Q8_0 would not fit the shared memory next to a 512-token B tile, Q3_K / IQ2_K / *_KS have planes that are not a
+// multiple of 16 bytes per 256 weights: those keep the bf16 scratch.)
 constexpr bool gemmq_supported(int type) {
-    return type == B200Q_TYPE_IQ4_NL || type == B200Q_TYPE_Q4_0 || type == B200Q_TYPE_Q4_K || type == B200Q_TYPE_IQ4_K;
+    return type == B200Q_TYPE_IQ4_NL || type == B200Q_TYPE_Q4_0 || type == B200Q_TYPE_Q4_K || type == B200Q_TYPE_IQ4_K ||
+           type == B200Q_TYPE_Q4_1 || type == B200Q_TYPE_Q5_0 || type == B200Q_TYPE_Q5_1 || type == B200Q_TYPE_Q5_K || type == B200Q_TYPE_IQ5_K;
 }
 
 template <int TYPE, int NB>
 int launch_gemm_q(const b200q_gemm_multi & d, int k_split, cudaStream_t st) {
-    using cfg = gemmq_cfg<NB>;
+    using cfg = gemmq_cfg<TYPE, NB>;
     gemmq_args a; memset(&a, 0, sizeof a);
-    const int64_t p1_row = (d.K / 256) * 16;
+    const int64_t p1_row = (d.K / 256) * cfg::P1, p2_row = (d.K / 256) * cfg::P2;
     int tiles = 0;
     for (int i = 0; i < d.n_seg; ++i) {
         b200q_layout L; if (b200q_make_layout(TYPE, d.M[i], d.K, &L)) return -1;
         if (make_tmap_u8(&a.tmP0[i], (const char *)d.W[i] + L.plane_off[0], d.M[i], d.K / 2, 128, BM, true)) return -10;
-        if (make_tmap_u8(&a.tmP1[i], (const char *)d.W[i] + L.plane_off[1], d.M[i], p1_row, 16, BM, false)) return -13;
+        if (make_tmap_u8(&a.tmP1[i], (const char *)d.W[i] + L.plane_off[1], d.M[i], p1_row, cfg::P1, BM, false)) return -13;
+        if (cfg::P2 && make_tmap_u8(&a.tmP2[i], (const char *)d.W[i] + L.plane_off[2], d.M[i], p2_row, cfg::P2, BM, false)) return -13;
         a.seg[i].dst = d.dst[i]; a.seg[i].mul = d.mul[i]; a.seg[i].dst_bf = (__nv_bfloat16 *)d.dst_bf[i]; a.seg[i].M = (int)d.M[i]; a.seg[i].tile0 = tiles;
         tiles += (int)((d.M[i] + BM - 1) / BM);
     }
@@ -954,6 +968,7 @@ int b200q_launch_gemm_multi_bf16x(const b200q_gemm_multi & d, void * wscratch, s
         switch (type) {
 #define GQ(T) case T: return nb == 2 ? launch_gemm_q<T, 2>(d, k_split, st) : nb == 1 ? launch_gemm_q<T, 1>(d, k_split, st) : launch_gemm_q<T, 0>(d, k_split, st);
             GQ(B200Q_TYPE_IQ4_NL) GQ(B200Q_TYPE_Q4_0) GQ(B200Q_TYPE_Q4_K) GQ(B200Q_TYPE_IQ4_K)
+            GQ(B200Q_TYPE_Q4_1) GQ(B200Q_TYPE_Q5_0) GQ(B200Q_TYPE_Q5_1) GQ(B200Q_TYPE_Q5_K) GQ(B200Q_TYPE_IQ5_K)
 #undef GQ
             default: break;
         }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""DRAM traffic per bench step from the ncu --set full captures of a 2-layer run (scripts/gpu_profile_r1.sh), scaled to the 32-layer
-model: profiles/r1_traffic.json, read by bench.py for roofline.traffic.  usage: make_traffic.py <mmvq.ncu-rep> <gemm.ncu-rep> <out.json>"""
+"""DRAM traffic per bench step from the ncu --set full captures of a 2-layer run (scripts/gpu_profile_r2.sh), scaled to the 32-layer
+model: profiles/r2_traffic.json, read by bench.py for roofline.traffic.  usage: make_traffic.py <mmvq.ncu-rep> <gemm.ncu-rep> <out.json>"""
 import csv
 import json
 import subprocess
@@ -26,7 +26,7 @@ def rows(path):
 def main():
     mm, gg, out = sys.argv[1:4]
     n_layer = 32
-    res = {"source": "ncu --set full --clock-control none, bench.py --layers 2 (scripts/gpu_profile_r1.sh), scaled to 32 layers"}
+    res = {"source": "ncu --set full --clock-control none, bench.py --layers 2 (scripts/gpu_profile_r2.sh), scaled to 32 layers"}
     r = rows(mm)
     if len(r) >= 9:
         step = r[-9:]                                   # one whole tg step of the 2-layer model: 8 layer launches + head
