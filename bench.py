@@ -258,6 +258,45 @@ class Model:
             be.mul_mat(self.head, x[-1:], out=self.logits)
 
 
+def bitnet_line(be, torch, steps, warmup, hbm_peak):
+    """BASELINE.json configs[3] / SURVEY App. A config 4: bitnet-b1.58-3B (n_embd 3200, n_ff 8640, 26 layers), IQ2_BN (2.0 bpw + f32 row scale), the
+    per-layer MUL_MAT nodes only (the output matrix of that model is not IQ2_BN).  K = 3200 / 8640 are not multiples of 256: decode takes the TMA ring
+    through the byte-granular geometry, prefill the int8 tensor-core path (ternary x int8 activations, tcgen05 kind::i8)."""
+    E, FF, NL, T = 3200, 8640, 26, 135
+    gen = torch.Generator(device="cuda"); gen.manual_seed(4321)
+    def mk(m, k):
+        rows = torch.randint(0, 256, (m, 4 + (k // 64) * 16), dtype=torch.uint8, device="cuda", generator=gen)
+        rs = (torch.rand(m, device="cuda", generator=gen) * 0.6 + 0.7) / k ** 0.5 * (torch.randint(0, 2, (m,), device="cuda", generator=gen).float() * 2 - 1)
+        rows[:, 0:4] = rs.view(torch.uint8).view(m, 4)
+        return be.set_tensor(T, rows.view(-1), m, k)
+    layers = [dict(wq=mk(E, E), wk=mk(E, E), wv=mk(E, E), wo=mk(E, E), up=mk(FF, E), gate=mk(FF, E), down=mk(E, FF)) for _ in range(NL)]
+    wbytes = sum(t.nbytes_wire for L in layers for t in L.values())
+    f = lambda *sh: torch.empty(sh, dtype=torch.float32, device="cuda")
+    out = {"workload": "bitnet-b1.58-3B IQ2_BN (BASELINE.json configs[3]): the 26 layers' MUL_MAT / FUSED_UP_GATE nodes in graph order, no output matrix",
+           "algorithmic_bytes_per_step": wbytes}
+    for n in (1, 512):
+        x, q, k_, v, h, a, x2 = f(n, E), f(n, E), f(n, E), f(n, E), f(n, E), f(n, FF), f(n, E)
+        x.normal_()
+        def step():
+            cur = x
+            for L in layers:
+                be.mul_mat_multi([L["wq"], L["wk"], L["wv"]], cur, [q, k_, v])
+                be.mul_mat(L["wo"], q, out=h)
+                be.fused_up_gate(L["up"], L["gate"], h, "silu", out=a)
+                be.mul_mat(L["down"], a, out=x2)
+                cur = x2
+        ms = time_graph(torch, step, steps if n == 1 else max(3, min(steps, 10)), warmup)
+        if n == 1:
+            ach = wbytes / (ms * 1e-3) / 1e9
+            out["tg"] = {"value": 1000.0 / ms, "unit": "tok/s", "ms_per_step": ms, "launches_per_step": 4 * NL,
+                         "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}}
+        else:
+            ops = 2.0 * sum(t.m * t.k for L in layers for t in L.values()) * n
+            out["pp512"] = {"value": n * 1000.0 / ms, "unit": "tok/s", "ms_per_step": ms, "dtype": "u8 (ternary) x s8 activations -> s32 (tcgen05 kind::i8), f32 rescale",
+                            "achieved_int8_TOP/s": ops / (ms * 1e-3) / 1e12}
+    return out
+
+
 def tp_correctness_gate(be, torch, dist, model, rank, world, n, n_check_layers=2, tol=5e-4):
     """N > 1 only, before anything is timed: the reduced hidden state of a 2-layer slice of THIS model, computed by the tensor-parallel
     path (all ranks, the collectives under test), must match what rank 0 gets by rebuilding every rank's shard locally (same seeds),
@@ -531,6 +570,11 @@ def main():
                             "roofline": {"bound": "tensor", "achieved": tfm, "peak": tf_peak, "unit": "TFLOP/s", "frac": tfm / tf_peak}}
         line["default_mix"] = mix
         del mm
+        torch.cuda.empty_cache()
+        try:
+            line["bitnet"] = bitnet_line(be, torch, args.steps, args.warmup, hbm_peak)
+        except Exception as e:      # a side line must never cost the headline
+            line["bitnet"] = {"error": repr(e)}
     # ---------------- cpu baseline (rank 0, N=1 only) ----------------
     if rank == 0 and world == 1 and not args.no_cpu:
         try:

@@ -40,6 +40,7 @@ struct mmvq_args {
     int64_t      x_stride;
     int          act;           // B200Q_ACT_* for the up/gate mode
     float        limit;         // clamp for swiglu variants (0 = none)
+    int tp_rowbuf_off, tp_rowbuf_rows;   // reduce_out: byte offset (in dynamic smem) / capacity of the CTA's row buffer (0 rows: send every row pair on its own)
     unsigned long long * trace_cta;   // tuning builds (B200Q_TRACE_FINE): per-CTA timeline, 4 words per CTA
     b200q_tp_comm tp;           // tensor-parallel decode: GGML_OP_REDUCE fused into the mat-vec (tp.in / tp.out), see k_mmvq_ring
     unsigned long long * trace; // optional phase timestamps (b200q_debug_trace): [slot][8] = entry, after griddepcontrol.wait, prologue done, last consumer done,
@@ -623,10 +624,18 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
                         v0 = b200q_glu<false>(a.act, v0, u0, a.limit); if (PAIR) v1 = b200q_glu<false>(a.act, v1, u1, a.limit);
                     } else if (sgm.bias) { v0 += sgm.bias[crow]; if (two) v1 += sgm.bias[crow + 1]; }
                     if (lane == 0) {
-                        if (TP && a.tp.out) {                                     // partial rows: broadcast to slot [parity][this rank] of every rank
-                            float2 * mc = a.tp.ll_mc + ((int64_t)(tps & 1) * a.tp.world + a.tp.rank) * a.tp.ll_stride + (int64_t)sgm.row0 + crow;
-                            if (two && !(((int64_t)sgm.row0 + crow) & 1)) tp_bcast2(mc, v0, v1, tps + 1);
-                            else { tp_bcast1(mc, v0, tps + 1); if (two) tp_bcast1(mc + 1, v1, tps + 1); }
+                        if (TP && a.tp.out) {
+                            // partial rows of a row-parallel mat-vec.  Optional (B200Q_TP_ROWBUF=1): collect the rows of this CTA (a contiguous range) in
+                            // shared memory and send them as contiguous 16-byte lanes of one warp at the end (fewer, larger packets)
+                            const int rel = (int)sgm.row0 + crow - RPU * c0;
+                            if (a.tp_rowbuf_rows > 0 && rel >= 0 && rel + 1 < a.tp_rowbuf_rows) {
+                                float * rb = reinterpret_cast<float *>(smem_raw + a.tp_rowbuf_off);
+                                rb[rel] = v0; if (two) rb[rel + 1] = v1;
+                            } else {
+                                float2 * mc = a.tp.ll_mc + ((int64_t)(tps & 1) * a.tp.world + a.tp.rank) * a.tp.ll_stride + (int64_t)sgm.row0 + crow;
+                                if (two && !(((int64_t)sgm.row0 + crow) & 1)) tp_bcast2(mc, v0, v1, tps + 1);
+                                else { tp_bcast1(mc, v0, tps + 1); if (two) tp_bcast1(mc + 1, v1, tps + 1); }
+                            }
                         } else { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
                     }
                 }
@@ -657,6 +666,18 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
                 if (mine) { __threadfence(); if (lane == 0) cnt0[blk] = 0; }
             }
             if (mine) q8_emit_block(a.q8_out, sgm.M, sgm.dst, sgm.M, blk, lane);
+        }
+    }
+    if (TP && a.tp.out && a.tp_rowbuf_rows > 0) {
+        asm volatile("bar.sync 1, %0;" ::"r"(cthreads) : "memory");           // every consumer warp of the CTA has deposited its rows
+        const int r0 = RPU * c0, r1 = min(RPU * c1, (int)a.M_total), n = min(r1 - r0, a.tp_rowbuf_rows - 1);
+        const float * rb = reinterpret_cast<const float *>(smem_raw + a.tp_rowbuf_off);
+        float2 * mc = a.tp.ll_mc + ((int64_t)(tps & 1) * a.tp.world + a.tp.rank) * a.tp.ll_stride + r0;
+        if (cw == 0) {
+            if (!(r0 & 1)) {                                                   // 16-byte lanes: {v, tag, v', tag}
+                for (int i = 2 * lane; i + 1 < n; i += 64) tp_bcast2(mc + i, rb[i], rb[i + 1], tps + 1);
+                if ((n & 1) && lane == 0) tp_bcast1(mc + n - 1, rb[n - 1], tps + 1);
+            } else for (int i = lane; i < n; i += 32) tp_bcast1(mc + i, rb[i], tps + 1);
         }
     }
     if (TP && a.tp.out) {
@@ -812,7 +833,7 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     int ncw, S;
     if (!ring_shape(NCOLS, a.K, pair_stage, n_pairs, sm_count, ncw, S)) return -100;     // does not fit: caller falls back to the LDG kernel
     ra.g.n_stages = S;
-    const size_t smem = (size_t)ncw * S * (pair_stage + 16) + xbytes + 64;
+    size_t smem = (size_t)ncw * S * (pair_stage + 16) + xbytes + 64;
     static bool configured[B200Q_MAX_DEVICES] = {};
     const int dev = b200q_current_device();
     if (!configured[dev]) {
@@ -824,6 +845,17 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
     int64_t grid = grid_full ? n_pairs : (n_pairs + ncw - 1) / ncw;
     if (grid > (int64_t)sm_count * ctas_per_sm) grid = (int64_t)sm_count * ctas_per_sm;
     if (grid < 1) grid = 1;
+    if (TP && a.tp.out && !MULTI) {
+        // row buffer of a reduce_out launch: the rows of one CTA (a contiguous range, +-1 unit) are sent in one coalesced burst at the end
+        const int64_t rows = (PAIR ? 2 : 1) * ((n_pairs + grid - 1) / grid + 1) + 2;
+        // (measured at 2 GPUs: 559 tok/s with the row buffer vs 575 without on the same box: no gain, the extra CTA barrier costs more than the
+        // coalescing saves -> off by default, B200Q_TP_ROWBUF=1 enables it)
+        static const int on = [] { const char * e = getenv("B200Q_TP_ROWBUF"); return e ? atoi(e) : 0; }();
+        if (on && rows <= 2048 && smem + rows * 4 + 16 <= budget) {
+            ra.a.tp_rowbuf_off = (int)((smem + 15) & ~(size_t)15); ra.a.tp_rowbuf_rows = (int)rows;
+            smem = (size_t)ra.a.tp_rowbuf_off + rows * 4;
+        }
+    }
     cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((ncw + 1) * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];

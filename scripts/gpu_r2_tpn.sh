@@ -19,3 +19,4 @@ run $NG n$NG X=1
 if [ "$NG" -gt 2 ]; then run 2 n2 X=1; fi
 if [ "$NG" -gt 4 ]; then run 4 n4 X=1; fi
 env LAYERS=6 B200Q_LIB_PATH=$PWD/experiments/_variants/libb200q_trace.so timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29513 scripts/trace_decode.py > gpurun_out/r2_tp${NG}_trace.txt 2>&1; tail -7 gpurun_out/r2_tp${NG}_trace.txt
+if [ "$NG" = "2" ]; then run 2 n2_norowbuf B200Q_TP_ROWBUF=0; fi
