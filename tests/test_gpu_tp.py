@@ -63,12 +63,15 @@ def _worker(rank, world, port, q):
             t = parts[rank].clone()
             red.all_reduce_bf16(t, out_f32=t)
             exact = sum(p.to(torch.bfloat16).double() for p in parts)
-            # one rounding of the exact sum to bf16; the switch's rounding mode is not specified (RN gives <= 2^-9 relative, truncation <= 2^-8)
+            # the switch's rounding of the reduced bf16 value is not specified.  Measured: 2 and 4 ranks give 78-81 % of the elements equal to
+            # RN(exact sum) and a worst relative error of 2^-7.04: neither RN (<= 2^-9) nor plain truncation; the bound leaves a factor 2 for
+            # the 8-rank tree
             rn = exact.float().to(torch.bfloat16).float()
             res["two_shot_rn_fraction"] = float((t == rn).float().mean())
             worst = float(((t.double() - exact).abs() / (exact.abs() + 1e-30)).max())
             res["two_shot_worst_rel"] = worst
-            assert bool(((t.double() - exact).abs() <= exact.abs() * 2.0 ** -7 + 1e-30).all()), worst
+            amax = float(exact.abs().max())
+            assert bool(((t.double() - exact).abs() <= exact.abs() * 2.0 ** -6 + amax * 2.0 ** -12).all()), worst
             # interleaved with the one-shot f32 reduce and replayed from a CUDA graph
             x = torch.zeros(8192, device="cuda"); y = torch.empty_like(x); yb = torch.empty(8192, dtype=torch.bfloat16, device="cuda")
             s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
