@@ -308,7 +308,7 @@ def mul_mat_host(w: QuantTensor, x_host: np.ndarray) -> np.ndarray:
 class NvlsComm(ctypes.Structure):
     """struct b200q_nvls_comm of include/b200q.h"""
     _fields_ = [("ll_mc", c_void_p), ("ll_local", c_void_p), ("ll_reduced", c_void_p), ("ll_stride", c_int64),
-                ("world_size", ctypes.c_uint32), ("rank", ctypes.c_uint32), ("ll_state", c_void_p)]
+                ("world_size", ctypes.c_uint32), ("rank", ctypes.c_uint32), ("ll_state", c_void_p), ("ll_peers", ctypes.POINTER(c_void_p))]
 
 
 class NvlsStage(ctypes.Structure):
@@ -385,8 +385,16 @@ class NvlsReducer:
         """ctypes b200q_nvls_comm for the fused tensor-parallel mat-vec (b200q_mul_mat_vec_tp)."""
         assert self.ok
         if not hasattr(self, "_comm"):
+            peers = None
+            try:        # every rank's mapping of the symmetric buffer (peer memory): unicast variant of the tagged-slot exchange
+                ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+                if len(ptrs) == self.world and self.world <= 8 and all(ptrs):
+                    self._peer_arr = (c_void_p * self.world)(*[p + self.ll_off for p in ptrs])
+                    peers = ctypes.cast(self._peer_arr, ctypes.POINTER(c_void_p))
+            except Exception:
+                peers = None
             self._comm = NvlsComm(self.mc + self.ll_off, self.local + self.ll_off, self.ll_reduced.data_ptr(), self.ll_stride, self.world, self.rank,
-                                  self.state.data_ptr() + 48)
+                                  self.state.data_ptr() + 48, peers)
         return self._comm
 
     def reduced_view(self, n: int) -> torch.Tensor:

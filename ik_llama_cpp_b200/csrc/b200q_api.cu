@@ -250,6 +250,15 @@ int b200q_mul_mat_vec_tp(int type, int n_tensors, const void * const * W, const 
     if (comm) {
         d.tp.ll_mc = (float2 *)comm->ll_mc; d.tp.ll_local = (const float2 *)comm->ll_local; d.tp.ll_red = (float2 *)comm->ll_reduced; d.tp.ll_stride = comm->ll_stride;
         d.tp.world = comm->world_size; d.tp.rank = comm->rank; d.tp.seq = (uint32_t *)comm->ll_state; d.tp.in = reduce_in != 0; d.tp.out = reduce_out != 0;
+        // unicast variant (peer stores, rows of a CTA coalesced): measured SLOWER than the multicast stores at 2 GPUs (578-583 vs 626 tok/s, same box,
+        // profiles/r2_tp_timeline.md) -> opt-in only
+        static const int ucast = [] { const char * e = getenv("B200Q_TP_UNICAST"); return e ? atoi(e) : 0; }();
+        if (ucast && comm->ll_peers && comm->world_size <= 8) {
+            for (uint32_t r = 0; r < comm->world_size; ++r) {
+                if (!comm->ll_peers[r] || ((uintptr_t)comm->ll_peers[r] & 15)) return fail(B200Q_E_ARG, "b200q_mul_mat_vec_tp: bad peer mapping");
+                d.tp.ll_peer[r] = (float2 *)comm->ll_peers[r];
+            }
+        }
     }
     return check_launch(b200q_launch_mmvq(d, (cudaStream_t)stream), "b200q_mul_mat_vec_tp");
 }

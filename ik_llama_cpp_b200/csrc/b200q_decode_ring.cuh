@@ -344,6 +344,14 @@ __device__ __forceinline__ void tp_bcast1(float2 * mc, float v, uint32_t id) {
 __device__ __forceinline__ void tp_bcast2(float2 * mc, float v0, float v1, uint32_t id) {       // two adjacent rows: 16 bytes, 16-byte aligned
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v0), "f"(__uint_as_float(id)), "f"(v1), "f"(__uint_as_float(id)) : "memory");
 }
+// the same entries as ordinary stores into ONE rank's copy (peer memory): lanes that write consecutive 16-byte entries are coalesced by the LSU into
+// 128-byte NVLink packets, which the multicast stores above are not (one packet per lane)
+__device__ __forceinline__ void tp_ucast1(float2 * p, float v, uint32_t id) {
+    asm volatile("st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v), "f"(__uint_as_float(id)) : "memory");
+}
+__device__ __forceinline__ void tp_ucast2(float2 * p, float v0, float v1, uint32_t id) {
+    asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v0), "f"(__uint_as_float(id)), "f"(v1), "f"(__uint_as_float(id)) : "memory");
+}
 
 __device__ __forceinline__ void rb_arrive(uint64_t * bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory"); }
 
@@ -632,9 +640,18 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
                                 float * rb = reinterpret_cast<float *>(smem_raw + a.tp_rowbuf_off);
                                 rb[rel] = v0; if (two) rb[rel + 1] = v1;
                             } else {
-                                float2 * mc = a.tp.ll_mc + ((int64_t)(tps & 1) * a.tp.world + a.tp.rank) * a.tp.ll_stride + (int64_t)sgm.row0 + crow;
-                                if (two && !(((int64_t)sgm.row0 + crow) & 1)) tp_bcast2(mc, v0, v1, tps + 1);
-                                else { tp_bcast1(mc, v0, tps + 1); if (two) tp_bcast1(mc + 1, v1, tps + 1); }
+                                const int64_t off = ((int64_t)(tps & 1) * a.tp.world + a.tp.rank) * a.tp.ll_stride + (int64_t)sgm.row0 + crow;
+                                const bool al = two && !(((int64_t)sgm.row0 + crow) & 1);
+                                if (a.tp.ll_peer[0]) {
+                                    for (uint32_t r = 0; r < a.tp.world; ++r) {
+                                        if (al) tp_ucast2(a.tp.ll_peer[r] + off, v0, v1, tps + 1);
+                                        else { tp_ucast1(a.tp.ll_peer[r] + off, v0, tps + 1); if (two) tp_ucast1(a.tp.ll_peer[r] + off + 1, v1, tps + 1); }
+                                    }
+                                } else {
+                                    float2 * mc = a.tp.ll_mc + off;
+                                    if (al) tp_bcast2(mc, v0, v1, tps + 1);
+                                    else { tp_bcast1(mc, v0, tps + 1); if (two) tp_bcast1(mc + 1, v1, tps + 1); }
+                                }
                             }
                         } else { sgm.dst[(int64_t)c * sgm.M + crow] = v0; if (two) sgm.dst[(int64_t)c * sgm.M + crow + 1] = v1; }
                     }
@@ -672,8 +689,18 @@ __global__ void __launch_bounds__(32 * (B200Q_RING_CONSUMERS + 1), B200Q_MIN_CTA
         asm volatile("bar.sync 1, %0;" ::"r"(cthreads) : "memory");           // every consumer warp of the CTA has deposited its rows
         const int r0 = RPU * c0, r1 = min(RPU * c1, (int)a.M_total), n = min(r1 - r0, a.tp_rowbuf_rows - 1);
         const float * rb = reinterpret_cast<const float *>(smem_raw + a.tp_rowbuf_off);
-        float2 * mc = a.tp.ll_mc + ((int64_t)(tps & 1) * a.tp.world + a.tp.rank) * a.tp.ll_stride + r0;
-        if (cw == 0) {
+        const int64_t off = ((int64_t)(tps & 1) * a.tp.world + a.tp.rank) * a.tp.ll_stride + r0;
+        if (a.tp.ll_peer[0]) {
+            // unicast: consumer warp w serves ranks w, w + ncw, ...; one warp-wide store of consecutive 16-byte entries per 64 rows
+            for (uint32_t r = (uint32_t)cw; r < a.tp.world; r += (uint32_t)ncw) {
+                float2 * p = a.tp.ll_peer[(r + a.tp.rank) % a.tp.world] + off;          // start with the own copy, then the peers in ring order
+                if (!(r0 & 1)) {
+                    for (int i = 2 * lane; i + 1 < n; i += 64) tp_ucast2(p + i, rb[i], rb[i + 1], tps + 1);
+                    if ((n & 1) && lane == 0) tp_ucast1(p + n - 1, rb[n - 1], tps + 1);
+                } else for (int i = lane; i < n; i += 32) tp_ucast1(p + i, rb[i], tps + 1);
+            }
+        } else if (cw == 0) {
+            float2 * mc = a.tp.ll_mc + off;
             if (!(r0 & 1)) {                                                   // 16-byte lanes: {v, tag, v', tag}
                 for (int i = 2 * lane; i + 1 < n; i += 64) tp_bcast2(mc + i, rb[i], rb[i + 1], tps + 1);
                 if ((n & 1) && lane == 0) tp_bcast1(mc + n - 1, rb[n - 1], tps + 1);
@@ -850,7 +877,8 @@ static int launch_mmvq_ring_tp(const mmvq_args & a, const ring_geom & g0, int sm
         const int64_t rows = (PAIR ? 2 : 1) * ((n_pairs + grid - 1) / grid + 1) + 2;
         // (measured at 2 GPUs: 559 tok/s with the row buffer vs 575 without on the same box: no gain, the extra CTA barrier costs more than the
         // coalescing saves -> off by default, B200Q_TP_ROWBUF=1 enables it)
-        static const int on = [] { const char * e = getenv("B200Q_TP_ROWBUF"); return e ? atoi(e) : 0; }();
+        static const int on_env = [] { const char * e = getenv("B200Q_TP_ROWBUF"); return e ? atoi(e) : -1; }();
+        const bool on = on_env >= 0 ? on_env != 0 : a.tp.ll_peer[0] != nullptr;       // the coalescing only exists for the unicast stores
         if (on && rows <= 2048 && smem + rows * 4 + 16 <= budget) {
             ra.a.tp_rowbuf_off = (int)((smem + 15) & ~(size_t)15); ra.a.tp_rowbuf_rows = (int)rows;
             smem = (size_t)ra.a.tp_rowbuf_off + rows * 4;

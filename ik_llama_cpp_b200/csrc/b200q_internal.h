@@ -53,6 +53,7 @@ struct b200q_tp_comm {
     const float2 * ll_local;     // this rank's mapping of the same
     float2 * ll_red;             // rank-local [2 parities][ll_stride]: the summed vector, same tagging (filled cooperatively by the consumer's CTAs)
     int64_t ll_stride; uint32_t world, rank;
+    float2 * ll_peer[8];         // optional: every rank's mapping of the slot array (peer memory over NVLink); ll_peer[0] != nullptr selects unicast stores
     uint32_t * seq;              // rank-local: [0] reduces issued by this rank, [1] CTA arrival counter
     int in; int out;
 };

@@ -135,6 +135,10 @@ B200Q_API int b200q_reduce_sum_nvls_bf16(const float * in, float * out_f32, void
  *   ll_reduced: rank-local, 2 * ll_stride entries, zero-initialised; ll_state: rank-local u32[2], zero-initialised; all 16-byte aligned. */
 typedef struct b200q_nvls_comm {
     void * ll_mc; const void * ll_local; void * ll_reduced; int64_t ll_stride; uint32_t world_size; uint32_t rank; void * ll_state;
+    void * const * ll_peers;    /* optional (HOST array of world_size device pointers, world_size <= 8): every rank's mapping of the slot array in THIS
+                                 * rank's address space (peer memory).  When given, reduce_out writes each peer's copy with ordinary stores, the rows of
+                                 * a CTA as consecutive 16-byte lanes of one warp (coalesced into 128-byte NVLink packets), instead of one multicast
+                                 * store per row pair.  NULL: multimem.st only. */
 } b200q_nvls_comm;
 B200Q_API int b200q_mul_mat_vec_tp(int type, int n_tensors, const void * const * W, const void * W_gate, float * const * dst, const int64_t * m,
                          int64_t k, const float * x, int unary, float limit, const b200q_nvls_comm * comm, int reduce_in, int reduce_out, void * stream);
