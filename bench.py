@@ -157,7 +157,10 @@ class Model:
         self.bf16_reduce = False
         if tp > 1 and collective and os.environ.get("B200Q_NCCL_REDUCE", "0") != "1":
             self.reducer = be.NvlsReducer(512 * N_EMBD)
-            self.fused_tp = self.reducer.ok and os.environ.get("B200Q_TP_FUSED", "1") == "1"
+            # decode: the reduce fused into the mat-vecs (tagged-slot exchange) wins at 2 ranks (595-631 vs 574 tok/s) but its cost grows with the number
+            # of ranks (+4.5 us per exchange at N = 2, +9.5 us at N = 4: 511-532 tok/s), while the one-shot reduce kernel's rendezvous did not grow with N
+            # in round 1 -> more than 2 ranks use the separate reduce kernel unless B200Q_TP_FUSED says otherwise (profiles/r2_tp_timeline.md)
+            self.fused_tp = self.reducer.ok and os.environ.get("B200Q_TP_FUSED", "1" if tp <= 2 else "0") == "1"
             self.bf16_reduce = self.reducer.ok and os.environ.get("B200Q_TP_BF16_REDUCE", "1") == "1"
             self.launches_tg += 2 * n_layer if (self.reducer.ok and not self.fused_tp) else 0
         self.weight_bytes = sum(t.nbytes_wire for L in self.layers for t in L.values()) + (self.head.nbytes_wire if self.head is not None else 0)
@@ -476,6 +479,9 @@ def main():
     model = Model(be, torch, args.layers, tp=world, rank=rank)
     if model.fused_tp:
         config["reduce"] = "tg: fused into the mat-vec kernels (wo/ffn_down epilogue broadcasts tagged partial rows with multimem.st, the next mat-vec's prologue sums them); pp512: " + \
+            ("two-shot bf16 NVLS kernel (multimem.ld_reduce + multimem.st)" if model.bf16_reduce else "one-shot f32 NVLS kernel")
+    elif model.reducer is not None and model.reducer.ok:
+        config["reduce"] = "tg: one-shot f32 NVLS reduce kernel after wo / ffn_down (multimem.red + multicast flag; default for more than 2 ranks, see Model); pp512: " + \
             ("two-shot bf16 NVLS kernel (multimem.ld_reduce + multimem.st)" if model.bf16_reduce else "one-shot f32 NVLS kernel")
     # ---------------- N > 1: correctness gate on the collectives, before anything is timed ----------------
     if world > 1:
