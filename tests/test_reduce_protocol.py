@@ -141,3 +141,73 @@ def test_tagged_slot_exchange_two_parities(world):
 def test_tagged_slot_exchange_needs_two_parities():
     """With a single buffer a fast rank's reduce i+1 overwrites entries a slow rank has not consumed yet: that rank then waits for tag i forever."""
     assert any(run_tagged(2, n_reduces=6, length=4, seed=s, parities=1)[1] for s in range(40))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# q8 hand-off (k_mmvq_ring<..., Q8 = 2>): the fused up/gate launch quantises its own result in the CTA tails.  A CTA owns a static row range;
+# 32-row blocks inside the range are quantised directly, blocks shared with a neighbour through an arrival counter (rows, not CTAs, are
+# counted): the CTA whose rows complete the block quantises it and re-arms the counter for the next launch.
+# ------------------------------------------------------------------------------------------------------------------------------------
+def run_q8_tail(M, grid, rpu, seed, launches=3):
+    rnd = random.Random(seed)
+    n_units = (M + rpu - 1) // rpu
+    nblk = (M + 31) // 32
+    cnt = [0] * nblk
+    for launch in range(launches):
+        written = [False] * M
+        quantised = [0] * nblk
+        ctas = list(range(grid))
+        rnd.shuffle(ctas)
+        # every CTA: (a) write its rows, (b) tail.  Tails of different CTAs interleave arbitrarily; the atomicAdd is the only shared step.
+        events = []
+        for b in ctas:
+            c0, c1 = n_units * b // grid, n_units * (b + 1) // grid
+            events.append(("rows", b, min(rpu * c0, M), min(rpu * c1, M)))
+        rnd.shuffle(events)
+        pending_tail = []
+        for ev in events:
+            _, b, r0, r1 = ev
+            for r in range(r0, r1):
+                written[r] = True
+            pending_tail.append((b, r0, r1))
+            # randomly run some of the pending tails now (a tail only starts after ITS OWN rows are written)
+            rnd.shuffle(pending_tail)
+            while pending_tail and rnd.random() < 0.5:
+                tb, t0, t1 = pending_tail.pop()
+                if t1 <= t0:
+                    continue
+                for blk in range(t0 >> 5, ((t1 - 1) >> 5) + 1):
+                    lo, hi = max(t0, 32 * blk), min(t1, 32 * blk + 32)
+                    need, own = min(32, M - 32 * blk), hi - lo
+                    mine = own == need
+                    if not mine:
+                        old = cnt[blk]; cnt[blk] += own              # atomicAdd
+                        mine = old + own == need
+                        if mine:
+                            cnt[blk] = 0
+                    if mine:
+                        assert all(written[32 * blk: 32 * blk + need]), ("block quantised before all its rows were written", blk)
+                        quantised[blk] += 1
+        for tb, t0, t1 in pending_tail:                               # the remaining tails
+            if t1 <= t0:
+                continue
+            for blk in range(t0 >> 5, ((t1 - 1) >> 5) + 1):
+                lo, hi = max(t0, 32 * blk), min(t1, 32 * blk + 32)
+                need, own = min(32, M - 32 * blk), hi - lo
+                mine = own == need
+                if not mine:
+                    old = cnt[blk]; cnt[blk] += own
+                    mine = old + own == need
+                    if mine:
+                        cnt[blk] = 0
+                if mine:
+                    assert all(written[32 * blk: 32 * blk + need]), blk
+                    quantised[blk] += 1
+        assert quantised == [1] * nblk, (launch, quantised)
+        assert cnt == [0] * nblk, "arrival counters must be re-armed for the next launch"
+
+
+@pytest.mark.parametrize("M,grid,rpu", [(14336, 296, 2), (7168, 296, 2), (1792, 82, 2), (4096, 296, 1), (200, 7, 2), (64, 3, 2)])
+def test_q8_handoff_tail_protocol(M, grid, rpu):
+    for seed in range(10):
+        run_q8_tail(M, grid, rpu, seed)
