@@ -251,14 +251,13 @@ GGML_CALL static bool b200_backend_supports_op(ggml_backend_t, const ggml_tensor
                    ggml_is_contiguous(op) && ggml_is_contiguous(op->src[0]) && ggml_is_contiguous(op->src[1]) && ggml_are_same_shape(op, op->src[0]) &&
                    op->src[1]->ne[0] == op->ne[0] && (ggml_nelements(op->src[1]) == op->ne[0] || ggml_are_same_shape(op, op->src[1]));
         case GGML_OP_MUL_MAT_ID: case GGML_OP_MOE_FUSED_UP_GATE: {
-            // MoE, small batches (decode): expert ids resolved on the device; larger batches are declined (the grouped prefill GEMM is the next step)
+            // MoE: expert ids resolved on the device; batches beyond the shared-memory capacity of one launch are walked in token chunks by the C ABI
             const bool ug = op->op == GGML_OP_MOE_FUSED_UP_GATE;
             const ggml_tensor * w = op->src[0]; const ggml_tensor * g = ug ? op->src[1] : nullptr; const ggml_tensor * x = op->src[ug ? 2 : 1]; const ggml_tensor * ids = op->src[ug ? 3 : 2];
             if (!w || !x || !ids || (ug && (!g || g->type != w->type || !ggml_are_same_shape(g, w) || op->src[4] || op->src[5] || b200_unary(b200_op_param_i32(op, 0)) < 0))) return false;
             if (!b200_weight_ok(w) || (g && !b200_weight_ok(g)) || x->type != GGML_TYPE_F32 || !ggml_is_contiguous(x) || ids->type != GGML_TYPE_I32 || !ggml_is_contiguous(ids)) return false;
             if (op->type != GGML_TYPE_F32 || !ggml_is_contiguous(op) || w->ne[0] != x->ne[0] || x->ne[3] != 1 || ids->ne[1] != x->ne[2] || ids->ne[0] % x->ne[1]) return false;
-            const int64_t ncx = x->ne[1] * x->ne[2];
-            return x->ne[2] <= 8 && ncx * (w->ne[0] + w->ne[0] / 4) <= 200 * 1024;
+            return x->ne[1] * (w->ne[0] + w->ne[0] / 4) <= 200 * 1024;      // one token's columns must fit
         }
         case GGML_OP_FUSED_UP_GATE:
             return op->src[0] && op->src[1] && !op->src[3] && !op->src[4] && op->src[0]->type == op->src[1]->type && op->src[2] && op->src[2]->ne[2] * op->src[2]->ne[3] == 1 &&

@@ -401,10 +401,24 @@ int b200q_mul_mat_id_vec(int type, const void * W, const void * W_gate, int n_ex
     if (!W || !ids || !x || !dst || m <= 0 || n_expert < 1) return fail(B200Q_E_ARG, "b200q_mul_mat_id_vec: bad argument");
     dev_info & di = device_info(); if (!di.ok) return fail(B200Q_E_CUDA, "b200q_mul_mat_id_vec: no CUDA device");
     if (((uintptr_t)x & 15) || (k & 3)) return fail(B200Q_E_ARG, "b200q_mul_mat_id_vec: activations must be 16-byte aligned");
-    b200q_mmvq_id_desc d; memset(&d, 0, sizeof d);
-    d.type = type; d.W = W; d.W2 = W_gate; d.ids = ids; d.x = x; d.dst = dst; d.M = m; d.K = k; d.n_expert = n_expert; d.n_used = n_used; d.nb1 = nb1; d.n_tokens = n_tokens;
-    d.act = unary; d.limit = limit; d.sm_count = di.sm_count; d.pdl = opt_pdl();
-    return check_launch(b200q_launch_mmvq_id(d, (cudaStream_t)stream), "b200q_mul_mat_id_vec");
+    if (n_tokens < 1 || n_used < 1 || nb1 < 1 || n_used % nb1) return fail(B200Q_E_ARG, "b200q_mul_mat_id_vec: bad token / slot counts");
+    // the quantised activation columns of a launch live in shared memory: larger batches are walked in token chunks (same kernel, the expert ids
+    // never leave the device).  This is the functional path for MoE prefill, not a tuned one: a grouped tensor-core GEMM is not built.
+    const int64_t col_bytes = (int64_t)nb1 * (k + k / 4);
+    int chunk = (int)((200 * 1024) / (col_bytes > 0 ? col_bytes : 1));
+    static const int forced = [] { const char * e = getenv("B200Q_MOE_CHUNK_TOKENS"); return e ? atoi(e) : 0; }();
+    if (forced > 0 && forced < chunk) chunk = forced;
+    if (chunk < 1) return fail(B200Q_E_SHAPE, "b200q_mul_mat_id_vec: one token's activation columns do not fit shared memory");
+    for (int t0 = 0; t0 < n_tokens; t0 += chunk) {
+        const int nt = n_tokens - t0 < chunk ? n_tokens - t0 : chunk;
+        b200q_mmvq_id_desc d; memset(&d, 0, sizeof d);
+        d.type = type; d.W = W; d.W2 = W_gate; d.ids = ids + (int64_t)t0 * n_used; d.x = x + (int64_t)t0 * nb1 * k; d.dst = dst + (int64_t)t0 * n_used * m;
+        d.M = m; d.K = k; d.n_expert = n_expert; d.n_used = n_used; d.nb1 = nb1; d.n_tokens = nt;
+        d.act = unary; d.limit = limit; d.sm_count = di.sm_count; d.pdl = opt_pdl();
+        const int rc = check_launch(b200q_launch_mmvq_id(d, (cudaStream_t)stream), "b200q_mul_mat_id_vec");
+        if (rc) return rc;
+    }
+    return B200Q_OK;
 }
 int b200q_mul_mat_host(int type, const void * W, const float * x_host, float * dst_host, int64_t m, int64_t k, int64_t n, void * stream) {
     cudaStream_t st = (cudaStream_t)stream; cudaError_t e; int rc;

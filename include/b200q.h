@@ -159,8 +159,9 @@ B200Q_API int b200q_add_rows(const float * a, const float * b, float * dst, int6
  * ggml-cuda.cu:2836-3540; mul_mat_vec_q with ids, mmvq-templates.cuh:293-302).  W: n_expert matrices [m x k] of `type`, each in the device layout,
  * b200q_plane_bytes(type, m, k) apart; ids: DEVICE int32 [n_tokens][n_used]; x f32 [n_tokens][nb1][k] (nb1 = 1: the column is shared by the slots of
  * a token, nb1 = n_used: one column per slot); dst f32 [n_tokens][n_used][m]:  dst[t][e] = W[ids[t][e]] . x[t][e % nb1]
- * (W_gate != NULL: unary(W_gate[id] . x) * (W[id] . x)).  One launch, expert ids resolved on the device.  n_tokens * nb1 activation columns must fit
- * shared memory (<= 200 KB of q8_1); larger batches go through the grouped prefill path. */
+ * (W_gate != NULL: unary(W_gate[id] . x) * (W[id] . x)).  Expert ids are resolved on the device.  The quantised activation columns of a launch live
+ * in shared memory (200 KB of q8_1): batches whose n_tokens * nb1 columns exceed that are walked in token chunks by the same kernel (functional
+ * path for MoE prefill; a grouped tensor-core GEMM over expert-sorted tokens is not built). */
 B200Q_API int b200q_mul_mat_id_vec(int type, const void * W, const void * W_gate, int n_expert, const int32_t * ids, const float * x, float * dst,
                          int64_t m, int64_t k, int n_used, int nb1, int n_tokens, int unary, float limit, void * stream);
 /* same through HOST activations/results: H2D(x) -> mul_mat -> D2H(dst), synchronous (end-to-end entry point) */

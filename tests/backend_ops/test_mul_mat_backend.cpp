@@ -303,6 +303,8 @@ int main(int argc, char ** argv) {
             fails += run_moe_case(be, cpu, t, 1, false, false, ++seed);    // ... then the down experts, one column per slot
             fails += run_moe_case(be, cpu, t, 4, true, false, ++seed);
         }
+        fails += run_moe_case(be, cpu, GGML_TYPE_IQ4_NL, 24, true, true, ++seed);       // prefill-sized batches: same kernel, walked in token chunks
+        fails += run_moe_case(be, cpu, GGML_TYPE_Q4_K, 24, false, false, ++seed);
         fails += run_async_case(be);
     }
     if (!quick) {   // bitnet shapes: K = 3200 is not a multiple of 256
