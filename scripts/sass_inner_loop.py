@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Static cost of the decode inner loop per quant type: instruction mix of the tightest IDP.4A loop of k_mmvq_ring<TYPE,1,false,false,true,false>
-(two items = the same 32 weights of a row pair per trip), from cuobjdump -sass.  usage: sass_inner_loop.py [libb200q.so] > profiles/r1_sass_inner_loops.md"""
+"""Static cost of the decode inner loop per quant type: instruction mix of the tightest IDP.4A loop of k_mmvq_ring<TYPE,1,false,false,true,false,0>
+(two items = the same 32 weights of a row pair per trip), from cuobjdump -sass.  usage: sass_inner_loop.py [libb200q.so] > profiles/r2_sass_inner_loops.md"""
 import collections
 import re
 import subprocess
@@ -35,7 +35,7 @@ def loops(fn):
 print("# decode inner loop per type (static, from SASS): one trip = the same 32-weight item of the two rows of a pair (IQ2_BN: 64 weights)\n")
 print("| type | bpw | instr / item | ALU pipe | FMA pipe (IDP.4A) | LDS | other | kernel instr |\n|---|---:|---:|---:|---:|---:|---:|---:|")
 for t, name in TYPES.items():
-    fn = f"_Z11k_mmvq_ringILi{t}ELi1ELb0ELb0ELb1ELb0EEv14mmvq_ring_args"
+    fn = f"_Z11k_mmvq_ringILi{t}ELi1ELb0ELb0ELb1ELb0ELi0EEv14mmvq_ring_args"
     total, body = loops(fn)
     if not body:
         print(f"| {name} | {BPW[name]} | (no loop found) | | | | | {total} |")
