@@ -290,34 +290,19 @@ def test_mul_mat_id(be, oracle, name, n_tokens, nb1, glu):
             assert np.abs(y[tk, e] - ref).max() <= 5e-5 * max(rms(ref), 1e-30), (tk, e)
 
 
-def test_mul_mat_id_token_chunks(be, oracle, monkeypatch):
-    """Batches beyond one launch's shared-memory capacity are walked in token chunks (forced to 3 tokens per launch here): 20 tokens, both column modes."""
-    import subprocess, sys, textwrap
-    # the chunk size is read once per process: run the check in a child with the knob set
-    code = textwrap.dedent('''
-        import os, sys, numpy as np, torch
-        sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
-        from conftest import make_wire
-        from ik_llama_cpp_b200 import backend as be
-        from oracle.oracle import GGML_TYPE, Oracle
-        orc = Oracle(); t = GGML_TYPE["IQ4_NL"]; n_expert, n_used, m, k, n_tokens = 5, 2, 132, 1024, 20
-        wires = [make_wire(orc, "IQ4_NL", m, k, seed=900 + e) for e in range(n_expert)]
-        W = be.set_expert_tensor(t, np.concatenate(wires), n_expert, m, k)
-        rng = np.random.default_rng(3)
-        for nb1 in (1, 2):
-            x = rng.standard_normal((n_tokens, nb1, k)).astype(np.float32)
-            ids = np.stack([rng.permutation(n_expert)[:n_used] for _ in range(n_tokens)]).astype(np.int32)
-            y = be.mul_mat_id(W, torch.from_numpy(x).cuda(), torch.from_numpy(ids).cuda()).cpu().numpy()
-            for tk in range(n_tokens):
-                for e in range(n_used):
-                    ref = orc.mul_mat_q8_1(t, wires[ids[tk, e]], x[tk, e % nb1][None, :], m, variant="b200")[0]
-                    assert np.abs(y[tk, e] - ref).max() <= 5e-5 * float(np.sqrt((ref.astype(np.float64) ** 2).mean())), (nb1, tk, e)
-        print("CHUNKS-OK")
-    ''')
+def test_mul_mat_id_token_chunks(be):
+    """Batches beyond one launch's shared-memory capacity are walked in token chunks: 20 tokens, both column modes, in one launch and forced to
+    3 tokens per launch.  The chunk size is read once per process, so the check (scripts/moe_chunk_check.py) runs in child processes."""
     import os
-    env = dict(os.environ, B200Q_MOE_CHUNK_TOKENS="3")
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), timeout=300)
-    assert "CHUNKS-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for forced in (None, "3"):
+        env = dict(os.environ)
+        if forced:
+            env["B200Q_MOE_CHUNK_TOKENS"] = forced
+        r = subprocess.run([sys.executable, os.path.join(root, "scripts", "moe_chunk_check.py")], capture_output=True, text=True, env=env, cwd=root, timeout=300)
+        assert "CHUNKS-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
 
 
 def test_add_rows(be):
