@@ -1,4 +1,5 @@
-"""MoE token-chunk check (run by tests/test_gpu_parity.py::test_mul_mat_id_token_chunks in child processes, with and without B200Q_MOE_CHUNK_TOKENS):\n20 tokens through b200q_mul_mat_id_vec, both activation-column modes, against the mat-vec oracle on the selected expert."""
+"""MoE token-chunk check (run by tests/test_gpu_parity.py::test_mul_mat_id_token_chunks in child processes, with and without B200Q_MOE_CHUNK_TOKENS):
+20 tokens through b200q_mul_mat_id_vec, both activation-column modes, against the mat-vec oracle on the selected expert."""
 import os, sys, numpy as np, torch
 sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 from conftest import make_wire
